@@ -1,0 +1,100 @@
+/*
+ * qv2x.h -- C ABI of libqv2x.so: the B200 (sm_100a) fast path for QuantV2X's fully quantized
+ * intermediate-fusion inference (quantized BEV backbone convs -> codebook encode -> [indices on the
+ * wire] -> codebook decode -> ego-side max / attention fusion -> detection heads).
+ *
+ * Every entry point replaces one PyTorch call site of the reference (paths relative to the reference
+ * repository root); the reference has no FFI of its own -- the binding a maintainer adds is the
+ * ctypes shim shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Pointers named d_* are DEVICE pointers; everything
+ *     else is host memory that is only read during the call.
+ *   - every function returns 0 on success or a negative qv2x_status; qv2x_last_error() returns a
+ *     thread-local message.  Nothing throws, exits or synchronises the device unless stated.
+ *   - forward calls are asynchronous on `stream` (a cudaStream_t passed as void*).  Handles are
+ *     immutable after create, so forwards are re-entrant across streams given distinct buffers.
+ *   - activations are uint8 NHWC ("pixel-major"): [n_img][H][W][channel stride]; activation zero
+ *     points are 0 (every quantized activation on this path follows a ReLU, reference
+ *     quant_layer.py:177-187 gives zp = 0 for a non-negative range).
+ */
+#ifndef QV2X_H_
+#define QV2X_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    QV2X_OK = 0,
+    QV2X_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    QV2X_ERR_CUDA = -2,        /* a CUDA runtime or driver call failed */
+    QV2X_ERR_DEVICE = -3,      /* not an sm_100 device */
+    QV2X_ERR_NOMEM = -4
+} qv2x_status;
+
+const char* qv2x_last_error(void);
+int qv2x_version(void);
+/* 0 when `device` is a compute-capability 10.x GPU (tcgen05/TMEM present). */
+int qv2x_device_check(int device);
+/* Number of kernels this library has launched since load (all threads); bench.py reports it. */
+long long qv2x_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * One quantized layer = reference QuantModule.forward (opencood/quant/quant_layer.py:391-410) with
+ * use_weight_quant = use_act_quant = True: fake-quant(weight) -> F.conv2d / F.conv_transpose2d (+bias)
+ * -> folded-BN identity -> ReLU -> fake-quant(activation), restated on integers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_layer qv2x_layer;
+
+typedef struct {
+    int kind;            /* 0: nn.Conv2d, 1: nn.ConvTranspose2d with kernel_size == stride, padding 0 */
+    int cin, cout;
+    int ksize;           /* conv: 1 or 3; transposed conv: == stride */
+    int stride;          /* conv: 1 or 2; transposed conv: 1, 2 or 4 */
+    int pad;             /* conv: zeros on every side (3x3 'same' = 1; ZeroPad2d(1)+padding 0 = 1) */
+    int w_bits;          /* 2..8 (reference UniformAffineQuantizer.n_bits) */
+    int relu;            /* activation_function is nn.ReLU */
+    int n_in_groups;     /* 1, or 3 when the input is torch.cat of three tensors with different scales
+                            (reference base_bev_backbone.py:111-112); cin is split evenly */
+    float in_delta[3];   /* act_quantizer.delta of the tensor(s) feeding this layer */
+    float out_delta;     /* this layer's act_quantizer.delta */
+    float out_zero_point;/* this layer's act_quantizer.zero_point (0 after ReLU) */
+    int out_bits;        /* act_quantizer.n_bits (<= 8) */
+} qv2x_layer_desc;
+
+/* w_int: the integer weight grid round(w/delta)+zp clamped to [0, 2^w_bits-1], in PyTorch layout
+ *        ([cout][cin][k][k] for conv, [cin][cout][k][k] for transposed conv), one byte each.
+ * w_delta / w_zero_point: per dim-0 channel (cout entries for conv, cin for transposed conv --
+ *        reference quant_layer.py:325-335 quantizes along dim 0 for both).
+ * bias: cout floats or NULL.  All host pointers. */
+int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const float* w_delta,
+                      const float* w_zero_point, const float* bias, qv2x_layer** out);
+void qv2x_layer_destroy(qv2x_layer* layer);
+/* 1 if forward needs d_rowsum_in (uint8 x uint8 path with per-channel weight zero-points). */
+int qv2x_layer_needs_rowsum(const qv2x_layer* layer);
+
+/* d_x: [n_img][hi][wi][in_cstride] uint8, the layer's channels start at in_cbase.
+ * d_rowsum_in: n_in_groups device pointers (host array), each [n_img][hi][wi] int32 = per-pixel sum of
+ *        that group's input bytes; may be NULL when qv2x_layer_needs_rowsum() == 0.
+ * d_y: [n_img][ho][wo][out_cstride] uint8, written at channel out_cbase.
+ * d_rowsum_out: [n_img][ho][wo] int32, ACCUMULATED into (caller zeroes it), or NULL.
+ * d_acc_dump: [n_groups][n_img*gemm_rows][n_cols] int32 zero-point-corrected accumulators, or NULL
+ *        (test hook for the "int32 accumulators bit-exact" check). */
+int qv2x_layer_forward(const qv2x_layer* layer, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
+                       int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride,
+                       int out_cbase, int32_t* d_rowsum_out, int32_t* d_acc_dump, void* stream);
+/* Output extent of a layer for a given input extent. */
+int qv2x_layer_out_shape(const qv2x_layer* layer, int hi, int wi, int* ho, int* wo);
+
+/* Per-pixel channel sums of a uint8 NHWC tensor: d_out[p] = sum_c d_x[p*cstride + cbase + c], c < c. */
+int qv2x_rowsum_u8(const uint8_t* d_x, long long n_pixels, int cstride, int cbase, int c, int32_t* d_out,
+                   void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QV2X_H_ */

@@ -1,0 +1,85 @@
+"""ctypes binding of libqv2x.so (C ABI declared in include/qv2x.h).
+
+The library is the product: there is no Python/CPU fallback.  Importing this module never needs a GPU
+(the shared object links the CUDA runtime statically and resolves driver symbols lazily), but every
+compute entry point fails loudly if the library or an sm_100 device is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_longlong, c_uint8, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqv2x.so")
+
+
+class Qv2xError(RuntimeError):
+    pass
+
+
+class LayerDesc(ctypes.Structure):
+    """Mirror of qv2x_layer_desc (include/qv2x.h)."""
+
+    _fields_ = [
+        ("kind", c_int),
+        ("cin", c_int),
+        ("cout", c_int),
+        ("ksize", c_int),
+        ("stride", c_int),
+        ("pad", c_int),
+        ("w_bits", c_int),
+        ("relu", c_int),
+        ("n_in_groups", c_int),
+        ("in_delta", c_float * 3),
+        ("out_delta", c_float),
+        ("out_zero_point", c_float),
+        ("out_bits", c_int),
+    ]
+
+
+_lib = None
+
+
+def _declare(lib):
+    lib.qv2x_last_error.restype = c_char_p
+    lib.qv2x_last_error.argtypes = []
+    lib.qv2x_version.restype = c_int
+    lib.qv2x_device_check.argtypes = [c_int]
+    lib.qv2x_launch_count.restype = c_longlong
+    lib.qv2x_layer_create.argtypes = [POINTER(LayerDesc), c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.qv2x_layer_destroy.argtypes = [c_void_p]
+    lib.qv2x_layer_destroy.restype = None
+    lib.qv2x_layer_needs_rowsum.argtypes = [c_void_p]
+    lib.qv2x_layer_out_shape.argtypes = [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int)]
+    lib.qv2x_layer_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, POINTER(c_void_p),
+                                       c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.qv2x_rowsum_u8.argtypes = [c_void_p, c_longlong, c_int, c_int, c_int, c_void_p, c_void_p]
+
+
+def lib():
+    """Load libqv2x.so once; raise if it has not been built (python __graft_entry__.py / make -C csrc)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise Qv2xError(f"{LIB_PATH} is missing: build it with `make -C quantv2x_b200/csrc` "
+                            "(there is no CPU fallback)")
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise Qv2xError(f"libqv2x error {rc}: {lib().qv2x_last_error().decode()}")
+
+
+def exported_symbols():
+    """Names declared in include/qv2x.h (used by the CPU test that the library exports all of them)."""
+    import re
+
+    hdr = os.path.join(os.path.dirname(_HERE), "include", "qv2x.h")
+    text = open(hdr).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qv2x_[a-z0-9_]+)\s*\(", text)))

@@ -1,0 +1,57 @@
+// Small HBM-bound helper kernels around the igemm path.
+#include <algorithm>
+
+#include "host_common.h"
+
+namespace qv2x {
+
+// Per-pixel channel sums of a uint8 NHWC tensor (the S term of the uint8 x uint8 zero-point algebra).
+// A group of L lanes owns one pixel; every lane reads 16-byte chunks, sums bytes with dp4a, then the
+// group reduces with shuffles.  Coalesced: consecutive lanes read consecutive 16-byte chunks.
+template <int L>
+__global__ void rowsum_u8_kernel(const uint8_t* __restrict__ x, long long n_pixels, int cstride, int cbase, int c,
+                                 int32_t* __restrict__ out) {
+    const int lane_in_group = threadIdx.x % L;
+    const long long group = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) / L;
+    const long long n_groups = static_cast<long long>(gridDim.x) * blockDim.x / L;
+    const int chunks = c / 16;
+    for (long long p = group; p < n_pixels; p += n_groups) {
+        const uint4* src = reinterpret_cast<const uint4*>(x + p * cstride + cbase);
+        unsigned int s = 0;
+        for (int i = lane_in_group; i < chunks; i += L) {
+            const uint4 v = __ldg(src + i);
+            s = __dp4a(v.x, 0x01010101u, s);
+            s = __dp4a(v.y, 0x01010101u, s);
+            s = __dp4a(v.z, 0x01010101u, s);
+            s = __dp4a(v.w, 0x01010101u, s);
+        }
+#pragma unroll
+        for (int o = L / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, L);
+        if (lane_in_group == 0) out[p] = static_cast<int32_t>(s);
+    }
+}
+
+}  // namespace qv2x
+
+using namespace qv2x;
+
+extern "C" int qv2x_rowsum_u8(const uint8_t* d_x, long long n_pixels, int cstride, int cbase, int c, int32_t* d_out,
+                              void* stream_) {
+    QV2X_REQUIRE(d_x && d_out, "qv2x_rowsum_u8: null argument");
+    QV2X_REQUIRE(c > 0 && c % 16 == 0 && cstride % 16 == 0 && cbase % 16 == 0, "channels must be multiples of 16");
+    if (n_pixels <= 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int threads = 256;
+    auto launch = [&](auto kern, int L) {
+        long long want = (n_pixels * L + threads - 1) / threads;
+        const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 16));
+        kern<<<grid, threads, 0, stream>>>(d_x, n_pixels, cstride, cbase, c, d_out);
+        g_launch_count.fetch_add(1);
+    };
+    if (c <= 64) launch(rowsum_u8_kernel<4>, 4);
+    else if (c <= 128) launch(rowsum_u8_kernel<8>, 8);
+    else if (c <= 256) launch(rowsum_u8_kernel<16>, 16);
+    else launch(rowsum_u8_kernel<32>, 32);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}

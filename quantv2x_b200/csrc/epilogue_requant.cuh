@@ -1,0 +1,115 @@
+// Fused requantization epilogue of the quantized conv / deconv layers.
+//
+// Reference semantics (opencood/quant/quant_layer.py:391-410 with :132-148): fake-quant weight ->
+// conv (+bias) -> folded BN = identity -> ReLU -> fake-quant activation.  Restated on integers
+// (SURVEY Appendix A.1); normative fp32 operation order, every operation rounded separately (no FMA):
+//     t_g = float( acc_g[p,n] - zpw_g[n] * S_g[p] )                     (int32 exact, then RN convert)
+//     v   = gs[0]*t_0  (+ gs[1]*t_1 + gs[2]*t_2, left to right)
+//     y   = v * cs[n] + bias[n] ;  y = max(y, 0) if relu
+//     q   = clamp( rint(y / delta_out) + zp_out, 0, qmax )              (true division, half-to-even)
+// S_g[p] is the sum of the group's input bytes over the receptive field of p (zero padding adds 0
+// because the activation zero-point is 0 after ReLU); it is rebuilt from per-pixel channel sums
+// ("rowsums") that the producing layer's epilogue emitted, so the tensor pipe does no extra work.
+#pragma once
+#include "igemm.cuh"
+
+namespace qv2x {
+
+template <int G>
+struct RequantEpilogue {
+    // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
+    // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
+    int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
+    int relu;
+    float qmax, delta_out, zp_out;
+    float gscale[kMaxGroups];
+    const float* cscale;                  // [N_total]
+    const float* bias;                    // [N_total]
+    const int32_t* zpw[kMaxGroups];       // [N_total] or nullptr (weights already zero-centred)
+    const int32_t* rowsum_in[kMaxGroups]; // [n_img*Hi*Wi] or nullptr
+    uint8_t* out;
+    int32_t* rowsum_out;                  // [n_img*Hout*Wout] (atomically accumulated) or nullptr
+    int32_t* acc_dump;                    // [G][n_img*Ho*Wo][N_total] zero-point-corrected accumulators, or nullptr
+    int n_total;
+
+    struct Tile {
+        int32_t S[G];
+        long long opix;   // output pixel index, -1 if this row is outside the image
+        long long mrow;   // GEMM row index (for acc_dump)
+        int rsum;
+    };
+
+    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row) const {
+        const int lx = row % g.tw, ly = row / g.tw;
+        const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
+        const bool valid = (ox < g.Wo) && (oy < g.Ho);
+        ts.rsum = 0;
+        ts.opix = -1;
+        ts.mrow = -1;
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) ts.S[grp] = 0;
+        if (!valid) return;
+        ts.mrow = (static_cast<long long>(tc.img) * g.Ho + oy) * g.Wo + ox;
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) {
+            if (rowsum_in[grp] == nullptr) continue;
+            const int32_t* rs = rowsum_in[grp] + static_cast<long long>(tc.img) * g.Hi * g.Wi;
+            int32_t s = 0;
+            for (int tap = 0; tap < g.taps; ++tap) {
+                const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+                if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) s += __ldg(rs + iy * g.Wi + ix);
+            }
+            ts.S[grp] = s;
+        }
+        // an N tile never straddles two sub-positions (BLOCK_N divides cout_sub)
+        const int sub = (tc.nt * g.block_n) / cout_sub;
+        const int dy = sub / up, dx = sub - dy * up;
+        ts.opix = (static_cast<long long>(tc.img) * Hout + oy * up + dy) * Wout + ox * up + dx;
+    }
+
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int n0,
+                                          const int32_t (*acc)[16]) const {
+        (void)g;
+        (void)tc;
+        uint32_t packed[4] = {0, 0, 0, 0};
+        int rsum = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int n = n0 + j;
+            float v = 0.f;
+#pragma unroll
+            for (int grp = 0; grp < G; ++grp) {
+                int32_t t = acc[grp][j];
+                if (zpw[grp] != nullptr) t -= __ldg(zpw[grp] + n) * ts.S[grp];
+                if (acc_dump != nullptr && ts.mrow >= 0) {
+                    acc_dump[(static_cast<long long>(grp) * (static_cast<long long>(g.n_img) * g.Ho * g.Wo) + ts.mrow) *
+                                 n_total + n] = t;
+                }
+                const float tf = __int2float_rn(t);
+                const float term = __fmul_rn(gscale[grp], tf);
+                v = (grp == 0) ? term : __fadd_rn(v, term);
+            }
+            float y = __fadd_rn(__fmul_rn(v, __ldg(cscale + n)), __ldg(bias + n));
+            if (relu) y = fmaxf(y, 0.f);
+            float q = __fadd_rn(rintf(__fdiv_rn(y, delta_out)), zp_out);
+            q = fminf(fmaxf(q, 0.f), qmax);
+            const uint32_t b = static_cast<uint32_t>(q);
+            rsum += static_cast<int>(b);
+            packed[j >> 2] |= b << ((j & 3) * 8);
+        }
+        if (ts.opix >= 0) {
+            const int ch = n0 % cout_sub;
+            st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);
+            ts.rsum += rsum;
+        }
+    }
+
+    __device__ __forceinline__ void end(Tile& ts, const IgemmGeom& g, const TileCoord& tc) const {
+        (void)g;
+        (void)tc;
+        if (rowsum_out != nullptr && ts.opix >= 0) atomicAdd(rowsum_out + ts.opix, ts.rsum);
+    }
+};
+
+}  // namespace qv2x

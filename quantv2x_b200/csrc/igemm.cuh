@@ -1,0 +1,222 @@
+// Persistent, warp-specialised int8 implicit-GEMM for sm_100a.
+//
+//   warp 0      : TMA producer   (A = activation tile via a 4-D tiled tensor map -> im2col for free,
+//                                 zero OOB fill = conv zero padding; B = weight tile via a 2-D map)
+//   warp 1      : MMA issuer     (tcgen05.mma kind::i8, M=128, N=BLOCK_N, K=32 per instruction,
+//                                 int32 accumulators in a ring of TMEM slots)
+//   warp 2      : TMEM allocator
+//   warps 4..11 : epilogue       (tcgen05.ld -> registers -> fused epilogue functor -> global)
+//
+// One output tile = 128 output pixels (a tw x th box of one image) x BLOCK_N output columns.
+// A tile reduces over G "groups"; every group owns one TMEM slot (its own int32 accumulator):
+//   G = 1 : ordinary quantized conv (QuantModule over nn.Conv2d, reference quant_layer.py:391-410)
+//   G = 3 : (a) the shrinker's first conv, whose input is the concat of three tensors with three
+//               activation scales (reference base_bev_backbone.py:111-112), one group per scale;
+//           (b) GEMMs whose real-valued weights are carried as three signed base-256 digits
+//               (deblocks with per-input-channel scales, folded codebook distance GEMM).
+// K is walked group-major, then tap-major, then BK-byte channel blocks.
+#pragma once
+#include "ptx.cuh"
+
+namespace qv2x {
+
+constexpr int kMaxGroups = 3;
+constexpr int kTileM = 128;
+constexpr int kNumEpiWarps = 8;
+constexpr int kNumThreads = (4 + kNumEpiWarps) * 32;
+
+struct IgemmGeom {
+    // M-tile grid: per image Ho x Wo "anchor" pixels covered by tw x th boxes (tw * th == 128)
+    int n_img, Ho, Wo, tw, th, tiles_x, tiles_y, n_tiles, block_n;
+    // A source image extent (pixels) -- used by epilogues that need input-side bounds
+    int Hi, Wi;
+    // taps and K structure
+    int taps, taps_w, stride, pad;
+    int groups, cblocks;
+    int a_c_base[kMaxGroups];    // channel coordinate of the group's first k-block in the A tensor
+    int b_row_base[kMaxGroups];  // row coordinate of the group's first output column in the B tensor
+    int b_k_base[kMaxGroups];    // K coordinate (within one tap) of the group's first k-block in B
+    int b_k_tap_stride;          // K distance between consecutive taps in B
+    uint32_t idesc;              // tcgen05 instruction descriptor (operand signedness, M, N)
+};
+
+template <int BLOCK_N, int BK>
+struct IgemmCfg {
+    static constexpr int kATile = kTileM * BK;
+    static constexpr int kBTile = BLOCK_N * BK;
+    static constexpr int kStageBytes = kATile + kBTile;
+    static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct TileCoord {
+    int img, ty, tx, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
+    TileCoord c;
+    c.nt = t % g.n_tiles;
+    int m = t / g.n_tiles;
+    c.tx = m % g.tiles_x;
+    m /= g.tiles_x;
+    c.ty = m % g.tiles_y;
+    c.img = m / g.tiles_y;
+    return c;
+}
+
+// Epilogue contract:
+//   struct Epi {
+//     struct Tile;                                     // per-thread, per-tile state
+//     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row) const;
+//         -- called BEFORE the accumulators are ready (prefetch side inputs here)
+//     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int col0, const int32_t (*acc)[16]) const;
+//         -- 16 consecutive columns [col0, col0+16) of this thread's row, acc[g][j]
+//     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
+//   };
+template <int BLOCK_N, int BK, int G, class Epi>
+__global__ void __launch_bounds__(kNumThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
+             const Epi epi) {
+    using Cfg = IgemmCfg<BLOCK_N, BK>;
+    constexpr int kStages = Cfg::kStages;
+    constexpr int kSlots = Cfg::kSlots;
+    static_assert(G <= kSlots, "every group needs its own TMEM slot");
+    static_assert(BLOCK_N % 32 == 0, "BLOCK_N must split into two 16-column-aligned halves");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kStages;
+    uint64_t* tfull_bar = bars + 2 * kStages;
+    uint64_t* tempty_bar = bars + 2 * kStages + kSlots;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kSlots);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            mbar_init(smem_u32(&full_bar[i]), 1);
+            mbar_init(smem_u32(&empty_bar[i]), 1);
+        }
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(smem_u32(&tfull_bar[i]), 1);
+            mbar_init(smem_u32(&tempty_bar[i]), kNumEpiWarps);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), 512);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    const int total_tiles = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
+    const int kblocks_per_group = g.taps * g.cblocks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const TileCoord tc = decode_tile(g, t);
+                const int x0 = tc.tx * g.tw * g.stride - g.pad;
+                const int y0 = tc.ty * g.th * g.stride - g.pad;
+                for (int grp = 0; grp < G; ++grp) {
+                    for (int tap = 0; tap < g.taps; ++tap) {
+                        const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                        for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
+                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                            const uint32_t fb = smem_u32(&full_bar[s]);
+                            mbar_expect_tx(fb, Cfg::kStageBytes);
+                            uint8_t* st = smem + s * Cfg::kStageBytes;
+                            tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky, tc.img);
+                            tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
+                                        tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK,
+                                        g.b_row_base[grp] + tc.nt * BLOCK_N);
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0, ac = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                for (int grp = 0; grp < G; ++grp, ++ac) {
+                    const uint32_t slot = ac % kSlots, aph = (ac / kSlots) & 1;
+                    mbar_wait(smem_u32(&tempty_bar[slot]), aph ^ 1);
+                    tcgen05_fence_after();
+                    const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
+                    for (int kb = 0; kb < kblocks_per_group; ++kb, ++it) {
+                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                        mbar_wait(smem_u32(&full_bar[s]), ph);
+                        tcgen05_fence_after();
+                        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+                        const uint64_t a_desc = umma_smem_desc(a_addr, BK);
+                        const uint64_t b_desc = umma_smem_desc(a_addr + Cfg::kATile, BK);
+#pragma unroll
+                        for (int k = 0; k < BK / 32; ++k) {
+                            // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
+                            umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | k) != 0);
+                        }
+                        umma_commit(smem_u32(&empty_bar[s]));
+                    }
+                    umma_commit(smem_u32(&tfull_bar[slot]));
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue
+        const int quad = warp & 3;            // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;     // which half of the tile's columns
+        const int row = quad * 32 + lane;     // tile row == TMEM lane
+        constexpr int kColsPerWarp = BLOCK_N / 2;
+        uint32_t ac = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ac += G) {
+            const TileCoord tc = decode_tile(g, t);
+            typename Epi::Tile ts;
+            epi.begin(ts, g, tc, row);
+#pragma unroll
+            for (int grp = 0; grp < G; ++grp) {
+                const uint32_t a = ac + grp;
+                mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
+            }
+            tcgen05_fence_after();
+            for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 16) {
+                uint32_t acc[G][16];
+#pragma unroll
+                for (int grp = 0; grp < G; ++grp) {
+                    const uint32_t slot = (ac + grp) % kSlots;
+                    tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * BLOCK_N + c0, acc[grp]);
+                }
+                tmem_ld_wait();
+                epi.chunk(ts, g, tc, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+                for (int grp = 0; grp < G; ++grp) mbar_arrive(smem_u32(&tempty_bar[(ac + grp) % kSlots]));
+            }
+            epi.end(ts, g, tc);
+        }
+    }
+
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tcgen05_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace qv2x

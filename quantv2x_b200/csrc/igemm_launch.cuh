@@ -1,0 +1,104 @@
+// Host-side launch helpers for igemm.cuh shared by the layer / codebook translation units.
+#pragma once
+#include <algorithm>
+#include <cmath>
+
+#include "host_common.h"
+#include "igemm.cuh"
+
+namespace qv2x {
+
+// Largest magnitude representable by three signed base-256 digits, each in [-128, 127].
+constexpr double kDigitMax = 127.0 * 65536.0 + 127.0 * 256.0 + 127.0;
+
+inline void split_digits(long long m, int8_t d[3]) {
+    // balanced base-256: m = d[0]*65536 + d[1]*256 + d[2], every digit in [-128, 127]
+    long long lo = ((m + 128) & 255) - 128;
+    m = (m - lo) / 256;
+    long long mid = ((m + 128) & 255) - 128;
+    m = (m - mid) / 256;
+    d[0] = static_cast<int8_t>(m);
+    d[1] = static_cast<int8_t>(mid);
+    d[2] = static_cast<int8_t>(lo);
+}
+
+inline uint32_t make_idesc_i8(int block_n, bool b_signed) {
+    uint32_t d = 0;
+    d |= 2u << 4;                               // accumulator format: S32
+    d |= 0u << 7;                               // A: unsigned 8-bit
+    d |= (b_signed ? 1u : 0u) << 10;            // B: signed / unsigned 8-bit
+    d |= static_cast<uint32_t>(block_n >> 3) << 17;
+    d |= static_cast<uint32_t>(kTileM >> 4) << 24;
+    return d;
+}
+
+inline void choose_tile_box(int ho, int wo, int* tw, int* th) {
+    long long best = -1;
+    for (int w = 128; w >= 8; w >>= 1) {
+        const int h = 128 / w;
+        const long long area = static_cast<long long>((wo + w - 1) / w) * w * ((ho + h - 1) / h) * h;
+        if (best < 0 || area < best) {
+            best = area;
+            *tw = w;
+            *th = h;
+        }
+    }
+}
+
+template <int BLOCK_N, int BK, int G, class Epi>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const Epi& epi,
+                        cudaStream_t stream) {
+    using Cfg = IgemmCfg<BLOCK_N, BK>;
+    auto kern = igemm_kernel<BLOCK_N, BK, G, Epi>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        QV2X_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int total = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
+    const int grid = std::min(total, num_sms());
+    kern<<<grid, kNumThreads, Cfg::kSmemBytes, stream>>>(tmA, tmB, g, epi);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int G, class Epi>
+int dispatch_igemm(int block_n, int bk, const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g,
+                   const Epi& epi, cudaStream_t stream) {
+#define QV2X_CASE(BN, BKK) \
+    if (block_n == BN && bk == BKK) return launch_igemm<BN, BKK, G, Epi>(tmA, tmB, g, epi, stream);
+    if constexpr (G == 1) {
+        QV2X_CASE(256, 128)
+        QV2X_CASE(256, 64)
+    }
+    QV2X_CASE(128, 128)
+    QV2X_CASE(128, 64)
+    QV2X_CASE(64, 128)
+    QV2X_CASE(64, 64)
+#undef QV2X_CASE
+    return set_error(QV2X_ERR_INVALID, "no igemm instantiation for BLOCK_N=%d BK=%d G=%d", block_n, bk, G);
+}
+
+
+inline int make_weight_tmap(CUtensorMap* tm, const void* d_w, int rows, int k_total, int block_n, int bk) {
+    const uint64_t dims[2] = {static_cast<uint64_t>(k_total), static_cast<uint64_t>(rows)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(k_total)};
+    const uint32_t box[2] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(block_n)};
+    const uint32_t es[2] = {1, 1};
+    return encode_tmap_u8(tm, d_w, 2, dims, strides, box, es, bk);
+}
+
+inline int make_act_tmap(CUtensorMap* tm, const void* d_x, int n_img, int hi, int wi, int cstride, int tw, int th,
+                  int stride, int bk) {
+    const uint64_t dims[4] = {static_cast<uint64_t>(cstride), static_cast<uint64_t>(wi), static_cast<uint64_t>(hi),
+                              static_cast<uint64_t>(n_img)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(cstride), static_cast<uint64_t>(cstride) * wi,
+                                 static_cast<uint64_t>(cstride) * wi * hi};
+    const uint32_t box[4] = {static_cast<uint32_t>(bk), static_cast<uint32_t>(tw * stride),
+                             static_cast<uint32_t>(th * stride), 1};
+    const uint32_t es[4] = {1, static_cast<uint32_t>(stride), static_cast<uint32_t>(stride), 1};
+    return encode_tmap_u8(tm, d_x, 4, dims, strides, box, es, bk);
+}
+
+}  // namespace qv2x

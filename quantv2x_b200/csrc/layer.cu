@@ -1,0 +1,261 @@
+// qv2x_layer: one quantized conv / transposed-conv layer (C ABI in include/qv2x.h).
+// Host side: weight packing, tile/launch selection, tensor maps.  Device side: igemm.cuh.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "epilogue_requant.cuh"
+#include "igemm_launch.cuh"
+
+
+
+using namespace qv2x;
+
+struct qv2x_layer {
+    qv2x_layer_desc d;
+    int groups;        // accumulator groups in the kernel
+    int n_total;       // GEMM columns
+    int k_total;       // bytes per B row
+    int block_n, bk;
+    bool b_signed, use_zp;
+    uint8_t* d_w = nullptr;
+    float* d_cscale = nullptr;
+    float* d_bias = nullptr;
+    int32_t* d_zpw = nullptr;
+    float gscale[3] = {1.f, 1.f, 1.f};
+};
+
+extern "C" {
+
+int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const float* w_delta,
+                      const float* w_zero_point, const float* bias, qv2x_layer** out) {
+    QV2X_REQUIRE(desc && w_int && w_delta && w_zero_point && out, "qv2x_layer_create: null argument");
+    const qv2x_layer_desc& d = *desc;
+    QV2X_REQUIRE(d.kind == 0 || d.kind == 1, "kind must be 0 (conv) or 1 (transposed conv)");
+    QV2X_REQUIRE(d.w_bits >= 2 && d.w_bits <= 8 && d.out_bits >= 2 && d.out_bits <= 8, "bit widths must be 2..8");
+    QV2X_REQUIRE(d.n_in_groups == 1 || d.n_in_groups == 3, "n_in_groups must be 1 or 3");
+    QV2X_REQUIRE(d.out_delta > 0.f, "out_delta must be positive");
+    auto L = new qv2x_layer();
+    L->d = d;
+    std::vector<uint8_t> wpack;
+    std::vector<float> cscale, biasv;
+    std::vector<int32_t> zpw;
+
+    if (d.kind == 0) {
+        QV2X_REQUIRE((d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2), "conv: ksize 1|3, stride 1|2");
+        QV2X_REQUIRE(d.cin % d.n_in_groups == 0, "cin must split evenly over the input groups");
+        const int cg = d.cin / d.n_in_groups;
+        QV2X_REQUIRE(cg % 64 == 0, "input channels per group must be a multiple of 64 (got %d)", cg);
+        QV2X_REQUIRE(d.cout % 64 == 0, "cout must be a multiple of 64 (got %d)", d.cout);
+        L->groups = d.n_in_groups;
+        L->bk = (cg % 128 == 0) ? 128 : 64;
+        L->n_total = d.cout;
+        if (L->groups == 1 && d.cout % 256 == 0) L->block_n = 256;
+        else if (d.cout % 128 == 0) L->block_n = 128;
+        else L->block_n = 64;
+        const int taps = d.ksize * d.ksize;
+        L->k_total = taps * d.cin;
+        L->b_signed = d.w_bits <= 7;   // (w - zp) in [-127, 127] fits a signed byte: no zero-point correction
+        L->use_zp = !L->b_signed;
+        wpack.resize(static_cast<size_t>(d.cout) * L->k_total);
+        cscale.resize(d.cout);
+        biasv.resize(d.cout);
+        zpw.resize(d.cout);
+        for (int co = 0; co < d.cout; ++co) {
+            const int zp = static_cast<int>(w_zero_point[co]);
+            zpw[co] = zp;
+            // G=1: y = float(acc) * fl(in_delta * w_delta[c]);  G=3: y = (sum_g in_delta[g]*acc_g) * w_delta[c]
+            cscale[co] = (L->groups == 1) ? d.in_delta[0] * w_delta[co] : w_delta[co];
+            biasv[co] = bias ? bias[co] : 0.f;
+            for (int ci = 0; ci < d.cin; ++ci)
+                for (int t = 0; t < taps; ++t) {
+                    const int w = w_int[(static_cast<size_t>(co) * d.cin + ci) * taps + t];
+                    const int v = L->b_signed ? (w - zp) : w;
+                    wpack[static_cast<size_t>(co) * L->k_total + static_cast<size_t>(t) * d.cin + ci] =
+                        static_cast<uint8_t>(v & 0xff);
+                }
+        }
+        for (int g = 0; g < 3; ++g) L->gscale[g] = (L->groups == 1) ? 1.f : d.in_delta[g];
+    } else {
+        QV2X_REQUIRE(d.ksize == d.stride && (d.stride == 1 || d.stride == 2 || d.stride == 4),
+                     "transposed conv: kernel == stride in {1,2,4}");
+        QV2X_REQUIRE(d.n_in_groups == 1 && d.pad == 0, "transposed conv: single input group, padding 0");
+        QV2X_REQUIRE(d.cin % 64 == 0 && d.cout % 64 == 0, "channels must be multiples of 64");
+        // Weight scale varies along the reduction (cin) axis (reference quant_layer.py:325-335 on a
+        // [cin, cout, k, k] tensor), so the real-valued weight w_hat = (W - zp[ci]) * delta[ci] is carried
+        // as a 24-bit fixed-point number per output column, split into three signed byte digits.
+        const int s = d.stride, sub = s * s;
+        L->groups = 3;
+        L->bk = (d.cin % 128 == 0) ? 128 : 64;
+        L->block_n = (d.cout % 128 == 0) ? 128 : 64;
+        L->n_total = sub * d.cout;
+        L->k_total = d.cin;
+        L->b_signed = true;
+        L->use_zp = false;
+        wpack.assign(static_cast<size_t>(3) * L->n_total * d.cin, 0);
+        cscale.resize(L->n_total);
+        biasv.resize(L->n_total);
+        std::vector<float> what(d.cin);
+        for (int sp = 0; sp < sub; ++sp)
+            for (int co = 0; co < d.cout; ++co) {
+                const int n = sp * d.cout + co;
+                double mx = 0.0;
+                for (int ci = 0; ci < d.cin; ++ci) {
+                    const float wq = static_cast<float>(w_int[(static_cast<size_t>(ci) * d.cout + co) * sub + sp]);
+                    what[ci] = (wq - w_zero_point[ci]) * w_delta[ci];   // fp32, as the reference dequantizes
+                    mx = std::max(mx, std::fabs(static_cast<double>(what[ci])));
+                }
+                const double sc = mx > 0.0 ? mx / kDigitMax : 1.0;
+                for (int ci = 0; ci < d.cin; ++ci) {
+                    const long long m = static_cast<long long>(std::nearbyint(static_cast<double>(what[ci]) / sc));
+                    int8_t dg[3];
+                    split_digits(m, dg);
+                    for (int g = 0; g < 3; ++g)
+                        wpack[(static_cast<size_t>(g) * L->n_total + n) * d.cin + ci] = static_cast<uint8_t>(dg[g]);
+                }
+                cscale[n] = static_cast<float>(static_cast<double>(d.in_delta[0]) * sc);
+                biasv[n] = bias ? bias[co] : 0.f;
+            }
+        L->gscale[0] = 65536.f;
+        L->gscale[1] = 256.f;
+        L->gscale[2] = 1.f;
+    }
+    int rc = upload(&L->d_w, wpack.data(), wpack.size());
+    if (rc == 0) rc = upload(&L->d_cscale, cscale.data(), cscale.size());
+    if (rc == 0) rc = upload(&L->d_bias, biasv.data(), biasv.size());
+    if (rc == 0 && L->use_zp) rc = upload(&L->d_zpw, zpw.data(), zpw.size());
+    if (rc != 0) {
+        qv2x_layer_destroy(L);
+        return rc;
+    }
+    *out = L;
+    return 0;
+}
+
+void qv2x_layer_destroy(qv2x_layer* L) {
+    if (!L) return;
+    cudaFree(L->d_w);
+    cudaFree(L->d_cscale);
+    cudaFree(L->d_bias);
+    cudaFree(L->d_zpw);
+    delete L;
+}
+
+int qv2x_layer_needs_rowsum(const qv2x_layer* L) { return (L && L->use_zp) ? 1 : 0; }
+
+int qv2x_layer_out_shape(const qv2x_layer* L, int hi, int wi, int* ho, int* wo) {
+    QV2X_REQUIRE(L && ho && wo, "qv2x_layer_out_shape: null argument");
+    const qv2x_layer_desc& d = L->d;
+    if (d.kind == 0) {
+        *ho = (hi + 2 * d.pad - d.ksize) / d.stride + 1;
+        *wo = (wi + 2 * d.pad - d.ksize) / d.stride + 1;
+    } else {
+        *ho = hi * d.stride;
+        *wo = wi * d.stride;
+    }
+    return 0;
+}
+
+int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
+                       int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride, int out_cbase,
+                       int32_t* d_rowsum_out, int32_t* d_acc_dump, void* stream_) {
+    QV2X_REQUIRE(L && d_x && d_y, "qv2x_layer_forward: null argument");
+    QV2X_REQUIRE(n_img > 0 && hi > 0 && wi > 0, "empty input (n_img=%d hi=%d wi=%d)", n_img, hi, wi);
+    QV2X_REQUIRE(in_cstride % 16 == 0 && in_cbase % 16 == 0 && out_cstride % 16 == 0 && out_cbase % 16 == 0,
+                 "channel strides / bases must be multiples of 16 bytes");
+    QV2X_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15) == 0,
+                 "activation pointers must be 16-byte aligned");
+    QV2X_REQUIRE(!L->use_zp || d_rowsum_in, "this layer needs d_rowsum_in (see qv2x_layer_needs_rowsum)");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const qv2x_layer_desc& d = L->d;
+    int ho, wo;
+    qv2x_layer_out_shape(L, hi, wi, &ho, &wo);
+    QV2X_REQUIRE(ho > 0 && wo > 0, "input %dx%d too small for this layer", hi, wi);
+
+    IgemmGeom g{};
+    g.n_img = n_img;
+    g.Hi = hi;
+    g.Wi = wi;
+    g.block_n = L->block_n;
+    g.n_tiles = L->n_total / L->block_n;
+    g.groups = L->groups;
+    g.idesc = make_idesc_i8(L->block_n, L->b_signed);
+    int out_h, out_w;
+    if (d.kind == 0) {
+        g.Ho = ho;
+        g.Wo = wo;
+        g.taps_w = d.ksize;
+        g.taps = d.ksize * d.ksize;
+        g.stride = d.stride;
+        g.pad = d.pad;
+        const int cg = d.cin / d.n_in_groups;
+        g.cblocks = cg / L->bk;
+        g.b_k_tap_stride = d.cin;
+        for (int i = 0; i < L->groups; ++i) {
+            g.a_c_base[i] = in_cbase + i * cg;
+            g.b_row_base[i] = 0;
+            g.b_k_base[i] = i * cg;
+        }
+        out_h = ho;
+        out_w = wo;
+    } else {
+        g.Ho = hi;   // GEMM rows are INPUT pixels; each N tile scatters to one output sub-position
+        g.Wo = wi;
+        g.taps_w = 1;
+        g.taps = 1;
+        g.stride = 1;
+        g.pad = 0;
+        g.cblocks = d.cin / L->bk;
+        g.b_k_tap_stride = 0;
+        for (int i = 0; i < 3; ++i) {
+            g.a_c_base[i] = in_cbase;
+            g.b_row_base[i] = i * L->n_total;
+            g.b_k_base[i] = 0;
+        }
+        out_h = ho;
+        out_w = wo;
+    }
+    choose_tile_box(g.Ho, g.Wo, &g.tw, &g.th);
+    g.tiles_x = (g.Wo + g.tw - 1) / g.tw;
+    g.tiles_y = (g.Ho + g.th - 1) / g.th;
+
+    CUtensorMap tmA, tmB;
+    int rc = make_act_tmap(&tmA, d_x, n_img, hi, wi, in_cstride, g.tw, g.th, g.stride, L->bk);
+    if (rc) return rc;
+    rc = make_weight_tmap(&tmB, L->d_w, (d.kind == 0 ? 1 : 3) * L->n_total, L->k_total, L->block_n, L->bk);
+    if (rc) return rc;
+
+    auto fill = [&](auto& e) {
+        e.up = (d.kind == 0) ? 1 : d.stride;
+        e.cout_sub = d.cout;
+        e.Hout = out_h;
+        e.Wout = out_w;
+        e.out_cstride = out_cstride;
+        e.out_cbase = out_cbase;
+        e.relu = d.relu;
+        e.qmax = static_cast<float>((1 << d.out_bits) - 1);
+        e.delta_out = d.out_delta;
+        e.zp_out = d.out_zero_point;
+        for (int i = 0; i < 3; ++i) {
+            e.gscale[i] = L->gscale[i];
+            e.zpw[i] = (L->use_zp && i < L->groups) ? L->d_zpw : nullptr;
+            e.rowsum_in[i] = (L->use_zp && i < L->groups) ? d_rowsum_in[i] : nullptr;
+        }
+        e.cscale = L->d_cscale;
+        e.bias = L->d_bias;
+        e.out = d_y;
+        e.rowsum_out = d_rowsum_out;
+        e.acc_dump = d_acc_dump;
+        e.n_total = L->n_total;
+    };
+    if (L->groups == 1) {
+        RequantEpilogue<1> e{};
+        fill(e);
+        return dispatch_igemm<1>(L->block_n, L->bk, tmA, tmB, g, e, stream);
+    }
+    RequantEpilogue<3> e{};
+    fill(e);
+    return dispatch_igemm<3>(L->block_n, L->bk, tmA, tmB, g, e, stream);
+}
+
+}  // extern "C"

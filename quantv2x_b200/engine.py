@@ -1,0 +1,107 @@
+"""Python handles over the C-ABI objects of libqv2x.so.  PyTorch is only the allocator / stream
+provider here: tensors are passed down as raw device pointers."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_int, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LayerDesc, check
+
+
+def _stream_ptr():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_ptr(a: np.ndarray):
+    return a.ctypes.data_as(c_void_p)
+
+
+class QLayer:
+    """One quantized conv / transposed-conv layer living on the GPU (qv2x_layer).
+
+    Parameters mirror what a calibrated reference ``QuantModule`` holds
+    (opencood/quant/quant_layer.py:349-410): integer weight grid, per-dim-0 weight delta / zero-point,
+    bias, the activation delta(s) of the tensor(s) feeding the layer and the layer's own act quantizer.
+    """
+
+    def __init__(self, *, kind, w_int, w_delta, w_zp, bias, ksize, stride, pad, w_bits, relu, in_delta,
+                 out_delta, out_zp=0.0, out_bits=8):
+        w_int = np.ascontiguousarray(w_int, dtype=np.uint8)
+        w_delta = np.ascontiguousarray(w_delta, dtype=np.float32).reshape(-1)
+        w_zp = np.ascontiguousarray(w_zp, dtype=np.float32).reshape(-1)
+        in_delta = [float(v) for v in np.atleast_1d(np.asarray(in_delta, dtype=np.float32))]
+        d = LayerDesc()
+        d.kind = int(kind)
+        if kind == 0:
+            d.cout, d.cin = int(w_int.shape[0]), int(w_int.shape[1])
+        else:
+            d.cin, d.cout = int(w_int.shape[0]), int(w_int.shape[1])
+        d.ksize, d.stride, d.pad = int(ksize), int(stride), int(pad)
+        d.w_bits, d.relu = int(w_bits), int(bool(relu))
+        d.n_in_groups = len(in_delta)
+        for i in range(3):
+            d.in_delta[i] = in_delta[i] if i < len(in_delta) else 0.0
+        d.out_delta, d.out_zero_point, d.out_bits = float(out_delta), float(out_zp), int(out_bits)
+        assert w_delta.size == w_int.shape[0] and w_zp.size == w_int.shape[0]
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        self.desc = d
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_layer_create(byref(d), _np_ptr(w_int), _np_ptr(w_delta), _np_ptr(w_zp),
+                                            None if b is None else _np_ptr(b), byref(self._h)))
+        self.needs_rowsum = bool(_lib.lib().qv2x_layer_needs_rowsum(self._h))
+        self.kind, self.cin, self.cout = d.kind, d.cin, d.cout
+        self.n_groups = 3 if (kind == 1 or d.n_in_groups == 3) else 1
+        self.n_cols = d.cout * (d.stride * d.stride if kind == 1 else 1)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_layer_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def out_shape(self, hi, wi):
+        ho, wo = c_int(), c_int()
+        check(_lib.lib().qv2x_layer_out_shape(self._h, hi, wi, byref(ho), byref(wo)))
+        return ho.value, wo.value
+
+    def forward(self, x: torch.Tensor, *, in_cbase=0, rowsum_in=None, out=None, out_cbase=0, rowsum_out=None,
+                acc_dump=None):
+        """x: uint8 NHWC [n, H, W, Cstride] on the GPU.  Returns the uint8 NHWC output tensor."""
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
+        n, hi, wi, cs = x.shape
+        ho, wo = self.out_shape(hi, wi)
+        if out is None:
+            out = torch.empty((n, ho, wo, self.cout), dtype=torch.uint8, device=x.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+        assert tuple(out.shape[:3]) == (n, ho, wo)
+        rs_arr = None
+        if self.needs_rowsum:
+            if rowsum_in is None:
+                g = self.desc.n_in_groups
+                cg = self.cin // g
+                rowsum_in = [rowsum_u8(x, in_cbase + i * cg, cg) for i in range(g)]
+            rs_arr = (c_void_p * len(rowsum_in))(*[c_void_p(t.data_ptr()) for t in rowsum_in])
+        check(_lib.lib().qv2x_layer_forward(
+            self._h, n, hi, wi, c_void_p(x.data_ptr()), cs, in_cbase, rs_arr,
+            c_void_p(out.data_ptr()), out.shape[3], out_cbase,
+            None if rowsum_out is None else c_void_p(rowsum_out.data_ptr()),
+            None if acc_dump is None else c_void_p(acc_dump.data_ptr()), _stream_ptr()))
+        return out
+
+
+def rowsum_u8(x: torch.Tensor, cbase: int, c: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Per-pixel channel sums (int32 [n, H, W]) of channels [cbase, cbase+c) of a uint8 NHWC tensor."""
+    assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
+    n, h, w, cs = x.shape
+    if out is None:
+        out = torch.empty((n, h, w), dtype=torch.int32, device=x.device)
+    check(_lib.lib().qv2x_rowsum_u8(c_void_p(x.data_ptr()), n * h * w, cs, cbase, c, c_void_p(out.data_ptr()),
+                                    _stream_ptr()))
+    return out
