@@ -74,6 +74,24 @@ struct RequantEpilogue {
         (void)tc;
         uint32_t packed[4] = {0, 0, 0, 0};
         int rsum = 0;
+        // per-column parameters: warp-uniform 16-byte loads (L1 broadcast)
+        float cs[16], bs[16];
+        int32_t zw[G][16];
+#pragma unroll
+        for (int v4 = 0; v4 < 4; ++v4) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(cscale + n0) + v4);
+            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + v4);
+            cs[4 * v4 + 0] = c.x, cs[4 * v4 + 1] = c.y, cs[4 * v4 + 2] = c.z, cs[4 * v4 + 3] = c.w;
+            bs[4 * v4 + 0] = b.x, bs[4 * v4 + 1] = b.y, bs[4 * v4 + 2] = b.z, bs[4 * v4 + 3] = b.w;
+#pragma unroll
+            for (int grp = 0; grp < G; ++grp) {
+                if (zpw[grp] != nullptr) {
+                    const int4 z = __ldg(reinterpret_cast<const int4*>(zpw[grp] + n0) + v4);
+                    zw[grp][4 * v4 + 0] = z.x, zw[grp][4 * v4 + 1] = z.y, zw[grp][4 * v4 + 2] = z.z,
+                                     zw[grp][4 * v4 + 3] = z.w;
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int n = n0 + j;
@@ -81,7 +99,7 @@ struct RequantEpilogue {
 #pragma unroll
             for (int grp = 0; grp < G; ++grp) {
                 int32_t t = acc[grp][j];
-                if (zpw[grp] != nullptr) t -= __ldg(zpw[grp] + n) * ts.S[grp];
+                if (zpw[grp] != nullptr) t -= zw[grp][j] * ts.S[grp];
                 if (acc_dump != nullptr && ts.mrow >= 0) {
                     acc_dump[(static_cast<long long>(grp) * (static_cast<long long>(g.n_img) * g.Ho * g.Wo) + ts.mrow) *
                                  n_total + n] = t;
@@ -90,9 +108,14 @@ struct RequantEpilogue {
                 const float term = __fmul_rn(gscale[grp], tf);
                 v = (grp == 0) ? term : __fadd_rn(v, term);
             }
-            float y = __fadd_rn(__fmul_rn(v, __ldg(cscale + n)), __ldg(bias + n));
+            float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
             if (relu) y = fmaxf(y, 0.f);
-            float q = __fadd_rn(rintf(__fdiv_rn(y, delta_out)), zp_out);
+            // y / delta_out with IEEE rounding.  A zero dividend (half of all post-ReLU values) would send
+            // the whole warp through the division's slow path, so it is divided as delta/delta and masked.
+            const bool nz = (y != 0.f);
+            float d = __fdiv_rn(nz ? y : delta_out, delta_out);
+            d = nz ? d : 0.f;
+            float q = __fadd_rn(rintf(d), zp_out);
             q = fminf(fmaxf(q, 0.f), qmax);
             const uint32_t b = static_cast<uint32_t>(q);
             rsum += static_cast<int>(b);
