@@ -94,6 +94,41 @@ int qv2x_layer_out_shape(const qv2x_layer* layer, int hi, int wi, int* ho, int* 
 int qv2x_rowsum_u8(const uint8_t* d_x, long long n_pixels, int cstride, int cbase, int c, int32_t* d_out,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Codebook compressor = reference UMGMQuantizer.encode / .decode
+ * (opencood/models/sub_modules/codebook.py:330-343 with :106-131, :192-201, :231-239, :263-269).
+ * The wire payload of an agent is levels*m byte planes of `rows` codes each.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_codebook qv2x_codebook;
+
+typedef struct {
+    int channel;         /* C: feature channels (256 on the V2X-Real path) */
+    int m;               /* seg_num: codebooks per level, each over C/m channels */
+    int levels;          /* len(dict_size) residual levels (3 in the reference models) */
+    int k[4];            /* dict_size per level, multiple of 16, <= 256 (codes are bytes) */
+} qv2x_codebook_desc;
+
+/* codebooks[l]: [m][k[l]][C/m] floats (nn.Parameter _codebook of level l).
+ * weights[l*6+h] / biases[l*6+h]: nn.Linear(C, C) weight [C][C] (out, in) and bias [C] of head h of level l, in
+ * the reference's component order: 0 latentStageEncoder, 1 quantizationHead, 2 latentHead, 3 dequantizationHead,
+ * 4 sideHead, 5 restoreHead.  latentHead and sideHead are NULL on the last level.  Host pointers. */
+int qv2x_codebook_create(const qv2x_codebook_desc* desc, const float* const* codebooks, const float* const* weights,
+                         const float* const* biases, qv2x_codebook** out);
+void qv2x_codebook_destroy(qv2x_codebook* cb);
+
+/* encode: d_feat [rows][feat_cstride] uint8 activation codes (first C channels used) with scale `delta`
+ * (x = delta * q, zero-point 0) -> d_codes [levels][m][rows] uint8.  argmin ties resolve to the lowest index. */
+int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t* d_feat, int feat_cstride,
+                         float delta, uint8_t* d_codes, void* stream);
+/* decode: d_codes [levels][m][rows] -> d_out [rows][C] float32 (pixel-major). */
+int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t* d_codes, float* d_out, void* stream);
+
+/* Test hook: the folded tables the kernels use.  which = 0 digits (int8 [sum_l 3*m*k_l][C], level-major then
+ * digit-major), 1 per-column scale (double), 2 per-column constant (double), 3 codeword cross terms (double),
+ * 4 decode constant (float [C]), 5 decode tables (float, level-major then segment-major [k_l][C]). */
+long long qv2x_codebook_folded_size(const qv2x_codebook* cb, int which);
+int qv2x_codebook_folded_copy(const qv2x_codebook* cb, int which, void* host_buf);
+
 #ifdef __cplusplus
 }
 #endif

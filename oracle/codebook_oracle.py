@@ -186,7 +186,7 @@ def decode_tables(fd, codes, dtype=np.float64):
 
 def quantize_fold(fe):
     """24-bit fixed point of every G row: digits int64 [3, N, C] and scales float64 [N], per level."""
-    return [fixed_point_columns(Gl.astype(np.float32).astype(np.float64)) for Gl in fe["G"]]
+    return [fixed_point_columns(Gl) for Gl in fe["G"]]
 
 
 def encode_fixed_point(fe, q_u8, delta, fixed=None):

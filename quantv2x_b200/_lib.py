@@ -65,7 +65,8 @@ def lib():
             raise Qv2xError(f"{LIB_PATH} is missing: build it with `make -C quantv2x_b200/csrc` "
                             "(there is no CPU fallback)")
         handle = ctypes.CDLL(LIB_PATH)
-        _declare(handle)
+        for fn in _DECLARERS:
+            fn(handle)
         _lib = handle
     return _lib
 
@@ -83,3 +84,24 @@ def exported_symbols():
     text = open(hdr).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(qv2x_[a-z0-9_]+)\s*\(", text)))
+
+
+class CodebookDesc(ctypes.Structure):
+    """Mirror of qv2x_codebook_desc (include/qv2x.h)."""
+
+    _fields_ = [("channel", c_int), ("m", c_int), ("levels", c_int), ("k", c_int * 4)]
+
+
+def _declare_codebook(lib):
+    lib.qv2x_codebook_create.argtypes = [POINTER(CodebookDesc), POINTER(c_void_p), POINTER(c_void_p),
+                                         POINTER(c_void_p), POINTER(c_void_p)]
+    lib.qv2x_codebook_destroy.argtypes = [c_void_p]
+    lib.qv2x_codebook_destroy.restype = None
+    lib.qv2x_codebook_encode.argtypes = [c_void_p, c_longlong, c_void_p, c_int, c_float, c_void_p, c_void_p]
+    lib.qv2x_codebook_decode.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
+    lib.qv2x_codebook_folded_size.argtypes = [c_void_p, c_int]
+    lib.qv2x_codebook_folded_size.restype = c_longlong
+    lib.qv2x_codebook_folded_copy.argtypes = [c_void_p, c_int, c_void_p]
+
+
+_DECLARERS = [_declare, _declare_codebook]

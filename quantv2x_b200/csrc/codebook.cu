@@ -1,0 +1,530 @@
+// qv2x_codebook: the multi-level residual multi-codebook quantizer (reference UMGMQuantizer,
+// opencood/models/sub_modules/codebook.py:280-343) as two kernels:
+//
+//   encode : every head is an affine map, so the distance score of every level is affine in the input
+//            row and in the codewords already chosen (oracle/codebook_oracle.py):
+//                score[l][(s,k)] = G_l[(s,k),:] . x + g0_l[(s,k)] + sum_{j<l,s'} B_{l,j,s'}[code_{j,s'}][(s,k)]
+//            x = delta * q with q the shrinker's uint8 output, so G_l . q is an int8 GEMM on the tensor
+//            cores (G carried as 24-bit fixed point = three signed byte digits, three exact int32
+//            accumulators); the rest of the score and the running argmin (ties -> lowest index) run in
+//            float64 in the epilogue, level after level on the same CTA.
+//   decode : the six heads collapse to  decode(codes) = const + sum_{l,s} T_{l,s}[code_{l,s}]  (fp32 tables).
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "igemm_launch.cuh"
+
+namespace qv2x {
+
+constexpr int kMaxLevels = 4;
+constexpr int kMaxSeg = 4;
+
+struct EncodeEpilogue {
+    static constexpr int kColSplit = 1;
+    int levels, m;
+    int k[kMaxLevels];            // codewords per segment
+    int n_level[kMaxLevels];      // m * k
+    int colbase[kMaxLevels];      // offset of the level's columns in sc / g0
+    int step_level[kMaxSteps];    // level of each step
+    int step_col0[kMaxSteps];     // first column (within the level) of each step
+    int step_last[kMaxSteps];     // 1 if the step closes its level
+    double delta;
+    const double* sc;             // per-column fixed-point scale
+    const double* g0;             // per-column constant
+    const double* btab;           // codeword cross terms, see boff
+    long long boff[kMaxLevels][kMaxLevels];  // boff[l][j]: start of [m][k_j][n_level[l]] doubles
+    uint8_t* codes;               // [levels][m][rows]
+    long long rows;
+
+    struct Tile {
+        long long r;
+        double best[kMaxSeg];
+        int bidx[kMaxSeg];
+        int code[kMaxLevels][kMaxSeg];
+    };
+
+    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row) const {
+        ts.r = static_cast<long long>(tc.tx) * g.tw + row;
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s) {
+            ts.best[s] = INFINITY;
+            ts.bidx[s] = 0;
+        }
+#pragma unroll
+        for (int l = 0; l < kMaxLevels; ++l)
+#pragma unroll
+            for (int s = 0; s < kMaxSeg; ++s) ts.code[l][s] = 0;
+    }
+
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int c0,
+                                          const int32_t (*acc)[16]) const {
+        const int l = step_level[step];
+        const int n0 = step_col0[step] + c0;          // column within the level; a chunk never straddles segments
+        const int nl = n_level[l];
+        const int seg = n0 / k[l];
+        const int kk0 = n0 - seg * k[l];
+        const double* scp = sc + colbase[l] + n0;
+        const double* g0p = g0 + colbase[l] + n0;
+        double score[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const long long V = static_cast<long long>(acc[0][j]) * 65536 + static_cast<long long>(acc[1][j]) * 256 +
+                                static_cast<long long>(acc[2][j]);
+            score[j] = __dadd_rn(__dmul_rn(static_cast<double>(V), __dmul_rn(delta, __ldg(scp + j))), __ldg(g0p + j));
+        }
+#pragma unroll
+        for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
+            if (jl < l) {
+#pragma unroll
+                for (int s2 = 0; s2 < kMaxSeg; ++s2) {
+                    if (s2 < m) {
+                        const double* bp = btab + boff[l][jl] +
+                                           (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0;
+#pragma unroll
+                        for (int j2 = 0; j2 < 8; ++j2) {
+                            const double2 b = __ldg(reinterpret_cast<const double2*>(bp) + j2);
+                            score[2 * j2] = __dadd_rn(score[2 * j2], b.x);
+                            score[2 * j2 + 1] = __dadd_rn(score[2 * j2 + 1], b.y);
+                        }
+                    }
+                }
+            }
+        }
+        double best = INFINITY;
+        int bidx = 0;
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s)
+            if (s == seg) best = ts.best[s], bidx = ts.bidx[s];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            if (score[j] < best) {      // strict: ties keep the lowest index
+                best = score[j];
+                bidx = kk0 + j;
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s)
+            if (s == seg) ts.best[s] = best, ts.bidx[s] = bidx;
+    }
+
+    __device__ __forceinline__ void step_end(Tile& ts, const IgemmGeom&, const TileCoord&, int step) const {
+        if (!step_last[step]) return;
+        const int l = step_level[step];
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s) {
+            if (s < m) {
+#pragma unroll
+                for (int ll = 0; ll < kMaxLevels; ++ll)
+                    if (ll == l) ts.code[ll][s] = ts.bidx[s];
+                if (ts.r < rows) codes[(static_cast<long long>(l) * m + s) * rows + ts.r] = static_cast<uint8_t>(ts.bidx[s]);
+                ts.best[s] = INFINITY;
+                ts.bidx[s] = 0;
+            }
+        }
+    }
+
+    __device__ __forceinline__ void end(Tile&, const IgemmGeom&, const TileCoord&) const {}
+};
+
+// out[r][:] = ((const + T[0][0][code]) + T[0][1][code]) + ... ; one warp per row, fixed summation order.
+__global__ void codebook_decode_kernel(const uint8_t* __restrict__ codes, long long rows, int levels, int m, int C,
+                                       const float* __restrict__ dconst, const float* __restrict__ tables,
+                                       const long long* __restrict__ toff, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int vec = C / 4;    // float4 per row
+    for (long long r = warp; r < rows; r += nwarps) {
+        int code[kMaxLevels * kMaxSeg];
+        for (int i = 0; i < levels * m; ++i) code[i] = __ldg(codes + static_cast<long long>(i) * rows + r);
+        for (int v = lane; v < vec; v += 32) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(dconst) + v);
+            for (int i = 0; i < levels * m; ++i) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(tables + toff[i] +
+                                                                       static_cast<long long>(code[i]) * C) + v);
+                a.x = __fadd_rn(a.x, t.x);
+                a.y = __fadd_rn(a.y, t.y);
+                a.z = __fadd_rn(a.z, t.z);
+                a.w = __fadd_rn(a.w, t.w);
+            }
+            reinterpret_cast<float4*>(out + r * C)[v] = a;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- host math
+struct Mat {
+    int r = 0, c = 0;
+    std::vector<double> v;
+    Mat() {}
+    Mat(int r_, int c_) : r(r_), c(c_), v(static_cast<size_t>(r_) * c_, 0.0) {}
+    double& at(int i, int j) { return v[static_cast<size_t>(i) * c + j]; }
+    double at(int i, int j) const { return v[static_cast<size_t>(i) * c + j]; }
+};
+static Mat matmul(const Mat& a, const Mat& b) {
+    Mat o(a.r, b.c);
+    for (int i = 0; i < a.r; ++i)
+        for (int k = 0; k < a.c; ++k) {
+            const double x = a.at(i, k);
+            if (x == 0.0) continue;
+            const double* bp = &b.v[static_cast<size_t>(k) * b.c];
+            double* op = &o.v[static_cast<size_t>(i) * o.c];
+            for (int j = 0; j < b.c; ++j) op[j] += x * bp[j];
+        }
+    return o;
+}
+static std::vector<double> matvec(const Mat& a, const std::vector<double>& x) {
+    std::vector<double> o(a.r, 0.0);
+    for (int i = 0; i < a.r; ++i) {
+        double s = 0.0;
+        for (int j = 0; j < a.c; ++j) s += a.at(i, j) * x[j];
+        o[i] = s;
+    }
+    return o;
+}
+static Mat eye(int n) {
+    Mat o(n, n);
+    for (int i = 0; i < n; ++i) o.at(i, i) = 1.0;
+    return o;
+}
+static Mat from_f32(const float* p, int r, int c) {
+    Mat o(r, c);
+    for (size_t i = 0; i < o.v.size(); ++i) o.v[i] = p[i];
+    return o;
+}
+static std::vector<double> vec_f32(const float* p, int n) {
+    std::vector<double> o(n, 0.0);
+    if (p) for (int i = 0; i < n; ++i) o[i] = p[i];
+    return o;
+}
+
+}  // namespace qv2x
+
+using namespace qv2x;
+
+struct qv2x_codebook {
+    qv2x_codebook_desc d;
+    int C, m, levels, dseg;
+    int k[kMaxLevels], n_level[kMaxLevels], colbase[kMaxLevels], rowbase[kMaxLevels];
+    int block_n, bk, n_steps;
+    long long boff[kMaxLevels][kMaxLevels];
+    // host copies (for qv2x_codebook_folded_copy) and device buffers
+    std::vector<int8_t> h_digits;
+    std::vector<double> h_sc, h_g0, h_btab;
+    std::vector<float> h_dconst, h_tables;
+    std::vector<long long> h_toff;
+    int8_t* d_digits = nullptr;
+    double *d_sc = nullptr, *d_g0 = nullptr, *d_btab = nullptr;
+    float *d_dconst = nullptr, *d_tables = nullptr;
+    long long* d_toff = nullptr;
+};
+
+extern "C" {
+
+void qv2x_codebook_destroy(qv2x_codebook* cb) {
+    if (!cb) return;
+    cudaFree(cb->d_digits);
+    cudaFree(cb->d_sc);
+    cudaFree(cb->d_g0);
+    cudaFree(cb->d_btab);
+    cudaFree(cb->d_dconst);
+    cudaFree(cb->d_tables);
+    cudaFree(cb->d_toff);
+    delete cb;
+}
+
+int qv2x_codebook_create(const qv2x_codebook_desc* desc, const float* const* codebooks, const float* const* weights,
+                         const float* const* biases, qv2x_codebook** out) {
+    QV2X_REQUIRE(desc && codebooks && weights && biases && out, "qv2x_codebook_create: null argument");
+    const int C = desc->channel, m = desc->m, L = desc->levels;
+    QV2X_REQUIRE(L >= 1 && L <= kMaxLevels, "levels must be 1..%d", kMaxLevels);
+    QV2X_REQUIRE(m >= 1 && m <= kMaxSeg && C % m == 0, "m must be 1..%d and divide channel", kMaxSeg);
+    QV2X_REQUIRE(C % 64 == 0, "channel must be a multiple of 64");
+    for (int l = 0; l < L; ++l)
+        QV2X_REQUIRE(desc->k[l] >= 16 && desc->k[l] <= 256 && desc->k[l] % 16 == 0,
+                     "dict size must be a multiple of 16 in [16, 256] (codes are bytes)");
+    const int d = C / m;
+    auto W = [&](int l, int h) { return weights[l * 6 + h]; };
+    auto Bv = [&](int l, int h) { return biases[l * 6 + h]; };
+    enum { H_ENC = 0, H_QH = 1, H_LAT = 2, H_DEQ = 3, H_SIDE = 4, H_RES = 5 };
+    for (int l = 0; l < L; ++l) {
+        QV2X_REQUIRE(W(l, H_ENC) && W(l, H_QH) && W(l, H_DEQ) && W(l, H_RES) && codebooks[l],
+                     "level %d: latentStageEncoder / quantizationHead / dequantizationHead / restoreHead required", l);
+        if (l < L - 1) QV2X_REQUIRE(W(l, H_LAT) && W(l, H_SIDE), "level %d: latentHead and sideHead required", l);
+    }
+    auto cb = new qv2x_codebook();
+    cb->d = *desc;
+    cb->C = C;
+    cb->m = m;
+    cb->levels = L;
+    cb->dseg = d;
+    int ncols = 0, nrows = 0;
+    for (int l = 0; l < L; ++l) {
+        cb->k[l] = desc->k[l];
+        cb->n_level[l] = m * desc->k[l];
+        cb->colbase[l] = ncols;
+        cb->rowbase[l] = nrows;
+        ncols += cb->n_level[l];
+        nrows += 3 * cb->n_level[l];
+    }
+    cb->bk = (C % 128 == 0) ? 128 : 64;
+    // one BLOCK_N for all levels: 128 when every level's width allows it, else 64, else 32... keep 64/128
+    cb->block_n = 128;
+    for (int l = 0; l < L; ++l)
+        if (cb->n_level[l] % 128 != 0) cb->block_n = 64;
+    for (int l = 0; l < L; ++l)
+        if (cb->n_level[l] % cb->block_n != 0) {
+            delete cb;
+            return set_error(QV2X_ERR_INVALID, "m * dict_size must be a multiple of 64 (level %d has %d)", l,
+                             m * desc->k[l]);
+        }
+    cb->n_steps = 0;
+    for (int l = 0; l < L; ++l) cb->n_steps += cb->n_level[l] / cb->block_n;
+    if (cb->n_steps > kMaxSteps) {
+        delete cb;
+        return set_error(QV2X_ERR_INVALID, "too many N steps (%d > %d)", cb->n_steps, kMaxSteps);
+    }
+
+    // ---------------------------------------------------------------- fold the encoder (float64)
+    cb->h_digits.assign(static_cast<size_t>(nrows) * C, 0);
+    cb->h_sc.assign(ncols, 1.0);
+    cb->h_g0.assign(ncols, 0.0);
+    Mat A = eye(C);
+    std::vector<double> a(C, 0.0);
+    std::vector<Mat> P;
+    long long bcount = 0;
+    for (int l = 0; l < L; ++l)
+        for (int j = 0; j < l; ++j) {
+            cb->boff[l][j] = bcount;
+            bcount += static_cast<long long>(m) * cb->k[j] * cb->n_level[l];
+        }
+    cb->h_btab.assign(static_cast<size_t>(bcount > 0 ? bcount : 1), 0.0);
+    for (int l = 0; l < L; ++l) {
+        const int k = cb->k[l], nl = cb->n_level[l];
+        const Mat We = from_f32(W(l, H_ENC), C, C), Wq = from_f32(W(l, H_QH), C, C);
+        const std::vector<double> be = vec_f32(Bv(l, H_ENC), C), bq = vec_f32(Bv(l, H_QH), C);
+        const Mat M = matmul(Wq, We);
+        std::vector<double> hb = matvec(Wq, be);
+        for (int i = 0; i < C; ++i) hb[i] += bq[i];
+        Mat Cmat(nl, C);
+        std::vector<double> c2(nl, 0.0);
+        for (int s = 0; s < m; ++s)
+            for (int kk = 0; kk < k; ++kk)
+                for (int t = 0; t < d; ++t) {
+                    const double cv = codebooks[l][(static_cast<size_t>(s) * k + kk) * d + t];
+                    Cmat.at(s * k + kk, s * d + t) = cv;
+                    c2[s * k + kk] += cv * cv;
+                }
+        Mat T = matmul(Cmat, M);
+        for (auto& x : T.v) x *= -2.0;
+        const Mat G = matmul(T, A);
+        const std::vector<double> Ta = matvec(T, a), Chb = matvec(Cmat, hb);
+        for (int n = 0; n < nl; ++n) {
+            cb->h_g0[cb->colbase[l] + n] = c2[n] - 2.0 * Chb[n] + Ta[n];
+            double mx = 0.0;
+            for (int i = 0; i < C; ++i) mx = std::max(mx, std::fabs(G.at(n, i)));
+            const double sc = mx > 0.0 ? mx / kDigitMax : 1.0;
+            cb->h_sc[cb->colbase[l] + n] = sc;
+            for (int i = 0; i < C; ++i) {
+                int8_t dg[3];
+                split_digits(static_cast<long long>(std::nearbyint(G.at(n, i) / sc)), dg);
+                for (int g3 = 0; g3 < 3; ++g3)
+                    cb->h_digits[(static_cast<size_t>(cb->rowbase[l]) + static_cast<size_t>(g3) * nl + n) * C + i] =
+                        dg[g3];
+            }
+        }
+        for (int j = 0; j < l; ++j) {
+            const Mat TP = matmul(T, P[j]);   // [nl, C]
+            const int kj = cb->k[j];
+            for (int s2 = 0; s2 < m; ++s2)
+                for (int kk = 0; kk < kj; ++kk)
+                    for (int n = 0; n < nl; ++n) {
+                        double sum = 0.0;
+                        for (int t = 0; t < d; ++t)
+                            sum += codebooks[j][(static_cast<size_t>(s2) * kj + kk) * d + t] * TP.at(n, s2 * d + t);
+                        cb->h_btab[cb->boff[l][j] + (static_cast<long long>(s2) * kj + kk) * nl + n] = -sum;
+                    }
+        }
+        if (l < L - 1) {
+            const Mat Wl = from_f32(W(l, H_LAT), C, C);
+            const std::vector<double> bl = vec_f32(Bv(l, H_LAT), C);
+            const Mat N = matmul(Wl, We);
+            for (auto& Pj : P) Pj = matmul(N, Pj);
+            P.push_back(eye(C));
+            std::vector<double> na = matvec(N, a), wbe = matvec(Wl, be);
+            for (int i = 0; i < C; ++i) a[i] = na[i] + wbe[i] + bl[i];
+            A = matmul(N, A);
+        }
+    }
+    // ---------------------------------------------------------------- fold the decoder (float64 -> fp32 tables)
+    {
+        std::vector<std::vector<Mat>> tabs(L);   // tabs[l][s]: [k, C]
+        std::vector<double> cst;
+        for (int l = L - 1; l >= 0; --l) {
+            const Mat Wd = from_f32(W(l, H_DEQ), C, C), Wr = from_f32(W(l, H_RES), C, C);
+            const std::vector<double> bd = vec_f32(Bv(l, H_DEQ), C), br = vec_f32(Bv(l, H_RES), C);
+            const Mat RD = matmul(Wr, Wd);   // [C, C]
+            std::vector<double> inner = bd;
+            if (l < L - 1) {
+                const Mat Ws = from_f32(W(l, H_SIDE), C, C);
+                const std::vector<double> bs = vec_f32(Bv(l, H_SIDE), C);
+                const Mat RS = matmul(Wr, Ws);
+                for (int ll = l + 1; ll < L; ++ll)
+                    for (auto& t : tabs[ll]) {
+                        Mat nt(t.r, C);
+                        for (int r = 0; r < t.r; ++r)
+                            for (int i = 0; i < C; ++i) {
+                                double sum = 0.0;
+                                for (int j = 0; j < C; ++j) sum += t.at(r, j) * RS.at(i, j);
+                                nt.at(r, i) = sum;
+                            }
+                        t = nt;
+                    }
+                const std::vector<double> wsc = matvec(Ws, cst);
+                for (int i = 0; i < C; ++i) inner[i] += wsc[i] + bs[i];
+            }
+            cst = matvec(Wr, inner);
+            for (int i = 0; i < C; ++i) cst[i] += br[i];
+            tabs[l].resize(m);
+            for (int s = 0; s < m; ++s) {
+                Mat t(cb->k[l], C);
+                for (int kk = 0; kk < cb->k[l]; ++kk)
+                    for (int i = 0; i < C; ++i) {
+                        double sum = 0.0;
+                        for (int t2 = 0; t2 < d; ++t2)
+                            sum += codebooks[l][(static_cast<size_t>(s) * cb->k[l] + kk) * d + t2] * RD.at(i, s * d + t2);
+                        t.at(kk, i) = sum;
+                    }
+                tabs[l][s] = t;
+            }
+        }
+        cb->h_dconst.resize(C);
+        for (int i = 0; i < C; ++i) cb->h_dconst[i] = static_cast<float>(cst[i]);
+        long long off = 0;
+        for (int l = 0; l < L; ++l)
+            for (int s = 0; s < m; ++s) {
+                cb->h_toff.push_back(off);
+                for (double x : tabs[l][s].v) cb->h_tables.push_back(static_cast<float>(x));
+                off += static_cast<long long>(cb->k[l]) * C;
+            }
+    }
+    int rc = upload(&cb->d_digits, cb->h_digits.data(), cb->h_digits.size());
+    if (!rc) rc = upload(&cb->d_sc, cb->h_sc.data(), cb->h_sc.size());
+    if (!rc) rc = upload(&cb->d_g0, cb->h_g0.data(), cb->h_g0.size());
+    if (!rc) rc = upload(&cb->d_btab, cb->h_btab.data(), cb->h_btab.size());
+    if (!rc) rc = upload(&cb->d_dconst, cb->h_dconst.data(), cb->h_dconst.size());
+    if (!rc) rc = upload(&cb->d_tables, cb->h_tables.data(), cb->h_tables.size());
+    if (!rc) rc = upload(&cb->d_toff, cb->h_toff.data(), cb->h_toff.size());
+    if (rc) {
+        qv2x_codebook_destroy(cb);
+        return rc;
+    }
+    *out = cb;
+    return 0;
+}
+
+int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t* d_feat, int feat_cstride,
+                         float delta, uint8_t* d_codes, void* stream_) {
+    QV2X_REQUIRE(cb && d_feat && d_codes, "qv2x_codebook_encode: null argument");
+    if (rows <= 0) return 0;
+    QV2X_REQUIRE(rows < (1ll << 31), "too many rows");
+    QV2X_REQUIRE(feat_cstride >= cb->C && feat_cstride % 16 == 0, "bad feature stride");
+    QV2X_REQUIRE(delta > 0.f, "delta must be positive");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    IgemmGeom g{};
+    g.n_img = 1;
+    g.Ho = 1;
+    g.Wo = static_cast<int>(rows);
+    g.Hi = 1;
+    g.Wi = static_cast<int>(rows);
+    g.tw = 128;
+    g.th = 1;
+    g.tiles_x = static_cast<int>((rows + 127) / 128);
+    g.tiles_y = 1;
+    g.n_tiles = 1;
+    g.block_n = cb->block_n;
+    g.taps = 1;
+    g.taps_w = 1;
+    g.stride = 1;
+    g.pad = 0;
+    g.groups = 3;
+    g.cblocks = cb->C / cb->bk;
+    g.idesc = make_idesc_i8(cb->block_n, true);
+    g.n_steps = cb->n_steps;
+    EncodeEpilogue e{};
+    e.levels = cb->levels;
+    e.m = cb->m;
+    int step = 0;
+    for (int l = 0; l < cb->levels; ++l) {
+        e.k[l] = cb->k[l];
+        e.n_level[l] = cb->n_level[l];
+        e.colbase[l] = cb->colbase[l];
+        for (int j = 0; j < kMaxLevels; ++j) e.boff[l][j] = cb->boff[l][j];
+        const int spl = cb->n_level[l] / cb->block_n;
+        for (int c = 0; c < spl; ++c, ++step) {
+            g.step_row_base[step] = cb->rowbase[l] + c * cb->block_n;
+            g.step_group_stride[step] = cb->n_level[l];
+            e.step_level[step] = l;
+            e.step_col0[step] = c * cb->block_n;
+            e.step_last[step] = (c == spl - 1);
+        }
+    }
+    e.delta = static_cast<double>(delta);
+    e.sc = cb->d_sc;
+    e.g0 = cb->d_g0;
+    e.btab = cb->d_btab;
+    e.codes = d_codes;
+    e.rows = rows;
+    CUtensorMap tmA, tmB;
+    int rc = make_act_tmap(&tmA, d_feat, 1, 1, static_cast<int>(rows), feat_cstride, 128, 1, 1, cb->bk);
+    if (rc) return rc;
+    int total_rows = 0;
+    for (int l = 0; l < cb->levels; ++l) total_rows += 3 * cb->n_level[l];
+    rc = make_weight_tmap(&tmB, cb->d_digits, total_rows, cb->C, cb->block_n, cb->bk);
+    if (rc) return rc;
+    return dispatch_igemm<3>(cb->block_n, cb->bk, tmA, tmB, g, e, stream);
+}
+
+int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t* d_codes, float* d_out, void* stream_) {
+    QV2X_REQUIRE(cb && d_codes && d_out, "qv2x_codebook_decode: null argument");
+    if (rows <= 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int threads = 256;
+    const long long want = (rows * 32 + threads - 1) / threads;
+    const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 8));
+    codebook_decode_kernel<<<grid, threads, 0, stream>>>(d_codes, rows, cb->levels, cb->m, cb->C, cb->d_dconst,
+                                                          cb->d_tables, cb->d_toff, d_out);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+long long qv2x_codebook_folded_size(const qv2x_codebook* cb, int which) {
+    if (!cb) return -1;
+    switch (which) {
+        case 0: return static_cast<long long>(cb->h_digits.size());
+        case 1: return static_cast<long long>(cb->h_sc.size());
+        case 2: return static_cast<long long>(cb->h_g0.size());
+        case 3: return static_cast<long long>(cb->h_btab.size());
+        case 4: return static_cast<long long>(cb->h_dconst.size());
+        case 5: return static_cast<long long>(cb->h_tables.size());
+        default: return -1;
+    }
+}
+
+int qv2x_codebook_folded_copy(const qv2x_codebook* cb, int which, void* host_buf) {
+    QV2X_REQUIRE(cb && host_buf, "qv2x_codebook_folded_copy: null argument");
+    switch (which) {
+        case 0: memcpy(host_buf, cb->h_digits.data(), cb->h_digits.size()); break;
+        case 1: memcpy(host_buf, cb->h_sc.data(), cb->h_sc.size() * sizeof(double)); break;
+        case 2: memcpy(host_buf, cb->h_g0.data(), cb->h_g0.size() * sizeof(double)); break;
+        case 3: memcpy(host_buf, cb->h_btab.data(), cb->h_btab.size() * sizeof(double)); break;
+        case 4: memcpy(host_buf, cb->h_dconst.data(), cb->h_dconst.size() * sizeof(float)); break;
+        case 5: memcpy(host_buf, cb->h_tables.data(), cb->h_tables.size() * sizeof(float)); break;
+        default: return set_error(QV2X_ERR_INVALID, "unknown table id %d", which);
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -17,6 +17,7 @@ namespace qv2x {
 
 template <int G>
 struct RequantEpilogue {
+    static constexpr int kColSplit = 2;
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
@@ -68,10 +69,10 @@ struct RequantEpilogue {
         ts.opix = (static_cast<long long>(tc.img) * Hout + oy * up + dy) * Wout + ox * up + dx;
     }
 
-    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int n0,
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int n0,
                                           const int32_t (*acc)[16]) const {
-        (void)g;
         (void)tc;
+        (void)step;
         uint32_t packed[4] = {0, 0, 0, 0};
         int rsum = 0;
         // per-column parameters: warp-uniform 16-byte loads (L1 broadcast)
@@ -127,6 +128,8 @@ struct RequantEpilogue {
             ts.rsum += rsum;
         }
     }
+
+    __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int) const {}
 
     __device__ __forceinline__ void end(Tile& ts, const IgemmGeom& g, const TileCoord& tc) const {
         (void)g;

@@ -21,9 +21,8 @@
 namespace qv2x {
 
 constexpr int kMaxGroups = 3;
+constexpr int kMaxSteps = 24;
 constexpr int kTileM = 128;
-constexpr int kNumEpiWarps = 8;
-constexpr int kNumThreads = (4 + kNumEpiWarps) * 32;
 
 struct IgemmGeom {
     // M-tile grid: per image Ho x Wo "anchor" pixels covered by tw x th boxes (tw * th == 128)
@@ -38,6 +37,12 @@ struct IgemmGeom {
     int b_k_base[kMaxGroups];    // K coordinate (within one tap) of the group's first k-block in B
     int b_k_tap_stride;          // K distance between consecutive taps in B
     uint32_t idesc;              // tcgen05 instruction descriptor (operand signedness, M, N)
+    // Sequential N steps per tile (1 for conv layers).  A tile visits its steps in order on ONE CTA, so an
+    // epilogue may carry state from step to step (the codebook's level-by-level argmin).  B rows of
+    // (step, group) start at b_row_base[g] + step_row_base[step] + g * step_group_stride[step].
+    int n_steps;
+    int step_row_base[kMaxSteps];
+    int step_group_stride[kMaxSteps];
 };
 
 template <int BLOCK_N, int BK>
@@ -68,21 +73,28 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 // Epilogue contract:
 //   struct Epi {
 //     struct Tile;                                     // per-thread, per-tile state
+//     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
 //     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row) const;
 //         -- called BEFORE the accumulators are ready (prefetch side inputs here)
-//     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int col0, const int32_t (*acc)[16]) const;
-//         -- 16 consecutive columns [col0, col0+16) of this thread's row, acc[g][j]
+//     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
+//                           const int32_t (*acc)[16]) const;
+//         -- 16 consecutive columns [col0, col0+16) of this thread's row in `step`, acc[g][j]
+//     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step) const;
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
 //   };
+template <class Epi>
+constexpr int igemm_threads() { return (4 + 4 * Epi::kColSplit) * 32; }
+
 template <int BLOCK_N, int BK, int G, class Epi>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(igemm_threads<Epi>(), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
              const Epi epi) {
     using Cfg = IgemmCfg<BLOCK_N, BK>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kSlots = Cfg::kSlots;
     static_assert(G <= kSlots, "every group needs its own TMEM slot");
-    static_assert(BLOCK_N % 32 == 0, "BLOCK_N must split into two 16-column-aligned halves");
+    constexpr int kNumEpiWarps = 4 * Epi::kColSplit;
+    static_assert(BLOCK_N % (16 * Epi::kColSplit) == 0, "BLOCK_N must split into 16-column-aligned parts");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,19 +140,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const TileCoord tc = decode_tile(g, t);
                 const int x0 = tc.tx * g.tw * g.stride - g.pad;
                 const int y0 = tc.ty * g.th * g.stride - g.pad;
-                for (int grp = 0; grp < G; ++grp) {
-                    for (int tap = 0; tap < g.taps; ++tap) {
-                        const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
-                        for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
-                            const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                            mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                            const uint32_t fb = smem_u32(&full_bar[s]);
-                            mbar_expect_tx(fb, Cfg::kStageBytes);
-                            uint8_t* st = smem + s * Cfg::kStageBytes;
-                            tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky, tc.img);
-                            tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
-                                        tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK,
-                                        g.b_row_base[grp] + tc.nt * BLOCK_N);
+                for (int step = 0; step < g.n_steps; ++step) {
+                    for (int grp = 0; grp < G; ++grp) {
+                        const int brow = g.b_row_base[grp] + g.step_row_base[step] + grp * g.step_group_stride[step] +
+                                         tc.nt * BLOCK_N;
+                        for (int tap = 0; tap < g.taps; ++tap) {
+                            const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                            for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
+                                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
+                                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                                const uint32_t fb = smem_u32(&full_bar[s]);
+                                mbar_expect_tx(fb, Cfg::kStageBytes);
+                                uint8_t* st = smem + s * Cfg::kStageBytes;
+                                tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky,
+                                            tc.img);
+                                tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
+                                            tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
+                            }
                         }
                     }
                 }
@@ -151,7 +167,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) {
             uint32_t it = 0, ac = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                for (int grp = 0; grp < G; ++grp, ++ac) {
+                for (int sg = 0; sg < g.n_steps * G; ++sg, ++ac) {
                     const uint32_t slot = ac % kSlots, aph = (ac / kSlots) & 1;
                     mbar_wait(smem_u32(&tempty_bar[slot]), aph ^ 1);
                     tcgen05_fence_after();
@@ -177,35 +193,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;     // which half of the tile's columns
+        const int part = (warp - 4) >> 2;     // which part of the step's columns (kColSplit parts)
         const int row = quad * 32 + lane;     // tile row == TMEM lane
-        constexpr int kColsPerWarp = BLOCK_N / 2;
+        constexpr int kColsPerWarp = BLOCK_N / Epi::kColSplit;
         uint32_t ac = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ac += G) {
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(g, t);
             typename Epi::Tile ts;
             epi.begin(ts, g, tc, row);
-#pragma unroll
-            for (int grp = 0; grp < G; ++grp) {
-                const uint32_t a = ac + grp;
-                mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
-            }
-            tcgen05_fence_after();
-            for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 16) {
-                uint32_t acc[G][16];
+            for (int step = 0; step < g.n_steps; ++step, ac += G) {
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp) {
-                    const uint32_t slot = (ac + grp) % kSlots;
-                    tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * BLOCK_N + c0, acc[grp]);
+                    const uint32_t a = ac + grp;
+                    mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
                 }
-                tmem_ld_wait();
-                epi.chunk(ts, g, tc, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
-            }
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
+                tcgen05_fence_after();
+                for (int c0 = part * kColsPerWarp; c0 < (part + 1) * kColsPerWarp; c0 += 16) {
+                    uint32_t acc[G][16];
 #pragma unroll
-                for (int grp = 0; grp < G; ++grp) mbar_arrive(smem_u32(&tempty_bar[(ac + grp) % kSlots]));
+                    for (int grp = 0; grp < G; ++grp) {
+                        const uint32_t slot = (ac + grp) % kSlots;
+                        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * BLOCK_N + c0,
+                                    acc[grp]);
+                    }
+                    tmem_ld_wait();
+                    epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int grp = 0; grp < G; ++grp) mbar_arrive(smem_u32(&tempty_bar[(ac + grp) % kSlots]));
+                }
+                epi.step_end(ts, g, tc, step);
             }
             epi.end(ts, g, tc);
         }

@@ -180,6 +180,7 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     g.n_tiles = L->n_total / L->block_n;
     g.groups = L->groups;
     g.idesc = make_idesc_i8(L->block_n, L->b_signed);
+    g.n_steps = 1;
     int out_h, out_w;
     if (d.kind == 0) {
         g.Ho = ho;

@@ -105,3 +105,84 @@ def rowsum_u8(x: torch.Tensor, cbase: int, c: int, out: torch.Tensor | None = No
     check(_lib.lib().qv2x_rowsum_u8(c_void_p(x.data_ptr()), n * h * w, cs, cbase, c, c_void_p(out.data_ptr()),
                                     _stream_ptr()))
     return out
+
+
+HEAD_ORDER = ("latentStageEncoder", "quantizationHead", "latentHead", "dequantizationHead", "sideHead",
+              "restoreHead")
+
+
+class CodebookEngine:
+    """GPU codebook compressor (qv2x_codebook): UMGMQuantizer.encode / .decode of the reference
+    (opencood/models/sub_modules/codebook.py:330-343).
+
+    codebooks: list (levels) of float32 [m, k, C/m]; heads: list (levels) of dicts name -> (W [C,C], b [C]) or None.
+    """
+
+    def __init__(self, codebooks, heads):
+        from ._lib import CodebookDesc
+
+        levels = len(codebooks)
+        cbs = [np.ascontiguousarray(c, dtype=np.float32) for c in codebooks]
+        m, _, dseg = cbs[0].shape
+        d = CodebookDesc()
+        d.channel, d.m, d.levels = int(m * dseg), int(m), int(levels)
+        for l in range(levels):
+            d.k[l] = int(cbs[l].shape[1])
+        keep = list(cbs)
+        cb_ptrs = (c_void_p * levels)(*[_np_ptr(c) for c in cbs])
+        w_ptrs = (c_void_p * (levels * 6))()
+        b_ptrs = (c_void_p * (levels * 6))()
+        for l in range(levels):
+            for h, name in enumerate(HEAD_ORDER):
+                wb = heads[l].get(name)
+                if wb is None:
+                    continue
+                w = np.ascontiguousarray(wb[0], dtype=np.float32)
+                b = np.ascontiguousarray(wb[1], dtype=np.float32)
+                keep += [w, b]
+                w_ptrs[l * 6 + h] = w.ctypes.data
+                b_ptrs[l * 6 + h] = b.ctypes.data
+        self.desc = d
+        self.channel, self.m, self.levels = d.channel, d.m, d.levels
+        self.k = [d.k[l] for l in range(levels)]
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_codebook_create(byref(d), cb_ptrs, w_ptrs, b_ptrs, byref(self._h)))
+        del keep
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_codebook_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def encode(self, feat_u8: torch.Tensor, delta: float, out: torch.Tensor | None = None) -> torch.Tensor:
+        """feat_u8: uint8 [rows, Cstride] (or any [..., Cstride] contiguous).  Returns uint8 [levels, m, rows]."""
+        assert feat_u8.is_cuda and feat_u8.dtype == torch.uint8 and feat_u8.is_contiguous()
+        cs = feat_u8.shape[-1]
+        rows = feat_u8.numel() // cs
+        if out is None:
+            out = torch.empty((self.levels, self.m, rows), dtype=torch.uint8, device=feat_u8.device)
+        check(_lib.lib().qv2x_codebook_encode(self._h, rows, c_void_p(feat_u8.data_ptr()), cs, float(delta),
+                                              c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
+    def decode(self, codes: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """codes: uint8 [levels, m, rows] -> float32 [rows, C]."""
+        assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+        rows = codes.shape[-1]
+        if out is None:
+            out = torch.empty((rows, self.channel), dtype=torch.float32, device=codes.device)
+        check(_lib.lib().qv2x_codebook_decode(self._h, rows, c_void_p(codes.data_ptr()), c_void_p(out.data_ptr()),
+                                              _stream_ptr()))
+        return out
+
+    def folded(self, which: int) -> np.ndarray:
+        """Test hook: the folded tables held by the library (see qv2x_codebook_folded_copy)."""
+        n = _lib.lib().qv2x_codebook_folded_size(self._h, which)
+        dt = {0: np.int8, 1: np.float64, 2: np.float64, 3: np.float64, 4: np.float32, 5: np.float32}[which]
+        buf = np.empty(n, dtype=dt)
+        check(_lib.lib().qv2x_codebook_folded_copy(self._h, which, _np_ptr(buf)))
+        return buf

@@ -1,0 +1,73 @@
+"""CPU tests of the oracle itself (no GPU): internal consistency of the restatements."""
+import numpy as np
+
+from oracle import codebook_oracle as co
+from oracle import int_oracle
+from tests.codebook_cases import make_codebook_params, make_features, oracle_params
+from tests.layer_cases import make_conv, make_deconv, make_input
+
+
+def test_fold_matches_sequential_fp64():
+    cbs, heads = make_codebook_params(3, 64, 2, [32, 32, 32])
+    p = oracle_params(cbs, heads)
+    q = make_features(0, 600, 64)
+    delta = np.float32(0.21)
+    x = q.astype(np.float64) * np.float64(delta)
+    c64 = co.encode_fp64(p, x)
+    cfx = co.encode_fixed_point(co.fold_encode(p), q, delta)
+    for a, b in zip(c64, cfx):
+        assert (a != b).mean() < 2e-3
+    d_seq = co.decode_fp64(p, c64)
+    d_tab = co.decode_tables(co.fold_decode(p), c64)
+    np.testing.assert_allclose(d_tab, d_seq, atol=1e-12)
+
+
+def test_split_digits_roundtrip():
+    rng = np.random.default_rng(0)
+    m = rng.integers(-8355711, 8355712, size=10000)
+    hi, mid, lo = int_oracle.split_digits(m)
+    assert np.array_equal(hi * 65536 + mid * 256 + lo, m)
+    assert lo.min() >= -128 and lo.max() <= 127 and mid.min() >= -128 and mid.max() <= 127
+
+
+def test_conv_oracle_matches_fakequant_float():
+    """Integer oracle vs the reference-style FP32 fake-quant evaluation: <= 1 LSB on a tiny fraction."""
+    rng = np.random.default_rng(11)
+    p = make_conv(rng, 64, 64, 3)
+    x = make_input(rng, 1, 10, 14, 64)
+    _, q = int_oracle.conv_oracle(x, p["w_int"], p["w_delta"], p["w_zp"], p["bias"], p["in_delta"], p["out_delta"])
+    w_fake = (p["w_int"].astype(np.float32) - p["w_zp"].reshape(-1, 1, 1, 1)) * p["w_delta"].reshape(-1, 1, 1, 1)
+    x_hat = (x.astype(np.float32) * p["in_delta"][0]).transpose(0, 3, 1, 2)
+    y = int_oracle.fakequant_layer_float(x_hat, w_fake, p["w_delta"], p["w_zp"], p["bias"], p["out_delta"], 0.0)
+    qf = np.rint(y / p["out_delta"]).astype(np.int64).transpose(0, 2, 3, 1)
+    diff = np.abs(qf - q.astype(np.int64))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_deconv_oracle_matches_fakequant_float():
+    rng = np.random.default_rng(12)
+    p = make_deconv(rng, 64, 128, 2)
+    x = make_input(rng, 1, 6, 10, 64)
+    _, q = int_oracle.deconv_oracle(x, p["w_int"], p["w_delta"], p["w_zp"], p["bias"], p["in_delta"][0],
+                                    p["out_delta"], stride=2)
+    w_fake = (p["w_int"].astype(np.float32) - p["w_zp"].reshape(-1, 1, 1, 1)) * p["w_delta"].reshape(-1, 1, 1, 1)
+    x_hat = (x.astype(np.float32) * p["in_delta"][0]).transpose(0, 3, 1, 2)
+    y = int_oracle.fakequant_layer_float(x_hat, w_fake, p["w_delta"], p["w_zp"], p["bias"], p["out_delta"], 0.0,
+                                         kind=1, stride=2)
+    qf = np.rint(y / p["out_delta"]).astype(np.int64).transpose(0, 2, 3, 1)
+    diff = np.abs(qf - q.astype(np.int64))
+    assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
+
+
+def test_library_exports_all_symbols():
+    """The C-ABI library loads without a GPU and exports every symbol include/qv2x.h declares."""
+    import ctypes
+
+    from quantv2x_b200 import _lib
+
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    names = _lib.exported_symbols()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(handle, n), f"libqv2x.so does not export {n}"
+    assert _lib.lib().qv2x_version() >= 100
