@@ -129,6 +129,64 @@ int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t*
 long long qv2x_codebook_folded_size(const qv2x_codebook* cb, int which);
 int qv2x_codebook_folded_copy(const qv2x_codebook* cb, int which, void* host_buf);
 
+/* ------------------------------------------------------------------------------------------------
+ * Ego-side fusion = reference MaxFusion / AttFusion .forward for one frame
+ * (opencood/models/fuse_modules/fusion_in_one.py:87-151), including the bilinear warp of every agent
+ * (the ego too) into the ego frame (warp_affine_simple, torch_transformation_utils.py:323-332).
+ * d_feat: [n_agents][H][W][C] float32 pixel-major, agent 0 = ego.
+ * affine: HOST [n_agents][2][3] = normalize_pairwise_tfm(...)[b][0, :n] (ego row of the pairwise matrices,
+ *         opencood/utils/transformation_utils.py:68-92).  mode 0 = max, 1 = attention (ego query row).
+ * d_out:  [H][W][C] float32 pixel-major.
+ * ---------------------------------------------------------------------------------------------- */
+int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* affine, float* d_out,
+              void* stream);
+
+/* Detection heads = the three 1x1 convs cls_head / reg_head / dir_head (reference
+ * heter_model_baseline_mc.py:137-142) concatenated along the output channel; weights are the de-quantized
+ * fake-quant weights (W-quant only, FP32 activations: quant_model.py:129-136).
+ * w: HOST [cout][cin], bias HOST [cout] or NULL.  d_x [pixels][cin] pixel-major -> d_out [cout][pixels]
+ * (= preds_tensor in NCHW for one frame). */
+typedef struct qv2x_heads qv2x_heads;
+int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out);
+void qv2x_heads_destroy(qv2x_heads* heads);
+int qv2x_heads_forward(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, void* stream);
+
+/* Layout / quantization converters for the module boundaries of the drop-in wrappers (the reference
+ * passes float32 NCHW between modules; the kernels work on uint8 / float32 pixel-major tensors).
+ * quantize: q = clamp(rint(x / delta) + zp, 0, 2^bits-1) (reference quant_layer.py:132-133). */
+int qv2x_quantize_nchw_to_nhwc_u8(const float* d_x, int n, int c, long long pixels, float delta, float zero_point,
+                                  int bits, uint8_t* d_y, int out_cstride, int out_cbase, void* stream);
+int qv2x_dequant_nhwc_u8_to_nchw_f32(const uint8_t* d_x, int n, int c, long long pixels, float delta,
+                                     float zero_point, float* d_y, void* stream);
+int qv2x_nchw_to_nhwc_f32(const float* d_x, int n, int c, long long pixels, float* d_y, void* stream);
+int qv2x_nhwc_to_nchw_f32(const float* d_x, int n, int c, long long pixels, float* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * A plan = the quantized BaseBEVBackbone + DownsampleConv of one modality as a fixed launch sequence
+ * (reference QuantBaseBEVBackbone.forward quant_block.py:280-303 + QuantDownsampleConv.forward :583-586).
+ * Buffers are numbered: 0 is the caller's input, n_bufs-1 the caller's output, the rest live in the
+ * caller-provided workspace.  Every step runs one layer from (in_buf, in_cbase) to (out_buf, out_cbase);
+ * several steps may write disjoint channel slices of one buffer (that is how torch.cat disappears).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_plan qv2x_plan;
+typedef struct {
+    const qv2x_layer* layer;
+    int in_buf, in_cbase;
+    int out_buf, out_cbase;
+} qv2x_plan_step;
+
+/* buf_channels[b]: channel stride (bytes per pixel) of buffer b.  Layers must outlive the plan. */
+int qv2x_plan_create(const qv2x_plan_step* steps, int n_steps, const int* buf_channels, int n_bufs, qv2x_plan** out);
+void qv2x_plan_destroy(qv2x_plan* plan);
+int qv2x_plan_out_shape(const qv2x_plan* plan, int H, int W, int* ho, int* wo, int* channels);
+int qv2x_plan_workspace_bytes(const qv2x_plan* plan, int n_img, int H, int W, size_t* bytes);
+/* d_in [n_img][H][W][buf_channels[0]] uint8 -> d_out [n_img][ho][wo][buf_channels[last]] uint8.
+ * dump_step / d_acc_dump: optional accumulator dump of one step (see qv2x_layer_forward), -1 / NULL to disable. */
+int qv2x_plan_forward(const qv2x_plan* plan, int n_img, int H, int W, const uint8_t* d_in, uint8_t* d_out,
+                      void* d_workspace, size_t workspace_bytes, int dump_step, int32_t* d_acc_dump, void* stream);
+/* Copy of the descriptor a layer was created with. */
+int qv2x_layer_desc_get(const qv2x_layer* layer, qv2x_layer_desc* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -105,3 +105,40 @@ def _declare_codebook(lib):
 
 
 _DECLARERS = [_declare, _declare_codebook]
+
+
+def _declare_fusion(lib):
+    lib.qv2x_fuse.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.qv2x_heads_create.argtypes = [c_int, c_int, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.qv2x_heads_destroy.argtypes = [c_void_p]
+    lib.qv2x_heads_destroy.restype = None
+    lib.qv2x_heads_forward.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
+    lib.qv2x_quantize_nchw_to_nhwc_u8.argtypes = [c_void_p, c_int, c_int, c_longlong, c_float, c_float, c_int,
+                                                  c_void_p, c_int, c_int, c_void_p]
+    lib.qv2x_dequant_nhwc_u8_to_nchw_f32.argtypes = [c_void_p, c_int, c_int, c_longlong, c_float, c_float, c_void_p,
+                                                     c_void_p]
+    lib.qv2x_nchw_to_nhwc_f32.argtypes = [c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p]
+    lib.qv2x_nhwc_to_nchw_f32.argtypes = [c_void_p, c_int, c_int, c_longlong, c_void_p, c_void_p]
+
+
+_DECLARERS.append(_declare_fusion)
+
+
+class PlanStep(ctypes.Structure):
+    """Mirror of qv2x_plan_step (include/qv2x.h)."""
+
+    _fields_ = [("layer", c_void_p), ("in_buf", c_int), ("in_cbase", c_int), ("out_buf", c_int), ("out_cbase", c_int)]
+
+
+def _declare_plan(lib):
+    lib.qv2x_plan_create.argtypes = [POINTER(PlanStep), c_int, POINTER(c_int), c_int, POINTER(c_void_p)]
+    lib.qv2x_plan_destroy.argtypes = [c_void_p]
+    lib.qv2x_plan_destroy.restype = None
+    lib.qv2x_plan_out_shape.argtypes = [c_void_p, c_int, c_int, POINTER(c_int), POINTER(c_int), POINTER(c_int)]
+    lib.qv2x_plan_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, POINTER(ctypes.c_size_t)]
+    lib.qv2x_plan_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_size_t,
+                                      c_int, c_void_p, c_void_p]
+    lib.qv2x_layer_desc_get.argtypes = [c_void_p, POINTER(LayerDesc)]
+
+
+_DECLARERS.append(_declare_plan)

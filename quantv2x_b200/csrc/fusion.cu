@@ -1,0 +1,367 @@
+// Ego-side kernels: warp neighbours into the ego frame + fuse (max / attention), detection heads,
+// and the layout / quantization converters used at the drop-in module boundaries.  All HBM-bound.
+//
+//   warp   : reference warp_affine_simple (opencood/models/sub_modules/torch_transformation_utils.py:323-332)
+//            = F.affine_grid + F.grid_sample(bilinear, zeros, align_corners=False)
+//   max    : reference MaxFusion.forward  (opencood/models/fuse_modules/fusion_in_one.py:87-124)
+//   att    : reference AttFusion.forward  (fusion_in_one.py:126-151) -- only the ego query row is kept by the
+//            reference (`[0, ...]`), so only that row is computed: out = sum_j softmax_j(x0.xj/sqrt(C)) xj
+//   heads  : cls/reg/dir 1x1 convs with fake-quant weights on FP32 features (quant_model.py:129-136)
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "host_common.h"
+
+namespace qv2x {
+
+constexpr int kMaxAgents = 8;
+
+struct FuseParams {
+    int n, H, W, C;
+    float aff[kMaxAgents][6];   // row-major 2x3, normalized coordinates (ego <- agent j)
+    float inv_sqrt_c;
+};
+
+// One warp per output pixel; lane owns float4 chunks v = lane + 32*t of the channel vector.
+template <int MODE, int VPL /* float4 chunks per lane */>
+__global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ feat, float* __restrict__ out,
+                                                   const FuseParams p) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const long long npix = static_cast<long long>(p.H) * p.W;
+    const int vec = p.C / 4;
+    for (long long pix = warp; pix < npix; pix += nwarps) {
+        const int i = static_cast<int>(pix / p.W), j = static_cast<int>(pix - static_cast<long long>(i) * p.W);
+        const float xn = (2.f * j + 1.f) / p.W - 1.f;
+        const float yn = (2.f * i + 1.f) / p.H - 1.f;
+        float4 xa[kMaxAgents][VPL];
+#pragma unroll
+        for (int a = 0; a < kMaxAgents; ++a) {
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) xa[a][t] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a < p.n) {
+                const float xs = p.aff[a][0] * xn + p.aff[a][1] * yn + p.aff[a][2];
+                const float ys = p.aff[a][3] * xn + p.aff[a][4] * yn + p.aff[a][5];
+                const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
+                const float iy = ((ys + 1.f) * p.H - 1.f) * 0.5f;
+                const float fx = floorf(ix), fy = floorf(iy);
+                const float tx = ix - fx, ty = iy - fy;
+                const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+                const float* base = feat + static_cast<long long>(a) * npix * p.C;
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                    const float w = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
+                    if (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H) {
+                        const float4* src =
+                            reinterpret_cast<const float4*>(base + (static_cast<long long>(yy) * p.W + xx) * p.C);
+#pragma unroll
+                        for (int t = 0; t < VPL; ++t) {
+                            const int v = lane + 32 * t;
+                            if (v < vec) {
+                                const float4 s = __ldg(src + v);
+                                xa[a][t].x += w * s.x;
+                                xa[a][t].y += w * s.y;
+                                xa[a][t].z += w * s.z;
+                                xa[a][t].w += w * s.w;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        float4 o[VPL];
+        if (MODE == 0) {
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) o[t] = xa[0][t];
+#pragma unroll
+            for (int a = 1; a < kMaxAgents; ++a)
+                if (a < p.n) {
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t) {
+                        o[t].x = fmaxf(o[t].x, xa[a][t].x);
+                        o[t].y = fmaxf(o[t].y, xa[a][t].y);
+                        o[t].z = fmaxf(o[t].z, xa[a][t].z);
+                        o[t].w = fmaxf(o[t].w, xa[a][t].w);
+                    }
+                }
+        } else {
+            float sc[kMaxAgents];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int a = 0; a < kMaxAgents; ++a) {
+                sc[a] = -INFINITY;
+                if (a < p.n) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t)
+                        d += xa[0][t].x * xa[a][t].x + xa[0][t].y * xa[a][t].y + xa[0][t].z * xa[a][t].z +
+                             xa[0][t].w * xa[a][t].w;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                    sc[a] = d * p.inv_sqrt_c;
+                    mx = fmaxf(mx, sc[a]);
+                }
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int a = 0; a < kMaxAgents; ++a)
+                if (a < p.n) {
+                    sc[a] = expf(sc[a] - mx);
+                    den += sc[a];
+                }
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < kMaxAgents; ++a)
+                if (a < p.n) {
+                    const float w = sc[a] / den;
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t) {
+                        o[t].x += w * xa[a][t].x;
+                        o[t].y += w * xa[a][t].y;
+                        o[t].z += w * xa[a][t].z;
+                        o[t].w += w * xa[a][t].w;
+                    }
+                }
+        }
+        float4* dst = reinterpret_cast<float4*>(out + pix * p.C);
+#pragma unroll
+        for (int t = 0; t < VPL; ++t) {
+            const int v = lane + 32 * t;
+            if (v < vec) dst[v] = o[t];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ heads
+// out[o][p] = bias[o] + sum_k x[p][k] * w[o][k]; CTA = 128 pixels x 72 outputs, thread = 4 pixels x 9 outputs.
+constexpr int kHeadsPix = 128, kHeadsOut = 72, kHeadsPitchPad = 4;
+
+__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                    const float* __restrict__ bias, float* __restrict__ out,
+                                                    long long npix, int C, int cout) {
+    extern __shared__ float hsm[];
+    const int pitch = C + kHeadsPitchPad;
+    float* xs = hsm;                           // [128][pitch]
+    float* ws = hsm + kHeadsPix * pitch;       // [72][pitch]
+    const int tid = threadIdx.x;
+    const long long p0 = static_cast<long long>(blockIdx.x) * kHeadsPix;
+    const int vec = C / 4;
+    for (int idx = tid; idx < kHeadsOut * vec; idx += 256) {
+        const int o = idx / vec, v = idx - o * vec;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o < cout) val = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(o) * C) + v);
+        *reinterpret_cast<float4*>(ws + o * pitch + 4 * v) = val;
+    }
+    for (int idx = tid; idx < kHeadsPix * vec; idx += 256) {
+        const int pp = idx / vec, v = idx - pp * vec;
+        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p0 + pp < npix) val = __ldg(reinterpret_cast<const float4*>(x + (p0 + pp) * C) + v);
+        *reinterpret_cast<float4*>(xs + pp * pitch + 4 * v) = val;
+    }
+    __syncthreads();
+    const int pg = tid & 31, og = tid >> 5;    // pixels pg + 32*i, outputs og*9 + j
+    float acc[4][9];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 9; ++j) acc[i][j] = 0.f;
+    for (int k = 0; k < C; k += 4) {
+        float4 xv[4], wv[9];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (pg + 32 * i) * pitch + k);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) wv[j] = *reinterpret_cast<const float4*>(ws + (og * 9 + j) * pitch + k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) {
+                acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
+                acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
+                acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
+                acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
+            }
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const int o = og * 9 + j;
+        if (o < cout) {
+            const float b = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long pp = p0 + pg + 32 * i;
+                if (pp < npix) out[static_cast<long long>(o) * npix + pp] = acc[i][j] + b;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ layout converters
+// Batched transpose between channel-major [n][C][P] and pixel-major [n][P][C] with a per-element conversion.
+struct QuantizeOp {   // float -> uint8 activation code (reference quant_layer.py:132-133)
+    float delta, zp, qmax;
+    __device__ uint8_t operator()(float v) const {
+        const float q = fminf(fmaxf(__fadd_rn(rintf(__fdiv_rn(v, delta)), zp), 0.f), qmax);
+        return static_cast<uint8_t>(q);
+    }
+};
+struct DequantOp {    // uint8 code -> float (reference quant_layer.py:148)
+    float delta, zp;
+    __device__ float operator()(uint8_t q) const { return __fmul_rn(__fsub_rn(static_cast<float>(q), zp), delta); }
+};
+struct CopyOp {
+    __device__ float operator()(float v) const { return v; }
+};
+
+// src [n][R][S] -> dst [n][S][R'] (dst row pitch dpitch >= R, written at column offset doff)
+template <class TI, class TO, class Op>
+__global__ void transpose_kernel(const TI* __restrict__ src, TO* __restrict__ dst, int R, long long S, int dpitch,
+                                 int doff, Op op) {
+    __shared__ TO tile[32][33];
+    const long long s0 = static_cast<long long>(blockIdx.x) * 32;
+    const int r0 = blockIdx.y * 32;
+    const int b = blockIdx.z;
+    const TI* sp = src + static_cast<long long>(b) * R * S;
+    TO* dp = dst + static_cast<long long>(b) * S * dpitch;
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const int r = r0 + y;
+        const long long s = s0 + threadIdx.x;
+        if (r < R && s < S) tile[y][threadIdx.x] = op(sp[static_cast<long long>(r) * S + s]);
+    }
+    __syncthreads();
+    for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+        const long long s = s0 + y;
+        const int r = r0 + threadIdx.x;
+        if (r < R && s < S) dp[s * dpitch + doff + r] = tile[threadIdx.x][y];
+    }
+}
+
+template <class TI, class TO, class Op>
+static int launch_transpose(const TI* src, TO* dst, int n, int R, long long S, int dpitch, int doff, Op op,
+                            cudaStream_t stream) {
+    dim3 grid(static_cast<unsigned>((S + 31) / 32), static_cast<unsigned>((R + 31) / 32), static_cast<unsigned>(n));
+    transpose_kernel<TI, TO, Op><<<grid, dim3(32, 8), 0, stream>>>(src, dst, R, S, dpitch, doff, op);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace qv2x
+
+using namespace qv2x;
+
+struct qv2x_heads {
+    int cin, cout;
+    float* d_w = nullptr;
+    float* d_b = nullptr;
+};
+
+extern "C" {
+
+int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* affine, float* d_out,
+              void* stream_) {
+    QV2X_REQUIRE(d_feat && affine && d_out, "qv2x_fuse: null argument");
+    QV2X_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (max) or 1 (attention)");
+    QV2X_REQUIRE(n_agents >= 1 && n_agents <= kMaxAgents, "n_agents must be 1..%d", kMaxAgents);
+    QV2X_REQUIRE(C % 4 == 0 && C <= 512, "C must be a multiple of 4 and <= 512");
+    QV2X_REQUIRE(H > 0 && W > 0, "empty feature map");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    FuseParams p{};
+    p.n = n_agents;
+    p.H = H;
+    p.W = W;
+    p.C = C;
+    for (int a = 0; a < n_agents; ++a)
+        for (int i = 0; i < 6; ++i) p.aff[a][i] = affine[a * 6 + i];
+    p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(C));
+    const long long npix = static_cast<long long>(H) * W;
+    const int threads = 256;
+    const int grid = static_cast<int>(std::min<long long>((npix * 32 + threads - 1) / threads,
+                                                          static_cast<long long>(num_sms()) * 8));
+    const int vpl = (C / 4 + 31) / 32;
+#define QV2X_FUSE(M, V) fuse_kernel<M, V><<<grid, threads, 0, stream>>>(d_feat, d_out, p)
+    if (mode == 0) {
+        if (vpl == 1) QV2X_FUSE(0, 1); else if (vpl == 2) QV2X_FUSE(0, 2); else QV2X_FUSE(0, 4);
+    } else {
+        if (vpl == 1) QV2X_FUSE(1, 1); else if (vpl == 2) QV2X_FUSE(1, 2); else QV2X_FUSE(1, 4);
+    }
+#undef QV2X_FUSE
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out) {
+    QV2X_REQUIRE(w && out, "qv2x_heads_create: null argument");
+    QV2X_REQUIRE(cin % 4 == 0 && cin <= 256, "cin must be a multiple of 4 and <= 256");
+    QV2X_REQUIRE(cout >= 1 && cout <= kHeadsOut, "cout must be 1..%d", kHeadsOut);
+    auto h = new qv2x_heads();
+    h->cin = cin;
+    h->cout = cout;
+    int rc = upload(&h->d_w, w, static_cast<size_t>(cin) * cout);
+    if (!rc && bias) rc = upload(&h->d_b, bias, static_cast<size_t>(cout));
+    if (rc) {
+        cudaFree(h->d_w);
+        delete h;
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+void qv2x_heads_destroy(qv2x_heads* h) {
+    if (!h) return;
+    cudaFree(h->d_w);
+    cudaFree(h->d_b);
+    delete h;
+}
+
+int qv2x_heads_forward(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, void* stream_) {
+    QV2X_REQUIRE(h && d_x && d_out, "qv2x_heads_forward: null argument");
+    if (pixels <= 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int smem = (kHeadsPix + kHeadsOut) * (h->cin + kHeadsPitchPad) * static_cast<int>(sizeof(float));
+    static bool attr = false;
+    if (!attr) {
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr = true;
+    }
+    const int grid = static_cast<int>((pixels + kHeadsPix - 1) / kHeadsPix);
+    heads_kernel<<<grid, 256, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int qv2x_quantize_nchw_to_nhwc_u8(const float* d_x, int n, int c, long long pixels, float delta, float zero_point,
+                                  int bits, uint8_t* d_y, int out_cstride, int out_cbase, void* stream) {
+    QV2X_REQUIRE(d_x && d_y && delta > 0.f && bits >= 2 && bits <= 8, "qv2x_quantize_nchw_to_nhwc_u8: bad argument");
+    QuantizeOp op{delta, zero_point, static_cast<float>((1 << bits) - 1)};
+    return launch_transpose<float, uint8_t>(d_x, d_y, n, c, pixels, out_cstride, out_cbase, op,
+                                            static_cast<cudaStream_t>(stream));
+}
+
+int qv2x_dequant_nhwc_u8_to_nchw_f32(const uint8_t* d_x, int n, int c, long long pixels, float delta,
+                                     float zero_point, float* d_y, void* stream) {
+    QV2X_REQUIRE(d_x && d_y, "qv2x_dequant_nhwc_u8_to_nchw_f32: null argument");
+    DequantOp op{delta, zero_point};
+    // src is [n][pixels][c] -> dst [n][c][pixels]
+    return launch_transpose<uint8_t, float>(d_x, d_y, n, static_cast<int>(pixels), c, static_cast<int>(pixels), 0, op,
+                                            static_cast<cudaStream_t>(stream));
+}
+
+int qv2x_nchw_to_nhwc_f32(const float* d_x, int n, int c, long long pixels, float* d_y, void* stream) {
+    QV2X_REQUIRE(d_x && d_y, "qv2x_nchw_to_nhwc_f32: null argument");
+    return launch_transpose<float, float>(d_x, d_y, n, c, pixels, c, 0, CopyOp{}, static_cast<cudaStream_t>(stream));
+}
+
+int qv2x_nhwc_to_nchw_f32(const float* d_x, int n, int c, long long pixels, float* d_y, void* stream) {
+    QV2X_REQUIRE(d_x && d_y, "qv2x_nhwc_to_nchw_f32: null argument");
+    return launch_transpose<float, float>(d_x, d_y, n, static_cast<int>(pixels), c, static_cast<int>(pixels), 0,
+                                          CopyOp{}, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

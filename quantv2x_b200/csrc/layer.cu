@@ -143,6 +143,12 @@ void qv2x_layer_destroy(qv2x_layer* L) {
 
 int qv2x_layer_needs_rowsum(const qv2x_layer* L) { return (L && L->use_zp) ? 1 : 0; }
 
+int qv2x_layer_desc_get(const qv2x_layer* L, qv2x_layer_desc* out) {
+    QV2X_REQUIRE(L && out, "qv2x_layer_desc_get: null argument");
+    *out = L->d;
+    return 0;
+}
+
 int qv2x_layer_out_shape(const qv2x_layer* L, int hi, int wi, int* ho, int* wo) {
     QV2X_REQUIRE(L && ho && wo, "qv2x_layer_out_shape: null argument");
     const qv2x_layer_desc& d = L->d;

@@ -186,3 +186,142 @@ class CodebookEngine:
         buf = np.empty(n, dtype=dt)
         check(_lib.lib().qv2x_codebook_folded_copy(self._h, which, _np_ptr(buf)))
         return buf
+
+
+def fuse(feat: torch.Tensor, affine, mode: str, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Warp + fuse one frame.  feat float32 [N, H, W, C] pixel-major (agent 0 = ego); affine [N, 2, 3]
+    normalized (host array / CPU tensor); mode 'max' | 'att'.  Returns float32 [H, W, C]."""
+    assert feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.dim() == 4
+    n, h, w, c = feat.shape
+    aff = np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(n, 6))
+    if out is None:
+        out = torch.empty((h, w, c), dtype=torch.float32, device=feat.device)
+    check(_lib.lib().qv2x_fuse({"max": 0, "att": 1}[mode], n, h, w, c, c_void_p(feat.data_ptr()), _np_ptr(aff),
+                               c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+class HeadsEngine:
+    """cls/reg/dir 1x1 heads as one [Cout, Cin] FP32 GEMM (qv2x_heads)."""
+
+    def __init__(self, w: np.ndarray, bias: np.ndarray | None):
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        self.cout, self.cin = w.shape
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_heads_create(self.cin, self.cout, _np_ptr(w), None if b is None else _np_ptr(b),
+                                            byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_heads_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """x float32 [..., Cin] pixel-major -> float32 [Cout, pixels]."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin
+        pixels = x.numel() // self.cin
+        if out is None:
+            out = torch.empty((self.cout, pixels), dtype=torch.float32, device=x.device)
+        check(_lib.lib().qv2x_heads_forward(self._h, pixels, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()),
+                                            _stream_ptr()))
+        return out
+
+
+def quantize_nchw_to_nhwc_u8(x: torch.Tensor, delta: float, zero_point: float = 0.0, bits: int = 8,
+                             out: torch.Tensor | None = None, out_cbase: int = 0) -> torch.Tensor:
+    """float32 NCHW -> uint8 NHWC activation codes (module-boundary converter)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+    check(_lib.lib().qv2x_quantize_nchw_to_nhwc_u8(c_void_p(x.data_ptr()), n, c, h * w, float(delta),
+                                                   float(zero_point), bits, c_void_p(out.data_ptr()), out.shape[3],
+                                                   out_cbase, _stream_ptr()))
+    return out
+
+
+def dequant_nhwc_u8_to_nchw_f32(x: torch.Tensor, delta: float, zero_point: float = 0.0) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().qv2x_dequant_nhwc_u8_to_nchw_f32(c_void_p(x.data_ptr()), n, c, h * w, float(delta),
+                                                      float(zero_point), c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def nchw_to_nhwc_f32(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), dtype=torch.float32, device=x.device)
+    check(_lib.lib().qv2x_nchw_to_nhwc_f32(c_void_p(x.data_ptr()), n, c, h * w, c_void_p(out.data_ptr()),
+                                           _stream_ptr()))
+    return out
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 4
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().qv2x_nhwc_to_nchw_f32(c_void_p(x.data_ptr()), n, c, h * w, c_void_p(out.data_ptr()),
+                                           _stream_ptr()))
+    return out
+
+
+class Plan:
+    """A fixed launch sequence of QLayers over numbered buffers (qv2x_plan): one modality's quantized
+    BaseBEVBackbone + DownsampleConv.  steps: list of (QLayer, in_buf, in_cbase, out_buf, out_cbase)."""
+
+    def __init__(self, steps, buf_channels):
+        from ._lib import PlanStep
+
+        self.layers = [s[0] for s in steps]          # keep the layers alive
+        arr = (PlanStep * len(steps))()
+        for i, (layer, ib, ic, ob, oc) in enumerate(steps):
+            arr[i].layer, arr[i].in_buf, arr[i].in_cbase, arr[i].out_buf, arr[i].out_cbase = layer._h, ib, ic, ob, oc
+        bc = (c_int * len(buf_channels))(*buf_channels)
+        self.buf_channels = list(buf_channels)
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_plan_create(arr, len(steps), bc, len(buf_channels), byref(self._h)))
+        self._ws = {}
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_plan_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def out_shape(self, h, w):
+        ho, wo, c = c_int(), c_int(), c_int()
+        check(_lib.lib().qv2x_plan_out_shape(self._h, h, w, byref(ho), byref(wo), byref(c)))
+        return ho.value, wo.value, c.value
+
+    def workspace(self, n, h, w, device):
+        key = (n, h, w, str(device))
+        if key not in self._ws:
+            nbytes = ctypes.c_size_t()
+            check(_lib.lib().qv2x_plan_workspace_bytes(self._h, n, h, w, byref(nbytes)))
+            self._ws[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
+        return self._ws[key]
+
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, dump_step: int = -1, acc_dump=None):
+        """x uint8 NHWC [n, H, W, C0] -> uint8 NHWC [n, ho, wo, C_last]."""
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
+        n, h, w, c = x.shape
+        assert c == self.buf_channels[0], f"input has {c} channels, plan expects {self.buf_channels[0]}"
+        ho, wo, co = self.out_shape(h, w)
+        if out is None:
+            out = torch.empty((n, ho, wo, co), dtype=torch.uint8, device=x.device)
+        ws = self.workspace(n, h, w, x.device)
+        check(_lib.lib().qv2x_plan_forward(self._h, n, h, w, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()),
+                                           c_void_p(ws.data_ptr()), ws.numel(), dump_step,
+                                           None if acc_dump is None else c_void_p(acc_dump.data_ptr()),
+                                           _stream_ptr()))
+        return out

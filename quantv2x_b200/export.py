@@ -1,0 +1,167 @@
+"""Export of a calibrated quantized model to libqv2x engines.
+
+The reference never persists PTQ results: every run re-calibrates and re-fake-quantizes
+the weights on every forward (quant_layer.py:393).  Here the integer parameters are extracted ONCE from the
+calibrated ``QuantModule``s -- integer weight grid, per-channel weight delta / zero-point, folded bias,
+activation deltas -- and handed to the C ABI, which packs them for the tcgen05 kernels.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from .quant.quant_block import QuantBaseBEVBackbone, QuantDownsampleConv
+from .quant.quant_layer import QuantModule, StraightThrough
+
+
+def _scalar(v) -> float:
+    return float(v.detach().reshape(-1)[0].item()) if isinstance(v, torch.Tensor) else float(v)
+
+
+def qlayer_from_module(qm: QuantModule, in_delta, extra_pad: int = 0) -> E.QLayer:
+    """Build the GPU layer for one calibrated QuantModule (conv or transposed conv).
+
+    in_delta: activation scale(s) of the tensor(s) feeding the module (1 value, or 3 for the concat input).
+    extra_pad: zero padding applied by an explicit nn.ZeroPad2d in front of the conv (the first conv of every
+    backbone stage: ZeroPad2d(1) + padding 0, reference base_bev_backbone.py:41-46)."""
+    if not isinstance(qm.norm_function, StraightThrough):
+        raise ValueError("BatchNorm must be folded before export (QuantModel(..., is_fusing=True))")
+    if not (qm.weight_quantizer.inited and qm.act_quantizer.inited):
+        raise ValueError("quantizers are not calibrated")
+    if qm.disable_act_quant:
+        raise ValueError("layer has no output quantizer; it does not belong to the integer path")
+    relu = isinstance(qm.activation_function, (nn.ReLU,))
+    out_zp = _scalar(qm.act_quantizer.zero_point)
+    if out_zp != 0.0:
+        raise ValueError(f"activation zero-point {out_zp} != 0: the integer path needs post-ReLU activations")
+    w_int, w_delta, w_zp = qm.integer_weight()
+    bias = None if qm.bias is None else qm.bias.detach().cpu().numpy()
+    kw = qm.fwd_kwargs
+    if qm.fwd_func is torch.nn.functional.conv2d:
+        k = w_int.shape[2]
+        assert w_int.shape[2] == w_int.shape[3] and kw["groups"] == 1 and tuple(kw["dilation"]) == (1, 1)
+        stride, pad = kw["stride"][0], kw["padding"][0] + extra_pad
+        kind = 0
+    elif qm.fwd_func is torch.nn.functional.conv_transpose2d:
+        k = w_int.shape[2]
+        stride, pad, kind = kw["stride"][0], 0, 1
+        assert k == stride and tuple(kw["padding"]) == (0, 0) and extra_pad == 0
+    else:
+        raise ValueError("only Conv2d / ConvTranspose2d modules run on the integer path")
+    return E.QLayer(kind=kind, w_int=w_int, w_delta=w_delta, w_zp=w_zp, bias=bias, ksize=k, stride=stride, pad=pad,
+                    w_bits=qm.weight_quantizer.n_bits, relu=relu, in_delta=in_delta,
+                    out_delta=_scalar(qm.act_quantizer.delta), out_zp=out_zp, out_bits=qm.act_quantizer.n_bits)
+
+
+class BlockEngine:
+    """A Plan plus the scales needed to enter / leave it from FP32 NCHW tensors (module-boundary drop-in)."""
+
+    def __init__(self, plan: E.Plan, in_deltas, in_group_channels, out_deltas, out_group_channels):
+        self.plan = plan
+        self.in_deltas, self.in_group_channels = list(in_deltas), list(in_group_channels)
+        self.out_deltas, self.out_group_channels = list(out_deltas), list(out_group_channels)
+
+    def forward_u8(self, x_u8, out=None):
+        return self.plan.forward(x_u8, out=out)
+
+    def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """FP32 NCHW (values on the producers' grids) -> FP32 NCHW de-quantized output of the block."""
+        if not x.is_cuda:
+            raise RuntimeError("quantized inference runs on the GPU library only (no CPU fallback)")
+        n, c, h, w = x.shape
+        xq = torch.empty((n, h, w, c), dtype=torch.uint8, device=x.device)
+        base = 0
+        for d, cg in zip(self.in_deltas, self.in_group_channels):
+            E.quantize_nchw_to_nhwc_u8(x[:, base:base + cg].contiguous().float(), d, out=xq, out_cbase=base)
+            base += cg
+        y = self.plan.forward(xq)
+        outs, base = [], 0
+        for d, cg in zip(self.out_deltas, self.out_group_channels):
+            outs.append(E.dequant_nhwc_u8_to_nchw_f32(y[..., base:base + cg].contiguous(), d))
+            base += cg
+        return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
+def _backbone_steps(qb: QuantBaseBEVBackbone, in_delta: float, first_buf: int, in_buf: int):
+    """Steps of blocks + deblocks.  Returns (steps, buf_channels dict, concat_buf, deltas of the concat groups, next_buf)."""
+    steps, chans = [], {}
+    nb = first_buf
+    deltas, widths = [], []
+    x_buf, x_delta = in_buf, in_delta
+    cat_buf = None
+    ups = []
+    for i, blk in enumerate(qb.blocks):
+        mods = list(blk)
+        assert isinstance(mods[0], nn.ZeroPad2d), "backbone stages start with ZeroPad2d"
+        pad = mods[0].padding
+        assert len(set(pad)) == 1, "ZeroPad2d must pad all sides equally"
+        ping = [nb, nb + 1]
+        nb += 2
+        for j, qm in enumerate(mods[1:]):
+            layer = qlayer_from_module(qm, [x_delta], extra_pad=pad[0] if j == 0 else 0)
+            ob = ping[j % 2]
+            chans[ob] = layer.cout
+            steps.append((layer, x_buf, 0, ob, 0))
+            x_buf, x_delta = ob, _scalar(qm.act_quantizer.delta)
+        ups.append((x_buf, x_delta))
+    if len(qb.deblocks) > 0:
+        assert len(qb.deblocks) == qb.num_levels, "an extra deblock after the concat is not supported"
+        cat_buf = nb
+        nb += 1
+        cbase = 0
+        for i, de in enumerate(qb.deblocks):
+            qm = de[0]
+            src_buf, src_delta = ups[i]
+            layer = qlayer_from_module(qm, [src_delta])
+            steps.append((layer, src_buf, 0, cat_buf, cbase))
+            deltas.append(_scalar(qm.act_quantizer.delta))
+            widths.append(layer.cout)
+            cbase += layer.cout
+        chans[cat_buf] = cbase
+    else:
+        raise ValueError("backbones without deblocks are not supported")
+    return steps, chans, cat_buf, deltas, widths, nb
+
+
+def _shrinker_steps(qs: QuantDownsampleConv, in_deltas, in_buf: int, first_buf: int):
+    steps, chans = [], {}
+    nb = first_buf
+    x_buf, x_deltas = in_buf, list(in_deltas)
+    for dc in qs.layers:
+        for qm in dc.double_conv:
+            layer = qlayer_from_module(qm, x_deltas)
+            chans[nb] = layer.cout
+            steps.append((layer, x_buf, 0, nb, 0))
+            x_buf, x_deltas = nb, [_scalar(qm.act_quantizer.delta)]
+            nb += 1
+    return steps, chans, x_buf, x_deltas[0], nb
+
+
+def _make_plan(steps, chans, in_channels, out_buf):
+    """Renumber buffers so that the output is the last id, as qv2x_plan expects."""
+    ids = sorted(chans)
+    order = [b for b in ids if b != out_buf] + [out_buf]
+    remap = {0: 0}
+    for new, old in enumerate(order, start=1):
+        remap[old] = new
+    buf_channels = [in_channels] + [chans[old] for old in order]
+    return E.Plan([(l, remap[ib], ic, remap[ob], oc) for (l, ib, ic, ob, oc) in steps], buf_channels)
+
+
+def build_modality_engines(backbone: QuantBaseBEVBackbone, shrinker: QuantDownsampleConv, bev_delta: float):
+    """Returns dict(fused=BlockEngine over backbone+shrinker, backbone=..., shrinker=...)."""
+    in_channels = backbone.blocks[0][1].weight.shape[1]
+    b_steps, b_ch, cat_buf, cat_deltas, cat_widths, nb = _backbone_steps(backbone, bev_delta, 1, 0)
+    s_steps, s_ch, out_buf, out_delta, nb = _shrinker_steps(shrinker, cat_deltas, cat_buf, nb)
+    fused = _make_plan(b_steps + s_steps, {**b_ch, **s_ch}, in_channels, out_buf)
+    engines = {"fused": BlockEngine(fused, [bev_delta], [in_channels], [out_delta], [s_ch[out_buf]])}
+    engines["backbone"] = BlockEngine(_make_plan(b_steps, b_ch, in_channels, cat_buf), [bev_delta], [in_channels],
+                                      cat_deltas, cat_widths)
+    # the shrinker alone: its input buffer 0 is the concat tensor
+    s_alone = [(l, 0 if ib == cat_buf else ib, ic, ob, oc) for (l, ib, ic, ob, oc) in s_steps]
+    engines["shrinker"] = BlockEngine(_make_plan(s_alone, s_ch, sum(cat_widths), out_buf), cat_deltas, cat_widths,
+                                      [out_delta], [s_ch[out_buf]])
+    engines["out_delta"] = out_delta
+    return engines

@@ -1,0 +1,65 @@
+"""GPU parity of warp + max/attention fusion, heads GEMM and the layout converters (tolerance tier:
+floating-point path, atol = 1e-4 * max|x| against the float64 oracle; converters are bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_oracle as fo
+
+pytestmark = pytest.mark.gpu
+
+
+def make_affines(n, rng, H=80.0, W=281.6):
+    """Ego row of pairwise poses: identity for the ego, agent j translated (3j, -1.5j) m and yawed 5j degrees."""
+    t = np.tile(np.eye(4), (1, n, n, 1, 1))
+    for j in range(1, n):
+        th = np.deg2rad(5.0 * j)
+        t[0, 0, j, :2, :2] = [[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]
+        t[0, 0, j, 0, 3] = 3.0 * j
+        t[0, 0, j, 1, 3] = -1.5 * j
+    return fo.normalize_pairwise_tfm(t, H, W, 1.0)[0, 0, :n]
+
+
+@pytest.mark.parametrize("mode", ["max", "att"])
+@pytest.mark.parametrize("shape", [(1, 12, 20, 64), (3, 25, 44, 256), (8, 10, 16, 256), (2, 9, 7, 128)])
+def test_fuse(cuda_device, mode, shape):
+    from quantv2x_b200.engine import fuse
+
+    n, H, W, C = shape
+    rng = np.random.default_rng(n * 1000 + H)
+    feat = (rng.random((n, H, W, C)) * 4 * (rng.random((n, H, W, C)) > 0.4)).astype(np.float32)
+    aff = make_affines(n, rng)
+    ref = (fo.max_fusion if mode == "max" else fo.att_fusion)(feat, aff)
+    out = fuse(torch.from_numpy(feat).to(cuda_device), aff, mode).cpu().numpy()
+    np.testing.assert_allclose(out, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+
+def test_heads(cuda_device):
+    from quantv2x_b200.engine import HeadsEngine
+
+    rng = np.random.default_rng(3)
+    for pixels, cin, cout in [(1000, 256, 72), (35200, 256, 72), (77, 64, 20)]:
+        x = rng.normal(size=(pixels, cin)).astype(np.float32)
+        w = rng.normal(size=(cout, cin)).astype(np.float32) / 16
+        b = rng.normal(size=cout).astype(np.float32)
+        ref = (x.astype(np.float64) @ w.astype(np.float64).T + b).T
+        out = HeadsEngine(w, b).forward(torch.from_numpy(x).to(cuda_device)).cpu().numpy()
+        np.testing.assert_allclose(out, ref, atol=1e-5 * np.abs(ref).max(), rtol=1e-5)
+
+
+def test_converters_bit_exact(cuda_device):
+    from quantv2x_b200 import engine
+
+    rng = np.random.default_rng(4)
+    x = (rng.random((2, 64, 13, 37)) * 30).astype(np.float32)
+    x[rng.random(x.shape) > 0.5] = 0
+    delta = np.float32(0.1137)
+    q_ref = np.clip(np.rint(x / delta), 0, 255).astype(np.uint8).transpose(0, 2, 3, 1)
+    xd = torch.from_numpy(x).to(cuda_device)
+    q = engine.quantize_nchw_to_nhwc_u8(xd, float(delta))
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+    back = engine.dequant_nhwc_u8_to_nchw_f32(q, float(delta)).cpu().numpy()
+    assert np.array_equal(back, (q_ref.astype(np.float32) * delta).transpose(0, 3, 1, 2))
+    nhwc = engine.nchw_to_nhwc_f32(xd)
+    assert np.array_equal(nhwc.cpu().numpy(), x.transpose(0, 2, 3, 1))
+    assert np.array_equal(engine.nhwc_to_nchw_f32(nhwc).cpu().numpy(), x)
