@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- W8A8 fused BEV frames/s of the quantized cooperative-perception forward on B200.
+
+A "step" = one cooperative frame: N_AGENTS (ego + 7) agents each run the W8A8 BEV backbone + shrinker +
+codebook encode; the code planes are gathered on the ego rank, which decodes, warps, fuses (attention) and
+runs the detection heads.  Agents are sharded over the GPUs (8/N per GPU, strong scaling); the only exchange is
+the gather of uint8 code planes to rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Prints ONE JSON line (rank 0).  See the repository's task contract for the keys.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = 8
+BEV_H, BEV_W, BEV_C = 200, 704, 64
+PILLARS = 6000
+METRIC = "W8A8 fused BEV frames/s (ego + 7 agents, PointPillars V2X-Real 704x200, codebook m=1 k=128, att fusion)"
+# algorithmic work per agent, SURVEY section 8(d): backbone blocks + shrinker (int8 GEMM-able)
+GMAC_INT8_PER_AGENT = 75.26
+SHRINK1_GMAC_PER_AGENT = 20.763       # the dominant kernel's layer: conv3x3 256->256 on 100x352
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fusion", default="att", choices=["att", "max"])
+    ap.add_argument("--w-bits", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------- model
+def build_calibrated_model(device, fusion, w_bits, seed=1234):
+    """Seeded float model from the yaml -> QuantModel -> weight qparams -> one calibration forward (float path,
+    on `device`) -> frozen W8A8.  Returns (qmodel, bev_delta)."""
+    import torch
+
+    from quantv2x_b200 import yaml_utils
+    from quantv2x_b200.quant import QuantModel, set_weight_quantize_params
+    from quantv2x_b200.synthetic import seeded_init, synthetic_bev
+
+    hypes = yaml_utils.load_yaml(yaml_utils.default_config(fusion))
+    torch.manual_seed(seed)
+    model = yaml_utils.create_model(hypes).eval()
+    seeded_init(model, seed)
+    wq = dict(n_bits=w_bits, channel_wise=True, scale_method="minmax")
+    aq = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
+    q = QuantModel(model, wq, aq).eval()
+    q.disable_network_output_quantization()
+    set_weight_quantize_params(q)
+    q.to(device)
+    # BEV-level calibration: one synthetic agent on the uint8 grid bev_delta (what the PFN block would emit)
+    bev_delta = 0.05
+    bev = synthetic_bev(0, 1, BEV_H, BEV_W, BEV_C, PILLARS)
+    x = torch.from_numpy(bev.astype(np.float32) * np.float32(bev_delta)).permute(0, 3, 1, 2).contiguous().to(device)
+    mods = [m for m in q.modules() if hasattr(m, "act_quantizer")]
+    q.set_quant_state(True, True)
+    for m in mods:
+        m.act_quantizer.set_inited(False)
+    with torch.no_grad():
+        feat = q.model.backbone_m1(x)
+        q.model.shrinker_m1(feat)
+    for m in mods:
+        m.act_quantizer.set_inited(True)
+    q.set_quant_state(True, True)
+    return q, bev_delta
+
+
+def clock_sampler(stop, out):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", "0"],
+                               capture_output=True, text=True, timeout=5)
+            if r.returncode == 0 and r.stdout.strip():
+                out.append([c.strip() for c in r.stdout.strip().split("\n")[0].split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def summarize_clocks(samples):
+    if not samples:
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(float(s[1]) for s in samples if s[1].replace(".", "").isdigit())
+    reasons = set()
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    for s in samples:
+        for name, v in zip(names, s[5:9]):
+            if v.lower().startswith("active"):
+                reasons.add(name)
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(samples[0][2]) if samples else None,
+            "reasons": sorted(reasons), "samples": len(samples)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_frames_per_s(spec, n_agents, steps, warmup, budget_s=60.0):
+    """The reference's CPU fake-quant path (oracle port) on a bounded sample of the 8-agent frame.
+
+    sample: `a` agents' backbone + shrinker + encode are run for real, the per-agent time is scaled to 8 agents
+    (agents are independent and identical work), and the ego stage (decode + warp + fuse + heads) runs on 8 agents'
+    codes (the a agents' codes tiled)."""
+    import torch
+
+    from oracle import frame_ref
+    from quantv2x_b200.synthetic import synthetic_bev, synthetic_poses
+    from oracle.fusion_oracle import normalize_pairwise_tfm
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    a = 1
+    bev = synthetic_bev(0, a, BEV_H, BEV_W, BEV_C, PILLARS)
+    aff = normalize_pairwise_tfm(synthetic_poses(n_agents), 80.0, 281.6, 1.0)[0, 0, :n_agents]
+    times = []
+    t_start = time.time()
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        feat, codes = frame_ref.agent_forward(spec, bev)
+        t1 = time.perf_counter()
+        _, _, h, w = feat.shape
+        codes8 = [c.repeat(n_agents // a, 1) for c in codes]
+        frame_ref.ego_forward(spec, codes8, n_agents, h, w, aff)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            times.append((t1 - t0) * (n_agents / a) + (t2 - t1))
+        if time.time() - t_start > budget_s and len(times) >= 1:
+            break
+    t = float(np.median(times))
+    sample = (f"{a} agent backbone+shrinker+encode timed and scaled x{n_agents // a}, plus the full {n_agents}-agent "
+              f"ego stage; {len(times)} timed frame(s), torch {torch.__version__} CPU fp32 fake-quant")
+    return 1.0 / t, cores, sample, t
+
+
+# ----------------------------------------------------------------------------------------------- main
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"ego+7 agents ({N_AGENTS}), BEV {BEV_W}x{BEV_H}x{BEV_C} uint8, {PILLARS} pillars/agent, "
+                          f"W{args.w_bits}A8 backbone+shrinker, codebook m=1 k=128 x3 levels, {args.fusion} fusion, "
+                          "heads 72 ch; SURVEY 8(d)",
+              "agents": N_AGENTS, "agents_per_gpu": N_AGENTS // max(world, 1), "parallelism": f"agents/{world}gpu",
+              "l2": "per-frame working set (72 MB inputs + ~45 MB activations per agent) exceeds the 126 MB L2; a "
+                    "256 MB buffer is also rewritten between timed steps"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import torch
+
+        from quantv2x_b200.export import export_spec
+        q, bev_delta = build_calibrated_model(torch.device("cpu"), args.fusion, args.w_bits)
+        spec = export_spec(q, bev_delta)
+        fps, cores, sample, t = cpu_reference_frames_per_s(spec, N_AGENTS, args.steps, min(args.warmup, 1),
+                                                            budget_s=120.0)
+        line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 fake-quant (simulated u8)", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from quantv2x_b200 import _lib
+    from quantv2x_b200.export import attach_engines, export_spec
+    from quantv2x_b200.synthetic import synthetic_bev, synthetic_poses
+    from quantv2x_b200.collab_model import normalize_pairwise_tfm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback (use --impl reference for the "
+                         "CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    _lib.check(_lib.lib().qv2x_device_check(local_rank))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert N_AGENTS % world == 0, "agent count must divide over the GPUs"
+    per = N_AGENTS // world
+
+    q, bev_delta = build_calibrated_model(device, args.fusion, args.w_bits)
+    attach_engines(q, bev_delta=bev_delta, device=device)
+    pipe = q.model._pipelines["m1"]
+
+    bev_all = synthetic_bev(0, N_AGENTS, BEV_H, BEV_W, BEV_C, PILLARS)
+    bev_host = torch.from_numpy(bev_all[rank * per:(rank + 1) * per]).pin_memory()
+    bev_dev = bev_host.to(device)
+    poses = torch.from_numpy(synthetic_poses(N_AGENTS)).float()
+    aff = normalize_pairwise_tfm(poses, 80.0, 281.6, 1)[0, 0, :N_AGENTS].contiguous().to(device)
+    levels, m, hw = pipe.codebook.levels, pipe.codebook.m, pipe.hw
+    codes_all = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device) if rank == 0 else None
+    preds_host = torch.empty((pipe.heads.cout, hw), dtype=torch.float32).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def exchange(codes):
+        """Gather every rank's code planes on the ego rank; returns [levels, m, N_AGENTS*hw] agent-major."""
+        if world == 1:
+            return codes
+        glist = [codes_all[i] for i in range(world)] if rank == 0 else None
+        dist.gather(codes, glist, dst=0)
+        if rank != 0:
+            return None
+        return codes_all.permute(1, 2, 0, 3).reshape(levels, m, N_AGENTS * hw).contiguous()
+
+    def step(bev):
+        codes = pipe.encode_agents(bev)
+        full = exchange(codes)
+        if rank == 0:
+            return pipe.decode_fuse_heads(full, aff)
+        return None
+
+    def timed_loop(fn, k):
+        """k steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
+        evs = []
+        for _ in range(k):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(bev_dev)
+    sync_all()
+    stop, samples = threading.Event(), []
+    th = None
+    if rank == 0:
+        th = threading.Thread(target=clock_sampler, args=(stop, samples), daemon=True)
+        th.start()
+    launches0 = _lib.lib().qv2x_launch_count()
+    sync_all()
+    total_ms = timed_loop(lambda: step(bev_dev), args.steps)
+    sync_all()
+    launches = _lib.lib().qv2x_launch_count() - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    fps = 1e3 / ms_per_step
+
+    # ---- e2e: host buffers in, host result out, through the same public calls
+    def e2e_step():
+        bev_dev.copy_(bev_host, non_blocking=True)
+        p = step(bev_dev)
+        if rank == 0:
+            preds_host.copy_(p, non_blocking=True)
+
+    for _ in range(3):
+        e2e_step()
+    sync_all()
+    e2e_ms = timed_loop(e2e_step, args.steps)
+    sync_all()
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_fps = 1e3 / (float(t.item()) / args.steps)
+
+    # ---- roofline of the dominant kernel (shrinker conv3x3 256->256, igemm_kernel<256,128,1>), timed alone
+    roof = None
+    if rank == 0:
+        from quantv2x_b200.engine import rowsum_u8
+        layer = pipe.fused.plan.layers[-1]
+        xin = torch.randint(0, 256, (per, pipe.ho, pipe.wo, 256), dtype=torch.uint8, device=device)
+        rs = [rowsum_u8(xin, 0, 256)]
+        yout = torch.empty((per, pipe.ho, pipe.wo, 256), dtype=torch.uint8, device=device)
+        for _ in range(3):
+            layer.forward(xin, rowsum_in=rs, out=yout)
+        torch.cuda.synchronize()
+        k_ms = timed_loop(lambda: layer.forward(xin, rowsum_in=rs, out=yout), max(args.steps, 10)) / max(args.steps, 10)
+        ops = 2.0 * SHRINK1_GMAC_PER_AGENT * 1e9 * per
+        achieved = ops / (k_ms * 1e-3) / 1e12
+        # measured int8 tensor-pipe peak: library int8 GEMM, same method as MEASURED_PEAKS.json's bf16 figure
+        a8 = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device=device)
+        b8 = torch.randint(-100, 100, (8192, 8192), dtype=torch.int8, device=device)
+        for _ in range(3):
+            torch._int_mm(a8, b8)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch._int_mm(a8, b8)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del a8, b8
+        roof = {"bound": "tensor", "kernel": "igemm_kernel<256,128,1,RequantEpilogue> (shrinker conv3x3 256->256)",
+                "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak,
+                "peak_source": "live cuBLASLt int8 GEMM 8192^3 (torch._int_mm), best of 10 -- MEASURED_PEAKS.json "
+                               "has no int8 entry; its bf16 burst figure x2 is the nominal ratio",
+                "traffic": None, "us_per_launch": k_ms * 1e3,
+                "step_tensor_frac": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * per / (ms_per_step * 1e-3) / 1e12 / peak}
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_file):
+            try:
+                roof["bf16_tflops_measured"] = json.load(open(peaks_file)).get("bf16_tflops")
+            except Exception:
+                pass
+
+    if rank == 0:
+        stop.set()
+        th.join(timeout=2)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        spec = export_spec(q.cpu(), bev_delta)
+        v, cores, sample, _ = cpu_reference_frames_per_s(spec, N_AGENTS, 1, 0, budget_s=40.0)
+        cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        h2d = int(bev_host.numel()) * world
+        line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "u8 (int8 tensor cores, int32 accumulate)",
+                "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": int(preds_host.numel() * 4)},
+                "gpu_launches": int(launches), "clocks": summarize_clocks(samples), "roofline": roof,
+                "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -134,11 +134,12 @@ int qv2x_codebook_folded_copy(const qv2x_codebook* cb, int which, void* host_buf
  * (opencood/models/fuse_modules/fusion_in_one.py:87-151), including the bilinear warp of every agent
  * (the ego too) into the ego frame (warp_affine_simple, torch_transformation_utils.py:323-332).
  * d_feat: [n_agents][H][W][C] float32 pixel-major, agent 0 = ego.
- * affine: HOST [n_agents][2][3] = normalize_pairwise_tfm(...)[b][0, :n] (ego row of the pairwise matrices,
- *         opencood/utils/transformation_utils.py:68-92).  mode 0 = max, 1 = attention (ego query row).
+ * d_affine: DEVICE [n_agents][2][3] float32 = normalize_pairwise_tfm(...)[b][0, :n] (ego row of the pairwise
+ *         matrices, opencood/utils/transformation_utils.py:68-92); on the device so that a captured CUDA graph
+ *         picks up new poses every frame.  mode 0 = max, 1 = attention (ego query row).
  * d_out:  [H][W][C] float32 pixel-major.
  * ---------------------------------------------------------------------------------------------- */
-int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* affine, float* d_out,
+int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine, float* d_out,
               void* stream);
 
 /* Detection heads = the three 1x1 convs cls_head / reg_head / dir_head (reference

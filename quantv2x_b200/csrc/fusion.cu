@@ -19,7 +19,7 @@ constexpr int kMaxAgents = 8;
 
 struct FuseParams {
     int n, H, W, C;
-    float aff[kMaxAgents][6];   // row-major 2x3, normalized coordinates (ego <- agent j)
+    const float* aff;           // DEVICE [n][6]: row-major 2x3, normalized coordinates (ego <- agent j)
     float inv_sqrt_c;
 };
 
@@ -42,8 +42,9 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ fea
 #pragma unroll
             for (int t = 0; t < VPL; ++t) xa[a][t] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (a < p.n) {
-                const float xs = p.aff[a][0] * xn + p.aff[a][1] * yn + p.aff[a][2];
-                const float ys = p.aff[a][3] * xn + p.aff[a][4] * yn + p.aff[a][5];
+                const float* m = p.aff + a * 6;
+                const float xs = __ldg(m + 0) * xn + __ldg(m + 1) * yn + __ldg(m + 2);
+                const float ys = __ldg(m + 3) * xn + __ldg(m + 4) * yn + __ldg(m + 5);
                 const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
                 const float iy = ((ys + 1.f) * p.H - 1.f) * 0.5f;
                 const float fx = floorf(ix), fy = floorf(iy);
@@ -261,9 +262,9 @@ struct qv2x_heads {
 
 extern "C" {
 
-int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* affine, float* d_out,
+int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine, float* d_out,
               void* stream_) {
-    QV2X_REQUIRE(d_feat && affine && d_out, "qv2x_fuse: null argument");
+    QV2X_REQUIRE(d_feat && d_affine && d_out, "qv2x_fuse: null argument");
     QV2X_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (max) or 1 (attention)");
     QV2X_REQUIRE(n_agents >= 1 && n_agents <= kMaxAgents, "n_agents must be 1..%d", kMaxAgents);
     QV2X_REQUIRE(C % 4 == 0 && C <= 512, "C must be a multiple of 4 and <= 512");
@@ -274,8 +275,7 @@ int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, 
     p.H = H;
     p.W = W;
     p.C = C;
-    for (int a = 0; a < n_agents; ++a)
-        for (int i = 0; i < 6; ++i) p.aff[a][i] = affine[a * 6 + i];
+    p.aff = d_affine;
     p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(C));
     const long long npix = static_cast<long long>(H) * W;
     const int threads = 256;

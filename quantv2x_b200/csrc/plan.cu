@@ -2,6 +2,7 @@
 // BaseBEVBackbone + DownsampleConv forward of one modality (reference quant_block.py:280-303, :567-586)
 // issued from C++ as back-to-back kernel launches on one stream: no host round trips, no torch.cat
 // (deblocks write straight into channel slices of the concat buffer), no NCHW<->NHWC copies.
+#include <array>
 #include <map>
 #include <vector>
 
@@ -10,12 +11,16 @@
 struct qv2x_plan {
     std::vector<qv2x_plan_step> steps;
     std::vector<int> buf_channels;
-    // (buffer, channel base) -> rowsum slot; a slot exists when some zero-point-correcting consumer reads the slice
-    std::map<std::pair<int, int>, int> rs_slot;
-    std::vector<std::pair<int, int>> slot_key;     // slot -> (buffer, cbase)
-    std::vector<int> slot_width;                   // channels summed by the slot
+    // Rowsum slots.  A slot holds the per-pixel channel sums of ONE tensor version: either a channel group of
+    // the plan input (producer -1) or the output of one step.  Buffers are reused (ping-pong) inside a stage,
+    // so slots are keyed by the producing step, never by the buffer.
+    struct Slot {
+        int producer;   // step index, or -1 for the plan input
+        int buf, cbase, width;
+    };
+    std::vector<Slot> slots;
     std::vector<int> step_out_slot;                // per step: slot its epilogue accumulates into, or -1
-    bool input_needs_rowsum = false;
+    std::vector<std::array<int, 3>> step_in_slot;  // per step: slot of each input group, or -1
 };
 
 namespace {
@@ -61,49 +66,51 @@ int qv2x_plan_create(const qv2x_plan_step* steps, int n_steps, const int* buf_ch
             return qv2x::set_error(QV2X_ERR_INVALID, "plan step %d: bad layer / buffer id", i);
         }
     }
-    // rowsum slots: for every consumer that applies the weight zero-point correction, one slot per input group
-    for (int i = 0; i < n_steps; ++i) {
-        const auto& st = steps[i];
-        if (!qv2x_layer_needs_rowsum(st.layer)) continue;
-        qv2x_layer_desc d;
-        qv2x_layer_desc_get(st.layer, &d);
-        const int cg = d.cin / d.n_in_groups;
-        for (int g = 0; g < d.n_in_groups; ++g) {
-            const auto key = std::make_pair(st.in_buf, st.in_cbase + g * cg);
-            if (!P->rs_slot.count(key)) {
-                P->rs_slot[key] = static_cast<int>(P->slot_key.size());
-                P->slot_key.push_back(key);
-                P->slot_width.push_back(cg);
-            }
-            if (st.in_buf == 0) P->input_needs_rowsum = true;
-        }
-    }
+    // rowsum slots: every consumer that applies the weight zero-point correction needs the channel sums of the
+    // tensor version it reads = the most recent writer of (in_buf, channel base) before it
     P->step_out_slot.assign(n_steps, -1);
+    P->step_in_slot.assign(n_steps, std::array<int, 3>{-1, -1, -1});
+    std::map<std::pair<int, int>, int> last_writer;     // (buffer, cbase) -> step
+    std::map<std::pair<int, int>, int> input_slot;      // (0, cbase) -> slot
     for (int i = 0; i < n_steps; ++i) {
         const auto& st = steps[i];
         qv2x_layer_desc d;
         qv2x_layer_desc_get(st.layer, &d);
-        auto it = P->rs_slot.find(std::make_pair(st.out_buf, st.out_cbase));
-        if (it != P->rs_slot.end()) {
-            if (P->slot_width[it->second] != d.cout) {
-                delete P;
-                return qv2x::set_error(QV2X_ERR_INVALID,
-                                       "plan step %d writes %d channels at (%d,%d) but a consumer sums %d channels there",
-                                       i, d.cout, st.out_buf, st.out_cbase, P->slot_width[it->second]);
+        if (qv2x_layer_needs_rowsum(st.layer)) {
+            const int cg = d.cin / d.n_in_groups;
+            for (int g = 0; g < d.n_in_groups; ++g) {
+                const auto key = std::make_pair(st.in_buf, st.in_cbase + g * cg);
+                auto lw = last_writer.find(key);
+                if (lw == last_writer.end()) {
+                    if (st.in_buf != 0) {
+                        delete P;
+                        return qv2x::set_error(QV2X_ERR_INVALID, "plan step %d: nothing wrote channels [%d,+%d) of buffer %d",
+                                               i, key.second, cg, st.in_buf);
+                    }
+                    if (!input_slot.count(key)) {
+                        input_slot[key] = static_cast<int>(P->slots.size());
+                        P->slots.push_back({-1, 0, key.second, cg});
+                    }
+                    P->step_in_slot[i][g] = input_slot[key];
+                } else {
+                    const int prod = lw->second;
+                    qv2x_layer_desc pd;
+                    qv2x_layer_desc_get(steps[prod].layer, &pd);
+                    if (pd.cout != cg) {
+                        delete P;
+                        return qv2x::set_error(QV2X_ERR_INVALID,
+                                               "plan step %d sums %d channels at (%d,%d) but step %d wrote %d there", i, cg,
+                                               key.first, key.second, prod, pd.cout);
+                    }
+                    if (P->step_out_slot[prod] < 0) {
+                        P->step_out_slot[prod] = static_cast<int>(P->slots.size());
+                        P->slots.push_back({prod, st.in_buf, key.second, cg});
+                    }
+                    P->step_in_slot[i][g] = P->step_out_slot[prod];
+                }
             }
-            P->step_out_slot[i] = it->second;
         }
-    }
-    // every slot on an internal buffer must have a producer
-    for (size_t s = 0; s < P->slot_key.size(); ++s) {
-        if (P->slot_key[s].first == 0) continue;
-        bool found = false;
-        for (int i = 0; i < n_steps; ++i) found |= (P->step_out_slot[i] == static_cast<int>(s));
-        if (!found) {
-            delete P;
-            return qv2x::set_error(QV2X_ERR_INVALID, "no plan step produces channels [%d,+%d) of buffer %d",
-                                   P->slot_key[s].second, P->slot_width[s], P->slot_key[s].first);
-        }
+        last_writer[std::make_pair(st.out_buf, st.out_cbase)] = i;
     }
     *out = P;
     return 0;
@@ -132,10 +139,8 @@ int qv2x_plan_workspace_bytes(const qv2x_plan* P, int n_img, int H, int W, size_
     const int nb = static_cast<int>(P->buf_channels.size());
     for (int b = 1; b < nb - 1; ++b)
         if (s.h[b] > 0) total += align256(static_cast<size_t>(n_img) * s.h[b] * s.w[b] * P->buf_channels[b]);
-    for (size_t k = 0; k < P->slot_key.size(); ++k) {
-        const int b = P->slot_key[k].first;
-        total += align256(static_cast<size_t>(n_img) * s.h[b] * s.w[b] * sizeof(int32_t));
-    }
+    for (const auto& sl : P->slots)
+        total += align256(static_cast<size_t>(n_img) * s.h[sl.buf] * s.w[sl.buf] * sizeof(int32_t));
     *bytes = total + 256;
     return 0;
 }
@@ -160,30 +165,25 @@ int qv2x_plan_forward(const qv2x_plan* P, int n_img, int H, int W, const uint8_t
             buf[b] = ws;
             ws += align256(static_cast<size_t>(n_img) * s.h[b] * s.w[b] * P->buf_channels[b]);
         }
-    std::vector<int32_t*> slot(P->slot_key.size(), nullptr);
+    std::vector<int32_t*> slot(P->slots.size(), nullptr);
     uint8_t* rs_begin = ws;
-    for (size_t k = 0; k < P->slot_key.size(); ++k) {
-        const int b = P->slot_key[k].first;
+    for (size_t k = 0; k < P->slots.size(); ++k) {
+        const int b = P->slots[k].buf;
         slot[k] = reinterpret_cast<int32_t*>(ws);
         ws += align256(static_cast<size_t>(n_img) * s.h[b] * s.w[b] * sizeof(int32_t));
     }
     if (ws > rs_begin) QV2X_CUDA_OK(cudaMemsetAsync(rs_begin, 0, static_cast<size_t>(ws - rs_begin), stream));
-    for (size_t k = 0; k < P->slot_key.size(); ++k) {
-        if (P->slot_key[k].first != 0) continue;
-        rc = qv2x_rowsum_u8(d_in, static_cast<long long>(n_img) * H * W, P->buf_channels[0], P->slot_key[k].second,
-                            P->slot_width[k], slot[k], stream);
+    for (size_t k = 0; k < P->slots.size(); ++k) {
+        if (P->slots[k].producer >= 0) continue;
+        rc = qv2x_rowsum_u8(d_in, static_cast<long long>(n_img) * H * W, P->buf_channels[0], P->slots[k].cbase,
+                            P->slots[k].width, slot[k], stream);
         if (rc) return rc;
     }
     for (size_t i = 0; i < P->steps.size(); ++i) {
         const auto& st = P->steps[i];
         const int32_t* rs_in[3] = {nullptr, nullptr, nullptr};
-        if (qv2x_layer_needs_rowsum(st.layer)) {
-            qv2x_layer_desc d;
-            qv2x_layer_desc_get(st.layer, &d);
-            const int cg = d.cin / d.n_in_groups;
-            for (int g = 0; g < d.n_in_groups; ++g)
-                rs_in[g] = slot[P->rs_slot.at(std::make_pair(st.in_buf, st.in_cbase + g * cg))];
-        }
+        for (int g = 0; g < 3; ++g)
+            if (P->step_in_slot[i][g] >= 0) rs_in[g] = slot[P->step_in_slot[i][g]];
         int32_t* rs_out = P->step_out_slot[i] >= 0 ? slot[P->step_out_slot[i]] : nullptr;
         rc = qv2x_layer_forward(st.layer, n_img, s.h[st.in_buf], s.w[st.in_buf], buf[st.in_buf],
                                 P->buf_channels[st.in_buf], st.in_cbase, rs_in, buf[st.out_buf],

@@ -190,14 +190,16 @@ class CodebookEngine:
 
 def fuse(feat: torch.Tensor, affine, mode: str, out: torch.Tensor | None = None) -> torch.Tensor:
     """Warp + fuse one frame.  feat float32 [N, H, W, C] pixel-major (agent 0 = ego); affine [N, 2, 3]
-    normalized (host array / CPU tensor); mode 'max' | 'att'.  Returns float32 [H, W, C]."""
+    normalized (CUDA tensor, or a host array that is copied over); mode 'max' | 'att'.  Returns float32 [H, W, C]."""
     assert feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.dim() == 4
     n, h, w, c = feat.shape
-    aff = np.ascontiguousarray(np.asarray(affine, dtype=np.float32).reshape(n, 6))
+    if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
+        affine = torch.as_tensor(np.asarray(affine, dtype=np.float32)).to(feat.device)
+    aff = affine.to(torch.float32).reshape(n, 6).contiguous()
     if out is None:
         out = torch.empty((h, w, c), dtype=torch.float32, device=feat.device)
-    check(_lib.lib().qv2x_fuse({"max": 0, "att": 1}[mode], n, h, w, c, c_void_p(feat.data_ptr()), _np_ptr(aff),
-                               c_void_p(out.data_ptr()), _stream_ptr()))
+    check(_lib.lib().qv2x_fuse({"max": 0, "att": 1}[mode], n, h, w, c, c_void_p(feat.data_ptr()),
+                               c_void_p(aff.data_ptr()), c_void_p(out.data_ptr()), _stream_ptr()))
     return out
 
 

@@ -165,3 +165,75 @@ def build_modality_engines(backbone: QuantBaseBEVBackbone, shrinker: QuantDownsa
                                       [out_delta], [s_ch[out_buf]])
     engines["out_delta"] = out_delta
     return engines
+
+
+# ---------------------------------------------------------------------------------------------------
+# model level
+# ---------------------------------------------------------------------------------------------------
+def attach_engines(qmodel, bev_delta: float | None = None, device=None):
+    """Build every libqv2x engine of a calibrated ``QuantModel(HeterBaselineCollabCodebookMC)`` and attach them:
+    block-level engines to the quantized backbone / shrinker wrappers (module-boundary drop-in) and a
+    frame-level ``CollabPipeline`` to the model (fast path used by encode_features / decode_features).
+
+    bev_delta: scale of the uint8 BEV grid; read from the quantized PointPillar encoder when omitted."""
+    from .pipeline import CollabPipeline, heads_from_quant_modules
+    from .quant.quant_block import QuantPointPillar
+
+    model = qmodel.model
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    for name in model.modality_name_list:
+        enc = getattr(model, f"encoder_{name}")
+        bb, sh = getattr(model, f"backbone_{name}"), getattr(model, f"shrinker_{name}")
+        d_in = bev_delta
+        if d_in is None:
+            if not isinstance(enc, QuantPointPillar):
+                raise ValueError("bev_delta is required when the encoder is not quantized")
+            d_in = enc.bev_delta()
+        engines = build_modality_engines(bb, sh, d_in)
+        bb.attach_engine(engines["backbone"])
+        sh.attach_engine(engines["shrinker"])
+        rng = model.cav_range
+        vs = model.args[name]["encoder_args"]["voxel_size"]
+        H, W = int(round((rng[4] - rng[1]) / vs[1])), int(round((rng[3] - rng[0]) / vs[0]))
+        pipe = CollabPipeline(engines["fused"], engines["out_delta"], model.codebook.engine(),
+                              heads_from_quant_modules(model.cls_head, model.reg_head, model.dir_head),
+                              model.fusion_method, (H, W), device)
+        pipe.bev_delta = d_in
+        model._pipelines[name] = pipe
+    return model
+
+
+def export_spec(qmodel, bev_delta: float, modality: str = "m1") -> dict:
+    """Plain-numpy description of the calibrated model (float weights + every quantizer's delta / zero-point).
+    This is what a serialized PTQ engine would hold, and what the CPU oracle (oracle/frame_ref.py) consumes."""
+    model = qmodel.model
+
+    def layer(qm, extra_pad=0):
+        _, w_delta, w_zp = qm.integer_weight()
+        kw = qm.fwd_kwargs
+        kind = 0 if qm.fwd_func is torch.nn.functional.conv2d else 1
+        aq = qm.act_quantizer
+        return dict(kind=kind, w=qm.weight.detach().cpu().numpy().copy(),
+                    bias=None if qm.bias is None else qm.bias.detach().cpu().numpy().copy(),
+                    w_bits=qm.weight_quantizer.n_bits, w_delta=w_delta, w_zp=w_zp, stride=kw["stride"][0],
+                    pad=(kw["padding"][0] + extra_pad) if kind == 0 else 0,
+                    relu=isinstance(qm.activation_function, nn.ReLU),
+                    act_delta=None if qm.disable_act_quant else _scalar(aq.delta),
+                    act_zp=_scalar(aq.zero_point), act_bits=aq.n_bits)
+
+    bb, sh = getattr(model, f"backbone_{modality}"), getattr(model, f"shrinker_{modality}")
+    spec = {"bev_delta": float(bev_delta), "fusion": model.fusion_method}
+    spec["blocks"] = [[layer(qm, extra_pad=blk[0].padding[0] if j == 0 else 0) for j, qm in enumerate(list(blk)[1:])]
+                      for blk in bb.blocks]
+    spec["deblocks"] = [layer(de[0]) for de in bb.deblocks]
+    spec["shrinker"] = [layer(qm) for dc in sh.layers for qm in dc.double_conv]
+    cbs, heads = model.codebook.head_params()
+    spec["codebook"] = dict(codebooks=cbs, heads=heads)
+    ws, bs = [], []
+    for qm in (model.cls_head, model.reg_head, model.dir_head):
+        with torch.no_grad():
+            w = qm.weight_quantizer(qm.weight) if qm.use_weight_quant else qm.org_weight
+        ws.append(w.detach().reshape(w.shape[0], -1).cpu().numpy())
+        bs.append(qm.bias.detach().cpu().numpy())
+    spec["heads"] = dict(w=np.concatenate(ws, 0), b=np.concatenate(bs, 0))
+    return spec

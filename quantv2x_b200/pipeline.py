@@ -1,0 +1,103 @@
+"""Frame-level pipeline of the quantized cooperative forward (BEV level).
+
+    per agent GPU : BEV uint8 -> quantized backbone + shrinker (qv2x_plan) -> codebook encode -> byte planes
+    exchange      : levels*m byte planes per agent (105.6 KB at m=1, H*W=35200) -> ego GPU
+    ego GPU       : decode all agents -> warp + max/att fusion -> cls/reg/dir heads
+
+Mirrors the data flow of the reference model forward (heter_baseline_collab_codebook_mc.py:71-169) with the
+deterministic encode/decode split of heter_pyramid_collab_codebook_mc_encdec.py:33-208; every stage is a
+libqv2x kernel sequence (no torch compute on the path).  Buffers are allocated once per agent count so the
+whole frame can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import engine as E
+
+
+class CollabPipeline:
+    def __init__(self, fused_engine, feat_delta: float, codebook: E.CodebookEngine, heads: E.HeadsEngine,
+                 fusion_mode: str, bev_hw, device):
+        self.fused = fused_engine            # export.BlockEngine over backbone + shrinker
+        self.feat_delta = float(feat_delta)  # activation scale of the shrinker output
+        self.codebook = codebook
+        self.heads = heads
+        self.fusion_mode = fusion_mode
+        self.device = device
+        self.H, self.W = bev_hw
+        self.ho, self.wo, self.c_feat = fused_engine.plan.out_shape(self.H, self.W)
+        self.hw = self.ho * self.wo
+        self._enc_buf = {}
+        self._ego_buf = {}
+
+    # ------------------------------------------------------------------ agent side
+    def bev_from_inputs(self, data_dict, modality: str = "m1") -> torch.Tensor:
+        """uint8 BEV codes [n, H, W, C] for the frame's agents.  BEV-level callers pass them directly as
+        data_dict['inputs_<m>']['bev_u8']; pillar-level inputs go through the PFN + scatter kernel."""
+        inp = data_dict[f"inputs_{modality}"]
+        if "bev_u8" in inp:
+            return inp["bev_u8"]
+        pillar = getattr(self, "pillar_engine", None)
+        if pillar is None:
+            raise NotImplementedError("pillar-level input needs the PFN + scatter engine (SURVEY 8(f)-1, a 'next' "
+                                      "row); pass inputs_m1['bev_u8'] (uint8 [n, H, W, 64]) instead")
+        return pillar.forward(inp)
+
+    def encode_buffers(self, n):
+        if n not in self._enc_buf:
+            d = self.device
+            self._enc_buf[n] = dict(
+                feat=torch.empty((n, self.ho, self.wo, self.c_feat), dtype=torch.uint8, device=d),
+                codes=torch.empty((self.codebook.levels, self.codebook.m, n * self.hw), dtype=torch.uint8, device=d))
+        return self._enc_buf[n]
+
+    def encode_agents(self, bev_u8: torch.Tensor) -> torch.Tensor:
+        """bev_u8 uint8 [n, H, W, C_bev] -> codes uint8 [levels, m, n*hw] (agent-major rows)."""
+        n = bev_u8.shape[0]
+        b = self.encode_buffers(n)
+        self.fused.forward_u8(bev_u8, out=b["feat"])
+        self.codebook.encode(b["feat"], self.feat_delta, out=b["codes"])
+        return b["codes"]
+
+    # ------------------------------------------------------------------ ego side
+    def ego_buffers(self, n):
+        if n not in self._ego_buf:
+            d = self.device
+            self._ego_buf[n] = dict(
+                feat=torch.empty((n, self.ho, self.wo, self.c_feat), dtype=torch.float32, device=d),
+                fused=torch.empty((self.ho, self.wo, self.c_feat), dtype=torch.float32, device=d),
+                preds=torch.empty((self.heads.cout, self.hw), dtype=torch.float32, device=d))
+        return self._ego_buf[n]
+
+    def decode_fuse_heads(self, codes: torch.Tensor, affine: torch.Tensor) -> torch.Tensor:
+        """codes uint8 [levels, m, n*hw]; affine CUDA float32 [n, 2, 3] -> preds float32 [Cout, hw]."""
+        n = codes.shape[-1] // self.hw
+        b = self.ego_buffers(n)
+        self.codebook.decode(codes, out=b["feat"].view(n * self.hw, self.c_feat))
+        E.fuse(b["feat"], affine, self.fusion_mode, out=b["fused"])
+        self.heads.forward(b["fused"], out=b["preds"])
+        return b["preds"]
+
+    def forward(self, bev_u8: torch.Tensor, affine: torch.Tensor) -> torch.Tensor:
+        return self.decode_fuse_heads(self.encode_agents(bev_u8), affine)
+
+    def split_preds(self, preds: torch.Tensor, n_cls: int, n_reg: int, n_dir: int):
+        """[Cout, hw] -> dict of NCHW tensors as the reference model returns them (batch 1)."""
+        p = preds.view(1, -1, self.ho, self.wo)
+        return {"cls_preds": p[:, :n_cls], "reg_preds": p[:, n_cls:n_cls + n_reg],
+                "dir_preds": p[:, n_cls + n_reg:n_cls + n_reg + n_dir], "preds_tensor": p}
+
+
+def heads_from_quant_modules(cls_head, reg_head, dir_head) -> E.HeadsEngine:
+    """Concatenate the three 1x1 head QuantModules (act-quant disabled) into one FP32 GEMM with the
+    de-quantized fake-quant weights the reference would use (quant_layer.py:392-398)."""
+    ws, bs = [], []
+    for qm in (cls_head, reg_head, dir_head):
+        with torch.no_grad():
+            w = qm.weight_quantizer(qm.weight) if qm.use_weight_quant else qm.org_weight
+            b = qm.bias if qm.use_weight_quant else qm.org_bias
+        ws.append(w.detach().reshape(w.shape[0], -1).cpu().numpy())
+        bs.append(np.zeros(w.shape[0], np.float32) if b is None else b.detach().cpu().numpy())
+    return E.HeadsEngine(np.concatenate(ws, 0), np.concatenate(bs, 0))

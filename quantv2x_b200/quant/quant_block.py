@@ -135,3 +135,77 @@ opencood_specials = {
 
 # modules the reference keeps in FP32 by attribute name (quant_block.py:1599-1615)
 specials_unquantized_names = ["aligner_m1", "aligner_m2", "codebook"]
+
+
+# --------------------------------------------------------------------------------------------------
+# PointPillars front end (reference quant_block.py:589-741).  Produces the uint8-grid BEV map the integer
+# backbone consumes: Linear(10->64, W-quant, pre-ReLU act-quant) -> ReLU -> block act-quant (zp = 0) -> max
+# over the pillar's points -> scatter.
+# --------------------------------------------------------------------------------------------------
+from ..pillar_modules import PFNLayer, PillarVFE, PointPillar, augment_pillars  # noqa: E402
+from .quant_layer import UniformAffineQuantizer  # noqa: E402
+import torch.nn.functional as F  # noqa: E402
+
+
+class QuantPFNLayer(BaseQuantBlock):
+    def __init__(self, pfn_layer: PFNLayer, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.last_vfe = pfn_layer.last_vfe
+        self.use_norm = pfn_layer.use_norm
+        self.part = pfn_layer.part
+        self.linear = QuantModule(pfn_layer.linear, weight_quant_params, act_quant_params)
+        if self.use_norm:
+            self.linear.norm_function = pfn_layer.norm        # StraightThrough once BN is folded
+        self.act_quantizer = UniformAffineQuantizer(**act_quant_params)
+
+    def forward(self, inputs):
+        x = F.relu(self.linear(inputs))
+        if self.use_act_quant:
+            x = self.act_quantizer(x)
+        x_max = torch.max(x, dim=1, keepdim=True)[0]
+        if self.last_vfe:
+            return x_max
+        return torch.cat([x, x_max.repeat(1, inputs.shape[1], 1)], dim=2)
+
+
+class QuantPillarVFE(nn.Module):
+    def __init__(self, pillar_vfe: PillarVFE, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.with_distance = pillar_vfe.with_distance
+        self.use_absolute_xyz = pillar_vfe.use_absolute_xyz
+        self.voxel_x, self.voxel_y, self.voxel_z = pillar_vfe.voxel_x, pillar_vfe.voxel_y, pillar_vfe.voxel_z
+        self.x_offset, self.y_offset, self.z_offset = pillar_vfe.x_offset, pillar_vfe.y_offset, pillar_vfe.z_offset
+        self.pfn_layers = nn.ModuleList(QuantPFNLayer(l, weight_quant_params, act_quant_params)
+                                        for l in pillar_vfe.pfn_layers)
+
+    def forward(self, batch_dict):
+        feats = augment_pillars(batch_dict["voxel_features"], batch_dict["voxel_num_points"],
+                                batch_dict["voxel_coords"], (self.voxel_x, self.voxel_y, self.voxel_z),
+                                (self.x_offset, self.y_offset, self.z_offset), self.use_absolute_xyz,
+                                self.with_distance)
+        for pfn in self.pfn_layers:
+            feats = pfn(feats)
+        batch_dict["pillar_features"] = feats.squeeze()
+        return batch_dict
+
+
+class QuantPointPillar(nn.Module):
+    def __init__(self, point_pillar: PointPillar, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.pillar_vfe = QuantPillarVFE(point_pillar.pillar_vfe, weight_quant_params, act_quant_params)
+        self.scatter = point_pillar.scatter
+
+    def forward(self, data_dict, modality_name):
+        inp = data_dict[f"inputs_{modality_name}"]
+        batch_dict = {"voxel_features": inp["voxel_features"], "voxel_coords": inp["voxel_coords"],
+                      "voxel_num_points": inp["voxel_num_points"]}
+        return self.scatter(self.pillar_vfe(batch_dict))["spatial_features"]
+
+    def bev_delta(self) -> float:
+        """Scale of the uint8 grid the BEV map lies on = the last PFN block's post-ReLU act quantizer."""
+        q = self.pillar_vfe.pfn_layers[-1].act_quantizer
+        d = q.delta
+        return float(d.detach().reshape(-1)[0].item()) if isinstance(d, torch.Tensor) else float(d)
+
+
+opencood_specials[PointPillar] = QuantPointPillar
