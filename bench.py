@@ -66,8 +66,8 @@ def build_calibrated_model(device, fusion, w_bits, seed=1234):
     aq = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
     q = QuantModel(model, wq, aq).eval()
     q.disable_network_output_quantization()
-    set_weight_quantize_params(q)
     q.to(device)
+    set_weight_quantize_params(q)
     # BEV-level calibration: one synthetic agent on the uint8 grid bev_delta (what the PFN block would emit)
     bev_delta = 0.05
     bev = synthetic_bev(0, 1, BEV_H, BEV_W, BEV_C, PILLARS)
