@@ -338,7 +338,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        spec = export_spec(q.cpu(), bev_delta)
+        spec = export_spec(q, bev_delta)
         v, cores, sample, _ = cpu_reference_frames_per_s(spec, N_AGENTS, 1, 0, budget_s=40.0)
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
 
