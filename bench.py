@@ -218,15 +218,11 @@ def main():
     preds_host = torch.empty((pipe.heads.cout, hw), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
+    from quantv2x_b200.distributed import gather_code_planes
+
     def exchange(codes):
         """Gather every rank's code planes on the ego rank; returns [levels, m, N_AGENTS*hw] agent-major."""
-        if world == 1:
-            return codes
-        glist = [codes_all[i] for i in range(world)] if rank == 0 else None
-        dist.gather(codes, glist, dst=0)
-        if rank != 0:
-            return None
-        return codes_all.permute(1, 2, 0, 3).reshape(levels, m, N_AGENTS * hw).contiguous()
+        return gather_code_planes(codes, hw, dst=0, recv=codes_all)
 
     def step(bev):
         codes = pipe.encode_agents(bev)

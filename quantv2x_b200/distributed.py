@@ -1,0 +1,34 @@
+"""Agent-per-GPU sharding of the cooperative frame (new design -- the reference has no
+multi-GPU inference).  One process per GPU; agents are split contiguously over the ranks; the only exchange
+is a gather of uint8 code planes (levels*m bytes per BEV cell per agent) to the ego rank.  Integers on the
+wire make the G-GPU result bit-identical to the 1-GPU result."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_agents(n_agents: int, world: int, rank: int) -> range:
+    """Contiguous block of agents owned by `rank` (agent 0 = ego lives on rank 0)."""
+    if n_agents % world != 0:
+        raise ValueError(f"{n_agents} agents do not divide over {world} ranks")
+    per = n_agents // world
+    return range(rank * per, (rank + 1) * per)
+
+
+def gather_code_planes(codes: torch.Tensor, hw: int, dst: int = 0, recv: torch.Tensor | None = None):
+    """codes: uint8 [levels, m, per*hw] of this rank's agents (agent-major rows).
+    Returns uint8 [levels, m, N*hw] with all agents in global order on rank `dst`, None elsewhere.
+    recv: optional preallocated [world, levels, m, per*hw] buffer on `dst` (keeps the step allocation-free)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return codes
+    world, rank = dist.get_world_size(), dist.get_rank()
+    levels, m, rows = codes.shape
+    assert rows % hw == 0
+    if rank == dst:
+        if recv is None:
+            recv = torch.empty((world, levels, m, rows), dtype=codes.dtype, device=codes.device)
+        dist.gather(codes, [recv[i] for i in range(world)], dst=dst)
+        return recv.permute(1, 2, 0, 3).reshape(levels, m, world * rows).contiguous()
+    dist.gather(codes, None, dst=dst)
+    return None
