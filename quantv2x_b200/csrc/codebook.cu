@@ -21,7 +21,8 @@ constexpr int kMaxLevels = 4;
 constexpr int kMaxSeg = 4;
 
 struct EncodeEpilogue {
-    static constexpr int kColSplit = 1;
+    static constexpr int kColSplit = 2;    // two epilogue warps per row quadrant, merged at the end of a level
+    static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
     int levels, m;
     int k[kMaxLevels];            // codewords per segment
     int n_level[kMaxLevels];      // m * k
@@ -69,9 +70,10 @@ struct EncodeEpilogue {
         double score[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const long long V = static_cast<long long>(acc[0][j]) * 65536 + static_cast<long long>(acc[1][j]) * 256 +
-                                static_cast<long long>(acc[2][j]);
-            score[j] = __dadd_rn(__dmul_rn(static_cast<double>(V), __dmul_rn(delta, __ldg(scp + j))), __ldg(g0p + j));
+            // V = acc_hi*65536 + acc_mid*256 + acc_lo, exact in float64 (|V| < 2^48)
+            const double V = fma(static_cast<double>(acc[0][j]), 65536.0,
+                                 fma(static_cast<double>(acc[1][j]), 256.0, static_cast<double>(acc[2][j])));
+            score[j] = __dadd_rn(__dmul_rn(V, __dmul_rn(delta, __ldg(scp + j))), __ldg(g0p + j));
         }
 #pragma unroll
         for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
@@ -108,20 +110,51 @@ struct EncodeEpilogue {
             if (s == seg) ts.best[s] = best, ts.bidx[s] = bidx;
     }
 
-    __device__ __forceinline__ void step_end(Tile& ts, const IgemmGeom&, const TileCoord&, int step) const {
+    __device__ __forceinline__ void step_end(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int part,
+                                             int quad, int lane, uint8_t* scratch) const {
         if (!step_last[step]) return;
         const int l = step_level[step];
+        // merge the two column halves of this row quadrant: part 1 publishes its running minima, part 0 keeps its
+        // own on ties (it owns the lower column indices) and publishes the final codes back.
+        struct Cand {
+            double best;
+            int idx;
+            int pad;
+        };
+        Cand* cand = reinterpret_cast<Cand*>(scratch) + (quad * 32 + lane) * kMaxSeg;
+        const int bar_id = 1 + quad;
+        if (part == 1) {
+#pragma unroll
+            for (int s = 0; s < kMaxSeg; ++s)
+                if (s < m) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if (part == 0) {
+#pragma unroll
+            for (int s = 0; s < kMaxSeg; ++s)
+                if (s < m) {
+                    const double ob = cand[s].best;
+                    const int oi = cand[s].idx;
+                    if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s])) ts.bidx[s] = oi;   // ties -> lowest index
+                    cand[s].idx = ts.bidx[s];
+                }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {
             if (s < m) {
+                const int code = (part == 0) ? ts.bidx[s] : cand[s].idx;
 #pragma unroll
                 for (int ll = 0; ll < kMaxLevels; ++ll)
-                    if (ll == l) ts.code[ll][s] = ts.bidx[s];
-                if (ts.r < rows) codes[(static_cast<long long>(l) * m + s) * rows + ts.r] = static_cast<uint8_t>(ts.bidx[s]);
+                    if (ll == l) ts.code[ll][s] = code;
+                if (part == 0 && ts.r < rows)
+                    codes[(static_cast<long long>(l) * m + s) * rows + ts.r] = static_cast<uint8_t>(code);
                 ts.best[s] = INFINITY;
                 ts.bidx[s] = 0;
             }
         }
+        // part 1 must have read the final codes before part 0 can overwrite the slots at the next level end
+        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     }
 
     __device__ __forceinline__ void end(Tile&, const IgemmGeom&, const TileCoord&) const {}

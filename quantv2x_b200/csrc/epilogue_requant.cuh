@@ -18,11 +18,14 @@ namespace qv2x {
 template <int G>
 struct RequantEpilogue {
     static constexpr int kColSplit = 2;
+    static constexpr int kMaxStages = 8;
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
     int relu;
     float qmax, delta_out, zp_out;
+    float rdelta;                         // fl(1 / delta_out)
+    int fast8;                            // 8-bit output, zero-point 0, ReLU: saturating fast path
     float gscale[kMaxGroups];
     const float* cscale;                  // [N_total]
     const float* bias;                    // [N_total]
@@ -93,32 +96,50 @@ struct RequantEpilogue {
                 }
             }
         }
+        if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
+            const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+#pragma unroll
+            for (int grp = 0; grp < G; ++grp)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    int32_t t = acc[grp][j];
+                    if (zpw[grp] != nullptr) t -= zw[grp][j] * ts.S[grp];
+                    acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t;
+                }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const int n = n0 + j;
             float v = 0.f;
 #pragma unroll
             for (int grp = 0; grp < G; ++grp) {
                 int32_t t = acc[grp][j];
                 if (zpw[grp] != nullptr) t -= zw[grp][j] * ts.S[grp];
-                if (acc_dump != nullptr && ts.mrow >= 0) {
-                    acc_dump[(static_cast<long long>(grp) * (static_cast<long long>(g.n_img) * g.Ho * g.Wo) + ts.mrow) *
-                                 n_total + n] = t;
-                }
                 const float tf = __int2float_rn(t);
-                const float term = __fmul_rn(gscale[grp], tf);
+                const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);   // gscale[0] == 1 when G == 1
                 v = (grp == 0) ? term : __fadd_rn(v, term);
             }
             float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
-            if (relu) y = fmaxf(y, 0.f);
-            // y / delta_out with IEEE rounding.  A zero dividend (half of all post-ReLU values) would send
-            // the whole warp through the division's slow path, so it is divided as delta/delta and masked.
-            const bool nz = (y != 0.f);
-            float d = __fdiv_rn(nz ? y : delta_out, delta_out);
-            d = nz ? d : 0.f;
-            float q = __fadd_rn(rintf(d), zp_out);
-            q = fminf(fmaxf(q, 0.f), qmax);
-            const uint32_t b = static_cast<uint32_t>(q);
+            uint32_t b;
+            if (fast8) {
+                // q = sat_u8(rint(y / delta)) for an 8-bit output with zero-point 0 (ReLU is subsumed by the
+                // saturation).  The IEEE quotient is replaced by y * fl(1/delta): both lie within 5.4e-5 of
+                // each other for |q| < 300, so they round to the same integer unless the product is within
+                // 1e-4 of a half-integer -- only then (about 2e-4 of all elements) the exact division runs.
+                const float t = __fmul_rn(y, rdelta);
+                float f = rintf(t);
+                if (fabsf(t - f) > 0.4999f && fabsf(t) < 300.f) f = rintf(__fdiv_rn(y, delta_out));
+                asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(f));
+            } else {
+                if (relu) y = fmaxf(y, 0.f);
+                // A zero dividend would send the whole warp through the division's slow path: divide
+                // delta/delta instead and mask.
+                const bool nz = (y != 0.f);
+                float d = __fdiv_rn(nz ? y : delta_out, delta_out);
+                d = nz ? d : 0.f;
+                float q = __fadd_rn(rintf(d), zp_out);
+                q = fminf(fmaxf(q, 0.f), qmax);
+                b = static_cast<uint32_t>(q);
+            }
             rsum += static_cast<int>(b);
             packed[j >> 2] |= b << ((j & 3) * 8);
         }
@@ -129,7 +150,8 @@ struct RequantEpilogue {
         }
     }
 
-    __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int) const {}
+    __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int, int, int, int,
+                                             uint8_t*) const {}
 
     __device__ __forceinline__ void end(Tile& ts, const IgemmGeom& g, const TileCoord& tc) const {
         (void)g;

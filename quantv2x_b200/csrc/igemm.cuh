@@ -45,15 +45,17 @@ struct IgemmGeom {
     int step_group_stride[kMaxSteps];
 };
 
-template <int BLOCK_N, int BK>
+constexpr int kEpiSmemBytes = 8192;   // scratch handed to the epilogue functor (cross-warp merges)
+
+template <int BLOCK_N, int BK, int MAX_STAGES = 8>
 struct IgemmCfg {
     static constexpr int kATile = kTileM * BK;
     static constexpr int kBTile = BLOCK_N * BK;
     static constexpr int kStageBytes = kATile + kBTile;
-    static constexpr int kStagesRaw = (196 * 1024) / kStageBytes;
-    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kStagesRaw = (188 * 1024) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > MAX_STAGES ? MAX_STAGES : kStagesRaw;
     static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiSmemBytes;
 };
 
 struct TileCoord {
@@ -74,12 +76,14 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //   struct Epi {
 //     struct Tile;                                     // per-thread, per-tile state
 //     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
+//     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
 //     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row) const;
 //         -- called BEFORE the accumulators are ready (prefetch side inputs here)
 //     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
 //                           const int32_t (*acc)[16]) const;
 //         -- 16 consecutive columns [col0, col0+16) of this thread's row in `step`, acc[g][j]
-//     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step) const;
+//     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step, int part, int quad, int lane,
+//                              uint8_t* scratch) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
 //   };
 template <class Epi>
@@ -89,7 +93,7 @@ template <int BLOCK_N, int BK, int G, class Epi>
 __global__ void __launch_bounds__(igemm_threads<Epi>(), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
              const Epi epi) {
-    using Cfg = IgemmCfg<BLOCK_N, BK>;
+    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kSlots = Cfg::kSlots;
     static_assert(G <= kSlots, "every group needs its own TMEM slot");
@@ -104,6 +108,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* tfull_bar = bars + 2 * kStages;
     uint64_t* tempty_bar = bars + 2 * kStages + kSlots;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kSlots);
+    uint8_t* epi_scratch = smem + kStages * Cfg::kStageBytes + 256;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -225,7 +230,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
                     for (int grp = 0; grp < G; ++grp) mbar_arrive(smem_u32(&tempty_bar[(ac + grp) % kSlots]));
                 }
-                epi.step_end(ts, g, tc, step);
+                epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
             }
             epi.end(ts, g, tc);
         }

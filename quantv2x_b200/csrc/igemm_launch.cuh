@@ -48,7 +48,7 @@ inline void choose_tile_box(int ho, int wo, int* tw, int* th) {
 template <int BLOCK_N, int BK, int G, class Epi>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const Epi& epi,
                         cudaStream_t stream) {
-    using Cfg = IgemmCfg<BLOCK_N, BK>;
+    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages>;
     auto kern = igemm_kernel<BLOCK_N, BK, G, Epi>;
     static bool attr_set = false;
     if (!attr_set) {

@@ -243,6 +243,8 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.qmax = static_cast<float>((1 << d.out_bits) - 1);
         e.delta_out = d.out_delta;
         e.zp_out = d.out_zero_point;
+        e.rdelta = 1.0f / d.out_delta;
+        e.fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
             e.gscale[i] = L->gscale[i];
             e.zpw[i] = (L->use_zp && i < L->groups) ? L->d_zpw : nullptr;
