@@ -42,6 +42,9 @@ int qv2x_version(void);
 int qv2x_device_check(int device);
 /* Number of kernels this library has launched since load (all threads); bench.py reports it. */
 long long qv2x_launch_count(void);
+/* Bring-up / profiling knobs for the igemm kernels (0 = normal operation): 1 skip the epilogue math and stores,
+ * 2 skip MMA issue, 4 skip activation (A) loads, 8 skip weight (B) loads.  Results are garbage when non-zero. */
+void qv2x_set_debug_flags(int flags);
 
 /* ------------------------------------------------------------------------------------------------
  * One quantized layer = reference QuantModule.forward (opencood/quant/quant_layer.py:391-410) with

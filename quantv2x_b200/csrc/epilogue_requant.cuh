@@ -19,6 +19,7 @@ template <int G>
 struct RequantEpilogue {
     static constexpr int kColSplit = 2;
     static constexpr int kMaxStages = 8;
+    static constexpr bool kCoopTileSetup = true;
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
@@ -41,9 +42,32 @@ struct RequantEpilogue {
         long long opix;   // output pixel index, -1 if this row is outside the image
         long long mrow;   // GEMM row index (for acc_dump)
         int rsum;
+        const float* sm_cs;      // this tile's per-column parameters in shared memory
+        const float* sm_bias;
+        const int32_t* sm_zpw;
+        int n_base;              // first global column of the tile
     };
 
-    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row) const {
+    // Shared-memory layout of the staged parameters (<= 256 columns): cs | bias | zpw, 1 KB each.
+    __device__ __forceinline__ void tile_setup(const IgemmGeom& g, const TileCoord& tc, int tid, int nthreads,
+                                               uint8_t* scratch) const {
+        float* s_cs = reinterpret_cast<float*>(scratch);
+        float* s_b = s_cs + 256;
+        int32_t* s_z = reinterpret_cast<int32_t*>(s_b + 256);
+        const int n_base = tc.nt * g.block_n;
+        for (int i = tid; i < g.block_n; i += nthreads) {
+            s_cs[i] = __ldg(cscale + n_base + i);
+            s_b[i] = __ldg(bias + n_base + i);
+            s_z[i] = (zpw[0] != nullptr) ? __ldg(zpw[0] + n_base + i) : 0;   // all groups share one zero-point array
+        }
+    }
+
+    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
+                                          uint8_t* scratch) const {
+        ts.sm_cs = reinterpret_cast<const float*>(scratch);
+        ts.sm_bias = ts.sm_cs + 256;
+        ts.sm_zpw = reinterpret_cast<const int32_t*>(ts.sm_bias + 256);
+        ts.n_base = tc.nt * g.block_n;
         const int lx = row % g.tw, ly = row / g.tw;
         const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
         const bool valid = (ox < g.Wo) && (oy < g.Ho);
@@ -77,24 +101,19 @@ struct RequantEpilogue {
         (void)tc;
         (void)step;
         uint32_t packed[4] = {0, 0, 0, 0};
-        int rsum = 0;
-        // per-column parameters: warp-uniform 16-byte loads (L1 broadcast)
+        unsigned rsum = 0;
+        // per-column parameters from shared memory: warp-uniform 16-byte loads (broadcast)
         float cs[16], bs[16];
-        int32_t zw[G][16];
+        int32_t zw[16];
+        const int nl = n0 - ts.n_base;
 #pragma unroll
         for (int v4 = 0; v4 < 4; ++v4) {
-            const float4 c = __ldg(reinterpret_cast<const float4*>(cscale + n0) + v4);
-            const float4 b = __ldg(reinterpret_cast<const float4*>(bias + n0) + v4);
+            const float4 c = *(reinterpret_cast<const float4*>(ts.sm_cs + nl) + v4);
+            const float4 b = *(reinterpret_cast<const float4*>(ts.sm_bias + nl) + v4);
+            const int4 z = *(reinterpret_cast<const int4*>(ts.sm_zpw + nl) + v4);
             cs[4 * v4 + 0] = c.x, cs[4 * v4 + 1] = c.y, cs[4 * v4 + 2] = c.z, cs[4 * v4 + 3] = c.w;
             bs[4 * v4 + 0] = b.x, bs[4 * v4 + 1] = b.y, bs[4 * v4 + 2] = b.z, bs[4 * v4 + 3] = b.w;
-#pragma unroll
-            for (int grp = 0; grp < G; ++grp) {
-                if (zpw[grp] != nullptr) {
-                    const int4 z = __ldg(reinterpret_cast<const int4*>(zpw[grp] + n0) + v4);
-                    zw[grp][4 * v4 + 0] = z.x, zw[grp][4 * v4 + 1] = z.y, zw[grp][4 * v4 + 2] = z.z,
-                                     zw[grp][4 * v4 + 3] = z.w;
-                }
-            }
+            zw[4 * v4 + 0] = z.x, zw[4 * v4 + 1] = z.y, zw[4 * v4 + 2] = z.z, zw[4 * v4 + 3] = z.w;
         }
         if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
             const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
@@ -103,33 +122,57 @@ struct RequantEpilogue {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     int32_t t = acc[grp][j];
-                    if (zpw[grp] != nullptr) t -= zw[grp][j] * ts.S[grp];
+                    if (zpw[grp] != nullptr) t -= zw[j] * ts.S[grp];
                     acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t;
                 }
         }
+        const bool use_zp = (zpw[0] != nullptr);
+        if (fast8) {
+            // q = sat_u8(rint(y / delta)) for an 8-bit output with zero-point 0 (ReLU is subsumed by the clamp),
+            // entirely on the FMA/ALU pipes:
+            //   t = y * fl(1/delta) lies within 5.4e-5 of the IEEE quotient for |q| < 300, so both round to the same
+            //   integer unless t is within 1e-4 of a half-integer -- only then (~2e-4 of elements) the exact division
+            //   runs.  r = (t + 1.5*2^23) - 1.5*2^23 is rint(t) (round-half-even) for |t| < 2^22; after the clamp,
+            //   (r + 2^23) carries the byte in its low mantissa bits.
+            uint32_t bits[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            float v = 0.f;
+            for (int j = 0; j < 16; ++j) {
+                float v = 0.f;
 #pragma unroll
-            for (int grp = 0; grp < G; ++grp) {
-                int32_t t = acc[grp][j];
-                if (zpw[grp] != nullptr) t -= zw[grp][j] * ts.S[grp];
-                const float tf = __int2float_rn(t);
-                const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);   // gscale[0] == 1 when G == 1
-                v = (grp == 0) ? term : __fadd_rn(v, term);
-            }
-            float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
-            uint32_t b;
-            if (fast8) {
-                // q = sat_u8(rint(y / delta)) for an 8-bit output with zero-point 0 (ReLU is subsumed by the
-                // saturation).  The IEEE quotient is replaced by y * fl(1/delta): both lie within 5.4e-5 of
-                // each other for |q| < 300, so they round to the same integer unless the product is within
-                // 1e-4 of a half-integer -- only then (about 2e-4 of all elements) the exact division runs.
+                for (int grp = 0; grp < G; ++grp) {
+                    int32_t t = acc[grp][j];
+                    if (use_zp) t -= zw[j] * ts.S[grp];
+                    const float tf = __int2float_rn(t);
+                    const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);   // gscale[0] == 1 when G == 1
+                    v = (grp == 0) ? term : __fadd_rn(v, term);
+                }
+                const float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
                 const float t = __fmul_rn(y, rdelta);
-                float f = rintf(t);
-                if (fabsf(t - f) > 0.4999f && fabsf(t) < 300.f) f = rintf(__fdiv_rn(y, delta_out));
-                asm("cvt.rni.sat.u8.f32 %0, %1;" : "=r"(b) : "f"(f));
-            } else {
+                float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+                if (fabsf(__fadd_rn(t, -r)) > 0.4999f && fabsf(t) < 300.f) r = rintf(__fdiv_rn(y, delta_out));
+                r = fminf(fmaxf(r, 0.f), 255.f);
+                bits[j] = __float_as_uint(__fadd_rn(r, 8388608.0f));
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const uint32_t lo = __byte_perm(bits[4 * w + 0], bits[4 * w + 1], 0x0040);
+                const uint32_t hi = __byte_perm(bits[4 * w + 2], bits[4 * w + 3], 0x0040);
+                packed[w] = __byte_perm(lo, hi, 0x5410);
+                rsum = __dp4a(packed[w], 0x01010101u, static_cast<unsigned>(rsum));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                float v = 0.f;
+#pragma unroll
+                for (int grp = 0; grp < G; ++grp) {
+                    int32_t t = acc[grp][j];
+                    if (use_zp) t -= zw[j] * ts.S[grp];
+                    const float tf = __int2float_rn(t);
+                    const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);
+                    v = (grp == 0) ? term : __fadd_rn(v, term);
+                }
+                float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
                 if (relu) y = fmaxf(y, 0.f);
                 // A zero dividend would send the whole warp through the division's slow path: divide
                 // delta/delta instead and mask.
@@ -138,15 +181,15 @@ struct RequantEpilogue {
                 d = nz ? d : 0.f;
                 float q = __fadd_rn(rintf(d), zp_out);
                 q = fminf(fmaxf(q, 0.f), qmax);
-                b = static_cast<uint32_t>(q);
+                const uint32_t b = static_cast<uint32_t>(q);
+                rsum += static_cast<int>(b);
+                packed[j >> 2] |= b << ((j & 3) * 8);
             }
-            rsum += static_cast<int>(b);
-            packed[j >> 2] |= b << ((j & 3) * 8);
         }
         if (ts.opix >= 0) {
             const int ch = n0 % cout_sub;
             st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);
-            ts.rsum += rsum;
+            ts.rsum += static_cast<int>(rsum);
         }
     }
 

@@ -17,6 +17,7 @@ namespace qv2x {
 std::string& last_error_ref();
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
+extern int g_debug_flags;
 int num_sms();
 
 #define QV2X_CUDA_OK(expr)                                                                            \

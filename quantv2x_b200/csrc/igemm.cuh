@@ -40,6 +40,7 @@ struct IgemmGeom {
     // Sequential N steps per tile (1 for conv layers).  A tile visits its steps in order on ONE CTA, so an
     // epilogue may carry state from step to step (the codebook's level-by-level argmin).  B rows of
     // (step, group) start at b_row_base[g] + step_row_base[step] + g * step_group_stride[step].
+    int debug;   // bring-up knobs (qv2x_set_debug_flags): 1 skip epilogue math, 2 skip MMA issue, 4 skip A loads, 8 skip B loads
     int n_steps;
     int step_row_base[kMaxSteps];
     int step_group_stride[kMaxSteps];
@@ -77,7 +78,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //     struct Tile;                                     // per-thread, per-tile state
 //     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
 //     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
-//     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row) const;
+//     static constexpr bool kCoopTileSetup;            // stage per-tile parameters in shared memory first
+//     __device__ void tile_setup(const IgemmGeom&, const TileCoord&, int tid, int nthreads, uint8_t* scratch) const;
+//     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row, uint8_t* scratch) const;
 //         -- called BEFORE the accumulators are ready (prefetch side inputs here)
 //     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
 //                           const int32_t (*acc)[16]) const;
@@ -155,12 +158,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                                 const uint32_t fb = smem_u32(&full_bar[s]);
-                                mbar_expect_tx(fb, Cfg::kStageBytes);
+                                mbar_expect_tx(fb, ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile));
                                 uint8_t* st = smem + s * Cfg::kStageBytes;
-                                tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky,
-                                            tc.img);
-                                tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
-                                            tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
+                                if (!(g.debug & 4))
+                                    tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky,
+                                                tc.img);
+                                if (!(g.debug & 8))
+                                    tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
+                                                tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
                             }
                         }
                     }
@@ -184,10 +189,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
                         const uint64_t a_desc = umma_smem_desc(a_addr, BK);
                         const uint64_t b_desc = umma_smem_desc(a_addr + Cfg::kATile, BK);
+                        if (!(g.debug & 2)) {
 #pragma unroll
-                        for (int k = 0; k < BK / 32; ++k) {
-                            // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
-                            umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | k) != 0);
+                            for (int k = 0; k < BK / 32; ++k) {
+                                // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
+                                umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | k) != 0);
+                            }
                         }
                         umma_commit(smem_u32(&empty_bar[s]));
                     }
@@ -202,10 +209,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row = quad * 32 + lane;     // tile row == TMEM lane
         constexpr int kColsPerWarp = BLOCK_N / Epi::kColSplit;
         uint32_t ac = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        uint32_t tile_par = 0;
+        const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_par ^= 1) {
             const TileCoord tc = decode_tile(g, t);
             typename Epi::Tile ts;
-            epi.begin(ts, g, tc, row);
+            uint8_t* scratch = epi_scratch + (Epi::kCoopTileSetup ? tile_par * (kEpiSmemBytes / 2) : 0);
+            if constexpr (Epi::kCoopTileSetup) {
+                // all epilogue threads stage this tile's per-column parameters in shared memory (double-buffered
+                // by tile parity, so one named barrier per tile is enough)
+                epi.tile_setup(g, tc, static_cast<int>(threadIdx.x) - 128, kNumEpiWarps * 32, scratch);
+                asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+            }
+            epi.begin(ts, g, tc, row, scratch);
             for (int step = 0; step < g.n_steps; ++step, ac += G) {
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp) {
@@ -213,16 +229,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
                 }
                 tcgen05_fence_after();
-                for (int c0 = part * kColsPerWarp; c0 < (part + 1) * kColsPerWarp; c0 += 16) {
-                    uint32_t acc[G][16];
-#pragma unroll
-                    for (int grp = 0; grp < G; ++grp) {
-                        const uint32_t slot = (ac + grp) % kSlots;
-                        tmem_ld_x16(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + slot * BLOCK_N + c0,
-                                    acc[grp]);
+                const int c_begin = part * kColsPerWarp, c_end = (part + 1) * kColsPerWarp;
+                if constexpr (G == 1 && (kColsPerWarp % 32 == 0)) {
+                    // software-pipelined TMEM reads: the load of chunk i+1 is in flight while chunk i is processed
+                    const uint32_t tbase = tmem_base + lane_base + (ac % kSlots) * BLOCK_N;
+                    uint32_t acc_a[1][16], acc_b[1][16];
+                    tmem_ld_x16(tbase + c_begin, acc_a[0]);
+                    for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+                        tmem_ld_wait();
+                        tmem_ld_x16(tbase + c0 + 16, acc_b[0]);
+                        if (!(g.debug & 1))
+                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc_a));
+                        tmem_ld_wait();
+                        if (c0 + 32 < c_end) tmem_ld_x16(tbase + c0 + 32, acc_a[0]);
+                        if (!(g.debug & 1))
+                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 16,
+                                      reinterpret_cast<const int32_t(*)[16]>(acc_b));
                     }
-                    tmem_ld_wait();
-                    epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+                } else {
+                    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                        uint32_t acc[G][16];
+#pragma unroll
+                        for (int grp = 0; grp < G; ++grp) {
+                            const uint32_t slot = (ac + grp) % kSlots;
+                            tmem_ld_x16(tmem_base + lane_base + slot * BLOCK_N + c0, acc[grp]);
+                        }
+                        tmem_ld_wait();
+                        if (!(g.debug & 1))
+                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+                    }
                 }
                 tcgen05_fence_before();
                 __syncwarp();

@@ -57,7 +57,9 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     }
     const int total = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
     const int grid = std::min(total, num_sms());
-    kern<<<grid, igemm_threads<Epi>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, g, epi);
+    IgemmGeom gg = g;
+    gg.debug = g_debug_flags;
+    kern<<<grid, igemm_threads<Epi>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, gg, epi);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -21,6 +21,10 @@ CFG = {
 which = sys.argv[1] if len(sys.argv) > 1 else "shrink1"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 use_graph = "--graph" in sys.argv
+dbg = [int(a.split("=")[1]) for a in sys.argv if a.startswith("--debug=")]
+if dbg:
+    from quantv2x_b200 import _lib
+    _lib.lib().qv2x_set_debug_flags(dbg[0])
 n, H, W, cin, cout, groups = CFG[which]
 dev = torch.device("cuda:0")
 rng = np.random.default_rng(1)
@@ -59,4 +63,4 @@ else:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-print(f"{which} graph={use_graph}: {ms * 1e3:.1f} us/launch  {ops / ms / 1e9:.1f} TOP/s", flush=True)
+print(f"{which} debug={dbg} graph={use_graph}: {ms * 1e3:.1f} us/launch  {ops / ms / 1e9:.1f} TOP/s", flush=True)
