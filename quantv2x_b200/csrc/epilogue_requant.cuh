@@ -135,8 +135,9 @@ struct RequantEpilogue {
             //   runs.  r = (t + 1.5*2^23) - 1.5*2^23 is rint(t) (round-half-even) for |t| < 2^22; after the clamp,
             //   (r + 2^23) carries the byte in its low mantissa bits.
             uint32_t bits[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            float rr[16];
+            uint32_t nearmask = 0;
+            auto real_value = [&](int j) -> float {
                 float v = 0.f;
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp) {
@@ -146,11 +147,26 @@ struct RequantEpilogue {
                     const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);   // gscale[0] == 1 when G == 1
                     v = (grp == 0) ? term : __fadd_rn(v, term);
                 }
-                const float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
-                const float t = __fmul_rn(y, rdelta);
-                float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
-                if (fabsf(__fadd_rn(t, -r)) > 0.4999f && fabsf(t) < 300.f) r = rintf(__fdiv_rn(y, delta_out));
-                r = fminf(fmaxf(r, 0.f), 255.f);
+                return __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
+            };
+            // phase 1, branch-free so the 16 independent chains interleave
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float t = __fmul_rn(real_value(j), rdelta);
+                const float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+                const bool near = (fabsf(__fadd_rn(t, -r)) > 0.4999f) && (fabsf(t) < 300.f);
+                nearmask |= (near ? 1u : 0u) << j;
+                rr[j] = r;
+            }
+            // phase 2, rare: exact IEEE division for the elements that sit next to a rounding boundary
+            if (nearmask != 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if ((nearmask >> j) & 1u) rr[j] = rintf(__fdiv_rn(real_value(j), delta_out));
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float r = fminf(fmaxf(rr[j], 0.f), 255.f);
                 bits[j] = __float_as_uint(__fadd_rn(r, 8388608.0f));
             }
 #pragma unroll
