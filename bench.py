@@ -85,34 +85,47 @@ def build_calibrated_model(device, fusion, w_bits, seed=1234):
     return q, bev_delta
 
 
-def clock_sampler(stop, out):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
-    q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+def clock_sampler(stop, out, device_index=0):
+    """SM clock / throttle reasons while the timed region runs (NVML every 5 ms; nvidia-smi as a fallback)."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+        while not stop.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                r = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            out.append((float(sm), float(mx), [k for k, v in bits.items() if r & v]))
+            stop.wait(0.005)
+        return
+    except Exception:
+        pass
+    q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     while not stop.is_set():
         try:
-            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", "0"],
-                               capture_output=True, text=True, timeout=5)
+            r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                str(device_index)], capture_output=True, text=True, timeout=5)
             if r.returncode == 0 and r.stdout.strip():
-                out.append([c.strip() for c in r.stdout.strip().split("\n")[0].split(",")])
+                c = [v.strip() for v in r.stdout.strip().split("\n")[0].split(",")]
+                out.append((float(c[0]), float(c[1]), [n for n, v in zip(names, c[2:6]) if v.lower().startswith("active")]))
         except Exception:
             pass
-        stop.wait(0.2)
+        stop.wait(0.05)
 
 
 def summarize_clocks(samples):
     if not samples:
-        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    sm = sorted(float(s[1]) for s in samples if s[1].replace(".", "").isdigit())
-    reasons = set()
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    for s in samples:
-        for name, v in zip(names, s[5:9]):
-            if v.lower().startswith("active"):
-                reasons.add(name)
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(samples[0][2]) if samples else None,
-            "reasons": sorted(reasons), "samples": len(samples)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+    sm = sorted(s[0] for s in samples)
+    reasons = sorted({r for s in samples for r in s[2]})
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": samples[0][1], "reasons": reasons, "samples": len(samples)}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -224,11 +237,21 @@ def main():
         """Gather every rank's code planes on the ego rank; returns [levels, m, N_AGENTS*hw] agent-major."""
         return gather_code_planes(codes, hw, dst=0, recv=codes_all)
 
+    # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (the exchange stays outside)
+    g_enc, codes_local = pipe.capture_encode(bev_dev)
+    codes_full = (codes_local if world == 1 else
+                  torch.empty((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)) if rank == 0 else None
+    g_ego, preds_dev = pipe.capture_ego(codes_full, aff) if rank == 0 else (None, None)
+
     def step(bev):
-        codes = pipe.encode_agents(bev)
-        full = exchange(codes)
+        """bev must be the static buffer bev_dev (graphs replay on fixed addresses)."""
+        g_enc.replay()
+        full = exchange(codes_local)
         if rank == 0:
-            return pipe.decode_fuse_heads(full, aff)
+            if world > 1:
+                codes_full.copy_(full)
+            g_ego.replay()
+            return preds_dev
         return None
 
     def timed_loop(fn, k):
@@ -255,7 +278,7 @@ def main():
     stop, samples = threading.Event(), []
     th = None
     if rank == 0:
-        th = threading.Thread(target=clock_sampler, args=(stop, samples), daemon=True)
+        th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
         th.start()
     launches0 = _lib.lib().qv2x_launch_count()
     sync_all()

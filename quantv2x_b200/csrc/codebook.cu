@@ -70,6 +70,21 @@ struct EncodeEpilogue {
         const int kk0 = n0 - seg * k[l];
         const double* scp = sc + colbase[l] + n0;
         const double* g0p = g0 + colbase[l] + n0;
+        // The cross-term rows are per-thread gathers (random rows, 128 B per 16-column chunk): pull the NEXT chunk's
+        // lines into L1 now so its loads do not expose the L2 latency.
+        if (n0 + 16 < nl) {
+#pragma unroll
+            for (int jl = 0; jl < kMaxLevels - 1; ++jl)
+                if (jl < l) {
+#pragma unroll
+                    for (int s2 = 0; s2 < kMaxSeg; ++s2)
+                        if (s2 < m) {
+                            const double* nx = btab + boff[l][jl] +
+                                               (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0 + 16;
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                        }
+                }
+        }
         double score[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {

@@ -83,6 +83,30 @@ class CollabPipeline:
     def forward(self, bev_u8: torch.Tensor, affine: torch.Tensor) -> torch.Tensor:
         return self.decode_fuse_heads(self.encode_agents(bev_u8), affine)
 
+    # ------------------------------------------------------------------ CUDA graphs
+    def _capture(self, fn):
+        """Capture `fn` (library launches on static buffers) into a CUDA graph: one launch replays the ~25 kernels
+        of a stage without host round trips."""
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                fn()                       # warm-up: one-time attribute / workspace setup must not be captured
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = fn()
+        return g, out
+
+    def capture_encode(self, bev_static: torch.Tensor):
+        """Graph of encode_agents over a STATIC input buffer; returns (graph, codes tensor it writes)."""
+        return self._capture(lambda: self.encode_agents(bev_static))
+
+    def capture_ego(self, codes_static: torch.Tensor, affine_static: torch.Tensor):
+        """Graph of decode_fuse_heads over STATIC code / pose buffers; returns (graph, preds tensor it writes)."""
+        return self._capture(lambda: self.decode_fuse_heads(codes_static, affine_static))
+
     def split_preds(self, preds: torch.Tensor, n_cls: int, n_reg: int, n_dir: int):
         """[Cout, hw] -> dict of NCHW tensors as the reference model returns them (batch 1)."""
         p = preds.view(1, -1, self.ho, self.wo)
