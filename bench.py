@@ -238,10 +238,15 @@ def main():
         return gather_code_planes(codes, hw, dst=0, recv=codes_all)
 
     # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (the exchange stays outside)
+    lc0 = _lib.lib().qv2x_launch_count()
     g_enc, codes_local = pipe.capture_encode(bev_dev)
+    lc1 = _lib.lib().qv2x_launch_count()
     codes_full = (codes_local if world == 1 else
                   torch.empty((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)) if rank == 0 else None
     g_ego, preds_dev = pipe.capture_ego(codes_full, aff) if rank == 0 else (None, None)
+    lc2 = _lib.lib().qv2x_launch_count()
+    # kernels per replay = launches recorded while capturing (2 warm-up calls + 1 captured call per stage)
+    launches_per_step = (lc1 - lc0) // 3 + (lc2 - lc1) // 3
 
     def step(bev):
         """bev must be the static buffer bev_dev (graphs replay on fixed addresses)."""
@@ -280,11 +285,10 @@ def main():
     if rank == 0:
         th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
         th.start()
-    launches0 = _lib.lib().qv2x_launch_count()
     sync_all()
     total_ms = timed_loop(lambda: step(bev_dev), args.steps)
     sync_all()
-    launches = _lib.lib().qv2x_launch_count() - launches0
+    launches = launches_per_step * args.steps      # kernels of this library replayed through the two CUDA graphs
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
