@@ -24,6 +24,7 @@ struct EncodeEpilogue {
     static constexpr int kColSplit = 2;    // two epilogue warps per row quadrant, merged at the end of a level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
     static constexpr bool kCoopTileSetup = false;
+    static constexpr bool kPipelined8 = false;
     int levels, m;
     int k[kMaxLevels];            // codewords per segment
     int n_level[kMaxLevels];      // m * k
@@ -61,8 +62,10 @@ struct EncodeEpilogue {
             for (int s = 0; s < kMaxSeg; ++s) ts.code[l][s] = 0;
     }
 
+    template <int W>
     __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int c0,
-                                          const int32_t (*acc)[16]) const {
+                                          const int32_t (*acc)[W]) const {
+        static_assert(W == 16, "the encode epilogue works on 16-column chunks");
         const int l = step_level[step];
         const int n0 = step_col0[step] + c0;          // column within the level; a chunk never straddles segments
         const int nl = n_level[l];

@@ -20,6 +20,7 @@ struct RequantEpilogue {
     static constexpr int kColSplit = 2;
     static constexpr int kMaxStages = 8;
     static constexpr bool kCoopTileSetup = true;
+    static constexpr bool kPipelined8 = (G > 1);
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
@@ -96,18 +97,20 @@ struct RequantEpilogue {
         ts.opix = (static_cast<long long>(tc.img) * Hout + oy * up + dy) * Wout + ox * up + dx;
     }
 
+    template <int W>
     __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int n0,
-                                          const int32_t (*acc)[16]) const {
+                                          const int32_t (*acc)[W]) const {
+        static_assert(W == 8 || W == 16, "chunk width");
         (void)tc;
         (void)step;
-        uint32_t packed[4] = {0, 0, 0, 0};
+        uint32_t packed[W / 4] = {};
         unsigned rsum = 0;
         // per-column parameters from shared memory: warp-uniform 16-byte loads (broadcast)
-        float cs[16], bs[16];
-        int32_t zw[16];
+        float cs[W], bs[W];
+        int32_t zw[W];
         const int nl = n0 - ts.n_base;
 #pragma unroll
-        for (int v4 = 0; v4 < 4; ++v4) {
+        for (int v4 = 0; v4 < W / 4; ++v4) {
             const float4 c = *(reinterpret_cast<const float4*>(ts.sm_cs + nl) + v4);
             const float4 b = *(reinterpret_cast<const float4*>(ts.sm_bias + nl) + v4);
             const int4 z = *(reinterpret_cast<const int4*>(ts.sm_zpw + nl) + v4);
@@ -120,7 +123,7 @@ struct RequantEpilogue {
 #pragma unroll
             for (int grp = 0; grp < G; ++grp)
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
+                for (int j = 0; j < W; ++j) {
                     int32_t t = acc[grp][j];
                     if (zpw[grp] != nullptr) t -= zw[j] * ts.S[grp];
                     acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t;
@@ -134,8 +137,8 @@ struct RequantEpilogue {
             //   integer unless t is within 1e-4 of a half-integer -- only then (~2e-4 of elements) the exact division
             //   runs.  r = (t + 1.5*2^23) - 1.5*2^23 is rint(t) (round-half-even) for |t| < 2^22; after the clamp,
             //   (r + 2^23) carries the byte in its low mantissa bits.
-            uint32_t bits[16];
-            float rr[16];
+            uint32_t bits[W];
+            float rr[W];
             uint32_t nearmask = 0;
             auto real_value = [&](int j) -> float {
                 float v = 0.f;
@@ -151,7 +154,7 @@ struct RequantEpilogue {
             };
             // phase 1, branch-free so the 16 independent chains interleave
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < W; ++j) {
                 const float t = __fmul_rn(real_value(j), rdelta);
                 const float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
                 const bool near = (fabsf(__fadd_rn(t, -r)) > 0.4999f) && (fabsf(t) < 300.f);
@@ -161,16 +164,16 @@ struct RequantEpilogue {
             // phase 2, rare: exact IEEE division for the elements that sit next to a rounding boundary
             if (nearmask != 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
+                for (int j = 0; j < W; ++j)
                     if ((nearmask >> j) & 1u) rr[j] = rintf(__fdiv_rn(real_value(j), delta_out));
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < W; ++j) {
                 const float r = fminf(fmaxf(rr[j], 0.f), 255.f);
                 bits[j] = __float_as_uint(__fadd_rn(r, 8388608.0f));
             }
 #pragma unroll
-            for (int w = 0; w < 4; ++w) {
+            for (int w = 0; w < W / 4; ++w) {
                 const uint32_t lo = __byte_perm(bits[4 * w + 0], bits[4 * w + 1], 0x0040);
                 const uint32_t hi = __byte_perm(bits[4 * w + 2], bits[4 * w + 3], 0x0040);
                 packed[w] = __byte_perm(lo, hi, 0x5410);
@@ -178,7 +181,7 @@ struct RequantEpilogue {
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < W; ++j) {
                 float v = 0.f;
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp) {
@@ -204,7 +207,10 @@ struct RequantEpilogue {
         }
         if (ts.opix >= 0) {
             const int ch = n0 % cout_sub;
-            st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);
+            if constexpr (W == 16)
+                st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);
+            else
+                st_global_v2(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1]);
             ts.rsum += static_cast<int>(rsum);
         }
     }

@@ -48,10 +48,14 @@ struct IgemmGeom {
 
 constexpr int kEpiSmemBytes = 8192;   // scratch handed to the epilogue functor (cross-warp merges)
 
-template <int BLOCK_N, int BK, int MAX_STAGES = 8>
+// TPS = taps per pipeline stage: layers with 64 input channels have only 64 bytes of K per tap, so three taps
+// share one stage (one mbarrier round trip per 192 bytes of K instead of per 64).
+template <int BLOCK_N, int BK, int MAX_STAGES = 8, int TPS = 1>
 struct IgemmCfg {
-    static constexpr int kATile = kTileM * BK;
-    static constexpr int kBTile = BLOCK_N * BK;
+    static constexpr int kASub = kTileM * BK;
+    static constexpr int kBSub = BLOCK_N * BK;
+    static constexpr int kATile = kASub * TPS;
+    static constexpr int kBTile = kBSub * TPS;
     static constexpr int kStageBytes = kATile + kBTile;
     static constexpr int kStagesRaw = (188 * 1024) / kStageBytes;
     static constexpr int kStages = kStagesRaw > MAX_STAGES ? MAX_STAGES : kStagesRaw;
@@ -82,9 +86,10 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //     __device__ void tile_setup(const IgemmGeom&, const TileCoord&, int tid, int nthreads, uint8_t* scratch) const;
 //     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row, uint8_t* scratch) const;
 //         -- called BEFORE the accumulators are ready (prefetch side inputs here)
-//     __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
-//                           const int32_t (*acc)[16]) const;
-//         -- 16 consecutive columns [col0, col0+16) of this thread's row in `step`, acc[g][j]
+//     static constexpr bool kPipelined8;               // G > 1: double-buffered 8-column chunks
+//     template <int W> __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
+//                           const int32_t (*acc)[W]) const;
+//         -- W (8 or 16) consecutive columns [col0, col0+W) of this thread's row in `step`, acc[g][j]
 //     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step, int part, int quad, int lane,
 //                              uint8_t* scratch) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
@@ -92,11 +97,11 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 template <class Epi>
 constexpr int igemm_threads() { return (4 + 4 * Epi::kColSplit) * 32; }
 
-template <int BLOCK_N, int BK, int G, class Epi>
+template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1>
 __global__ void __launch_bounds__(igemm_threads<Epi>(), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
              const Epi epi) {
-    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages>;
+    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages, TPS>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kSlots = Cfg::kSlots;
     static_assert(G <= kSlots, "every group needs its own TMEM slot");
@@ -138,7 +143,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_ptr;
 
     const int total_tiles = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
-    const int kblocks_per_group = g.taps * g.cblocks;
+    const int kblocks_per_group = (g.taps / TPS) * g.cblocks;   // pipeline stages per accumulator group
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -152,20 +157,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int grp = 0; grp < G; ++grp) {
                         const int brow = g.b_row_base[grp] + g.step_row_base[step] + grp * g.step_group_stride[step] +
                                          tc.nt * BLOCK_N;
-                        for (int tap = 0; tap < g.taps; ++tap) {
-                            const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                        for (int tap0 = 0; tap0 < g.taps; tap0 += TPS) {
                             for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
                                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
                                 mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
                                 const uint32_t fb = smem_u32(&full_bar[s]);
                                 mbar_expect_tx(fb, ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile));
                                 uint8_t* st = smem + s * Cfg::kStageBytes;
-                                if (!(g.debug & 4))
-                                    tma_load_4d(smem_u32(st), &tmA, fb, g.a_c_base[grp] + cb * BK, x0 + kx, y0 + ky,
-                                                tc.img);
-                                if (!(g.debug & 8))
-                                    tma_load_2d(smem_u32(st + Cfg::kATile), &tmB, fb,
-                                                tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
+#pragma unroll
+                                for (int i = 0; i < TPS; ++i) {
+                                    const int tap = tap0 + i;
+                                    const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
+                                    if (!(g.debug & 4))
+                                        tma_load_4d(smem_u32(st + i * Cfg::kASub), &tmA, fb, g.a_c_base[grp] + cb * BK,
+                                                    x0 + kx, y0 + ky, tc.img);
+                                    if (!(g.debug & 8))
+                                        tma_load_2d(smem_u32(st + Cfg::kATile + i * Cfg::kBSub), &tmB, fb,
+                                                    tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
+                                }
                             }
                         }
                     }
@@ -187,13 +196,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         mbar_wait(smem_u32(&full_bar[s]), ph);
                         tcgen05_fence_after();
                         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-                        const uint64_t a_desc = umma_smem_desc(a_addr, BK);
-                        const uint64_t b_desc = umma_smem_desc(a_addr + Cfg::kATile, BK);
                         if (!(g.debug & 2)) {
 #pragma unroll
-                            for (int k = 0; k < BK / 32; ++k) {
-                                // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
-                                umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | k) != 0);
+                            for (int i = 0; i < TPS; ++i) {
+                                const uint64_t a_desc = umma_smem_desc(a_addr + i * Cfg::kASub, BK);
+                                const uint64_t b_desc = umma_smem_desc(a_addr + Cfg::kATile + i * Cfg::kBSub, BK);
+#pragma unroll
+                                for (int k = 0; k < BK / 32; ++k) {
+                                    // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
+                                    umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | i | k) != 0);
+                                }
                             }
                         }
                         umma_commit(smem_u32(&empty_bar[s]));
@@ -239,12 +251,35 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tmem_ld_wait();
                         tmem_ld_x16(tbase + c0 + 16, acc_b[0]);
                         if (!(g.debug & 1))
-                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc_a));
+                            epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
+                                                   reinterpret_cast<const int32_t(*)[16]>(acc_a));
                         tmem_ld_wait();
                         if (c0 + 32 < c_end) tmem_ld_x16(tbase + c0 + 32, acc_a[0]);
                         if (!(g.debug & 1))
-                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 16,
-                                      reinterpret_cast<const int32_t(*)[16]>(acc_b));
+                            epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 16,
+                                                   reinterpret_cast<const int32_t(*)[16]>(acc_b));
+                    }
+                } else if constexpr (Epi::kPipelined8) {
+                    // G accumulators per column: 8-column chunks, double-buffered, so the TMEM reads of the next chunk
+                    // overlap the math of the current one within the same register budget
+                    uint32_t acc_a[G][8], acc_b[G][8];
+                    auto load8 = [&](uint32_t (&dst)[G][8], int c) {
+#pragma unroll
+                        for (int grp = 0; grp < G; ++grp)
+                            tmem_ld_x8(tmem_base + lane_base + ((ac + grp) % kSlots) * BLOCK_N + c, dst[grp]);
+                    };
+                    load8(acc_a, c_begin);
+                    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
+                        tmem_ld_wait();
+                        load8(acc_b, c0 + 8);
+                        if (!(g.debug & 1))
+                            epi.template chunk<8>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
+                                                  reinterpret_cast<const int32_t(*)[8]>(acc_a));
+                        tmem_ld_wait();
+                        if (c0 + 16 < c_end) load8(acc_a, c0 + 16);
+                        if (!(g.debug & 1))
+                            epi.template chunk<8>(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 8,
+                                                  reinterpret_cast<const int32_t(*)[8]>(acc_b));
                     }
                 } else {
                     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
@@ -256,7 +291,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         }
                         tmem_ld_wait();
                         if (!(g.debug & 1))
-                            epi.chunk(ts, g, tc, step, tc.nt * BLOCK_N + c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+                            epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
+                                                   reinterpret_cast<const int32_t(*)[16]>(acc));
                     }
                 }
                 tcgen05_fence_before();

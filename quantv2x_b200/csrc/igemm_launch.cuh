@@ -45,11 +45,11 @@ inline void choose_tile_box(int ho, int wo, int* tw, int* th) {
     }
 }
 
-template <int BLOCK_N, int BK, int G, class Epi>
+template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const Epi& epi,
                         cudaStream_t stream) {
-    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages>;
-    auto kern = igemm_kernel<BLOCK_N, BK, G, Epi>;
+    using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages, TPS>;
+    auto kern = igemm_kernel<BLOCK_N, BK, G, Epi, TPS>;
     static bool attr_set = false;
     if (!attr_set) {
         QV2X_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -71,6 +71,11 @@ int dispatch_igemm(int block_n, int bk, const CUtensorMap& tmA, const CUtensorMa
 #define QV2X_CASE(BN, BKK) \
     if (block_n == BN && bk == BKK) return launch_igemm<BN, BKK, G, Epi>(tmA, tmB, g, epi, stream);
     if constexpr (G == 1) {
+        // 3x3 convs over 64-byte channel blocks: three taps per pipeline stage
+        if (bk == 64 && g.taps == 9 && g.cblocks == 1) {
+            if (block_n == 64) return launch_igemm<64, 64, G, Epi, 3>(tmA, tmB, g, epi, stream);
+            if (block_n == 128) return launch_igemm<128, 64, G, Epi, 3>(tmA, tmB, g, epi, stream);
+        }
         QV2X_CASE(256, 128)
         QV2X_CASE(256, 64)
     }
