@@ -227,37 +227,41 @@ def main():
     poses = torch.from_numpy(synthetic_poses(N_AGENTS)).float()
     aff = normalize_pairwise_tfm(poses, 80.0, 281.6, 1)[0, 0, :N_AGENTS].contiguous().to(device)
     levels, m, hw = pipe.codebook.levels, pipe.codebook.m, pipe.hw
-    codes_all = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device) if rank == 0 else None
     preds_host = torch.empty((pipe.heads.cout, hw), dtype=torch.float32).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
-    from quantv2x_b200.distributed import gather_code_planes
+    from quantv2x_b200.distributed import all_gather_code_planes, gather_pred_tiles, rank_tile
 
-    def exchange(codes):
-        """Gather every rank's code planes on the ego rank; returns [levels, m, N_AGENTS*hw] agent-major."""
-        return gather_code_planes(codes, hw, dst=0, recv=codes_all)
-
-    # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (the exchange stays outside)
+    # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (collectives stay outside).
+    #   1 GPU : encode graph (8 agents) -> ego graph (decode + warp/fuse + heads on the whole map)
+    #   G GPUs: encode graph (8/G agents) -> all_gather of the uint8 code planes -> ego graph on this rank's output
+    #           TILE (decode only the source rectangles the tile samples, fuse, heads) -> gather of the head tiles
     lc0 = _lib.lib().qv2x_launch_count()
     g_enc, codes_local = pipe.capture_encode(bev_dev)
     lc1 = _lib.lib().qv2x_launch_count()
-    codes_full = (codes_local if world == 1 else
-                  torch.empty((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)) if rank == 0 else None
-    g_ego, preds_dev = pipe.capture_ego(codes_full, aff) if rank == 0 else (None, None)
+    aff_host = aff.cpu().numpy()
+    if world == 1:
+        g_ego, preds_dev = pipe.capture_ego(codes_local, aff)
+    else:
+        tile = rank_tile(rank, world, pipe.ho, pipe.wo)
+        recv_codes = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
+        codes_full = torch.empty((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
+        g_ego, preds_dev = pipe._capture(lambda: pipe.decode_fuse_heads_tile(codes_full, aff, aff_host, tile))
+        recv_preds = (torch.empty((world,) + tuple(preds_dev.shape), dtype=torch.float32, device=device)
+                      if rank == 0 else None)
     lc2 = _lib.lib().qv2x_launch_count()
     # kernels per replay = launches recorded while capturing (2 warm-up calls + 1 captured call per stage)
     launches_per_step = (lc1 - lc0) // 3 + (lc2 - lc1) // 3
 
     def step(bev):
-        """bev must be the static buffer bev_dev (graphs replay on fixed addresses)."""
+        """bev must be the static buffer bev_dev (graphs replay on fixed addresses).  Returns preds on rank 0."""
         g_enc.replay()
-        full = exchange(codes_local)
-        if rank == 0:
-            if world > 1:
-                codes_full.copy_(full)
+        if world == 1:
             g_ego.replay()
             return preds_dev
-        return None
+        codes_full.copy_(all_gather_code_planes(codes_local, hw, recv=recv_codes))
+        g_ego.replay()
+        return gather_pred_tiles(preds_dev, pipe.ho, pipe.wo, dst=0, recv=recv_preds)
 
     def timed_loop(fn, k):
         """k steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""

@@ -126,6 +126,14 @@ int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t*
 /* decode: d_codes [levels][m][rows] -> d_out [rows][C] float32 (pixel-major). */
 int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t* d_codes, float* d_out, void* stream);
 
+/* decode only rectangles of the (agent-major) row grid: region a covers rows base_row[a] + y * pitch + x for
+ * y in [rect[4a], rect[4a+1]), x in [rect[4a+2], rect[4a+3]).  d_codes planes are plane_stride rows apart; d_out is
+ * the full-size [rows][C] buffer, only the listed rows are written.  Used when the ego stage is sharded over GPUs:
+ * every GPU decodes just the source area its output tile samples from.  base_row / rect are HOST arrays. */
+int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride, int pitch, int n_regions,
+                                 const long long* base_row, const int* rect, const uint8_t* d_codes, float* d_out,
+                                 void* stream);
+
 /* Test hook: the folded tables the kernels use.  which = 0 digits (int8 [sum_l 3*m*k_l][C], level-major then
  * digit-major), 1 per-column scale (double), 2 per-column constant (double), 3 codeword cross terms (double),
  * 4 decode constant (float [C]), 5 decode tables (float, level-major then segment-major [k_l][C]). */
@@ -144,6 +152,9 @@ int qv2x_codebook_folded_copy(const qv2x_codebook* cb, int which, void* host_buf
  * ---------------------------------------------------------------------------------------------- */
 int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine, float* d_out,
               void* stream);
+/* Same, restricted to the output tile rows [y0, y1) x columns [x0, x1); d_out is compact [(y1-y0)*(x1-x0)][C]. */
+int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine,
+                   float* d_out, int y0, int y1, int x0, int x1, void* stream);
 
 /* Detection heads = the three 1x1 convs cls_head / reg_head / dir_head (reference
  * heter_model_baseline_mc.py:137-142) concatenated along the output channel; weights are the de-quantized

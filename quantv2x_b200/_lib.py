@@ -142,3 +142,15 @@ def _declare_plan(lib):
 
 
 _DECLARERS.append(_declare_plan)
+
+
+def _declare_tiles(lib):
+    lib.qv2x_fuse_tile.argtypes = [c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                   c_int, c_int, c_void_p]
+    lib.qv2x_codebook_decode_regions.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                 c_void_p, c_void_p]
+    lib.qv2x_set_debug_flags.argtypes = [c_int]
+    lib.qv2x_set_debug_flags.restype = None
+
+
+_DECLARERS.append(_declare_tiles)

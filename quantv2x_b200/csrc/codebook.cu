@@ -207,6 +207,46 @@ __global__ void codebook_decode_kernel(const uint8_t* __restrict__ codes, long l
     }
 }
 
+// Region variant: only the listed source rectangles are decoded (the ego stage sharded over GPUs needs, per agent,
+// just the bounding box its output tile samples from).  Row index = base + y * pitch + x, same as the full decode.
+struct DecodeRegions {
+    int n;
+    long long base[8];
+    int y0[8], y1[8], x0[8], x1[8];
+    long long start[9];      // prefix sums of the region sizes
+};
+__global__ void codebook_decode_region_kernel(const uint8_t* __restrict__ codes, long long plane_stride, int pitch,
+                                              int levels, int m, int C, const float* __restrict__ dconst,
+                                              const float* __restrict__ tables, const long long* __restrict__ toff,
+                                              float* __restrict__ out, const DecodeRegions rg) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const int vec = C / 4;
+    for (long long t = warp; t < rg.start[rg.n]; t += nwarps) {
+        int a = 0;
+        while (t >= rg.start[a + 1]) ++a;
+        const long long local = t - rg.start[a];
+        const int w = rg.x1[a] - rg.x0[a];
+        const int yy = rg.y0[a] + static_cast<int>(local / w), xx = rg.x0[a] + static_cast<int>(local % w);
+        const long long r = rg.base[a] + static_cast<long long>(yy) * pitch + xx;
+        int code[kMaxLevels * kMaxSeg];
+        for (int i = 0; i < levels * m; ++i) code[i] = __ldg(codes + static_cast<long long>(i) * plane_stride + r);
+        for (int v = lane; v < vec; v += 32) {
+            float4 acc = __ldg(reinterpret_cast<const float4*>(dconst) + v);
+            for (int i = 0; i < levels * m; ++i) {
+                const float4 tv = __ldg(reinterpret_cast<const float4*>(tables + toff[i] +
+                                                                        static_cast<long long>(code[i]) * C) + v);
+                acc.x = __fadd_rn(acc.x, tv.x);
+                acc.y = __fadd_rn(acc.y, tv.y);
+                acc.z = __fadd_rn(acc.z, tv.z);
+                acc.w = __fadd_rn(acc.w, tv.w);
+            }
+            reinterpret_cast<float4*>(out + r * C)[v] = acc;
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------- host math
 struct Mat {
     int r = 0, c = 0;
@@ -549,6 +589,35 @@ int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t*
     const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 8));
     codebook_decode_kernel<<<grid, threads, 0, stream>>>(d_codes, rows, cb->levels, cb->m, cb->C, cb->d_dconst,
                                                           cb->d_tables, cb->d_toff, d_out);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride, int pitch, int n_regions,
+                                 const long long* base_row, const int* rect, const uint8_t* d_codes, float* d_out,
+                                 void* stream_) {
+    QV2X_REQUIRE(cb && base_row && rect && d_codes && d_out, "qv2x_codebook_decode_regions: null argument");
+    QV2X_REQUIRE(n_regions >= 1 && n_regions <= 8, "1..8 regions");
+    DecodeRegions rg{};
+    rg.n = n_regions;
+    rg.start[0] = 0;
+    for (int a = 0; a < n_regions; ++a) {
+        rg.base[a] = base_row[a];
+        rg.y0[a] = rect[4 * a + 0];
+        rg.y1[a] = rect[4 * a + 1];
+        rg.x0[a] = rect[4 * a + 2];
+        rg.x1[a] = rect[4 * a + 3];
+        QV2X_REQUIRE(rg.y1[a] >= rg.y0[a] && rg.x1[a] >= rg.x0[a] && rg.x1[a] <= pitch, "bad region %d", a);
+        rg.start[a + 1] = rg.start[a] + static_cast<long long>(rg.y1[a] - rg.y0[a]) * (rg.x1[a] - rg.x0[a]);
+    }
+    if (rg.start[n_regions] == 0) return 0;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const int threads = 256;
+    const long long want = (rg.start[n_regions] * 32 + threads - 1) / threads;
+    const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 8));
+    codebook_decode_region_kernel<<<grid, threads, 0, stream>>>(d_codes, plane_stride, pitch, cb->levels, cb->m, cb->C,
+                                                                 cb->d_dconst, cb->d_tables, cb->d_toff, d_out, rg);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

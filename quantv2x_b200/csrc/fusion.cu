@@ -19,6 +19,7 @@ constexpr int kMaxAgents = 8;
 
 struct FuseParams {
     int n, H, W, C;
+    int y0, x0, th, tw;         // output tile (rows [y0, y0+th), columns [x0, x0+tw)); the result is stored compactly
     const float* aff;           // DEVICE [n][6]: row-major 2x3, normalized coordinates (ego <- agent j)
     float inv_sqrt_c;
 };
@@ -31,9 +32,11 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ fea
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const long long npix = static_cast<long long>(p.H) * p.W;
+    const long long tpix = static_cast<long long>(p.th) * p.tw;
     const int vec = p.C / 4;
-    for (long long pix = warp; pix < npix; pix += nwarps) {
-        const int i = static_cast<int>(pix / p.W), j = static_cast<int>(pix - static_cast<long long>(i) * p.W);
+    for (long long pix = warp; pix < tpix; pix += nwarps) {
+        const int ti = static_cast<int>(pix / p.tw);
+        const int i = p.y0 + ti, j = p.x0 + static_cast<int>(pix - static_cast<long long>(ti) * p.tw);
         const float xn = (2.f * j + 1.f) / p.W - 1.f;
         const float yn = (2.f * i + 1.f) / p.H - 1.f;
         float4 xa[kMaxAgents][VPL];
@@ -264,7 +267,13 @@ extern "C" {
 
 int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine, float* d_out,
               void* stream_) {
+    return qv2x_fuse_tile(mode, n_agents, H, W, C, d_feat, d_affine, d_out, 0, H, 0, W, stream_);
+}
+
+int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine,
+                   float* d_out, int y0, int y1, int x0, int x1, void* stream_) {
     QV2X_REQUIRE(d_feat && d_affine && d_out, "qv2x_fuse: null argument");
+    QV2X_REQUIRE(0 <= y0 && y0 < y1 && y1 <= H && 0 <= x0 && x0 < x1 && x1 <= W, "bad output tile");
     QV2X_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (max) or 1 (attention)");
     QV2X_REQUIRE(n_agents >= 1 && n_agents <= kMaxAgents, "n_agents must be 1..%d", kMaxAgents);
     QV2X_REQUIRE(C % 4 == 0 && C <= 512, "C must be a multiple of 4 and <= 512");
@@ -276,8 +285,12 @@ int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, 
     p.W = W;
     p.C = C;
     p.aff = d_affine;
+    p.y0 = y0;
+    p.x0 = x0;
+    p.th = y1 - y0;
+    p.tw = x1 - x0;
     p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(C));
-    const long long npix = static_cast<long long>(H) * W;
+    const long long npix = static_cast<long long>(p.th) * p.tw;
     const int threads = 256;
     const int grid = static_cast<int>(std::min<long long>((npix * 32 + threads - 1) / threads,
                                                           static_cast<long long>(num_sms()) * 8));

@@ -182,10 +182,7 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     g.n_img = n_img;
     g.Hi = hi;
     g.Wi = wi;
-    g.block_n = L->block_n;
-    g.n_tiles = L->n_total / L->block_n;
     g.groups = L->groups;
-    g.idesc = make_idesc_i8(L->block_n, L->b_signed);
     g.n_steps = 1;
     int out_h, out_w;
     if (d.kind == 0) {
@@ -225,11 +222,31 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     choose_tile_box(g.Ho, g.Wo, &g.tw, &g.th);
     g.tiles_x = (g.Wo + g.tw - 1) / g.tw;
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
+    // Column-tile width: the widest tile has the best operand reuse, but small maps (deep stages, one agent per
+    // GPU) would leave most SMs idle.  Cost model: waves x bytes staged per k-block (128 rows of A + bn rows of B).
+    int block_n = L->block_n;
+    {
+        const long long m_tiles = static_cast<long long>(n_img) * g.tiles_x * g.tiles_y;
+        const int sub_cols = (d.kind == 0) ? L->n_total : d.cout;   // a tile must not straddle sub-positions
+        long long best = -1;
+        for (int bn = L->block_n; bn >= 64; bn >>= 1) {
+            if (sub_cols % bn != 0) continue;
+            const long long tiles = m_tiles * (L->n_total / bn);
+            const long long cost = ((tiles + num_sms() - 1) / num_sms()) * (128 + bn);
+            if (best < 0 || cost < best) {
+                best = cost;
+                block_n = bn;
+            }
+        }
+    }
+    g.block_n = block_n;
+    g.n_tiles = L->n_total / block_n;
+    g.idesc = make_idesc_i8(block_n, L->b_signed);
 
     CUtensorMap tmA, tmB;
     int rc = make_act_tmap(&tmA, d_x, n_img, hi, wi, in_cstride, g.tw, g.th, g.stride, L->bk);
     if (rc) return rc;
-    rc = make_weight_tmap(&tmB, L->d_w, (d.kind == 0 ? 1 : 3) * L->n_total, L->k_total, L->block_n, L->bk);
+    rc = make_weight_tmap(&tmB, L->d_w, (d.kind == 0 ? 1 : 3) * L->n_total, L->k_total, block_n, L->bk);
     if (rc) return rc;
 
     auto fill = [&](auto& e) {
@@ -260,11 +277,11 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     if (L->groups == 1) {
         RequantEpilogue<1> e{};
         fill(e);
-        return dispatch_igemm<1>(L->block_n, L->bk, tmA, tmB, g, e, stream);
+        return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
     }
     RequantEpilogue<3> e{};
     fill(e);
-    return dispatch_igemm<3>(L->block_n, L->bk, tmA, tmB, g, e, stream);
+    return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
 }
 
 }  // extern "C"

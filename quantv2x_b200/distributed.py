@@ -32,3 +32,47 @@ def gather_code_planes(codes: torch.Tensor, hw: int, dst: int = 0, recv: torch.T
         return recv.permute(1, 2, 0, 3).reshape(levels, m, world * rows).contiguous()
     dist.gather(codes, None, dst=dst)
     return None
+
+
+def tile_grid(world: int):
+    """How the ego output map is cut over `world` ranks: (rows, cols) of tiles."""
+    return {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (2, 4)}[world]
+
+
+def rank_tile(rank: int, world: int, h: int, w: int):
+    """(y0, y1, x0, x1) of the output tile owned by `rank`."""
+    gy, gx = tile_grid(world)
+    assert h % gy == 0 and w % gx == 0, "feature map must divide over the tile grid"
+    ty, tx = rank // gx, rank % gx
+    th, tw = h // gy, w // gx
+    return (ty * th, (ty + 1) * th, tx * tw, (tx + 1) * tw)
+
+
+def all_gather_code_planes(codes: torch.Tensor, hw: int, recv: torch.Tensor | None = None) -> torch.Tensor:
+    """Every rank ends up with all agents' code planes [levels, m, N*hw] (agent-major)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return codes
+    world = dist.get_world_size()
+    levels, m, rows = codes.shape
+    if recv is None:
+        recv = torch.empty((world, levels, m, rows), dtype=codes.dtype, device=codes.device)
+    dist.all_gather_into_tensor(recv.view(-1), codes.reshape(-1))
+    return recv.permute(1, 2, 0, 3).reshape(levels, m, world * rows).contiguous()
+
+
+def gather_pred_tiles(preds_tile: torch.Tensor, h: int, w: int, dst: int = 0, recv: torch.Tensor | None = None):
+    """preds_tile: [Cout, tile_pixels] of this rank's tile.  Returns [Cout, h*w] on `dst`, None elsewhere."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return preds_tile
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cout = preds_tile.shape[0]
+    if rank != dst:
+        dist.gather(preds_tile, None, dst=dst)
+        return None
+    if recv is None:
+        recv = torch.empty((world,) + tuple(preds_tile.shape), dtype=preds_tile.dtype, device=preds_tile.device)
+    dist.gather(preds_tile, [recv[i] for i in range(world)], dst=dst)
+    gy, gx = tile_grid(world)
+    th, tw = h // gy, w // gx
+    full = recv.view(gy, gx, cout, th, tw).permute(2, 0, 3, 1, 4).reshape(cout, h * w)
+    return full.contiguous()

@@ -179,6 +179,16 @@ class CodebookEngine:
                                               _stream_ptr()))
         return out
 
+    def decode_regions(self, codes: torch.Tensor, pitch: int, base_rows, rects, out: torch.Tensor) -> torch.Tensor:
+        """Decode only rectangles of the row grid (see qv2x_codebook_decode_regions).  codes uint8 [levels, m, rows];
+        base_rows: first row of each region's image; rects: (y0, y1, x0, x1) per region; out float32 [rows, C]."""
+        br = np.ascontiguousarray(base_rows, dtype=np.int64)
+        rc = np.ascontiguousarray(rects, dtype=np.int32).reshape(-1)
+        check(_lib.lib().qv2x_codebook_decode_regions(self._h, codes.shape[-1], pitch, len(br), _np_ptr(br),
+                                                      _np_ptr(rc), c_void_p(codes.data_ptr()),
+                                                      c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
     def folded(self, which: int) -> np.ndarray:
         """Test hook: the folded tables held by the library (see qv2x_codebook_folded_copy)."""
         n = _lib.lib().qv2x_codebook_folded_size(self._h, which)
@@ -186,6 +196,16 @@ class CodebookEngine:
         buf = np.empty(n, dtype=dt)
         check(_lib.lib().qv2x_codebook_folded_copy(self._h, which, _np_ptr(buf)))
         return buf
+
+
+def fuse_tile(feat: torch.Tensor, affine: torch.Tensor, mode: str, tile, out: torch.Tensor) -> torch.Tensor:
+    """Warp + fuse the output tile (y0, y1, x0, x1) only; out is compact float32 [(y1-y0)*(x1-x0), C]."""
+    n, h, w, c = feat.shape
+    y0, y1, x0, x1 = tile
+    aff = affine.to(torch.float32).reshape(n, 6).contiguous()
+    check(_lib.lib().qv2x_fuse_tile({"max": 0, "att": 1}[mode], n, h, w, c, c_void_p(feat.data_ptr()),
+                                    c_void_p(aff.data_ptr()), c_void_p(out.data_ptr()), y0, y1, x0, x1, _stream_ptr()))
+    return out
 
 
 def fuse(feat: torch.Tensor, affine, mode: str, out: torch.Tensor | None = None) -> torch.Tensor:

@@ -83,6 +83,51 @@ class CollabPipeline:
     def forward(self, bev_u8: torch.Tensor, affine: torch.Tensor) -> torch.Tensor:
         return self.decode_fuse_heads(self.encode_agents(bev_u8), affine)
 
+    # ------------------------------------------------------------------ ego side, one output tile (multi-GPU)
+    def source_rects(self, affine_host: np.ndarray, tile):
+        """Per agent, the (y0, y1, x0, x1) source rectangle that the bilinear warp of output tile `tile` samples
+        from (bounding box of the affinely mapped tile corners, padded by 2 pixels)."""
+        y0, y1, x0, x1 = tile
+        H, W = self.ho, self.wo
+        rects = []
+        for M in np.asarray(affine_host, dtype=np.float64).reshape(-1, 2, 3):
+            xs, ys = [], []
+            for i in (y0, y1 - 1):
+                for j in (x0, x1 - 1):
+                    xn, yn = (2.0 * j + 1.0) / W - 1.0, (2.0 * i + 1.0) / H - 1.0
+                    xs.append(((M[0, 0] * xn + M[0, 1] * yn + M[0, 2] + 1.0) * W - 1.0) / 2.0)
+                    ys.append(((M[1, 0] * xn + M[1, 1] * yn + M[1, 2] + 1.0) * H - 1.0) / 2.0)
+            lo_x, hi_x = int(np.floor(min(xs))) - 2, int(np.floor(max(xs))) + 4
+            lo_y, hi_y = int(np.floor(min(ys))) - 2, int(np.floor(max(ys))) + 4
+            cx0, cx1 = min(max(lo_x, 0), W), min(max(hi_x, 0), W)
+            cy0, cy1 = min(max(lo_y, 0), H), min(max(hi_y, 0), H)
+            rects.append((cy0, max(cy1, cy0), cx0, max(cx1, cx0)))
+        return rects
+
+    def ego_tile_buffers(self, n, tile):
+        key = (n, tuple(tile))
+        if key not in self._ego_buf:
+            d = self.device
+            tp = (tile[1] - tile[0]) * (tile[3] - tile[2])
+            self._ego_buf[key] = dict(
+                feat=torch.zeros((n, self.ho, self.wo, self.c_feat), dtype=torch.float32, device=d),
+                fused=torch.empty((tp, self.c_feat), dtype=torch.float32, device=d),
+                preds=torch.empty((self.heads.cout, tp), dtype=torch.float32, device=d))
+        return self._ego_buf[key]
+
+    def decode_fuse_heads_tile(self, codes: torch.Tensor, affine: torch.Tensor, affine_host, tile) -> torch.Tensor:
+        """The ego stage for ONE output tile (y0, y1, x0, x1): decode only the source rectangles the tile samples
+        from, warp + fuse the tile, run the heads on it.  Returns compact preds [Cout, tile_pixels].  Per-pixel
+        arithmetic is identical to decode_fuse_heads, so tiles assembled from several GPUs equal the 1-GPU result."""
+        n = codes.shape[-1] // self.hw
+        b = self.ego_tile_buffers(n, tile)
+        rects = self.source_rects(affine_host, tile)
+        self.codebook.decode_regions(codes, self.wo, [a * self.hw for a in range(n)], rects,
+                                     b["feat"].view(n * self.hw, self.c_feat))
+        E.fuse_tile(b["feat"], affine, self.fusion_mode, tile, b["fused"])
+        self.heads.forward(b["fused"], out=b["preds"])
+        return b["preds"]
+
     # ------------------------------------------------------------------ CUDA graphs
     def _capture(self, fn):
         """Capture `fn` (library launches on static buffers) into a CUDA graph: one launch replays the ~25 kernels

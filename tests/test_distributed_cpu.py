@@ -53,3 +53,32 @@ def test_shard_agents():
         assert False
     except ValueError:
         pass
+
+
+def _worker_tiles(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantv2x_b200.distributed import all_gather_code_planes, gather_pred_tiles, rank_tile
+
+    h, w, cout, hw_codes = 4, 6, 3, 5
+    full = np.arange(cout * h * w, dtype=np.float32).reshape(cout, h, w)
+    y0, y1, x0, x1 = rank_tile(rank, world, h, w)
+    tile = torch.from_numpy(np.ascontiguousarray(full[:, y0:y1, x0:x1]).reshape(cout, -1))
+    out = gather_pred_tiles(tile, h, w)
+    codes_full = np.arange(2 * 1 * world * hw_codes, dtype=np.uint8).reshape(2, 1, world * hw_codes)
+    mine = torch.from_numpy(np.ascontiguousarray(codes_full[:, :, rank * hw_codes:(rank + 1) * hw_codes]))
+    allc = all_gather_code_planes(mine, hw_codes)
+    ok = bool(np.array_equal(allc.numpy(), codes_full))
+    if rank == 0:
+        ok = ok and bool(np.array_equal(out.numpy(), full.reshape(cout, -1)))
+    ret[rank] = ok
+    dist.destroy_process_group()
+
+
+def test_two_rank_tiles_and_allgather():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_tiles, args=(2, port, ret), nprocs=2, join=True)
+        assert ret[0] and ret[1]

@@ -63,3 +63,41 @@ def test_converters_bit_exact(cuda_device):
     nhwc = engine.nchw_to_nhwc_f32(xd)
     assert np.array_equal(nhwc.cpu().numpy(), x.transpose(0, 2, 3, 1))
     assert np.array_equal(engine.nhwc_to_nchw_f32(nhwc).cpu().numpy(), x)
+
+
+def test_tiled_ego_stage_equals_whole(cuda_device):
+    """decode_regions + fuse_tile + heads per tile, assembled, must equal the whole-frame ego stage bit for bit
+    (this is what makes the multi-GPU result identical to the single-GPU one)."""
+    from quantv2x_b200 import engine as E
+    from quantv2x_b200.distributed import rank_tile, tile_grid
+    from quantv2x_b200.pipeline import CollabPipeline
+    from tests.codebook_cases import make_codebook_params
+
+    rng = np.random.default_rng(0)
+    n, ho, wo, C = 5, 20, 48, 256
+    cbs, heads = make_codebook_params(3, C, 1, [128] * 3)
+    cb = E.CodebookEngine(cbs, heads)
+    hd = E.HeadsEngine(rng.normal(size=(72, C)).astype(np.float32) / 16, rng.normal(size=72).astype(np.float32))
+
+    class _Plan:
+        def out_shape(self, h, w):
+            return ho, wo, C
+
+    class _Fused:
+        plan = _Plan()
+
+    aff = make_affines(n, rng)
+    aff[3, 0, 2] += 0.4           # push one agent partly out of view
+    aff_d = torch.from_numpy(aff.astype(np.float32)).to(cuda_device)
+    codes = torch.from_numpy(rng.integers(0, 128, size=(3, 1, n * ho * wo), dtype=np.uint8)).to(cuda_device)
+    for mode in ("att", "max"):
+        pipe = CollabPipeline(_Fused(), 0.1, cb, hd, mode, (2 * ho, 2 * wo), cuda_device)
+        whole = pipe.decode_fuse_heads(codes, aff_d).clone()
+        for world in (2, 4, 8):
+            gy, gx = tile_grid(world)
+            th, tw = ho // gy, wo // gx
+            out = torch.empty((world, 72, th * tw), dtype=torch.float32, device=cuda_device)
+            for r in range(world):
+                out[r] = pipe.decode_fuse_heads_tile(codes, aff_d, aff, rank_tile(r, world, ho, wo))
+            full = out.view(gy, gx, 72, th, tw).permute(2, 0, 3, 1, 4).reshape(72, ho * wo)
+            assert torch.equal(full, whole), f"{mode}, {world} tiles: tiled ego stage differs from the whole frame"
