@@ -181,69 +181,110 @@ struct EncodeEpilogue {
     __device__ __forceinline__ void end(Tile&, const IgemmGeom&, const TileCoord&) const {}
 };
 
-// out[r][:] = ((const + T[0][0][code]) + T[0][1][code]) + ... ; one warp per row, fixed summation order.
-__global__ void codebook_decode_kernel(const uint8_t* __restrict__ codes, long long rows, int levels, int m, int C,
-                                       const float* __restrict__ dconst, const float* __restrict__ tables,
-                                       const long long* __restrict__ toff, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    const int vec = C / 4;    // float4 per row
-    for (long long r = warp; r < rows; r += nwarps) {
-        int code[kMaxLevels * kMaxSeg];
-        for (int i = 0; i < levels * m; ++i) code[i] = __ldg(codes + static_cast<long long>(i) * rows + r);
-        for (int v = lane; v < vec; v += 32) {
-            float4 a = __ldg(reinterpret_cast<const float4*>(dconst) + v);
-            for (int i = 0; i < levels * m; ++i) {
-                const float4 t = __ldg(reinterpret_cast<const float4*>(tables + toff[i] +
-                                                                       static_cast<long long>(code[i]) * C) + v);
-                a.x = __fadd_rn(a.x, t.x);
-                a.y = __fadd_rn(a.y, t.y);
-                a.z = __fadd_rn(a.z, t.z);
-                a.w = __fadd_rn(a.w, t.w);
-            }
-            reinterpret_cast<float4*>(out + r * C)[v] = a;
-        }
-    }
+// Decode: out[r][:] = ((const + T_0[code_0]) + T_1[code_1]) + ... in fp32, fixed summation order.
+//
+// The tables (levels*m*k*C floats, 384 KB at k=128 C=256) would be re-read from L2 three times per output row if
+// gathered from global memory (3x the bytes the kernel writes).  Instead the channel axis is cut into S slices so
+// that one slice of ALL tables fits in shared memory (<= 200 KB); a persistent CTA owns one slice, stages it once,
+// and then streams rows: 3 code bytes in, Cs*4 contiguous bytes out.  The kernel is then bound by the HBM write.
+// Rows are either [0, rows) or the union of up to 8 rectangles of per-agent row grids (multi-GPU ego tiles).
+constexpr int kMaxTables = kMaxLevels * kMaxSeg;
+struct DecodeRegions {
+    int n;                   // 0: plain rows [0, total)
+    long long base[8];
+    int y0[8], x0[8], w[8];
+    long long start[9];      // prefix sums of the region sizes; start[n] (or start[0] when n == 0) = total rows
+    int pitch;
+};
+struct DecodeTables {
+    int nt, C, S, Cs;
+    int k[kMaxTables];
+    long long toff[kMaxTables];   // float offset of table i in the global tables array ([k][C])
+    int soff[kMaxTables];         // float offset of table i's slice in shared memory ([k][Cs])
+};
+
+__device__ __forceinline__ long long decode_row_of(const DecodeRegions& rg, long long t) {
+    if (rg.n == 0) return t;
+    int a = 0;
+    while (a + 1 < rg.n && t >= rg.start[a + 1]) ++a;
+    const long long local = t - rg.start[a];
+    const int yy = rg.y0[a] + static_cast<int>(local / rg.w[a]), xx = rg.x0[a] + static_cast<int>(local % rg.w[a]);
+    return rg.base[a] + static_cast<long long>(yy) * rg.pitch + xx;
 }
 
-// Region variant: only the listed source rectangles are decoded (the ego stage sharded over GPUs needs, per agent,
-// just the bounding box its output tile samples from).  Row index = base + y * pitch + x, same as the full decode.
-struct DecodeRegions {
-    int n;
-    long long base[8];
-    int y0[8], y1[8], x0[8], x1[8];
-    long long start[9];      // prefix sums of the region sizes
-};
-__global__ void codebook_decode_region_kernel(const uint8_t* __restrict__ codes, long long plane_stride, int pitch,
-                                              int levels, int m, int C, const float* __restrict__ dconst,
-                                              const float* __restrict__ tables, const long long* __restrict__ toff,
-                                              float* __restrict__ out, const DecodeRegions rg) {
-    const int lane = threadIdx.x & 31;
-    const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    const int vec = C / 4;
-    for (long long t = warp; t < rg.start[rg.n]; t += nwarps) {
-        int a = 0;
-        while (t >= rg.start[a + 1]) ++a;
-        const long long local = t - rg.start[a];
-        const int w = rg.x1[a] - rg.x0[a];
-        const int yy = rg.y0[a] + static_cast<int>(local / w), xx = rg.x0[a] + static_cast<int>(local % w);
-        const long long r = rg.base[a] + static_cast<long long>(yy) * pitch + xx;
-        int code[kMaxLevels * kMaxSeg];
-        for (int i = 0; i < levels * m; ++i) code[i] = __ldg(codes + static_cast<long long>(i) * plane_stride + r);
-        for (int v = lane; v < vec; v += 32) {
-            float4 acc = __ldg(reinterpret_cast<const float4*>(dconst) + v);
-            for (int i = 0; i < levels * m; ++i) {
-                const float4 tv = __ldg(reinterpret_cast<const float4*>(tables + toff[i] +
-                                                                        static_cast<long long>(code[i]) * C) + v);
-                acc.x = __fadd_rn(acc.x, tv.x);
-                acc.y = __fadd_rn(acc.y, tv.y);
-                acc.z = __fadd_rn(acc.z, tv.z);
-                acc.w = __fadd_rn(acc.w, tv.w);
-            }
-            reinterpret_cast<float4*>(out + r * C)[v] = acc;
+template <int NT>
+__global__ void __launch_bounds__(1024, 1)
+codebook_decode_kernel(const uint8_t* __restrict__ codes, long long plane_stride, const float* __restrict__ dconst,
+                       const float* __restrict__ tables, float* __restrict__ out, const DecodeTables tb,
+                       const DecodeRegions rg) {
+    extern __shared__ float4 dsm4[];
+    float* s_tab = reinterpret_cast<float*>(dsm4);
+    const int split = blockIdx.x % tb.S;
+    const int group = blockIdx.x / tb.S, ngroups = gridDim.x / tb.S;
+    const int c0 = split * tb.Cs;
+    const int vec = tb.Cs / 4;
+    // stage this channel slice of every table (+ the constant as the last row)
+    const int s_const = tb.soff[NT - 1] + tb.k[NT - 1] * tb.Cs;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const float4* src = reinterpret_cast<const float4*>(tables + tb.toff[i] + c0);
+        float4* dst = reinterpret_cast<float4*>(s_tab + tb.soff[i]);
+        for (int idx = threadIdx.x; idx < tb.k[i] * vec; idx += blockDim.x) {
+            const int row = idx / vec, v = idx - row * vec;
+            dst[idx] = __ldg(src + static_cast<long long>(row) * (tb.C / 4) + v);
         }
+    }
+    for (int v = threadIdx.x; v < vec; v += blockDim.x)
+        reinterpret_cast<float4*>(s_tab + s_const)[v] = __ldg(reinterpret_cast<const float4*>(dconst + c0) + v);
+    __syncthreads();
+
+    constexpr int R = NT <= 3 ? 4 : (NT <= 6 ? 2 : 1);   // rows per warp iteration (loads / stores in flight)
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long total = rg.start[rg.n];
+    const long long nwarps = static_cast<long long>(ngroups) * wpb;
+    const long long wid = static_cast<long long>(group) * wpb + wib;
+    long long rowi[R];
+    int code[R][NT];
+    auto fetch = [&](long long t0) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            const long long t = t0 + rr;
+            rowi[rr] = (t < total) ? decode_row_of(rg, t) : -1;
+#pragma unroll
+            for (int i = 0; i < NT; ++i)
+                code[rr][i] = (rowi[rr] >= 0) ? __ldg(codes + static_cast<long long>(i) * plane_stride + rowi[rr]) : 0;
+        }
+    };
+    long long t0 = wid * R;
+    if (t0 < total) fetch(t0);
+    while (t0 < total) {
+        long long crow[R];
+        int soffs[R][NT];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) {
+            crow[rr] = rowi[rr];
+#pragma unroll
+            for (int i = 0; i < NT; ++i) soffs[rr][i] = tb.soff[i] + code[rr][i] * tb.Cs;
+        }
+        const long long tn = t0 + nwarps * R;
+        if (tn < total) fetch(tn);      // next iteration's codes are in flight while this one is gathered and stored
+        for (int v = lane; v < vec; v += 32) {
+            const float4 cst = reinterpret_cast<const float4*>(s_tab + s_const)[v];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) {
+                float4 a = cst;
+#pragma unroll
+                for (int i = 0; i < NT; ++i) {
+                    const float4 t = reinterpret_cast<const float4*>(s_tab + soffs[rr][i])[v];
+                    a.x = __fadd_rn(a.x, t.x);
+                    a.y = __fadd_rn(a.y, t.y);
+                    a.z = __fadd_rn(a.z, t.z);
+                    a.w = __fadd_rn(a.w, t.w);
+                }
+                if (crow[rr] >= 0) reinterpret_cast<float4*>(out + crow[rr] * tb.C + c0)[v] = a;
+            }
+        }
+        t0 = tn;
     }
 }
 
@@ -580,18 +621,77 @@ int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t*
     return dispatch_igemm<3>(cb->block_n, cb->bk, tmA, tmB, g, e, stream);
 }
 
-int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t* d_codes, float* d_out, void* stream_) {
-    QV2X_REQUIRE(cb && d_codes && d_out, "qv2x_codebook_decode: null argument");
-    if (rows <= 0) return 0;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int threads = 256;
-    const long long want = (rows * 32 + threads - 1) / threads;
-    const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 8));
-    codebook_decode_kernel<<<grid, threads, 0, stream>>>(d_codes, rows, cb->levels, cb->m, cb->C, cb->d_dconst,
-                                                          cb->d_tables, cb->d_toff, d_out);
+// Shared launcher of the two decode entry points.
+static int launch_decode(const qv2x_codebook* cb, long long plane_stride, const DecodeRegions& rg,
+                         const uint8_t* d_codes, float* d_out, cudaStream_t stream) {
+    const int nt = cb->levels * cb->m;
+    QV2X_REQUIRE(nt >= 1 && nt <= kMaxTables, "too many code planes");
+    QV2X_REQUIRE(cb->C % 4 == 0, "C must be a multiple of 4");
+    DecodeTables tb{};
+    tb.nt = nt;
+    tb.C = cb->C;
+    long long krows = 1;       // + the constant row
+    for (int l = 0; l < cb->levels; ++l)
+        for (int sgm = 0; sgm < cb->m; ++sgm) {
+            tb.k[l * cb->m + sgm] = cb->k[l];
+            tb.toff[l * cb->m + sgm] = cb->h_toff[l * cb->m + sgm];
+            krows += cb->k[l];
+        }
+    // smallest number of channel slices whose table slice fits in 200 KB (slice width a multiple of 4 floats)
+    int S = 0;
+    for (int cand = 1; cand <= cb->C / 4; ++cand) {
+        if (cb->C % (4 * cand) != 0) continue;
+        if (krows * (cb->C / cand) * 4 <= 200 * 1024) {
+            S = cand;
+            break;
+        }
+    }
+    QV2X_REQUIRE(S > 0 && S <= num_sms(), "decode tables do not fit in shared memory at any channel split");
+    tb.S = S;
+    tb.Cs = cb->C / S;
+    int off = 0;
+    for (int i = 0; i < nt; ++i) {
+        tb.soff[i] = off;
+        off += tb.k[i] * tb.Cs;
+    }
+    const int smem = static_cast<int>(krows * tb.Cs * 4);
+    const long long total = rg.start[rg.n];
+    const int threads = 1024;
+    // persistent: one CTA per SM, a whole number of slice groups; small inputs use fewer groups
+    const long long want_groups = (total + (threads / 32) * 4 - 1) / ((threads / 32) * 4);
+    const int groups = static_cast<int>(std::max<long long>(1, std::min<long long>(num_sms() / S, want_groups)));
+    const int grid = groups * S;
+#define QV2X_DECODE_CASE(N)                                                                                        \
+    case N: {                                                                                                      \
+        static bool attr = false;                                                                                  \
+        if (!attr) {                                                                                               \
+            QV2X_CUDA_OK(cudaFuncSetAttribute(codebook_decode_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              208 * 1024));                                                        \
+            attr = true;                                                                                           \
+        }                                                                                                          \
+        codebook_decode_kernel<N><<<grid, threads, smem, stream>>>(d_codes, plane_stride, cb->d_dconst, cb->d_tables, \
+                                                                   d_out, tb, rg);                                 \
+        break;                                                                                                     \
+    }
+    switch (nt) {
+        QV2X_DECODE_CASE(1) QV2X_DECODE_CASE(2) QV2X_DECODE_CASE(3) QV2X_DECODE_CASE(4) QV2X_DECODE_CASE(5)
+        QV2X_DECODE_CASE(6) QV2X_DECODE_CASE(7) QV2X_DECODE_CASE(8) QV2X_DECODE_CASE(9) QV2X_DECODE_CASE(10)
+        QV2X_DECODE_CASE(11) QV2X_DECODE_CASE(12) QV2X_DECODE_CASE(13) QV2X_DECODE_CASE(14) QV2X_DECODE_CASE(15)
+        QV2X_DECODE_CASE(16)
+    }
+#undef QV2X_DECODE_CASE
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int qv2x_codebook_decode(const qv2x_codebook* cb, long long rows, const uint8_t* d_codes, float* d_out, void* stream_) {
+    QV2X_REQUIRE(cb && d_codes && d_out, "qv2x_codebook_decode: null argument");
+    if (rows <= 0) return 0;
+    DecodeRegions rg{};
+    rg.n = 0;
+    rg.start[0] = rows;
+    return launch_decode(cb, rows, rg, d_codes, d_out, static_cast<cudaStream_t>(stream_));
 }
 
 int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride, int pitch, int n_regions,
@@ -600,27 +700,23 @@ int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride
     QV2X_REQUIRE(cb && base_row && rect && d_codes && d_out, "qv2x_codebook_decode_regions: null argument");
     QV2X_REQUIRE(n_regions >= 1 && n_regions <= 8, "1..8 regions");
     DecodeRegions rg{};
-    rg.n = n_regions;
+    rg.pitch = pitch;
     rg.start[0] = 0;
+    int n = 0;
     for (int a = 0; a < n_regions; ++a) {
-        rg.base[a] = base_row[a];
-        rg.y0[a] = rect[4 * a + 0];
-        rg.y1[a] = rect[4 * a + 1];
-        rg.x0[a] = rect[4 * a + 2];
-        rg.x1[a] = rect[4 * a + 3];
-        QV2X_REQUIRE(rg.y1[a] >= rg.y0[a] && rg.x1[a] >= rg.x0[a] && rg.x1[a] <= pitch, "bad region %d", a);
-        rg.start[a + 1] = rg.start[a] + static_cast<long long>(rg.y1[a] - rg.y0[a]) * (rg.x1[a] - rg.x0[a]);
+        const int y0 = rect[4 * a + 0], y1 = rect[4 * a + 1], x0 = rect[4 * a + 2], x1 = rect[4 * a + 3];
+        QV2X_REQUIRE(y1 >= y0 && x1 >= x0 && y0 >= 0 && x0 >= 0 && x1 <= pitch, "bad region %d", a);
+        if (y1 == y0 || x1 == x0) continue;     // empty regions are dropped (the row mapping divides by the width)
+        rg.base[n] = base_row[a];
+        rg.y0[n] = y0;
+        rg.x0[n] = x0;
+        rg.w[n] = x1 - x0;
+        rg.start[n + 1] = rg.start[n] + static_cast<long long>(y1 - y0) * (x1 - x0);
+        ++n;
     }
-    if (rg.start[n_regions] == 0) return 0;
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int threads = 256;
-    const long long want = (rg.start[n_regions] * 32 + threads - 1) / threads;
-    const int grid = static_cast<int>(std::min<long long>(want, static_cast<long long>(num_sms()) * 8));
-    codebook_decode_region_kernel<<<grid, threads, 0, stream>>>(d_codes, plane_stride, pitch, cb->levels, cb->m, cb->C,
-                                                                 cb->d_dconst, cb->d_tables, cb->d_toff, d_out, rg);
-    g_launch_count.fetch_add(1);
-    QV2X_CUDA_OK(cudaGetLastError());
-    return 0;
+    if (n == 0) return 0;
+    rg.n = n;
+    return launch_decode(cb, plane_stride, rg, d_codes, d_out, static_cast<cudaStream_t>(stream_));
 }
 
 long long qv2x_codebook_folded_size(const qv2x_codebook* cb, int which) {

@@ -25,8 +25,12 @@ struct FuseParams {
 };
 
 // One warp per output pixel; lane owns float4 chunks v = lane + 32*t of the channel vector.
-template <int MODE, int VPL /* float4 chunks per lane */>
-__global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ feat, float* __restrict__ out,
+// NA (agents) and VPL are compile-time so that every load of a pixel -- NA agents x 4 bilinear taps x VPL chunks --
+// is independent of every branch: out-of-image taps read a clamped address with weight 0 (adds +-0, exact), and
+// the compiler can keep all of an agent's loads (and the next agent's) in flight together.  The kernel is
+// HBM/L2-latency bound, so memory-level parallelism per warp is what sets its speed.
+template <int MODE, int NA, int VPL /* float4 chunks per lane */>
+__global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const float* __restrict__ feat, float* __restrict__ out,
                                                    const FuseParams p) {
     const int lane = threadIdx.x & 31;
     const long long warp = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -34,46 +38,54 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ fea
     const long long npix = static_cast<long long>(p.H) * p.W;
     const long long tpix = static_cast<long long>(p.th) * p.tw;
     const int vec = p.C / 4;
+    __shared__ float am[kMaxAgents][6];
+    if (threadIdx.x < NA * 6) am[threadIdx.x / 6][threadIdx.x % 6] = __ldg(p.aff + threadIdx.x);
+    __syncthreads();
     for (long long pix = warp; pix < tpix; pix += nwarps) {
         const int ti = static_cast<int>(pix / p.tw);
         const int i = p.y0 + ti, j = p.x0 + static_cast<int>(pix - static_cast<long long>(ti) * p.tw);
         const float xn = (2.f * j + 1.f) / p.W - 1.f;
         const float yn = (2.f * i + 1.f) / p.H - 1.f;
-        float4 xa[kMaxAgents][VPL];
+        float4 xa[NA][VPL];
 #pragma unroll
-        for (int a = 0; a < kMaxAgents; ++a) {
+        for (int a = 0; a < NA; ++a) {
+            const float xs = am[a][0] * xn + am[a][1] * yn + am[a][2];
+            const float ys = am[a][3] * xn + am[a][4] * yn + am[a][5];
+            const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
+            const float iy = ((ys + 1.f) * p.H - 1.f) * 0.5f;
+            // clamp far-away coordinates before the int conversion (every tap is out of the image there anyway)
+            const float fx = fminf(fmaxf(floorf(ix), -2.f), static_cast<float>(p.W) + 1.f);
+            const float fy = fminf(fmaxf(floorf(iy), -2.f), static_cast<float>(p.H) + 1.f);
+            const float tx = ix - fx, ty = iy - fy;
+            const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
+            const float4* base = reinterpret_cast<const float4*>(feat + static_cast<long long>(a) * npix * p.C);
+            float4 s[4][VPL];
+            float w[4];
 #pragma unroll
-            for (int t = 0; t < VPL; ++t) xa[a][t] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a < p.n) {
-                const float* m = p.aff + a * 6;
-                const float xs = __ldg(m + 0) * xn + __ldg(m + 1) * yn + __ldg(m + 2);
-                const float ys = __ldg(m + 3) * xn + __ldg(m + 4) * yn + __ldg(m + 5);
-                const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
-                const float iy = ((ys + 1.f) * p.H - 1.f) * 0.5f;
-                const float fx = floorf(ix), fy = floorf(iy);
-                const float tx = ix - fx, ty = iy - fy;
-                const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
-                const float* base = feat + static_cast<long long>(a) * npix * p.C;
+            for (int tap = 0; tap < 4; ++tap) {
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                const bool inb = (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H);
+                const float wt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
+                w[tap] = inb ? wt : 0.f;
+                const int xc = min(max(xx, 0), p.W - 1), yc = min(max(yy, 0), p.H - 1);
+                const float4* src = base + (static_cast<long long>(yc) * p.W + xc) * vec;
+#pragma unroll
+                for (int t = 0; t < VPL; ++t) {
+                    const int v = lane + 32 * t;
+                    s[tap][t] = (v < vec) ? __ldg(src + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) {
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int tap = 0; tap < 4; ++tap) {
-                    const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-                    const float w = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
-                    if (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H) {
-                        const float4* src =
-                            reinterpret_cast<const float4*>(base + (static_cast<long long>(yy) * p.W + xx) * p.C);
-#pragma unroll
-                        for (int t = 0; t < VPL; ++t) {
-                            const int v = lane + 32 * t;
-                            if (v < vec) {
-                                const float4 s = __ldg(src + v);
-                                xa[a][t].x += w * s.x;
-                                xa[a][t].y += w * s.y;
-                                xa[a][t].z += w * s.z;
-                                xa[a][t].w += w * s.w;
-                            }
-                        }
-                    }
+                    acc.x = fmaf(w[tap], s[tap][t].x, acc.x);
+                    acc.y = fmaf(w[tap], s[tap][t].y, acc.y);
+                    acc.z = fmaf(w[tap], s[tap][t].z, acc.z);
+                    acc.w = fmaf(w[tap], s[tap][t].w, acc.w);
                 }
+                xa[a][t] = acc;
             }
         }
         float4 o[VPL];
@@ -81,55 +93,49 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ fea
 #pragma unroll
             for (int t = 0; t < VPL; ++t) o[t] = xa[0][t];
 #pragma unroll
-            for (int a = 1; a < kMaxAgents; ++a)
-                if (a < p.n) {
+            for (int a = 1; a < NA; ++a) {
 #pragma unroll
-                    for (int t = 0; t < VPL; ++t) {
-                        o[t].x = fmaxf(o[t].x, xa[a][t].x);
-                        o[t].y = fmaxf(o[t].y, xa[a][t].y);
-                        o[t].z = fmaxf(o[t].z, xa[a][t].z);
-                        o[t].w = fmaxf(o[t].w, xa[a][t].w);
-                    }
+                for (int t = 0; t < VPL; ++t) {
+                    o[t].x = fmaxf(o[t].x, xa[a][t].x);
+                    o[t].y = fmaxf(o[t].y, xa[a][t].y);
+                    o[t].z = fmaxf(o[t].z, xa[a][t].z);
+                    o[t].w = fmaxf(o[t].w, xa[a][t].w);
                 }
+            }
         } else {
-            float sc[kMaxAgents];
+            float sc[NA];
             float mx = -INFINITY;
 #pragma unroll
-            for (int a = 0; a < kMaxAgents; ++a) {
-                sc[a] = -INFINITY;
-                if (a < p.n) {
-                    float d = 0.f;
+            for (int a = 0; a < NA; ++a) {
+                float d = 0.f;
 #pragma unroll
-                    for (int t = 0; t < VPL; ++t)
-                        d += xa[0][t].x * xa[a][t].x + xa[0][t].y * xa[a][t].y + xa[0][t].z * xa[a][t].z +
-                             xa[0][t].w * xa[a][t].w;
+                for (int t = 0; t < VPL; ++t)
+                    d += xa[0][t].x * xa[a][t].x + xa[0][t].y * xa[a][t].y + xa[0][t].z * xa[a][t].z +
+                         xa[0][t].w * xa[a][t].w;
 #pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-                    sc[a] = d * p.inv_sqrt_c;
-                    mx = fmaxf(mx, sc[a]);
-                }
+                for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
+                sc[a] = d * p.inv_sqrt_c;
+                mx = fmaxf(mx, sc[a]);
             }
             float den = 0.f;
 #pragma unroll
-            for (int a = 0; a < kMaxAgents; ++a)
-                if (a < p.n) {
-                    sc[a] = expf(sc[a] - mx);
-                    den += sc[a];
-                }
+            for (int a = 0; a < NA; ++a) {
+                sc[a] = expf(sc[a] - mx);
+                den += sc[a];
+            }
 #pragma unroll
             for (int t = 0; t < VPL; ++t) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int a = 0; a < kMaxAgents; ++a)
-                if (a < p.n) {
-                    const float w = sc[a] / den;
+            for (int a = 0; a < NA; ++a) {
+                const float w = sc[a] / den;
 #pragma unroll
-                    for (int t = 0; t < VPL; ++t) {
-                        o[t].x += w * xa[a][t].x;
-                        o[t].y += w * xa[a][t].y;
-                        o[t].z += w * xa[a][t].z;
-                        o[t].w += w * xa[a][t].w;
-                    }
+                for (int t = 0; t < VPL; ++t) {
+                    o[t].x += w * xa[a][t].x;
+                    o[t].y += w * xa[a][t].y;
+                    o[t].z += w * xa[a][t].z;
+                    o[t].w += w * xa[a][t].w;
                 }
+            }
         }
         float4* dst = reinterpret_cast<float4*>(out + pix * p.C);
 #pragma unroll
@@ -137,6 +143,21 @@ __global__ void __launch_bounds__(256) fuse_kernel(const float* __restrict__ fea
             const int v = lane + 32 * t;
             if (v < vec) dst[v] = o[t];
         }
+    }
+}
+
+template <int MODE, int VPL>
+static void launch_fuse(int n, int grid, int threads, cudaStream_t stream, const float* feat, float* out,
+                        const FuseParams& p) {
+    switch (n) {
+        case 1: fuse_kernel<MODE, 1, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 2: fuse_kernel<MODE, 2, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 3: fuse_kernel<MODE, 3, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 4: fuse_kernel<MODE, 4, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 5: fuse_kernel<MODE, 5, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 6: fuse_kernel<MODE, 6, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 7: fuse_kernel<MODE, 7, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        default: fuse_kernel<MODE, 8, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
     }
 }
 
@@ -295,13 +316,15 @@ int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_f
     const int grid = static_cast<int>(std::min<long long>((npix * 32 + threads - 1) / threads,
                                                           static_cast<long long>(num_sms()) * 8));
     const int vpl = (C / 4 + 31) / 32;
-#define QV2X_FUSE(M, V) fuse_kernel<M, V><<<grid, threads, 0, stream>>>(d_feat, d_out, p)
     if (mode == 0) {
-        if (vpl == 1) QV2X_FUSE(0, 1); else if (vpl == 2) QV2X_FUSE(0, 2); else QV2X_FUSE(0, 4);
+        if (vpl == 1) launch_fuse<0, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else if (vpl == 2) launch_fuse<0, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else launch_fuse<0, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
     } else {
-        if (vpl == 1) QV2X_FUSE(1, 1); else if (vpl == 2) QV2X_FUSE(1, 2); else QV2X_FUSE(1, 4);
+        if (vpl == 1) launch_fuse<1, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else if (vpl == 2) launch_fuse<1, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else launch_fuse<1, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
     }
-#undef QV2X_FUSE
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
