@@ -45,6 +45,9 @@ long long qv2x_launch_count(void);
 /* Bring-up / profiling knobs for the igemm kernels (0 = normal operation): 1 skip the epilogue math and stores,
  * 2 skip MMA issue, 4 skip activation (A) loads, 8 skip weight (B) loads.  Results are garbage when non-zero. */
 void qv2x_set_debug_flags(int flags);
+/* Bring-up: when d_buf != NULL the conv kernels record clock64 stamps per CTA / tile / role into
+ * d_buf[grid][32 tiles][16 slots] (int64, device memory owned by the caller); NULL switches it off. */
+void qv2x_debug_trace(long long* d_buf);
 
 /* ------------------------------------------------------------------------------------------------
  * One quantized layer = reference QuantModule.forward (opencood/quant/quant_layer.py:391-410) with

@@ -151,6 +151,8 @@ def _declare_tiles(lib):
                                                  c_void_p, c_void_p]
     lib.qv2x_set_debug_flags.argtypes = [c_int]
     lib.qv2x_set_debug_flags.restype = None
+    lib.qv2x_debug_trace.argtypes = [c_void_p]
+    lib.qv2x_debug_trace.restype = None
 
 
 _DECLARERS.append(_declare_tiles)

@@ -24,7 +24,8 @@ struct EncodeEpilogue {
     static constexpr int kColSplit = 2;    // two epilogue warps per row quadrant, merged at the end of a level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
     static constexpr bool kCoopTileSetup = false;
-    static constexpr bool kPipelined8 = false;
+    static constexpr bool kSeqDrain = false;
+    static constexpr bool kPrefetchNextTile = false;
     int levels, m;
     int k[kMaxLevels];            // codewords per segment
     int n_level[kMaxLevels];      // m * k
@@ -47,9 +48,12 @@ struct EncodeEpilogue {
         int code[kMaxLevels][kMaxSeg];
     };
 
+    struct Prefetch {};
     __device__ __forceinline__ void tile_setup(const IgemmGeom&, const TileCoord&, int, int, uint8_t*) const {}
+    __device__ __forceinline__ void prefetch(Prefetch&, const IgemmGeom&, const TileCoord&, int) const {}
 
-    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row, uint8_t*) const {
+    __device__ __forceinline__ void begin(Tile& ts, const Prefetch&, const IgemmGeom& g, const TileCoord& tc, int row,
+                                          uint8_t*) const {
         ts.r = static_cast<long long>(tc.tx) * g.tw + row;
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {

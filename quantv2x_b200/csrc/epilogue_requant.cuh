@@ -20,7 +20,8 @@ struct RequantEpilogue {
     static constexpr int kColSplit = 2;
     static constexpr int kMaxStages = 8;
     static constexpr bool kCoopTileSetup = true;
-    static constexpr bool kPipelined8 = (G > 1);
+    static constexpr bool kSeqDrain = (G > 1);     // groups are drained one by one into fp32 partial sums
+    static constexpr bool kPrefetchNextTile = (G == 1);
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
@@ -48,6 +49,12 @@ struct RequantEpilogue {
         const int32_t* sm_zpw;
         int n_base;              // first global column of the tile
     };
+    // Receptive-field input sums of ONE tile row, as raw loads: issued one tile ahead (G == 1) so that their
+    // L2 latency never sits on the epilogue's critical path.
+    static constexpr int kMaxTaps = 9;
+    struct Prefetch {
+        int32_t v[G][kMaxTaps];
+    };
 
     // Shared-memory layout of the staged parameters (<= 256 columns): cs | bias | zpw, 1 KB each.
     __device__ __forceinline__ void tile_setup(const IgemmGeom& g, const TileCoord& tc, int tid, int nthreads,
@@ -63,114 +70,159 @@ struct RequantEpilogue {
         }
     }
 
-    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
-                                          uint8_t* scratch) const {
+    __device__ __forceinline__ void prefetch(Prefetch& pf, const IgemmGeom& g, const TileCoord& tc, int row) const {
+        const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;      // tw is a power of two
+        const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
+        const bool valid = (ox < g.Wo) && (oy < g.Ho);
+        const int taps_h = g.taps_h;               // taps are at most 3 x 3
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) {
+            const int32_t* rs = rowsum_in[grp];
+            if (rs != nullptr) rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    int32_t v = 0;
+                    const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
+                    if (rs != nullptr && valid && ky < taps_h && kx < g.taps_w && iy >= 0 && iy < g.Hi && ix >= 0 &&
+                        ix < g.Wi)
+                        v = __ldg(rs + iy * g.Wi + ix);
+                    pf.v[grp][ky * 3 + kx] = v;
+                }
+            }
+        }
+    }
+
+    __device__ __forceinline__ void begin(Tile& ts, const Prefetch& pf, const IgemmGeom& g, const TileCoord& tc,
+                                          int row, uint8_t* scratch) const {
         ts.sm_cs = reinterpret_cast<const float*>(scratch);
         ts.sm_bias = ts.sm_cs + 256;
         ts.sm_zpw = reinterpret_cast<const int32_t*>(ts.sm_bias + 256);
         ts.n_base = tc.nt * g.block_n;
-        const int lx = row % g.tw, ly = row / g.tw;
+        const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;
         const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
         const bool valid = (ox < g.Wo) && (oy < g.Ho);
         ts.rsum = 0;
         ts.opix = -1;
         ts.mrow = -1;
 #pragma unroll
-        for (int grp = 0; grp < G; ++grp) ts.S[grp] = 0;
-        if (!valid) return;
-        ts.mrow = (static_cast<long long>(tc.img) * g.Ho + oy) * g.Wo + ox;
-#pragma unroll
         for (int grp = 0; grp < G; ++grp) {
-            if (rowsum_in[grp] == nullptr) continue;
-            const int32_t* rs = rowsum_in[grp] + static_cast<long long>(tc.img) * g.Hi * g.Wi;
+            // The empty volatile asm pins the first use of each prefetched value HERE (volatile asm statements keep
+            // their order): otherwise the compiler folds the sum into the iteration that issued the loads and the
+            // epilogue stalls on their L2 latency every tile.
             int32_t s = 0;
-            for (int tap = 0; tap < g.taps; ++tap) {
-                const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
-                const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
-                if (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi) s += __ldg(rs + iy * g.Wi + ix);
+#pragma unroll
+            for (int tap = 0; tap < kMaxTaps; ++tap) {
+                int32_t x = pf.v[grp][tap];
+                asm volatile("" : "+r"(x));
+                s += x;
             }
             ts.S[grp] = s;
         }
+        if (!valid) return;
+        ts.mrow = (static_cast<long long>(tc.img) * g.Ho + oy) * g.Wo + ox;
         // an N tile never straddles two sub-positions (BLOCK_N divides cout_sub)
-        const int sub = (tc.nt * g.block_n) / cout_sub;
-        const int dy = sub / up, dx = sub - dy * up;
+        int dy = 0, dx = 0;
+        if (up > 1) {
+            const int sub = (tc.nt * g.block_n) / cout_sub;
+            dy = sub / up;
+            dx = sub - dy * up;
+        }
         ts.opix = (static_cast<long long>(tc.img) * Hout + oy * up + dy) * Wout + ox * up + dx;
     }
 
+    // Per-column parameters of W consecutive columns from shared memory: warp-uniform 16-byte loads (broadcast).
     template <int W>
-    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int n0,
-                                          const int32_t (*acc)[W]) const {
+    __device__ __forceinline__ void load_zw(const Tile& ts, int nl, int32_t (&zw)[W]) const {
+#pragma unroll
+        for (int v4 = 0; v4 < W / 4; ++v4) {
+            const int4 z = *(reinterpret_cast<const int4*>(ts.sm_zpw + nl) + v4);
+            zw[4 * v4 + 0] = z.x, zw[4 * v4 + 1] = z.y, zw[4 * v4 + 2] = z.z, zw[4 * v4 + 3] = z.w;
+        }
+    }
+
+    // One accumulator group of W columns -> running fp32 sum v (normative order: groups left to right).
+    template <int W>
+    __device__ __forceinline__ void accum(const Tile& ts, const IgemmGeom& g, int grp, int n0, const int32_t (&acc)[W],
+                                          float (&v)[W]) const {
+        const bool use_zp = (zpw[0] != nullptr);
+        int32_t t[W];
+        if (use_zp) {
+            int32_t zw[W];
+            load_zw<W>(ts, n0 - ts.n_base, zw);
+            int32_t sg = 0;
+#pragma unroll
+            for (int q = 0; q < G; ++q)
+                if (q == grp) sg = ts.S[q];
+#pragma unroll
+            for (int j = 0; j < W; ++j) t[j] = acc[j] - zw[j] * sg;
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) t[j] = acc[j];
+        }
+        if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
+            const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+#pragma unroll
+            for (int j = 0; j < W; ++j) acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t[j];
+        }
+        float gs = 1.f;
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+            if (q == grp) gs = gscale[q];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const float tf = __int2float_rn(t[j]);
+            const float term = (G == 1) ? tf : __fmul_rn(gs, tf);   // gscale[0] == 1 when G == 1
+            v[j] = (grp == 0) ? term : __fadd_rn(v[j], term);
+        }
+    }
+
+    // v (the scaled accumulator sum) -> bias, ReLU, output quantization, packed store of W bytes.
+    template <int W>
+    __device__ __forceinline__ void finish(Tile& ts, int n0, const float (&v)[W]) const {
         static_assert(W == 8 || W == 16, "chunk width");
-        (void)tc;
-        (void)step;
         uint32_t packed[W / 4] = {};
         unsigned rsum = 0;
-        // per-column parameters from shared memory: warp-uniform 16-byte loads (broadcast)
         float cs[W], bs[W];
-        int32_t zw[W];
         const int nl = n0 - ts.n_base;
 #pragma unroll
         for (int v4 = 0; v4 < W / 4; ++v4) {
             const float4 c = *(reinterpret_cast<const float4*>(ts.sm_cs + nl) + v4);
             const float4 b = *(reinterpret_cast<const float4*>(ts.sm_bias + nl) + v4);
-            const int4 z = *(reinterpret_cast<const int4*>(ts.sm_zpw + nl) + v4);
             cs[4 * v4 + 0] = c.x, cs[4 * v4 + 1] = c.y, cs[4 * v4 + 2] = c.z, cs[4 * v4 + 3] = c.w;
             bs[4 * v4 + 0] = b.x, bs[4 * v4 + 1] = b.y, bs[4 * v4 + 2] = b.z, bs[4 * v4 + 3] = b.w;
-            zw[4 * v4 + 0] = z.x, zw[4 * v4 + 1] = z.y, zw[4 * v4 + 2] = z.z, zw[4 * v4 + 3] = z.w;
         }
-        if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
-            const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
-#pragma unroll
-            for (int grp = 0; grp < G; ++grp)
-#pragma unroll
-                for (int j = 0; j < W; ++j) {
-                    int32_t t = acc[grp][j];
-                    if (zpw[grp] != nullptr) t -= zw[j] * ts.S[grp];
-                    acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t;
-                }
-        }
-        const bool use_zp = (zpw[0] != nullptr);
         if (fast8) {
             // q = sat_u8(rint(y / delta)) for an 8-bit output with zero-point 0 (ReLU is subsumed by the clamp),
             // entirely on the FMA/ALU pipes:
             //   t = y * fl(1/delta) lies within 5.4e-5 of the IEEE quotient for |q| < 300, so both round to the same
             //   integer unless t is within 1e-4 of a half-integer -- only then (~2e-4 of elements) the exact division
-            //   runs.  r = (t + 1.5*2^23) - 1.5*2^23 is rint(t) (round-half-even) for |t| < 2^22; after the clamp,
-            //   (r + 2^23) carries the byte in its low mantissa bits.
+            //   runs.  The clamp is applied to t (to [-0.25, 255.25], which rounds to 0 / 255 and is never "near"),
+            //   and s = t + 1.5*2^23 carries rint(t) (round-half-even) in its low mantissa byte.
             uint32_t bits[W];
-            float rr[W];
-            uint32_t nearmask = 0;
-            auto real_value = [&](int j) -> float {
-                float v = 0.f;
+            float y[W];
+            float worst = 0.f;
 #pragma unroll
-                for (int grp = 0; grp < G; ++grp) {
-                    int32_t t = acc[grp][j];
-                    if (use_zp) t -= zw[j] * ts.S[grp];
-                    const float tf = __int2float_rn(t);
-                    const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);   // gscale[0] == 1 when G == 1
-                    v = (grp == 0) ? term : __fadd_rn(v, term);
+            for (int j = 0; j < W; ++j) {
+                y[j] = __fadd_rn(__fmul_rn(v[j], cs[j]), bs[j]);
+                const float t = fminf(fmaxf(__fmul_rn(y[j], rdelta), -0.25f), 255.25f);
+                const float sft = __fadd_rn(t, 12582912.0f);
+                const float r = __fadd_rn(sft, -12582912.0f);
+                worst = fmaxf(worst, fabsf(__fadd_rn(t, -r)));
+                bits[j] = __float_as_uint(sft);
+            }
+            // rare: exact IEEE division for the elements that sit next to a rounding boundary
+            if (worst > 0.4999f) {
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    const float t = fminf(fmaxf(__fmul_rn(y[j], rdelta), -0.25f), 255.25f);
+                    const float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
+                    if (fabsf(__fadd_rn(t, -r)) > 0.4999f) {
+                        const float q = fminf(fmaxf(rintf(__fdiv_rn(y[j], delta_out)), 0.f), 255.f);
+                        bits[j] = __float_as_uint(__fadd_rn(q, 12582912.0f));
+                    }
                 }
-                return __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
-            };
-            // phase 1, branch-free so the 16 independent chains interleave
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const float t = __fmul_rn(real_value(j), rdelta);
-                const float r = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);
-                const bool near = (fabsf(__fadd_rn(t, -r)) > 0.4999f) && (fabsf(t) < 300.f);
-                nearmask |= (near ? 1u : 0u) << j;
-                rr[j] = r;
-            }
-            // phase 2, rare: exact IEEE division for the elements that sit next to a rounding boundary
-            if (nearmask != 0) {
-#pragma unroll
-                for (int j = 0; j < W; ++j)
-                    if ((nearmask >> j) & 1u) rr[j] = rintf(__fdiv_rn(real_value(j), delta_out));
-            }
-#pragma unroll
-            for (int j = 0; j < W; ++j) {
-                const float r = fminf(fmaxf(rr[j], 0.f), 255.f);
-                bits[j] = __float_as_uint(__fadd_rn(r, 8388608.0f));
             }
 #pragma unroll
             for (int w = 0; w < W / 4; ++w) {
@@ -182,16 +234,7 @@ struct RequantEpilogue {
         } else {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                float v = 0.f;
-#pragma unroll
-                for (int grp = 0; grp < G; ++grp) {
-                    int32_t t = acc[grp][j];
-                    if (use_zp) t -= zw[j] * ts.S[grp];
-                    const float tf = __int2float_rn(t);
-                    const float term = (G == 1) ? tf : __fmul_rn(gscale[grp], tf);
-                    v = (grp == 0) ? term : __fadd_rn(v, term);
-                }
-                float y = __fadd_rn(__fmul_rn(v, cs[j]), bs[j]);
+                float y = __fadd_rn(__fmul_rn(v[j], cs[j]), bs[j]);
                 if (relu) y = fmaxf(y, 0.f);
                 // A zero dividend would send the whole warp through the division's slow path: divide
                 // delta/delta instead and mask.
@@ -213,6 +256,17 @@ struct RequantEpilogue {
                 st_global_v2(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1]);
             ts.rsum += static_cast<int>(rsum);
         }
+    }
+
+    // G == 1 convenience: one chunk straight from the accumulator to the output.
+    template <int W>
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int n0,
+                                          const int32_t (*acc)[W]) const {
+        (void)tc;
+        (void)step;
+        float v[W];
+        accum<W>(ts, g, 0, n0, acc[0], v);
+        finish<W>(ts, n0, v);
     }
 
     __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int, int, int, int,

@@ -23,6 +23,7 @@ int set_error(int code, const char* fmt, ...) {
 
 std::atomic<long long> g_launch_count{0};
 int g_debug_flags = 0;
+long long* g_trace_ptr = nullptr;
 
 int num_sms() {
     static int n = 0;
@@ -79,6 +80,7 @@ const char* qv2x_last_error(void) { return qv2x::last_error_ref().c_str(); }
 int qv2x_version(void) { return 100; }
 long long qv2x_launch_count(void) { return qv2x::g_launch_count.load(); }
 void qv2x_set_debug_flags(int flags) { qv2x::g_debug_flags = flags; }
+void qv2x_debug_trace(long long* d_buf) { qv2x::g_trace_ptr = d_buf; }
 
 int qv2x_device_check(int device) {
     cudaDeviceProp prop;

@@ -18,6 +18,7 @@ std::string& last_error_ref();
 int set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_launch_count;
 extern int g_debug_flags;
+extern long long* g_trace_ptr;   // device buffer for igemm role timelines (qv2x_debug_trace), or nullptr
 int num_sms();
 
 #define QV2X_CUDA_OK(expr)                                                                            \

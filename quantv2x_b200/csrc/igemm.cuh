@@ -30,7 +30,8 @@ struct IgemmGeom {
     // A source image extent (pixels) -- used by epilogues that need input-side bounds
     int Hi, Wi;
     // taps and K structure
-    int taps, taps_w, stride, pad;
+    int taps, taps_w, taps_h, stride, pad;
+    int tw_shift;                // log2(tw)
     int groups, cblocks;
     int a_c_base[kMaxGroups];    // channel coordinate of the group's first k-block in the A tensor
     int b_row_base[kMaxGroups];  // row coordinate of the group's first output column in the B tensor
@@ -40,11 +41,18 @@ struct IgemmGeom {
     // Sequential N steps per tile (1 for conv layers).  A tile visits its steps in order on ONE CTA, so an
     // epilogue may carry state from step to step (the codebook's level-by-level argmin).  B rows of
     // (step, group) start at b_row_base[g] + step_row_base[step] + g * step_group_stride[step].
+    long long* trace;   // optional [grid][kTraceTiles][16] clock64 stamps per role (qv2x_debug_trace), else nullptr
     int debug;   // bring-up knobs (qv2x_set_debug_flags): 1 skip epilogue math, 2 skip MMA issue, 4 skip A loads, 8 skip B loads
     int n_steps;
     int step_row_base[kMaxSteps];
     int step_group_stride[kMaxSteps];
 };
+
+constexpr int kTraceTiles = 32;
+__device__ __forceinline__ void trace_stamp(const IgemmGeom& g, int tile_local, int slot) {
+    if (g.trace != nullptr && tile_local < kTraceTiles)
+        g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tile_local) * 16 + slot] = clock64();
+}
 
 constexpr int kEpiSmemBytes = 8192;   // scratch handed to the epilogue functor (cross-warp merges)
 
@@ -80,16 +88,23 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 // Epilogue contract:
 //   struct Epi {
 //     struct Tile;                                     // per-thread, per-tile state
+//     struct Prefetch;                                 // per-thread side inputs of a tile, loaded ahead of time
 //     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
 //     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
-//     static constexpr bool kCoopTileSetup;            // stage per-tile parameters in shared memory first
+//     static constexpr bool kCoopTileSetup;            // stage per-column parameters in shared memory
+//     static constexpr bool kSeqDrain;                 // G > 1: accumulator groups are drained one by one
+//     static constexpr bool kPrefetchNextTile;         // issue prefetch() one tile ahead
 //     __device__ void tile_setup(const IgemmGeom&, const TileCoord&, int tid, int nthreads, uint8_t* scratch) const;
-//     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row, uint8_t* scratch) const;
-//         -- called BEFORE the accumulators are ready (prefetch side inputs here)
-//     static constexpr bool kPipelined8;               // G > 1: double-buffered 8-column chunks
+//     __device__ void prefetch(Prefetch&, const IgemmGeom&, const TileCoord&, int row) const;
+//     __device__ void begin(Tile&, const Prefetch&, const IgemmGeom&, const TileCoord&, int row, uint8_t* scratch) const;
+//         -- called BEFORE the accumulators are ready
 //     template <int W> __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
 //                           const int32_t (*acc)[W]) const;
-//         -- W (8 or 16) consecutive columns [col0, col0+W) of this thread's row in `step`, acc[g][j]
+//         -- W consecutive columns [col0, col0+W) of this thread's row in `step`, acc[g][j] (all groups at once)
+//     kSeqDrain only:
+//     template <int W> __device__ void accum(const Tile&, const IgemmGeom&, int grp, int col0, const int32_t (&acc)[W],
+//                           float (&v)[W]) const;      -- fold group grp's accumulators into the running sum v
+//     template <int W> __device__ void finish(Tile&, int col0, const float (&v)[W]) const;
 //     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step, int part, int quad, int lane,
 //                              uint8_t* scratch) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
@@ -149,8 +164,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int tl = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
                 const TileCoord tc = decode_tile(g, t);
+                trace_stamp(g, tl, 0);
+                long long waited = 0;
                 const int x0 = tc.tx * g.tw * g.stride - g.pad;
                 const int y0 = tc.ty * g.th * g.stride - g.pad;
                 for (int step = 0; step < g.n_steps; ++step) {
@@ -160,7 +178,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         for (int tap0 = 0; tap0 < g.taps; tap0 += TPS) {
                             for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
                                 const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                                if (g.trace != nullptr) {
+                                    const long long w0 = clock64();
+                                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                                    waited += clock64() - w0;
+                                } else {
+                                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
+                                }
                                 const uint32_t fb = smem_u32(&full_bar[s]);
                                 mbar_expect_tx(fb, ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile));
                                 uint8_t* st = smem + s * Cfg::kStageBytes;
@@ -179,22 +203,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         }
                     }
                 }
+                trace_stamp(g, tl, 1);
+                if (g.trace != nullptr && tl < kTraceTiles)
+                    g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 14] = waited;
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t it = 0, ac = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            int tl = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+                trace_stamp(g, tl, 2);
+                long long waited = 0;
                 for (int sg = 0; sg < g.n_steps * G; ++sg, ++ac) {
                     const uint32_t slot = ac % kSlots, aph = (ac / kSlots) & 1;
                     mbar_wait(smem_u32(&tempty_bar[slot]), aph ^ 1);
                     tcgen05_fence_after();
+                    if (sg == 0) trace_stamp(g, tl, 3);
                     const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
                     for (int kb = 0; kb < kblocks_per_group; ++kb, ++it) {
                         const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        mbar_wait(smem_u32(&full_bar[s]), ph);
+                        if (g.trace != nullptr) {
+                            const long long w0 = clock64();
+                            mbar_wait(smem_u32(&full_bar[s]), ph);
+                            waited += clock64() - w0;
+                        } else {
+                            mbar_wait(smem_u32(&full_bar[s]), ph);
+                        }
                         tcgen05_fence_after();
+                        if (sg == 0 && kb == 0) trace_stamp(g, tl, 4);
                         const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
                         if (!(g.debug & 2)) {
 #pragma unroll
@@ -212,6 +250,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     umma_commit(smem_u32(&tfull_bar[slot]));
                 }
+                trace_stamp(g, tl, 5);
+                if (g.trace != nullptr && tl < kTraceTiles)
+                    g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 15] = waited;
             }
         }
     } else if (warp >= 4) {
@@ -223,25 +264,85 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t ac = 0;
         uint32_t tile_par = 0;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_par ^= 1) {
+        int staged_nt[2] = {-1, -1};          // which column tile's parameters each scratch half currently holds
+        typename Epi::Prefetch pf;
+        if constexpr (Epi::kPrefetchNextTile) {
+            if (static_cast<int>(blockIdx.x) < total_tiles) epi.prefetch(pf, g, decode_tile(g, blockIdx.x), row);
+        }
+        int tl = 0;
+        const bool tracer = (lane == 0 && quad == 0);
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_par ^= 1, ++tl) {
             const TileCoord tc = decode_tile(g, t);
+            if (tracer) trace_stamp(g, tl, part == 0 ? 6 : 11);
             typename Epi::Tile ts;
             uint8_t* scratch = epi_scratch + (Epi::kCoopTileSetup ? tile_par * (kEpiSmemBytes / 2) : 0);
             if constexpr (Epi::kCoopTileSetup) {
-                // all epilogue threads stage this tile's per-column parameters in shared memory (double-buffered
-                // by tile parity, so one named barrier per tile is enough)
-                epi.tile_setup(g, tc, static_cast<int>(threadIdx.x) - 128, kNumEpiWarps * 32, scratch);
-                asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+                // all epilogue threads stage this tile's per-column parameters in shared memory, double-buffered by
+                // tile parity; a half that already holds this column tile (always, when the layer has one column
+                // tile) is reused without any synchronisation
+                if (staged_nt[tile_par] != tc.nt) {
+                    asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // readers of the old content
+                    epi.tile_setup(g, tc, static_cast<int>(threadIdx.x) - 128, kNumEpiWarps * 32, scratch);
+                    asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
+                    staged_nt[tile_par] = tc.nt;
+                }
             }
-            epi.begin(ts, g, tc, row, scratch);
+            if constexpr (!Epi::kPrefetchNextTile) epi.prefetch(pf, g, tc, row);
+            epi.begin(ts, pf, g, tc, row, scratch);
+            if constexpr (Epi::kPrefetchNextTile) {
+                if (t + static_cast<int>(gridDim.x) < total_tiles)
+                    epi.prefetch(pf, g, decode_tile(g, t + gridDim.x), row);
+            }
+            if (tracer && part == 0) trace_stamp(g, tl, 7);
             for (int step = 0; step < g.n_steps; ++step, ac += G) {
+                const int c_begin = part * kColsPerWarp, c_end = (part + 1) * kColsPerWarp;
+                if constexpr (Epi::kSeqDrain) {
+                    // Accumulator groups are drained in order as soon as each is complete: group g's TMEM slot is
+                    // released right after it has been folded into the fp32 running sums (registers), so the MMAs
+                    // of the following groups / tiles never wait for a whole tile's epilogue.
+                    static_assert(kColsPerWarp % 32 == 0, "sequential drain works on 32-column pairs of chunks");
+                    float vsum[kColsPerWarp / 16][16];
+#pragma unroll
+                    for (int grp = 0; grp < G; ++grp) {
+                        const uint32_t a = ac + grp;
+                        mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
+                        tcgen05_fence_after();
+                        const uint32_t tbase = tmem_base + lane_base + (a % kSlots) * BLOCK_N + c_begin;
+                        uint32_t acc_a[16], acc_b[16];
+                        tmem_ld_x16(tbase, acc_a);
+#pragma unroll
+                        for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
+                            tmem_ld_wait();
+                            tmem_ld_x16(tbase + c0 + 16, acc_b);
+                            if (!(g.debug & 1)) {
+                                const int n0 = tc.nt * BLOCK_N + c_begin + c0;
+                                epi.template accum<16>(ts, g, grp, n0, reinterpret_cast<const int32_t(&)[16]>(acc_a),
+                                                       vsum[c0 / 16]);
+                                if (grp == G - 1) epi.template finish<16>(ts, n0, vsum[c0 / 16]);
+                            }
+                            tmem_ld_wait();
+                            if (c0 + 32 < kColsPerWarp) tmem_ld_x16(tbase + c0 + 32, acc_a);
+                            if (!(g.debug & 1)) {
+                                const int n0 = tc.nt * BLOCK_N + c_begin + c0 + 16;
+                                epi.template accum<16>(ts, g, grp, n0, reinterpret_cast<const int32_t(&)[16]>(acc_b),
+                                                       vsum[c0 / 16 + 1]);
+                                if (grp == G - 1) epi.template finish<16>(ts, n0, vsum[c0 / 16 + 1]);
+                            }
+                        }
+                        tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a % kSlots]));
+                    }
+                    epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
+                    continue;
+                }
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp) {
                     const uint32_t a = ac + grp;
                     mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
                 }
                 tcgen05_fence_after();
-                const int c_begin = part * kColsPerWarp, c_end = (part + 1) * kColsPerWarp;
+                if (tracer && step == 0) trace_stamp(g, tl, part == 0 ? 8 : 12);
                 if constexpr (G == 1 && (kColsPerWarp % 32 == 0)) {
                     // software-pipelined TMEM reads: the load of chunk i+1 is in flight while chunk i is processed
                     const uint32_t tbase = tmem_base + lane_base + (ac % kSlots) * BLOCK_N;
@@ -259,28 +360,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 16,
                                                    reinterpret_cast<const int32_t(*)[16]>(acc_b));
                     }
-                } else if constexpr (Epi::kPipelined8) {
-                    // G accumulators per column: 8-column chunks, double-buffered, so the TMEM reads of the next chunk
-                    // overlap the math of the current one within the same register budget
-                    uint32_t acc_a[G][8], acc_b[G][8];
-                    auto load8 = [&](uint32_t (&dst)[G][8], int c) {
-#pragma unroll
-                        for (int grp = 0; grp < G; ++grp)
-                            tmem_ld_x8(tmem_base + lane_base + ((ac + grp) % kSlots) * BLOCK_N + c, dst[grp]);
-                    };
-                    load8(acc_a, c_begin);
-                    for (int c0 = c_begin; c0 < c_end; c0 += 16) {
-                        tmem_ld_wait();
-                        load8(acc_b, c0 + 8);
-                        if (!(g.debug & 1))
-                            epi.template chunk<8>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
-                                                  reinterpret_cast<const int32_t(*)[8]>(acc_a));
-                        tmem_ld_wait();
-                        if (c0 + 16 < c_end) load8(acc_a, c0 + 16);
-                        if (!(g.debug & 1))
-                            epi.template chunk<8>(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 8,
-                                                  reinterpret_cast<const int32_t(*)[8]>(acc_b));
-                    }
                 } else {
                     for (int c0 = c_begin; c0 < c_end; c0 += 16) {
                         uint32_t acc[G][16];
@@ -295,6 +374,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                                    reinterpret_cast<const int32_t(*)[16]>(acc));
                     }
                 }
+                if (tracer && part == 0 && step == 0) trace_stamp(g, tl, 9);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -304,6 +384,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
             }
             epi.end(ts, g, tc);
+            if (tracer) trace_stamp(g, tl, part == 0 ? 10 : 13);
         }
     }
 

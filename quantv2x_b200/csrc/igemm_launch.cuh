@@ -59,6 +59,11 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     const int grid = std::min(total, num_sms());
     IgemmGeom gg = g;
     gg.debug = g_debug_flags;
+    gg.trace = g_trace_ptr;
+    gg.taps_h = g.taps / g.taps_w;
+    gg.tw_shift = 0;
+    while ((1 << gg.tw_shift) < g.tw) ++gg.tw_shift;
+    if ((1 << gg.tw_shift) != g.tw) return set_error(QV2X_ERR_INVALID, "tile width %d is not a power of two", g.tw);
     kern<<<grid, igemm_threads<Epi>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, gg, epi);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
