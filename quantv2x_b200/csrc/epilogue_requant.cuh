@@ -25,6 +25,8 @@ struct RequantEpilogue {
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
+    int up_shift;                         // log2(up); up is 1, 2 or 4
+    FastDiv fd_cout_sub;
     int relu;
     float qmax, delta_out, zp_out;
     float rdelta;                         // fl(1 / delta_out)
@@ -44,10 +46,9 @@ struct RequantEpilogue {
         long long opix;   // output pixel index, -1 if this row is outside the image
         long long mrow;   // GEMM row index (for acc_dump)
         int rsum;
-        const float* sm_cs;      // this tile's per-column parameters in shared memory
-        const float* sm_bias;
-        const int32_t* sm_zpw;
+        uint32_t sm_par;         // shared-window address of this tile's per-column parameters: cs | bias | zpw
         int n_base;              // first global column of the tile
+        int ch_off;              // output channel of column n = n - ch_off (a tile never straddles sub-positions)
     };
     // Receptive-field input sums of ONE tile row, as raw loads: issued one tile ahead (G == 1) so that their
     // L2 latency never sits on the epilogue's critical path.
@@ -96,10 +97,9 @@ struct RequantEpilogue {
 
     __device__ __forceinline__ void begin(Tile& ts, const Prefetch& pf, const IgemmGeom& g, const TileCoord& tc,
                                           int row, uint8_t* scratch) const {
-        ts.sm_cs = reinterpret_cast<const float*>(scratch);
-        ts.sm_bias = ts.sm_cs + 256;
-        ts.sm_zpw = reinterpret_cast<const int32_t*>(ts.sm_bias + 256);
+        ts.sm_par = smem_u32(scratch);
         ts.n_base = tc.nt * g.block_n;
+        ts.ch_off = (up > 1) ? fd_cout_sub.div(ts.n_base) * cout_sub : 0;
         const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;
         const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
         const bool valid = (ox < g.Wo) && (oy < g.Ho);
@@ -125,9 +125,9 @@ struct RequantEpilogue {
         // an N tile never straddles two sub-positions (BLOCK_N divides cout_sub)
         int dy = 0, dx = 0;
         if (up > 1) {
-            const int sub = (tc.nt * g.block_n) / cout_sub;
-            dy = sub / up;
-            dx = sub - dy * up;
+            const int sub = fd_cout_sub.div(ts.n_base);
+            dy = sub >> up_shift;
+            dx = sub - (dy << up_shift);
         }
         ts.opix = (static_cast<long long>(tc.img) * Hout + oy * up + dy) * Wout + ox * up + dx;
     }
@@ -137,7 +137,7 @@ struct RequantEpilogue {
     __device__ __forceinline__ void load_zw(const Tile& ts, int nl, int32_t (&zw)[W]) const {
 #pragma unroll
         for (int v4 = 0; v4 < W / 4; ++v4) {
-            const int4 z = *(reinterpret_cast<const int4*>(ts.sm_zpw + nl) + v4);
+            const int4 z = lds_i4(ts.sm_par + 2048 + 4 * nl + 16 * v4);
             zw[4 * v4 + 0] = z.x, zw[4 * v4 + 1] = z.y, zw[4 * v4 + 2] = z.z, zw[4 * v4 + 3] = z.w;
         }
     }
@@ -188,8 +188,8 @@ struct RequantEpilogue {
         const int nl = n0 - ts.n_base;
 #pragma unroll
         for (int v4 = 0; v4 < W / 4; ++v4) {
-            const float4 c = *(reinterpret_cast<const float4*>(ts.sm_cs + nl) + v4);
-            const float4 b = *(reinterpret_cast<const float4*>(ts.sm_bias + nl) + v4);
+            const float4 c = lds_f4(ts.sm_par + 4 * nl + 16 * v4);
+            const float4 b = lds_f4(ts.sm_par + 1024 + 4 * nl + 16 * v4);
             cs[4 * v4 + 0] = c.x, cs[4 * v4 + 1] = c.y, cs[4 * v4 + 2] = c.z, cs[4 * v4 + 3] = c.w;
             bs[4 * v4 + 0] = b.x, bs[4 * v4 + 1] = b.y, bs[4 * v4 + 2] = b.z, bs[4 * v4 + 3] = b.w;
         }
@@ -249,7 +249,7 @@ struct RequantEpilogue {
             }
         }
         if (ts.opix >= 0) {
-            const int ch = n0 % cout_sub;
+            const int ch = n0 - ts.ch_off;
             if constexpr (W == 16)
                 st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);
             else

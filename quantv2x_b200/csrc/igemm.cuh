@@ -24,6 +24,18 @@ constexpr int kMaxGroups = 3;
 constexpr int kMaxSteps = 24;
 constexpr int kTileM = 128;
 
+// Exact division of a tile / column index by a run-time constant without the ~35-instruction division sequence:
+// q = umulhi(n, ceil(2^32 / d)) is exact for n * d < 2^32 (tile counts and column counts are far below that).
+struct FastDiv {
+    uint32_t mul, d;
+    __host__ __device__ FastDiv() : mul(0), d(1) {}
+    __host__ explicit FastDiv(int dd) : mul(dd > 1 ? static_cast<uint32_t>((0x100000000ull + dd - 1) / dd) : 0u),
+                                        d(static_cast<uint32_t>(dd)) {}
+    __device__ __forceinline__ int div(int n) const {
+        return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mul));
+    }
+};
+
 struct IgemmGeom {
     // M-tile grid: per image Ho x Wo "anchor" pixels covered by tw x th boxes (tw * th == 128)
     int n_img, Ho, Wo, tw, th, tiles_x, tiles_y, n_tiles, block_n;
@@ -32,6 +44,7 @@ struct IgemmGeom {
     // taps and K structure
     int taps, taps_w, taps_h, stride, pad;
     int tw_shift;                // log2(tw)
+    FastDiv fd_ntiles, fd_tx, fd_ty;   // dividers of decode_tile (filled in by launch_igemm)
     int groups, cblocks;
     int a_c_base[kMaxGroups];    // channel coordinate of the group's first k-block in the A tensor
     int b_row_base[kMaxGroups];  // row coordinate of the group's first output column in the B tensor
@@ -76,12 +89,14 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
     TileCoord c;
-    c.nt = t % g.n_tiles;
-    int m = t / g.n_tiles;
-    c.tx = m % g.tiles_x;
-    m /= g.tiles_x;
-    c.ty = m % g.tiles_y;
-    c.img = m / g.tiles_y;
+    int m = g.fd_ntiles.div(t);
+    c.nt = t - m * g.n_tiles;
+    int q = g.fd_tx.div(m);
+    c.tx = m - q * g.tiles_x;
+    m = q;
+    q = g.fd_ty.div(m);
+    c.ty = m - q * g.tiles_y;
+    c.img = q;
     return c;
 }
 
@@ -160,49 +175,67 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int total_tiles = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
     const int kblocks_per_group = (g.taps / TPS) * g.cblocks;   // pipeline stages per accumulator group
 
+    // The producer and MMA roles run their loops on the WHOLE warp (every lane computes the same, warp-uniform
+    // values, so they live in uniform registers) and elect one lane only for the instructions that must be issued
+    // once.  All addressing is incremental: a single thread's dependent integer chain (divisions, 64-bit
+    // descriptor assembly) between two TMA / MMA instructions was what paced these roles before.
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
-        if (lane == 0) {
-            uint32_t it = 0;
-            int tl = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-                const TileCoord tc = decode_tile(g, t);
-                trace_stamp(g, tl, 0);
-                long long waited = 0;
-                const int x0 = tc.tx * g.tw * g.stride - g.pad;
-                const int y0 = tc.ty * g.th * g.stride - g.pad;
-                for (int step = 0; step < g.n_steps; ++step) {
-                    for (int grp = 0; grp < G; ++grp) {
-                        const int brow = g.b_row_base[grp] + g.step_row_base[step] + grp * g.step_group_stride[step] +
-                                         tc.nt * BLOCK_N;
-                        for (int tap0 = 0; tap0 < g.taps; tap0 += TPS) {
-                            for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
-                                const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                                if (g.trace != nullptr) {
-                                    const long long w0 = clock64();
-                                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                                    waited += clock64() - w0;
-                                } else {
-                                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1);
-                                }
-                                const uint32_t fb = smem_u32(&full_bar[s]);
-                                mbar_expect_tx(fb, ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile));
-                                uint8_t* st = smem + s * Cfg::kStageBytes;
+        const bool leader = elect_one();
+        const uint32_t smem_base = smem_u32(smem);
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t tx_bytes = ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile);
+        uint32_t s = 0, ph = 0;
+        int tl = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+            const TileCoord tc = decode_tile(g, t);
+            if (leader) trace_stamp(g, tl, 0);
+            long long waited = 0;
+            const int x0 = tc.tx * g.tw * g.stride - g.pad;
+            const int y0 = tc.ty * g.th * g.stride - g.pad;
+            const int ncol0 = tc.nt * BLOCK_N;
+            for (int step = 0; step < g.n_steps; ++step) {
+                for (int grp = 0; grp < G; ++grp) {
+                    const int brow = g.b_row_base[grp] + g.step_row_base[step] + grp * g.step_group_stride[step] + ncol0;
+                    const int a_c0 = g.a_c_base[grp];
+                    int ky = 0, kx = 0;                 // tap coordinates of the stage's first tap
+                    int b_k0 = g.b_k_base[grp];         // its K coordinate in B
+                    for (int tap0 = 0; tap0 < g.taps; tap0 += TPS) {
+                        for (int cb = 0; cb < g.cblocks; ++cb) {
+                            if (g.trace != nullptr) {
+                                const long long w0 = clock64();
+                                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                                waited += clock64() - w0;
+                            } else {
+                                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                            }
+                            if (leader) {
+                                const uint32_t fb = full0 + 8 * s;
+                                mbar_expect_tx(fb, tx_bytes);
+                                const uint32_t st = smem_base + s * Cfg::kStageBytes;
+                                int kyi = ky, kxi = kx, bki = b_k0 + cb * BK;
 #pragma unroll
                                 for (int i = 0; i < TPS; ++i) {
-                                    const int tap = tap0 + i;
-                                    const int ky = tap / g.taps_w, kx = tap - ky * g.taps_w;
                                     if (!(g.debug & 4))
-                                        tma_load_4d(smem_u32(st + i * Cfg::kASub), &tmA, fb, g.a_c_base[grp] + cb * BK,
-                                                    x0 + kx, y0 + ky, tc.img);
+                                        tma_load_4d(st + i * Cfg::kASub, &tmA, fb, a_c0 + cb * BK, x0 + kxi, y0 + kyi,
+                                                    tc.img);
                                     if (!(g.debug & 8))
-                                        tma_load_2d(smem_u32(st + Cfg::kATile + i * Cfg::kBSub), &tmB, fb,
-                                                    tap * g.b_k_tap_stride + g.b_k_base[grp] + cb * BK, brow);
+                                        tma_load_2d(st + Cfg::kATile + i * Cfg::kBSub, &tmB, fb, bki, brow);
+                                    bki += g.b_k_tap_stride;
+                                    if (++kxi == g.taps_w) kxi = 0, ++kyi;
                                 }
                             }
+                            if (++s == kStages) s = 0, ph ^= 1;
+                        }
+#pragma unroll
+                        for (int i = 0; i < TPS; ++i) {
+                            b_k0 += g.b_k_tap_stride;
+                            if (++kx == g.taps_w) kx = 0, ++ky;
                         }
                     }
                 }
+            }
+            if (leader) {
                 trace_stamp(g, tl, 1);
                 if (g.trace != nullptr && tl < kTraceTiles)
                     g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 14] = waited;
@@ -210,46 +243,56 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            uint32_t it = 0, ac = 0;
-            int tl = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-                trace_stamp(g, tl, 2);
-                long long waited = 0;
-                for (int sg = 0; sg < g.n_steps * G; ++sg, ++ac) {
-                    const uint32_t slot = ac % kSlots, aph = (ac / kSlots) & 1;
-                    mbar_wait(smem_u32(&tempty_bar[slot]), aph ^ 1);
+        const bool leader = elect_one();
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+        // descriptors of stage 0; stage s / tap i / K step k only add to the 14-bit (address >> 4) field
+        const uint64_t a_desc0 = umma_smem_desc(smem_u32(smem), BK);
+        const uint64_t b_desc0 = umma_smem_desc(smem_u32(smem) + Cfg::kATile, BK);
+        uint32_t s = 0, ph = 0, slot = 0, aph = 0;
+        int tl = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+            if (leader) trace_stamp(g, tl, 2);
+            long long waited = 0;
+            for (int sg = 0; sg < g.n_steps * G; ++sg) {
+                mbar_wait(tempty0 + 8 * slot, aph ^ 1);
+                tcgen05_fence_after();
+                if (leader && sg == 0) trace_stamp(g, tl, 3);
+                const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
+                for (int kb = 0; kb < kblocks_per_group; ++kb) {
+                    if (g.trace != nullptr) {
+                        const long long w0 = clock64();
+                        mbar_wait(full0 + 8 * s, ph);
+                        waited += clock64() - w0;
+                    } else {
+                        mbar_wait(full0 + 8 * s, ph);
+                    }
                     tcgen05_fence_after();
-                    if (sg == 0) trace_stamp(g, tl, 3);
-                    const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
-                    for (int kb = 0; kb < kblocks_per_group; ++kb, ++it) {
-                        const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-                        if (g.trace != nullptr) {
-                            const long long w0 = clock64();
-                            mbar_wait(smem_u32(&full_bar[s]), ph);
-                            waited += clock64() - w0;
-                        } else {
-                            mbar_wait(smem_u32(&full_bar[s]), ph);
-                        }
-                        tcgen05_fence_after();
+                    if (leader) {
                         if (sg == 0 && kb == 0) trace_stamp(g, tl, 4);
-                        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
                         if (!(g.debug & 2)) {
+                            const uint64_t soff = static_cast<uint64_t>(s * (Cfg::kStageBytes >> 4));
 #pragma unroll
                             for (int i = 0; i < TPS; ++i) {
-                                const uint64_t a_desc = umma_smem_desc(a_addr + i * Cfg::kASub, BK);
-                                const uint64_t b_desc = umma_smem_desc(a_addr + Cfg::kATile + i * Cfg::kBSub, BK);
 #pragma unroll
                                 for (int k = 0; k < BK / 32; ++k) {
                                     // +32 bytes of K inside the swizzle row = +2 in the (addr >> 4) field
-                                    umma_i8(d_tmem, a_desc + 2 * k, b_desc + 2 * k, g.idesc, (kb | i | k) != 0);
+                                    umma_i8(d_tmem, a_desc0 + soff + (i * (Cfg::kASub >> 4) + 2 * k),
+                                            b_desc0 + soff + (i * (Cfg::kBSub >> 4) + 2 * k), g.idesc,
+                                            (kb | i | k) != 0);
                                 }
                             }
                         }
-                        umma_commit(smem_u32(&empty_bar[s]));
+                        umma_commit(empty0 + 8 * s);
                     }
-                    umma_commit(smem_u32(&tfull_bar[slot]));
+                    __syncwarp();
+                    if (++s == kStages) s = 0, ph ^= 1;
                 }
+                if (leader) umma_commit(tfull0 + 8 * slot);
+                __syncwarp();
+                if (++slot == kSlots) slot = 0, aph ^= 1;
+            }
+            if (leader) {
                 trace_stamp(g, tl, 5);
                 if (g.trace != nullptr && tl < kTraceTiles)
                     g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 15] = waited;
@@ -264,7 +307,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t ac = 0;
         uint32_t tile_par = 0;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        int staged_nt[2] = {-1, -1};          // which column tile's parameters each scratch half currently holds
+        int staged_nt0 = -1, staged_nt1 = -1;  // which column tile's parameters each scratch half currently holds
         typename Epi::Prefetch pf;
         if constexpr (Epi::kPrefetchNextTile) {
             if (static_cast<int>(blockIdx.x) < total_tiles) epi.prefetch(pf, g, decode_tile(g, blockIdx.x), row);
@@ -280,11 +323,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 // all epilogue threads stage this tile's per-column parameters in shared memory, double-buffered by
                 // tile parity; a half that already holds this column tile (always, when the layer has one column
                 // tile) is reused without any synchronisation
-                if (staged_nt[tile_par] != tc.nt) {
+                if ((tile_par ? staged_nt1 : staged_nt0) != tc.nt) {
                     asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // readers of the old content
                     epi.tile_setup(g, tc, static_cast<int>(threadIdx.x) - 128, kNumEpiWarps * 32, scratch);
                     asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
-                    staged_nt[tile_par] = tc.nt;
+                    if (tile_par) staged_nt1 = tc.nt; else staged_nt0 = tc.nt;
                 }
             }
             if constexpr (!Epi::kPrefetchNextTile) epi.prefetch(pf, g, tc, row);

@@ -61,6 +61,9 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     gg.debug = g_debug_flags;
     gg.trace = g_trace_ptr;
     gg.taps_h = g.taps / g.taps_w;
+    gg.fd_ntiles = FastDiv(g.n_tiles);
+    gg.fd_tx = FastDiv(g.tiles_x);
+    gg.fd_ty = FastDiv(g.tiles_y);
     gg.tw_shift = 0;
     while ((1 << gg.tw_shift) < g.tw) ++gg.tw_shift;
     if ((1 << gg.tw_shift) != g.tw) return set_error(QV2X_ERR_INVALID, "tile width %d is not a power of two", g.tw);

@@ -252,6 +252,8 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     auto fill = [&](auto& e) {
         e.up = (d.kind == 0) ? 1 : d.stride;
         e.cout_sub = d.cout;
+        e.up_shift = (e.up == 4) ? 2 : (e.up == 2 ? 1 : 0);
+        e.fd_cout_sub = FastDiv(d.cout);
         e.Hout = out_h;
         e.Wout = out_w;
         e.out_cstride = out_cstride;
