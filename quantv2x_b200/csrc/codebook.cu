@@ -23,9 +23,8 @@ constexpr int kMaxSeg = 4;
 struct EncodeEpilogue {
     static constexpr int kColSplit = 2;    // two epilogue warps per row quadrant, merged at the end of a level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
-    static constexpr bool kCoopTileSetup = false;
+    static constexpr bool kSideWarp = false;
     static constexpr bool kSeqDrain = false;
-    static constexpr bool kPrefetchNextTile = false;
     int levels, m;
     int k[kMaxLevels];            // codewords per segment
     int n_level[kMaxLevels];      // m * k
@@ -48,12 +47,10 @@ struct EncodeEpilogue {
         int code[kMaxLevels][kMaxSeg];
     };
 
-    struct Prefetch {};
-    __device__ __forceinline__ void tile_setup(const IgemmGeom&, const TileCoord&, int, int, uint8_t*) const {}
-    __device__ __forceinline__ void prefetch(Prefetch&, const IgemmGeom&, const TileCoord&, int) const {}
+    __device__ __forceinline__ void side_load(const IgemmGeom&, const TileCoord&, int, uint8_t*, int32_t*, int&) const {}
 
-    __device__ __forceinline__ void begin(Tile& ts, const Prefetch&, const IgemmGeom& g, const TileCoord& tc, int row,
-                                          uint8_t*) const {
+    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
+                                          const uint8_t*) const {
         ts.r = static_cast<long long>(tc.tx) * g.tw + row;
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {

@@ -19,9 +19,8 @@ template <int G>
 struct RequantEpilogue {
     static constexpr int kColSplit = 2;
     static constexpr int kMaxStages = 8;
-    static constexpr bool kCoopTileSetup = true;
+    static constexpr bool kSideWarp = true;        // per-column parameters and per-row input sums come via warp 3
     static constexpr bool kSeqDrain = (G > 1);     // groups are drained one by one into fp32 partial sums
-    static constexpr bool kPrefetchNextTile = (G == 1);
     // output addressing: pixel (oy*up + dy, ox*up + dx) of an [n_img, Hout, Wout, out_cstride] u8 tensor,
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
@@ -50,54 +49,76 @@ struct RequantEpilogue {
         int n_base;              // first global column of the tile
         int ch_off;              // output channel of column n = n - ch_off (a tile never straddles sub-positions)
     };
-    // Receptive-field input sums of ONE tile row, as raw loads: issued one tile ahead (G == 1) so that their
-    // L2 latency never sits on the epilogue's critical path.
-    static constexpr int kMaxTaps = 9;
-    struct Prefetch {
-        int32_t v[G][kMaxTaps];
-    };
+    // Shared-memory slot written by the side warp for one tile (kEpiSmemBytes / 2 = 5 KB):
+    //   [0, 1K) cs[256] f32 | [1K, 2K) bias[256] f32 | [2K, 3K) zpw[256] i32 | [3K, 3K + G*512) S[G][128] i32
+    // S[g][row] = sum of group g's input bytes over the receptive field of the tile's row (zero padding adds 0),
+    // rebuilt from the producing layer's per-pixel channel sums.
+    static constexpr int kSlotS = 3072;
 
-    // Shared-memory layout of the staged parameters (<= 256 columns): cs | bias | zpw, 1 KB each.
-    __device__ __forceinline__ void tile_setup(const IgemmGeom& g, const TileCoord& tc, int tid, int nthreads,
-                                               uint8_t* scratch) const {
-        float* s_cs = reinterpret_cast<float*>(scratch);
-        float* s_b = s_cs + 256;
-        int32_t* s_z = reinterpret_cast<int32_t*>(s_b + 256);
-        const int n_base = tc.nt * g.block_n;
-        for (int i = tid; i < g.block_n; i += nthreads) {
-            s_cs[i] = __ldg(cscale + n_base + i);
-            s_b[i] = __ldg(bias + n_base + i);
-            s_z[i] = (zpw[0] != nullptr) ? __ldg(zpw[0] + n_base + i) : 0;   // all groups share one zero-point array
+    static constexpr int kHaloInts = 1024;   // >= (2*127+3)*3, the widest halo (stride 2, 128 x 1 tile box)
+
+    __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
+                                              int32_t* halo, int& staged_nt) const {
+        if (staged_nt != tc.nt) {       // per-column parameters change only with the column tile
+            float* s_cs = reinterpret_cast<float*>(slot);
+            float* s_b = s_cs + 256;
+            int32_t* s_z = reinterpret_cast<int32_t*>(s_b + 256);
+            const int n_base = tc.nt * g.block_n;
+            const bool has_zp = (zpw[0] != nullptr);                  // groups share one zero-point array
+            for (int i = lane; i < g.block_n; i += 32) {
+                cp_async_4(smem_u32(s_cs + i), cscale + n_base + i, true);
+                cp_async_4(smem_u32(s_b + i), bias + n_base + i, true);
+                cp_async_4(smem_u32(s_z + i), has_zp ? static_cast<const void*>(zpw[0] + n_base + i) : cscale, has_zp);
+            }
+            staged_nt = tc.nt;
         }
-    }
-
-    __device__ __forceinline__ void prefetch(Prefetch& pf, const IgemmGeom& g, const TileCoord& tc, int row) const {
-        const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;      // tw is a power of two
-        const int ox = tc.tx * g.tw + lx, oy = tc.ty * g.th + ly;
-        const bool valid = (ox < g.Wo) && (oy < g.Ho);
-        const int taps_h = g.taps_h;               // taps are at most 3 x 3
+        // Receptive-field sums through a halo in shared memory: the (th-1)*stride+taps_h by (tw-1)*stride+taps_w
+        // window of per-pixel sums is loaded once (coalesced rows, zero outside the image), then every tile row
+        // adds its taps from shared memory.  ~10x fewer global loads than taps x rows.
+        int32_t* s_S = reinterpret_cast<int32_t*>(slot + kSlotS);
+        const int hw = (g.tw - 1) * g.stride + g.taps_w, hh = (g.th - 1) * g.stride + g.taps_h;
+        const int ix0 = tc.tx * g.tw * g.stride - g.pad, iy0 = tc.ty * g.th * g.stride - g.pad;
 #pragma unroll
         for (int grp = 0; grp < G; ++grp) {
             const int32_t* rs = rowsum_in[grp];
-            if (rs != nullptr) rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
+            if (rs == nullptr) {
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    int32_t v = 0;
-                    const int iy = oy * g.stride + ky - g.pad, ix = ox * g.stride + kx - g.pad;
-                    if (rs != nullptr && valid && ky < taps_h && kx < g.taps_w && iy >= 0 && iy < g.Hi && ix >= 0 &&
-                        ix < g.Wi)
-                        v = __ldg(rs + iy * g.Wi + ix);
-                    pf.v[grp][ky * 3 + kx] = v;
+                for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = 0;
+                continue;
+            }
+            rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
+            __syncwarp();                                   // the previous group's readers are done with the halo
+            for (int hy = 0; hy < hh; ++hy) {
+                const int iy = iy0 + hy;
+                const bool yok = (iy >= 0 && iy < g.Hi);
+                for (int hx = lane; hx < hw; hx += 32) {
+                    const int ix = ix0 + hx;
+                    const bool ok = yok && ix >= 0 && ix < g.Wi;
+                    cp_async_4(smem_u32(halo + hy * hw + hx), ok ? rs + iy * g.Wi + ix : rs, ok);
                 }
             }
+            cp_async_wait_all();
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int row = lane + 32 * rr;
+                const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;      // tw is a power of two
+                const int32_t* h0 = halo + ly * g.stride * hw + lx * g.stride;
+                int32_t sum = 0;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx)
+                        if (ky < g.taps_h && kx < g.taps_w) sum += h0[ky * hw + kx];
+                s_S[grp * kTileM + row] = sum;     // rows outside the image are never stored by the epilogue
+            }
         }
+        cp_async_wait_all();                       // the parameter copies, when no group waited for them
     }
 
-    __device__ __forceinline__ void begin(Tile& ts, const Prefetch& pf, const IgemmGeom& g, const TileCoord& tc,
-                                          int row, uint8_t* scratch) const {
-        ts.sm_par = smem_u32(scratch);
+    __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
+                                          const uint8_t* slot) const {
+        ts.sm_par = smem_u32(slot);
         ts.n_base = tc.nt * g.block_n;
         ts.ch_off = (up > 1) ? fd_cout_sub.div(ts.n_base) * cout_sub : 0;
         const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;
@@ -107,19 +128,8 @@ struct RequantEpilogue {
         ts.opix = -1;
         ts.mrow = -1;
 #pragma unroll
-        for (int grp = 0; grp < G; ++grp) {
-            // The empty volatile asm pins the first use of each prefetched value HERE (volatile asm statements keep
-            // their order): otherwise the compiler folds the sum into the iteration that issued the loads and the
-            // epilogue stalls on their L2 latency every tile.
-            int32_t s = 0;
-#pragma unroll
-            for (int tap = 0; tap < kMaxTaps; ++tap) {
-                int32_t x = pf.v[grp][tap];
-                asm volatile("" : "+r"(x));
-                s += x;
-            }
-            ts.S[grp] = s;
-        }
+        for (int grp = 0; grp < G; ++grp)
+            ts.S[grp] = *reinterpret_cast<const int32_t*>(slot + kSlotS + 4 * (grp * kTileM + row));
         if (!valid) return;
         ts.mrow = (static_cast<long long>(tc.img) * g.Ho + oy) * g.Wo + ox;
         // an N tile never straddles two sub-positions (BLOCK_N divides cout_sub)

@@ -67,7 +67,8 @@ __device__ __forceinline__ void trace_stamp(const IgemmGeom& g, int tile_local, 
         g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tile_local) * 16 + slot] = clock64();
 }
 
-constexpr int kEpiSmemBytes = 8192;   // scratch handed to the epilogue functor (cross-warp merges)
+constexpr int kEpiSmemBytes = 10240;   // two side-input slots / epilogue scratch
+constexpr int kHaloSmemBytes = 8192;   // two halo buffers, one per side warp   // scratch handed to the epilogue functor (cross-warp merges)
 
 // TPS = taps per pipeline stage: layers with 64 input channels have only 64 bytes of K per tap, so three taps
 // share one stage (one mbarrier round trip per 192 bytes of K instead of per 64).
@@ -81,7 +82,7 @@ struct IgemmCfg {
     static constexpr int kStagesRaw = (188 * 1024) / kStageBytes;
     static constexpr int kStages = kStagesRaw > MAX_STAGES ? MAX_STAGES : kStagesRaw;
     static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiSmemBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiSmemBytes + kHaloSmemBytes;
 };
 
 struct TileCoord {
@@ -103,15 +104,15 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 // Epilogue contract:
 //   struct Epi {
 //     struct Tile;                                     // per-thread, per-tile state
-//     struct Prefetch;                                 // per-thread side inputs of a tile, loaded ahead of time
 //     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
 //     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
-//     static constexpr bool kCoopTileSetup;            // stage per-column parameters in shared memory
+//     static constexpr bool kSideWarp;                 // warp 3 stages the tile's side inputs in shared memory
 //     static constexpr bool kSeqDrain;                 // G > 1: accumulator groups are drained one by one
-//     static constexpr bool kPrefetchNextTile;         // issue prefetch() one tile ahead
-//     __device__ void tile_setup(const IgemmGeom&, const TileCoord&, int tid, int nthreads, uint8_t* scratch) const;
-//     __device__ void prefetch(Prefetch&, const IgemmGeom&, const TileCoord&, int row) const;
-//     __device__ void begin(Tile&, const Prefetch&, const IgemmGeom&, const TileCoord&, int row, uint8_t* scratch) const;
+//     __device__ void side_load(const IgemmGeom&, const TileCoord&, int lane, uint8_t* slot, int32_t* halo,
+//                               int& staged_nt) const;
+//         -- kSideWarp: run by the 32 lanes of warp 3, one tile AHEAD of the epilogue, into one of two
+//            kEpiSmemBytes/2 slots (per-column parameters, per-row receptive-field sums, ...)
+//     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row, const uint8_t* slot) const;
 //         -- called BEFORE the accumulators are ready
 //     template <int W> __device__ void chunk(Tile&, const IgemmGeom&, const TileCoord&, int step, int col0,
 //                           const int32_t (*acc)[W]) const;
@@ -145,7 +146,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tfull_bar = bars + 2 * kStages;
     uint64_t* tempty_bar = bars + 2 * kStages + kSlots;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2 * kSlots);
+    uint64_t* side_full = bars + 2 * kStages + 2 * kSlots;      // [2] side-input slots (warp 3 -> epilogue)
+    uint64_t* side_empty = side_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(side_empty + 2);
     uint8_t* epi_scratch = smem + kStages * Cfg::kStageBytes + 256;
 
     const int warp = threadIdx.x >> 5;
@@ -163,6 +166,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int i = 0; i < kSlots; ++i) {
             mbar_init(smem_u32(&tfull_bar[i]), 1);
             mbar_init(smem_u32(&tempty_bar[i]), kNumEpiWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&side_full[i]), 1);
+            mbar_init(smem_u32(&side_empty[i]), kNumEpiWarps);
         }
         fence_mbar_init();
     }
@@ -298,6 +305,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 15] = waited;
             }
         }
+    } else if (warp == 2 || warp == 3) {
+        // ------------------------------------------------------------ side inputs, ahead of the epilogue
+        // Warp 2 serves the even tiles of this CTA into slot 0, warp 3 the odd tiles into slot 1: each has two tile
+        // periods for one tile's work, and each owns a private halo buffer.
+        if constexpr (Epi::kSideWarp) {
+            const uint32_t par = warp - 2;
+            uint8_t* slot = epi_scratch + par * (kEpiSmemBytes / 2);
+            int32_t* halo = reinterpret_cast<int32_t*>(epi_scratch + kEpiSmemBytes + par * (kHaloSmemBytes / 2));
+            int staged_nt = -1;
+            uint32_t sph = 0;
+            for (int t = blockIdx.x + par * gridDim.x; t < total_tiles; t += 2 * gridDim.x, sph ^= 1) {
+                const TileCoord tc = decode_tile(g, t);
+                mbar_wait(smem_u32(&side_empty[par]), sph ^ 1);
+                epi.side_load(g, tc, lane, slot, halo, staged_nt);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&side_full[par]));     // release: the slot's writes are visible
+            }
+        }
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
@@ -307,35 +332,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t ac = 0;
         uint32_t tile_par = 0;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
-        int staged_nt0 = -1, staged_nt1 = -1;  // which column tile's parameters each scratch half currently holds
-        typename Epi::Prefetch pf;
-        if constexpr (Epi::kPrefetchNextTile) {
-            if (static_cast<int>(blockIdx.x) < total_tiles) epi.prefetch(pf, g, decode_tile(g, blockIdx.x), row);
-        }
+        uint32_t sph = 0;
         int tl = 0;
         const bool tracer = (lane == 0 && quad == 0);
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, tile_par ^= 1, ++tl) {
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
             const TileCoord tc = decode_tile(g, t);
             if (tracer) trace_stamp(g, tl, part == 0 ? 6 : 11);
             typename Epi::Tile ts;
-            uint8_t* scratch = epi_scratch + (Epi::kCoopTileSetup ? tile_par * (kEpiSmemBytes / 2) : 0);
-            if constexpr (Epi::kCoopTileSetup) {
-                // all epilogue threads stage this tile's per-column parameters in shared memory, double-buffered by
-                // tile parity; a half that already holds this column tile (always, when the layer has one column
-                // tile) is reused without any synchronisation
-                if ((tile_par ? staged_nt1 : staged_nt0) != tc.nt) {
-                    asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");   // readers of the old content
-                    epi.tile_setup(g, tc, static_cast<int>(threadIdx.x) - 128, kNumEpiWarps * 32, scratch);
-                    asm volatile("bar.sync 6, %0;" ::"n"(kNumEpiWarps * 32) : "memory");
-                    if (tile_par) staged_nt1 = tc.nt; else staged_nt0 = tc.nt;
-                }
-            }
-            if constexpr (!Epi::kPrefetchNextTile) epi.prefetch(pf, g, tc, row);
-            epi.begin(ts, pf, g, tc, row, scratch);
-            if constexpr (Epi::kPrefetchNextTile) {
-                if (t + static_cast<int>(gridDim.x) < total_tiles)
-                    epi.prefetch(pf, g, decode_tile(g, t + gridDim.x), row);
-            }
+            const uint8_t* slot = epi_scratch + (Epi::kSideWarp ? tile_par * (kEpiSmemBytes / 2) : 0);
+            if constexpr (Epi::kSideWarp) mbar_wait(smem_u32(&side_full[tile_par]), sph);
+            epi.begin(ts, g, tc, row, slot);
             if (tracer && part == 0) trace_stamp(g, tl, 7);
             for (int step = 0; step < g.n_steps; ++step, ac += G) {
                 const int c_begin = part * kColsPerWarp, c_end = (part + 1) * kColsPerWarp;
@@ -427,6 +433,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
             }
             epi.end(ts, g, tc);
+            if constexpr (Epi::kSideWarp) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&side_empty[tile_par]));
+            }
+            if ((tile_par ^= 1) == 0) sph ^= 1;
             if (tracer) trace_stamp(g, tl, part == 0 ? 10 : 13);
         }
     }

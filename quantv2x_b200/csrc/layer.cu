@@ -222,6 +222,10 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
     choose_tile_box(g.Ho, g.Wo, &g.tw, &g.th);
     g.tiles_x = (g.Wo + g.tw - 1) / g.tw;
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
+    {   // the side warp's halo of per-pixel input sums must fit its shared-memory buffer
+        const int hw = (g.tw - 1) * g.stride + g.taps_w, hh = (g.th - 1) * g.stride + g.taps / g.taps_w;
+        QV2X_REQUIRE(hw * hh <= RequantEpilogue<1>::kHaloInts, "halo %d x %d exceeds the side buffer", hh, hw);
+    }
     // Column-tile width: the widest tile has the best operand reuse, but small maps (deep stages, one agent per
     // GPU) would leave most SMs idle.  Cost model: waves x bytes staged per k-block (128 rows of A + bn rows of B).
     int block_n = L->block_n;

@@ -152,6 +152,14 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS), 4-byte elements
+// Copies 4 bytes global -> shared without a register round trip (the issuing warp does not stall on the load);
+// `valid == false` writes zero instead (src-size 0).
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---------------------------------------------------------------- misc
 // 16-byte shared-memory loads through the shared window (LDS, not a generic LD that has to resolve the window first)
 __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
