@@ -21,7 +21,7 @@ constexpr int kMaxLevels = 4;
 constexpr int kMaxSeg = 4;
 
 struct EncodeEpilogue {
-    static constexpr int kColSplit = 2;    // two epilogue warps per row quadrant, merged at the end of a level
+    static constexpr int col_split(int) { return 2; }   // two epilogue warps per row quadrant, merged per level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
     static constexpr bool kSideWarp = false;
     static constexpr bool kSeqDrain = false;

@@ -17,7 +17,8 @@ namespace qv2x {
 
 template <int G>
 struct RequantEpilogue {
-    static constexpr int kColSplit = 2;
+    // epilogue warps per TMEM lane quadrant: more warps hide the latencies of the (ALU-pipe bound) requant math
+    static constexpr int col_split(int) { return 2; }   // (4 was measured: spills and no gain -- not latency bound)
     static constexpr int kMaxStages = 8;
     static constexpr bool kSideWarp = true;        // per-column parameters and per-row input sums come via warp 3
     static constexpr bool kSeqDrain = (G > 1);     // groups are drained one by one into fp32 partial sums
@@ -25,6 +26,7 @@ struct RequantEpilogue {
     // (dy, dx) = sub-position owned by this N tile (transposed conv with kernel == stride == up)
     int up, cout_sub, Hout, Wout, out_cstride, out_cbase;
     int up_shift;                         // log2(up); up is 1, 2 or 4
+    int debug;                            // qv2x_set_debug_flags: 16 skips the output stores
     FastDiv fd_cout_sub;
     int relu;
     float qmax, delta_out, zp_out;
@@ -258,7 +260,7 @@ struct RequantEpilogue {
                 packed[j >> 2] |= b << ((j & 3) * 8);
             }
         }
-        if (ts.opix >= 0) {
+        if (ts.opix >= 0 && !(debug & 16)) {
             const int ch = n0 - ts.ch_off;
             if constexpr (W == 16)
                 st_global_v4(out + ts.opix * out_cstride + out_cbase + ch, packed[0], packed[1], packed[2], packed[3]);

@@ -104,7 +104,7 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 // Epilogue contract:
 //   struct Epi {
 //     struct Tile;                                     // per-thread, per-tile state
-//     static constexpr int kColSplit;                  // 1 or 2: epilogue warps per TMEM lane quadrant
+//     static constexpr int col_split(int block_n);     // 1, 2 or 4: epilogue warps per TMEM lane quadrant
 //     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
 //     static constexpr bool kSideWarp;                 // warp 3 stages the tile's side inputs in shared memory
 //     static constexpr bool kSeqDrain;                 // G > 1: accumulator groups are drained one by one
@@ -125,19 +125,20 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //                              uint8_t* scratch) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
 //   };
-template <class Epi>
-constexpr int igemm_threads() { return (4 + 4 * Epi::kColSplit) * 32; }
+template <class Epi, int BLOCK_N>
+constexpr int igemm_threads() { return (4 + 4 * Epi::col_split(BLOCK_N)) * 32; }
 
 template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1>
-__global__ void __launch_bounds__(igemm_threads<Epi>(), 1)
+__global__ void __launch_bounds__(igemm_threads<Epi, BLOCK_N>(), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
              const Epi epi) {
     using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages, TPS>;
     constexpr int kStages = Cfg::kStages;
     constexpr int kSlots = Cfg::kSlots;
     static_assert(G <= kSlots, "every group needs its own TMEM slot");
-    constexpr int kNumEpiWarps = 4 * Epi::kColSplit;
-    static_assert(BLOCK_N % (16 * Epi::kColSplit) == 0, "BLOCK_N must split into 16-column-aligned parts");
+    constexpr int kColSplit = Epi::col_split(BLOCK_N);
+    constexpr int kNumEpiWarps = 4 * kColSplit;
+    static_assert(BLOCK_N % (16 * kColSplit) == 0, "BLOCK_N must split into 16-column-aligned parts");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -328,7 +329,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
         const int part = (warp - 4) >> 2;     // which part of the step's columns (kColSplit parts)
         const int row = quad * 32 + lane;     // tile row == TMEM lane
-        constexpr int kColsPerWarp = BLOCK_N / Epi::kColSplit;
+        constexpr int kColsPerWarp = BLOCK_N / kColSplit;
         uint32_t ac = 0;
         uint32_t tile_par = 0;
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
@@ -356,6 +357,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         const uint32_t a = ac + grp;
                         mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
                         tcgen05_fence_after();
+                        if (tracer && step == 0 && grp == 0) trace_stamp(g, tl, part == 0 ? 8 : 12);
                         const uint32_t tbase = tmem_base + lane_base + (a % kSlots) * BLOCK_N + c_begin;
                         uint32_t acc_a[16], acc_b[16];
                         tmem_ld_x16(tbase, acc_a);
@@ -382,6 +384,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         __syncwarp();
                         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a % kSlots]));
                     }
+                    if (tracer && part == 0 && step == 0) trace_stamp(g, tl, 9);
                     epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
                     continue;
                 }

@@ -67,7 +67,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     gg.tw_shift = 0;
     while ((1 << gg.tw_shift) < g.tw) ++gg.tw_shift;
     if ((1 << gg.tw_shift) != g.tw) return set_error(QV2X_ERR_INVALID, "tile width %d is not a power of two", g.tw);
-    kern<<<grid, igemm_threads<Epi>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, gg, epi);
+    kern<<<grid, igemm_threads<Epi, BLOCK_N>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, gg, epi);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -227,16 +227,19 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         QV2X_REQUIRE(hw * hh <= RequantEpilogue<1>::kHaloInts, "halo %d x %d exceeds the side buffer", hh, hw);
     }
     // Column-tile width: the widest tile has the best operand reuse, but small maps (deep stages, one agent per
-    // GPU) would leave most SMs idle.  Cost model: waves x bytes staged per k-block (128 rows of A + bn rows of B).
+    // GPU) would leave most SMs idle or pay a nearly empty second wave.  Cost model in SM cycles per CTA:
+    // waves x (fixed per-tile overhead: pipeline fill + the last tile's epilogue tail, + MMA time K/32 x bn/2).
     int block_n = L->block_n;
     {
         const long long m_tiles = static_cast<long long>(n_img) * g.tiles_x * g.tiles_y;
         const int sub_cols = (d.kind == 0) ? L->n_total : d.cout;   // a tile must not straddle sub-positions
+        const long long k_steps = static_cast<long long>(L->groups) * g.taps * g.cblocks * (L->bk / 32);
         long long best = -1;
         for (int bn = L->block_n; bn >= 64; bn >>= 1) {
             if (sub_cols % bn != 0) continue;
             const long long tiles = m_tiles * (L->n_total / bn);
-            const long long cost = ((tiles + num_sms() - 1) / num_sms()) * (128 + bn);
+            const long long waves = (tiles + num_sms() - 1) / num_sms();
+            const long long cost = waves * (4500 + k_steps * (bn / 2));
             if (best < 0 || cost < best) {
                 best = cost;
                 block_n = bn;
@@ -257,6 +260,7 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.up = (d.kind == 0) ? 1 : d.stride;
         e.cout_sub = d.cout;
         e.up_shift = (e.up == 4) ? 2 : (e.up == 2 ? 1 : 0);
+        e.debug = g_debug_flags;
         e.fd_cout_sub = FastDiv(d.cout);
         e.Hout = out_h;
         e.Wout = out_w;

@@ -7,38 +7,23 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 sys.path.insert(0, ROOT)
 from ctypes import c_void_p  # noqa: E402
 
+from _layers import build  # noqa: E402
 from quantv2x_b200 import _lib  # noqa: E402
-from quantv2x_b200.engine import QLayer, rowsum_u8  # noqa: E402
-from tests.layer_cases import make_conv, make_input  # noqa: E402
 
-CFG = {
-    "shrink1": (4, 100, 352, 256, 256, 1),
-    "shrink0": (4, 100, 352, 384, 256, 3),
-    "s0": (4, 100, 352, 64, 64, 1),
-    "s1": (4, 50, 176, 128, 128, 1),
-    "s2": (4, 25, 88, 256, 256, 1),
-}
 which = sys.argv[1] if len(sys.argv) > 1 else "s0"
 cta = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-n, H, W, cin, cout, groups = CFG[which]
 dev = torch.device("cuda:0")
-rng = np.random.default_rng(1)
-p = make_conv(rng, cin, cout, 3, 8, groups)
-x = torch.from_numpy(make_input(rng, n, H, W, cin)).to(dev)
-layer = QLayer(kind=0, w_int=p["w_int"], w_delta=p["w_delta"], w_zp=p["w_zp"], bias=p["bias"], ksize=3, stride=1,
-               pad=1, w_bits=8, relu=True, in_delta=p["in_delta"], out_delta=p["out_delta"])
-cg = cin // groups
-rs = [rowsum_u8(x, i * cg, cg) for i in range(groups)]
-out = torch.empty((n, H, W, cout), dtype=torch.uint8, device=dev)
+run, _ = build(which, dev)
 for _ in range(5):
-    layer.forward(x, rowsum_in=rs, out=out)
+    run()
 torch.cuda.synchronize()
 buf = torch.zeros((148, 32, 16), dtype=torch.int64, device=dev)
 _lib.lib().qv2x_debug_trace(c_void_p(buf.data_ptr()))
-layer.forward(x, rowsum_in=rs, out=out)
+run()
 torch.cuda.synchronize()
 _lib.lib().qv2x_debug_trace(c_void_p(0))
 tr = buf.cpu().numpy()[cta]
