@@ -20,6 +20,11 @@ namespace qv2x {
 constexpr int kMaxLevels = 4;
 constexpr int kMaxSeg = 4;
 
+// int32 -> float64, exact, without a conversion instruction: the integer is planted in the mantissa of 2^52 + 2^31
+__device__ __forceinline__ double i2d_exact(int x) {
+    return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;
+}
+
 struct EncodeEpilogue {
     static constexpr int col_split(int) { return 2; }   // two epilogue warps per row quadrant, merged per level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
@@ -33,18 +38,30 @@ struct EncodeEpilogue {
     int step_col0[kMaxSteps];     // first column (within the level) of each step
     int step_last[kMaxSteps];     // 1 if the step closes its level
     double delta;
-    const double* sc;             // per-column fixed-point scale
+    const double* dsc;            // fl64(delta * sc[j]): the value of one fixed-point unit of column j
     const double* g0;             // per-column constant
     const double* btab;           // codeword cross terms, see boff
     long long boff[kMaxLevels][kMaxLevels];  // boff[l][j]: start of [m][k_j][n_level[l]] doubles
     uint8_t* codes;               // [levels][m][rows]
     long long rows;
+    // fp32 filter (fast != 0; needs one step per level so that the level's accumulators are still in TMEM when a
+    // row turns out to need the exact evaluation):
+    //   the scores are first evaluated in fp32 with a rigorous error bound eps(row); if the best score beats the
+    //   runner-up by more than 2*eps the fp32 argmin IS the float64 argmin, otherwise (~1e-4 of rows) the warp
+    //   re-reads the accumulators and evaluates the level in float64 exactly as the slow path does.
+    int fast, pack16;
+    const float* d32;             // float(delta * sc[j])
+    const float* g32;             // float(g0[j])
+    const float* btab32;          // float(btab), same layout
+    float dmax[kMaxLevels];       // max_j |d32[j]| of the level
+    float cabs[kMaxLevels];       // max_j |g0[j]| + sum_{j<l} max |B_{l,j}|
 
     struct Tile {
         long long r;
         double best[kMaxSeg];
         int bidx[kMaxSeg];
         int code[kMaxLevels][kMaxSeg];
+        float fbest[kMaxSeg], fsecond[kMaxSeg], vmax;
     };
 
     __device__ __forceinline__ void side_load(const IgemmGeom&, const TileCoord&, int, uint8_t*, int32_t*, int&) const {}
@@ -56,7 +73,10 @@ struct EncodeEpilogue {
         for (int s = 0; s < kMaxSeg; ++s) {
             ts.best[s] = INFINITY;
             ts.bidx[s] = 0;
+            ts.fbest[s] = INFINITY;
+            ts.fsecond[s] = INFINITY;
         }
+        ts.vmax = 0.f;
 #pragma unroll
         for (int l = 0; l < kMaxLevels; ++l)
 #pragma unroll
@@ -64,15 +84,88 @@ struct EncodeEpilogue {
     }
 
     template <int W>
-    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int c0,
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int c0,
                                           const int32_t (*acc)[W]) const {
         static_assert(W == 16, "the encode epilogue works on 16-column chunks");
+        if (fast) chunk_fast(ts, step, c0, acc);
+        else chunk_exact(ts, g, tc, step, c0, acc);
+    }
+
+    // fp32 scores of 16 columns + running (best, runner-up, index) and max |V| of the row
+    __device__ __forceinline__ void chunk_fast(Tile& ts, int step, int c0, const int32_t (*acc)[16]) const {
+        const int l = step_level[step];
+        const int n0 = step_col0[step] + c0;
+        const int nl = n_level[l];
+        const int seg = n0 / k[l];
+        const int kk0 = n0 - seg * k[l];
+        float sc16[16];
+        {
+            const float4* dp = reinterpret_cast<const float4*>(d32 + colbase[l] + n0);
+            const float4* gp = reinterpret_cast<const float4*>(g32 + colbase[l] + n0);
+            float vm = ts.vmax;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 dv = __ldg(dp + q), gv = __ldg(gp + q);
+                const float dd[4] = {dv.x, dv.y, dv.z, dv.w}, gg[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int j = 4 * q + e;
+                    const float hi = __int2float_rn(acc[0][j]);
+                    // |256 * mid + lo| < 2^31 when the reduction has at most 256 terms (pack16)
+                    const float lo = pack16 ? __int2float_rn(acc[1][j] * 256 + acc[2][j])
+                                            : fmaf(__int2float_rn(acc[1][j]), 256.f, __int2float_rn(acc[2][j]));
+                    const float vf = fmaf(hi, 65536.f, lo);
+                    vm = fmaxf(vm, fabsf(vf));
+                    sc16[j] = fmaf(vf, dd[e], gg[e]);
+                }
+            }
+            ts.vmax = vm;
+        }
+#pragma unroll
+        for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
+            if (jl < l) {
+#pragma unroll
+                for (int s2 = 0; s2 < kMaxSeg; ++s2) {
+                    if (s2 < m) {
+                        const float* bp =
+                            btab32 + boff[l][jl] + (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0;
+#pragma unroll
+                        for (int q = 0; q < 2; ++q) {
+                            float b[8];
+                            ldg_nc_f8(bp + 8 * q, b);
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) sc16[8 * q + e] += b[e];
+                        }
+                    }
+                }
+            }
+        }
+        float best = INFINITY, second = INFINITY;
+        int bidx = 0;
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s)
+            if (s == seg) best = ts.fbest[s], second = ts.fsecond[s], bidx = ts.bidx[s];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float v = sc16[j];
+            second = fminf(second, fmaxf(best, v));
+            if (v < best) bidx = kk0 + j;      // the exact index only matters when the gap test passes
+            best = fminf(best, v);
+        }
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s)
+            if (s == seg) ts.fbest[s] = best, ts.fsecond[s] = second, ts.bidx[s] = bidx;
+    }
+
+    template <int W>
+    __device__ __forceinline__ void chunk_exact(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int c0,
+                                                const int32_t (*acc)[W]) const {
         const int l = step_level[step];
         const int n0 = step_col0[step] + c0;          // column within the level; a chunk never straddles segments
         const int nl = n_level[l];
         const int seg = n0 / k[l];
         const int kk0 = n0 - seg * k[l];
-        const double* scp = sc + colbase[l] + n0;
+        const double* scp = dsc + colbase[l] + n0;
         const double* g0p = g0 + colbase[l] + n0;
         // The cross-term rows are per-thread gathers (random rows, 128 B per 16-column chunk): pull the NEXT chunk's
         // lines into L1 now so its loads do not expose the L2 latency.
@@ -92,10 +185,12 @@ struct EncodeEpilogue {
         double score[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            // V = acc_hi*65536 + acc_mid*256 + acc_lo, exact in float64 (|V| < 2^48)
-            const double V = fma(static_cast<double>(acc[0][j]), 65536.0,
-                                 fma(static_cast<double>(acc[1][j]), 256.0, static_cast<double>(acc[2][j])));
-            score[j] = __dadd_rn(__dmul_rn(V, __dmul_rn(delta, __ldg(scp + j))), __ldg(g0p + j));
+            // V = acc_hi*65536 + acc_mid*256 + acc_lo, exact in float64 (|V| < 2^48); the int -> double conversions
+            // go through the 2^52 mantissa trick (one LOP + one DADD) instead of the slow conversion unit
+            const double lo = pack16 ? i2d_exact(acc[1][j] * 256 + acc[2][j])
+                                     : fma(i2d_exact(acc[1][j]), 256.0, i2d_exact(acc[2][j]));
+            const double V = fma(i2d_exact(acc[0][j]), 65536.0, lo);
+            score[j] = __dadd_rn(__dmul_rn(V, __ldg(scp + j)), __ldg(g0p + j));     // scp = fl64(delta * sc)
         }
 #pragma unroll
         for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
@@ -132,40 +227,110 @@ struct EncodeEpilogue {
             if (s == seg) ts.best[s] = best, ts.bidx[s] = bidx;
     }
 
-    __device__ __forceinline__ void step_end(Tile& ts, const IgemmGeom&, const TileCoord&, int step, int part,
-                                             int quad, int lane, uint8_t* scratch) const {
+    static constexpr bool kHoldSlots = true;     // the level's accumulators may be re-read in step_end
+    static constexpr float kEpsRel = 9.5367431640625e-07f;   // 2^-20 = 16 ulp(fp32): see the bound in step_end
+
+    __device__ __forceinline__ void step_end(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int part,
+                                             int quad, int lane, uint8_t* scratch, const TmemView& tv) const {
         if (!step_last[step]) return;
         const int l = step_level[step];
-        // merge the two column halves of this row quadrant: part 1 publishes its running minima, part 0 keeps its
-        // own on ties (it owns the lower column indices) and publishes the final codes back.
+        const int bar_id = 1 + quad;
+        bool exact_merge = true;
+        if (fast) {
+            // ---- merge the fp32 candidates of the two column halves and test the gap.
+            // Error bound of one fp32 score against the float64 evaluation: conversions of the digit accumulators
+            // (<= 2 roundings), two fma roundings, the rounded parameters d32 / g32 / btab32 and the l additions
+            // add up to less than 10 * 2^-24 * T with T = max|V| * max|d| + max|g0| + sum max|B| >= every partial
+            // sum; kEpsRel = 16 * 2^-24 leaves margin.  best + eps < second - eps  =>  same argmin in float64.
+            struct FCand {
+                float best, second;
+                int idx;
+                float vmax;
+            };
+            FCand* fc = reinterpret_cast<FCand*>(scratch) + (quad * 32 + lane) * kMaxSeg;
+            int* qflag = reinterpret_cast<int*>(scratch + 8192);
+            if (part == 1) {
+#pragma unroll
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m) fc[s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            if (part == 0) {
+                bool unsafe = false;
+#pragma unroll
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m) {
+                        const FCand o = fc[s];
+                        const float b0 = ts.fbest[s];
+                        const float best = fminf(b0, o.best);
+                        const float second = fminf(fminf(ts.fsecond[s], o.second), fmaxf(b0, o.best));
+                        const int idx = (o.best < b0) ? o.idx : ts.bidx[s];
+                        const float eps = kEpsRel * fmaf(fmaxf(ts.vmax, o.vmax), dmax[l], cabs[l]);
+                        unsafe |= !(second - best > 2.f * eps);      // also true for NaN
+                        ts.bidx[s] = idx;
+                        fc[s].idx = idx;
+                    }
+                const int any = __any_sync(0xffffffffu, unsafe) ? 1 : 0;
+                if (lane == 0) qflag[quad] = any;
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            exact_merge = (qflag[quad] != 0);
+            if (exact_merge) {
+                // rare: some row of this quadrant sits in a near-tie -- evaluate the level exactly for all 32 rows
+                // (the accumulators are still in TMEM because the slots are released only after step_end)
+#pragma unroll
+                for (int s = 0; s < kMaxSeg; ++s) ts.best[s] = INFINITY, ts.bidx[s] = 0;
+                for (int c0 = tv.c_begin; c0 < tv.c_end; c0 += 16) {
+                    uint32_t acc[3][16];
+#pragma unroll
+                    for (int grp = 0; grp < 3; ++grp) tmem_ld_x16(tv.addr[grp] + c0, acc[grp]);
+                    tmem_ld_wait();
+                    chunk_exact<16>(ts, g, tc, step, c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+                }
+                // part 0 may still be reading fc[] above when part 1 starts overwriting the slots below
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            } else {
+#pragma unroll
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m && part == 1) ts.bidx[s] = fc[s].idx;
+            }
+        }
         struct Cand {
             double best;
             int idx;
             int pad;
         };
         Cand* cand = reinterpret_cast<Cand*>(scratch) + (quad * 32 + lane) * kMaxSeg;
-        const int bar_id = 1 + quad;
-        if (part == 1) {
+        if (exact_merge) {
+            // merge the two column halves of this row quadrant: part 1 publishes its running minima, part 0 keeps
+            // its own on ties (it owns the lower column indices) and publishes the final codes back.
+            if (part == 1) {
 #pragma unroll
-            for (int s = 0; s < kMaxSeg; ++s)
-                if (s < m) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-        if (part == 0) {
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            if (part == 0) {
 #pragma unroll
-            for (int s = 0; s < kMaxSeg; ++s)
-                if (s < m) {
-                    const double ob = cand[s].best;
-                    const int oi = cand[s].idx;
-                    if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s])) ts.bidx[s] = oi;   // ties -> lowest index
-                    cand[s].idx = ts.bidx[s];
-                }
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m) {
+                        const double ob = cand[s].best;
+                        const int oi = cand[s].idx;
+                        if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s])) ts.bidx[s] = oi;   // ties -> lowest
+                        cand[s].idx = ts.bidx[s];
+                    }
+            }
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            if (part == 1) {
+#pragma unroll
+                for (int s = 0; s < kMaxSeg; ++s)
+                    if (s < m) ts.bidx[s] = cand[s].idx;
+            }
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {
             if (s < m) {
-                const int code = (part == 0) ? ts.bidx[s] : cand[s].idx;
+                const int code = ts.bidx[s];
 #pragma unroll
                 for (int ll = 0; ll < kMaxLevels; ++ll)
                     if (ll == l) ts.code[ll][s] = code;
@@ -173,8 +338,11 @@ struct EncodeEpilogue {
                     codes[(static_cast<long long>(l) * m + s) * rows + ts.r] = static_cast<uint8_t>(code);
                 ts.best[s] = INFINITY;
                 ts.bidx[s] = 0;
+                ts.fbest[s] = INFINITY;
+                ts.fsecond[s] = INFINITY;
             }
         }
+        ts.vmax = 0.f;
         // part 1 must have read the final codes before part 0 can overwrite the slots at the next level end
         asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
     }
@@ -354,6 +522,13 @@ struct qv2x_codebook {
     double *d_sc = nullptr, *d_g0 = nullptr, *d_btab = nullptr;
     float *d_dconst = nullptr, *d_tables = nullptr;
     long long* d_toff = nullptr;
+    // fp32 filter of the encoder: copies of g0 / btab, and delta * sc for the delta seen last (re-derived, with a
+    // synchronous upload, only when a call passes a different delta)
+    float *d_g32 = nullptr, *d_btab32 = nullptr, *d_d32 = nullptr;
+    double* d_dsc = nullptr;      // fl64(delta * sc[j])
+    float cached_delta = -1.f;
+    float dmax[kMaxLevels] = {}, cabs[kMaxLevels] = {};
+    bool fast = false;
 };
 
 extern "C" {
@@ -367,6 +542,10 @@ void qv2x_codebook_destroy(qv2x_codebook* cb) {
     cudaFree(cb->d_dconst);
     cudaFree(cb->d_tables);
     cudaFree(cb->d_toff);
+    cudaFree(cb->d_g32);
+    cudaFree(cb->d_btab32);
+    cudaFree(cb->d_d32);
+    cudaFree(cb->d_dsc);
     delete cb;
 }
 
@@ -552,6 +731,29 @@ int qv2x_codebook_create(const qv2x_codebook_desc* desc, const float* const* cod
     if (!rc) rc = upload(&cb->d_dconst, cb->h_dconst.data(), cb->h_dconst.size());
     if (!rc) rc = upload(&cb->d_tables, cb->h_tables.data(), cb->h_tables.size());
     if (!rc) rc = upload(&cb->d_toff, cb->h_toff.data(), cb->h_toff.size());
+    {   // fp32 filter tables and the per-level magnitudes of its error bound (rounded up)
+        std::vector<float> g32(cb->h_g0.size()), b32(cb->h_btab.size());
+        for (size_t i = 0; i < g32.size(); ++i) g32[i] = static_cast<float>(cb->h_g0[i]);
+        for (size_t i = 0; i < b32.size(); ++i) b32[i] = static_cast<float>(cb->h_btab[i]);
+        if (!rc) rc = upload(&cb->d_g32, g32.data(), g32.size());
+        if (!rc) rc = upload(&cb->d_btab32, b32.data(), b32.size());
+        if (!rc && (cudaMalloc(reinterpret_cast<void**>(&cb->d_d32), cb->h_sc.size() * sizeof(float)) != cudaSuccess ||
+                    cudaMalloc(reinterpret_cast<void**>(&cb->d_dsc), cb->h_sc.size() * sizeof(double)) != cudaSuccess))
+            rc = set_error(QV2X_ERR_CUDA, "cudaMalloc failed");
+        for (int l = 0; l < L; ++l) {
+            double c = 0.0;
+            for (int n = 0; n < cb->n_level[l]; ++n) c = std::max(c, std::fabs(cb->h_g0[cb->colbase[l] + n]));
+            for (int j = 0; j < l; ++j) {
+                double bm = 0.0;
+                const long long cnt = static_cast<long long>(m) * cb->k[j] * cb->n_level[l];
+                for (long long i = 0; i < cnt; ++i) bm = std::max(bm, std::fabs(cb->h_btab[cb->boff[l][j] + i]));
+                c += bm * m;     // one row per segment of level j is added
+            }
+            cb->cabs[l] = std::nextafter(static_cast<float>(c * (1.0 + 1e-6)), INFINITY);
+        }
+        // the level's accumulators must still be in TMEM at the end of the level: one N step per level
+        cb->fast = (cb->n_steps == L);
+    }
     if (rc) {
         qv2x_codebook_destroy(cb);
         return rc;
@@ -606,8 +808,34 @@ int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t*
             e.step_last[step] = (c == spl - 1);
         }
     }
+    if (delta != cb->cached_delta) {
+        auto* mcb = const_cast<qv2x_codebook*>(cb);
+        std::vector<float> d32(cb->h_sc.size());
+        std::vector<double> dsc(cb->h_sc.size());
+        for (size_t i = 0; i < d32.size(); ++i) {
+            dsc[i] = static_cast<double>(delta) * cb->h_sc[i];       // one float64 rounding, as the oracle does
+            d32[i] = static_cast<float>(dsc[i]);
+        }
+        QV2X_CUDA_OK(cudaMemcpy(cb->d_dsc, dsc.data(), dsc.size() * sizeof(double), cudaMemcpyHostToDevice));
+        for (int l = 0; l < cb->levels; ++l) {
+            float mx = 0.f;
+            for (int n = 0; n < cb->n_level[l]; ++n) mx = std::max(mx, std::fabs(d32[cb->colbase[l] + n]));
+            mcb->dmax[l] = mx;
+        }
+        QV2X_CUDA_OK(cudaMemcpy(cb->d_d32, d32.data(), d32.size() * sizeof(float), cudaMemcpyHostToDevice));
+        mcb->cached_delta = delta;
+    }
+    e.fast = (cb->fast && !(g_debug_flags & 64)) ? 1 : 0;      // debug 64: force the float64 path
+    e.pack16 = (cb->C <= 256) ? 1 : 0;
+    e.d32 = cb->d_d32;
+    e.g32 = cb->d_g32;
+    e.btab32 = cb->d_btab32;
+    for (int l = 0; l < cb->levels; ++l) {
+        e.dmax[l] = cb->dmax[l];
+        e.cabs[l] = cb->cabs[l];
+    }
     e.delta = static_cast<double>(delta);
-    e.sc = cb->d_sc;
+    e.dsc = cb->d_dsc;
     e.g0 = cb->d_g0;
     e.btab = cb->d_btab;
     e.codes = d_codes;

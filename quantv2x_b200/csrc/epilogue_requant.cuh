@@ -281,8 +281,9 @@ struct RequantEpilogue {
         finish<W>(ts, n0, v);
     }
 
-    __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int, int, int, int,
-                                             uint8_t*) const {}
+    static constexpr bool kHoldSlots = false;
+    __device__ __forceinline__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int, int, int, int, uint8_t*,
+                                             const TmemView&) const {}
 
     __device__ __forceinline__ void end(Tile& ts, const IgemmGeom& g, const TileCoord& tc) const {
         (void)g;

@@ -88,6 +88,12 @@ struct IgemmCfg {
 struct TileCoord {
     int img, ty, tx, nt;
 };
+// Where the accumulators of the current step live in TMEM, for epilogues that re-read them in step_end:
+// addr[g] = column 0 of group g's slot for the calling warp's lane quadrant; the warp owns columns [c_begin, c_end).
+struct TmemView {
+    uint32_t addr[kMaxGroups];
+    int c_begin, c_end;
+};
 __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
     TileCoord c;
     int m = g.fd_ntiles.div(t);
@@ -121,8 +127,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //     template <int W> __device__ void accum(const Tile&, const IgemmGeom&, int grp, int col0, const int32_t (&acc)[W],
 //                           float (&v)[W]) const;      -- fold group grp's accumulators into the running sum v
 //     template <int W> __device__ void finish(Tile&, int col0, const float (&v)[W]) const;
+//     static constexpr bool kHoldSlots;                -- step_end runs BEFORE the step's TMEM slots are released
 //     __device__ void step_end(Tile&, const IgemmGeom&, const TileCoord&, int step, int part, int quad, int lane,
-//                              uint8_t* scratch) const;   -- scratch: kEpiSmemBytes of shared memory
+//                              uint8_t* scratch, const TmemView&) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
 //   };
 template <class Epi, int BLOCK_N>
@@ -385,7 +392,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[a % kSlots]));
                     }
                     if (tracer && part == 0 && step == 0) trace_stamp(g, tl, 9);
-                    epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
+                    epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch, TmemView{});
                     continue;
                 }
 #pragma unroll
@@ -427,13 +434,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                 }
                 if (tracer && part == 0 && step == 0) trace_stamp(g, tl, 9);
+                TmemView tv{};
+#pragma unroll
+                for (int grp = 0; grp < G; ++grp)
+                    tv.addr[grp] = tmem_base + lane_base + ((ac + grp) % kSlots) * BLOCK_N;
+                tv.c_begin = c_begin;
+                tv.c_end = c_end;
+                if constexpr (Epi::kHoldSlots) epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch, tv);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
 #pragma unroll
                     for (int grp = 0; grp < G; ++grp) mbar_arrive(smem_u32(&tempty_bar[(ac + grp) % kSlots]));
                 }
-                epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch);
+                if constexpr (!Epi::kHoldSlots) epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch, tv);
             }
             epi.end(ts, g, tc);
             if constexpr (Epi::kSideWarp) {

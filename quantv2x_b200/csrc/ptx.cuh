@@ -152,6 +152,13 @@ __device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32-byte read-only global load (sm_100: LDG.256): halves the L1 line visits of per-thread row gathers
+__device__ __forceinline__ void ldg_nc_f8(const float* p, float (&v)[8]) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS), 4-byte elements
 // Copies 4 bytes global -> shared without a register round trip (the issuing warp does not stall on the load);
 // `valid == false` writes zero instead (src-size 0).

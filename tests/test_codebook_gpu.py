@@ -113,3 +113,26 @@ def test_argmin_tie_lowest_index(cuda_device):
     q = make_features(2, 1024, C)
     codes = eng.encode(torch.from_numpy(q).to(cuda_device), 0.2).cpu().numpy()
     assert codes.max() < 64
+
+
+def test_encode_exact_ties_lowest_index(cuda_device):
+    """Duplicate codewords make exact ties in every level: the fp32 filter cannot separate them, so the kernel must
+    fall back to its float64 evaluation and pick the LOWEST index (reference torch.argmin semantics, codebook.py:131);
+    the result must still equal the exact restatement bit for bit, and a duplicated index must never be chosen."""
+    from quantv2x_b200.engine import CodebookEngine
+
+    C, m, ks, rows = 256, 1, [128] * 3, 3000
+    cbs, heads = make_codebook_params(77, C, m, ks)
+    for l in range(3):
+        cbs[l][0, 64:, :] = cbs[l][0, :64, :]          # codeword 64 + i == codeword i
+    p = oracle_params(cbs, heads)
+    q = make_features(3, rows, C)
+    delta = np.float32(0.21)
+    eng = CodebookEngine(cbs, heads)
+    lib_fe, fixed = library_fold(eng, co.fold_encode(p))
+    codes = eng.encode(torch.from_numpy(q).to(cuda_device), float(delta)).cpu().numpy()
+    ref_fx = co.encode_fixed_point(lib_fe, q, delta, fixed)
+    for l in range(3):
+        assert np.array_equal(codes[l].T, ref_fx[l]), f"level {l}: kernel codes differ from the fixed-point oracle"
+    # the folded columns of duplicated codewords are identical bit for bit at level 0 (same digits, scale, g0)
+    assert codes[0].max() < 64, "a duplicate (higher) index won an exact tie at level 0"
