@@ -246,7 +246,7 @@ def main():
     else:
         tile = rank_tile(rank, world, pipe.ho, pipe.wo)
         recv_codes = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
-        codes_full = torch.empty((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
+        codes_full = torch.zeros((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
         g_ego, preds_dev = pipe._capture(lambda: pipe.decode_fuse_heads_tile(codes_full, aff, aff_host, tile))
         recv_preds = (torch.empty((world,) + tuple(preds_dev.shape), dtype=torch.float32, device=device)
                       if rank == 0 else None)

@@ -433,7 +433,8 @@ codebook_decode_kernel(const uint8_t* __restrict__ codes, long long plane_stride
         for (int rr = 0; rr < R; ++rr) {
             crow[rr] = rowi[rr];
 #pragma unroll
-            for (int i = 0; i < NT; ++i) soffs[rr][i] = tb.soff[i] + code[rr][i] * tb.Cs;
+            for (int i = 0; i < NT; ++i)      // an out-of-range code (corrupt input) must not index past the table
+                soffs[rr][i] = tb.soff[i] + min(code[rr][i], tb.k[i] - 1) * tb.Cs;
         }
         const long long tn = t0 + nwarps * R;
         if (tn < total) fetch(tn);      // next iteration's codes are in flight while this one is gathered and stored
