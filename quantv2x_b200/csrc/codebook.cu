@@ -64,7 +64,10 @@ struct EncodeEpilogue {
         float fbest[kMaxSeg], fsecond[kMaxSeg], vmax;
     };
 
-    __device__ __forceinline__ void side_load(const IgemmGeom&, const TileCoord&, int, uint8_t*, int32_t*, int&) const {}
+    struct Side {};
+    __device__ __forceinline__ void side_init(Side&, const IgemmGeom&, int) const {}
+    __device__ __forceinline__ void side_load(const IgemmGeom&, const TileCoord&, int, uint8_t*, int32_t*, int&,
+                                              const Side&) const {}
 
     __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
                                           const uint8_t*) const {

@@ -114,8 +114,9 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //     static constexpr int kMaxStages;                 // cap of the smem ring depth (frees L1 for gathers)
 //     static constexpr bool kSideWarp;                 // warp 3 stages the tile's side inputs in shared memory
 //     static constexpr bool kSeqDrain;                 // G > 1: accumulator groups are drained one by one
+//     struct Side; __device__ void side_init(Side&, const IgemmGeom&, int lane) const;   -- once per kernel
 //     __device__ void side_load(const IgemmGeom&, const TileCoord&, int lane, uint8_t* slot, int32_t* halo,
-//                               int& staged_nt) const;
+//                               int& staged_nt, const Side&) const;
 //         -- kSideWarp: run by the 32 lanes of warp 3, one tile AHEAD of the epilogue, into one of two
 //            kEpiSmemBytes/2 slots (per-column parameters, per-row receptive-field sums, ...)
 //     __device__ void begin(Tile&, const IgemmGeom&, const TileCoord&, int row, const uint8_t* slot) const;
@@ -323,10 +324,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int32_t* halo = reinterpret_cast<int32_t*>(epi_scratch + kEpiSmemBytes + par * (kHaloSmemBytes / 2));
             int staged_nt = -1;
             uint32_t sph = 0;
+            typename Epi::Side sd;
+            epi.side_init(sd, g, lane);
             for (int t = blockIdx.x + par * gridDim.x; t < total_tiles; t += 2 * gridDim.x, sph ^= 1) {
                 const TileCoord tc = decode_tile(g, t);
                 mbar_wait(smem_u32(&side_empty[par]), sph ^ 1);
-                epi.side_load(g, tc, lane, slot, halo, staged_nt);
+                epi.side_load(g, tc, lane, slot, halo, staged_nt, sd);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&side_full[par]));     // release: the slot's writes are visible
             }
