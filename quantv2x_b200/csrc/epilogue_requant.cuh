@@ -32,6 +32,7 @@ struct RequantEpilogue {
     float qmax, delta_out, zp_out;
     float rdelta;                         // fl(1 / delta_out)
     int fast8;                            // 8-bit output, zero-point 0, ReLU: saturating fast path
+    int digits;                           // G == 3 digit GEMM reduced in the order mid, lo, hi (see accum)
     float gscale[kMaxGroups];
     const float* cscale;                  // [N_total]
     const float* bias;                    // [N_total]
@@ -201,6 +202,24 @@ struct RequantEpilogue {
     template <int W>
     __device__ __forceinline__ void accum(const Tile& ts, const IgemmGeom& g, int grp, int n0, const int32_t (&acc)[W],
                                           float (&v)[W]) const {
+        if (G == 3 && digits) {
+            // 24-bit fixed-point weights as three signed byte digits, groups arrive in the order mid, lo, hi:
+            //   v = fl32( 65536 * hi + fl32(256 * mid + lo) )     (256 * mid + lo is exact in int32, hi exact in fp32)
+            // the running "sum" holds the raw mid accumulator (as bits) between the first two groups
+            if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook: dumped in hi, mid, lo order
+                const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+                const int dg = (grp == 0) ? 1 : (grp == 1 ? 2 : 0);
+#pragma unroll
+                for (int j = 0; j < W; ++j) acc_dump[(dg * gstride + ts.mrow) * n_total + n0 + j] = acc[j];
+            }
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                if (grp == 0) v[j] = __int_as_float(acc[j]);
+                else if (grp == 1) v[j] = __int2float_rn(__float_as_int(v[j]) * 256 + acc[j]);
+                else v[j] = fmaf(__int2float_rn(acc[j]), 65536.f, v[j]);
+            }
+            return;
+        }
         const bool use_zp = (zpw[0] != nullptr);
         int32_t t[W];
         if (use_zp) {

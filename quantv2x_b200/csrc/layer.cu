@@ -211,9 +211,14 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         g.pad = 0;
         g.cblocks = d.cin / L->bk;
         g.b_k_tap_stride = 0;
+        // B rows are stored digit-major (hi, mid, lo).  With at most 256 reduction terms 256 * acc_mid + acc_lo
+        // fits an int32, so the digits are reduced in the order mid, lo, hi and combined as
+        // fl32(65536 * hi + fl32(256 * mid + lo)) -- two conversions and one fma instead of three of each.
+        const bool packed = (d.cin <= 256);
+        const int order[3] = {packed ? 1 : 0, packed ? 2 : 1, packed ? 0 : 2};
         for (int i = 0; i < 3; ++i) {
             g.a_c_base[i] = in_cbase;
-            g.b_row_base[i] = i * L->n_total;
+            g.b_row_base[i] = order[i] * L->n_total;
             g.b_k_base[i] = 0;
         }
         out_h = ho;
@@ -272,6 +277,7 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.zp_out = d.out_zero_point;
         e.rdelta = 1.0f / d.out_delta;
         e.fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) ? 1 : 0;
+        e.digits = (d.kind == 1 && d.cin <= 256) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
             e.gscale[i] = L->gscale[i];
             e.zpw[i] = (L->use_zp && i < L->groups) ? L->d_zpw : nullptr;
