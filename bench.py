@@ -264,6 +264,31 @@ def main():
         g_ego.replay()
         return gather_pred_tiles(preds_dev, pipe.ho, pipe.wo, dst=0, recv=recv_preds)
 
+    def phase_times(k=10):
+        """Device time of the step's phases on this rank (CUDA events between them), averaged over k steps."""
+        names = ["encode_graph", "exchange_codes", "ego_graph", "gather_preds"] if world > 1 else ["encode_graph", "ego_graph"]
+        acc = [0.0] * len(names)
+        for _ in range(k):
+            flush.fill_(1)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            evs[0].record()
+            g_enc.replay()
+            evs[1].record()
+            if world == 1:
+                g_ego.replay()
+                evs[2].record()
+            else:
+                codes_full.copy_(all_gather_code_planes(codes_local, hw, recv=recv_codes))
+                evs[2].record()
+                g_ego.replay()
+                evs[3].record()
+                gather_pred_tiles(preds_dev, pipe.ho, pipe.wo, dst=0, recv=recv_preds)
+                evs[4].record()
+            torch.cuda.synchronize()
+            for i in range(len(names)):
+                acc[i] += evs[i].elapsed_time(evs[i + 1])
+        return {n: a / k for n, a in zip(names, acc)}
+
     def timed_loop(fn, k):
         """k steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
         evs = []
@@ -292,6 +317,8 @@ def main():
         th.start()
     sync_all()
     total_ms = timed_loop(lambda: step(bev_dev), args.steps)
+    sync_all()
+    phases = phase_times()
     sync_all()
     launches = launches_per_step * args.steps      # kernels of this library replayed through the two CUDA graphs
     t = torch.tensor([total_ms], dtype=torch.float64, device=device)
@@ -446,7 +473,7 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": int(preds_host.numel() * 4)},
                 "gpu_launches": int(launches), "clocks": summarize_clocks(samples), "preds_sha1": preds_sha1,
-                "roofline": roof,
+                "phases_ms_rank0": phases, "roofline": roof,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
