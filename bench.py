@@ -224,76 +224,96 @@ def main():
 
     bev_all = synthetic_bev(0, N_AGENTS, BEV_H, BEV_W, BEV_C, PILLARS)
     bev_host = torch.from_numpy(bev_all[rank * per:(rank + 1) * per]).pin_memory()
-    bev_dev = bev_host.to(device)
     poses = torch.from_numpy(synthetic_poses(N_AGENTS)).float()
     aff = normalize_pairwise_tfm(poses, 80.0, 281.6, 1)[0, 0, :N_AGENTS].contiguous().to(device)
+    aff_host = aff.cpu().numpy()
     levels, m, hw = pipe.codebook.levels, pipe.codebook.m, pipe.hw
     preds_host = torch.empty((pipe.heads.cout, hw), dtype=torch.float32).pin_memory()
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
 
     from quantv2x_b200.distributed import all_gather_code_planes, gather_pred_tiles, rank_tile
+
+    # ---- frames in flight and input rotation.
+    # INFLIGHT frames are processed concurrently on their own streams and buffer sets (a serving loop pipelines
+    # frames: frame i+1's backbone overlaps frame i's exchange + ego stage); every frame still runs the complete
+    # path.  The input of step i is buffer i % R of a pool of R distinct frames whose total size exceeds the 126 MB
+    # L2, so no step finds its input in L2 (this replaces the flush buffer, which would serialise the pipeline).
+    INFLIGHT = 2
+    in_bytes = per * BEV_H * BEV_W * BEV_C
+    R = max(INFLIGHT, -(-(140 * 1024 * 1024) // in_bytes))
+    R += R % INFLIGHT
+    bev0 = bev_host.to(device)
+    bev_pool = [bev0] + [torch.roll(bev0, shifts=(3 * r, 5 * r), dims=(1, 2)).contiguous() for r in range(1, R)]
+    config["inflight"] = INFLIGHT
+    config["l2"] = (f"the input of step i is buffer i % {R} of {R} distinct frames ({R * in_bytes / 2**20:.0f} MB per rank, "
+                    "more than the 126 MB L2); no flush between steps because frames are pipelined")
 
     # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (collectives stay outside).
     #   1 GPU : encode graph (8 agents) -> ego graph (decode + warp/fuse + heads on the whole map)
     #   G GPUs: encode graph (8/G agents) -> all_gather of the uint8 code planes -> ego graph on this rank's output
     #           TILE (decode only the source rectangles the tile samples, fuse, heads) -> gather of the head tiles
     lc0 = _lib.lib().qv2x_launch_count()
-    g_enc, codes_local = pipe.capture_encode(bev_dev)
+    g_enc, codes_local = [None] * R, [None] * INFLIGHT
+    for r in range(R):
+        g_enc[r], codes_local[r % INFLIGHT] = pipe.capture_encode(bev_pool[r], slot=r % INFLIGHT)
     lc1 = _lib.lib().qv2x_launch_count()
-    aff_host = aff.cpu().numpy()
-    if world == 1:
-        g_ego, preds_dev = pipe.capture_ego(codes_local, aff)
-    else:
-        tile = rank_tile(rank, world, pipe.ho, pipe.wo)
-        recv_codes = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
-        codes_full = torch.zeros((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
-        g_ego, preds_dev = pipe._capture(lambda: pipe.decode_fuse_heads_tile(codes_full, aff, aff_host, tile))
-        recv_preds = (torch.empty((world,) + tuple(preds_dev.shape), dtype=torch.float32, device=device)
-                      if rank == 0 else None)
-    lc2 = _lib.lib().qv2x_launch_count()
-    # kernels per replay = launches recorded while capturing (2 warm-up calls + 1 captured call per stage)
-    launches_per_step = (lc1 - lc0) // 3 + (lc2 - lc1) // 3
-
-    def step(bev):
-        """bev must be the static buffer bev_dev (graphs replay on fixed addresses).  Returns preds on rank 0."""
-        g_enc.replay()
+    g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
+    recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT
+    tile = rank_tile(rank, world, pipe.ho, pipe.wo) if world > 1 else None
+    for sl in range(INFLIGHT):
         if world == 1:
-            g_ego.replay()
-            return preds_dev
-        codes_full.copy_(all_gather_code_planes(codes_local, hw, recv=recv_codes))
-        g_ego.replay()
-        return gather_pred_tiles(preds_dev, pipe.ho, pipe.wo, dst=0, recv=recv_preds)
+            g_ego[sl], preds_dev[sl] = pipe.capture_ego(codes_local[sl], aff, slot=sl)
+        else:
+            recv_codes[sl] = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
+            codes_full[sl] = torch.zeros((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
+            g_ego[sl], preds_dev[sl] = pipe._capture(
+                lambda sl=sl: pipe.decode_fuse_heads_tile(codes_full[sl], aff, aff_host, tile, slot=sl))
+            recv_preds[sl] = (torch.empty((world,) + tuple(preds_dev[sl].shape), dtype=torch.float32, device=device)
+                              if rank == 0 else None)
+    lc2 = _lib.lib().qv2x_launch_count()
+    # kernels per replay = launches recorded while capturing (2 warm-up calls + 1 captured call per graph)
+    launches_per_step = (lc1 - lc0) // (3 * R) + (lc2 - lc1) // (3 * INFLIGHT)
+    streams = [torch.cuda.Stream() for _ in range(INFLIGHT)]
+
+    def step(i):
+        """Step i on the CURRENT stream: input buffer i % R, buffer set i % INFLIGHT.  Returns preds on rank 0."""
+        r, sl = i % R, i % INFLIGHT
+        g_enc[r].replay()
+        if world == 1:
+            g_ego[sl].replay()
+            return preds_dev[sl]
+        codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
+        g_ego[sl].replay()
+        return gather_pred_tiles(preds_dev[sl], pipe.ho, pipe.wo, dst=0, recv=recv_preds[sl])
 
     def phase_times(k=10):
-        """Device time of the step's phases on this rank (CUDA events between them), averaged over k steps."""
+        """Device time of the step's phases on this rank (CUDA events between them, one frame at a time)."""
         names = ["encode_graph", "exchange_codes", "ego_graph", "gather_preds"] if world > 1 else ["encode_graph", "ego_graph"]
         acc = [0.0] * len(names)
-        for _ in range(k):
-            flush.fill_(1)
+        for i in range(k):
+            r, sl = i % R, i % INFLIGHT
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
             evs[0].record()
-            g_enc.replay()
+            g_enc[r].replay()
             evs[1].record()
             if world == 1:
-                g_ego.replay()
+                g_ego[sl].replay()
                 evs[2].record()
             else:
-                codes_full.copy_(all_gather_code_planes(codes_local, hw, recv=recv_codes))
+                codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
                 evs[2].record()
-                g_ego.replay()
+                g_ego[sl].replay()
                 evs[3].record()
-                gather_pred_tiles(preds_dev, pipe.ho, pipe.wo, dst=0, recv=recv_preds)
+                gather_pred_tiles(preds_dev[sl], pipe.ho, pipe.wo, dst=0, recv=recv_preds[sl])
                 evs[4].record()
             torch.cuda.synchronize()
-            for i in range(len(names)):
-                acc[i] += evs[i].elapsed_time(evs[i + 1])
+            for j in range(len(names)):
+                acc[j] += evs[j].elapsed_time(evs[j + 1])
         return {n: a / k for n, a in zip(names, acc)}
 
     def timed_loop(fn, k):
-        """k steps, each bracketed by CUDA events on the launching stream; L2 flushed between steps."""
+        """k calls of fn on the current stream, each bracketed by CUDA events (used for single kernels)."""
         evs = []
         for _ in range(k):
-            flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -302,13 +322,28 @@ def main():
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs)
 
+    def run_steps(k, inflight):
+        """k steps, `inflight` frames concurrently (step i on stream i % inflight); one event pair around all."""
+        main = torch.cuda.current_stream()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(main)
+        for st in streams[:inflight]:
+            st.wait_event(start)
+        for i in range(k):
+            with torch.cuda.stream(streams[i % inflight]):
+                step(i)
+        for st in streams[:inflight]:
+            main.wait_stream(st)
+        end.record(main)
+        torch.cuda.synchronize()
+        return start.elapsed_time(end)
+
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step(bev_dev)
+    run_steps(max(args.warmup, 3), INFLIGHT)
     sync_all()
     stop, samples = threading.Event(), []
     th = None
@@ -316,72 +351,76 @@ def main():
         th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
         th.start()
     sync_all()
-    total_ms = timed_loop(lambda: step(bev_dev), args.steps)
+    total_ms = run_steps(args.steps, INFLIGHT)
+    sync_all()
+    serial_ms = run_steps(args.steps, 1)          # one frame at a time: the single-frame latency
     sync_all()
     phases = phase_times()
     sync_all()
-    launches = launches_per_step * args.steps      # kernels of this library replayed through the two CUDA graphs
-    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    launches = launches_per_step * args.steps      # kernels of this library replayed through the CUDA graphs
+    t = torch.tensor([total_ms, serial_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms, serial_ms = float(t[0].item()), float(t[1].item())
     ms_per_step = total_ms / args.steps
     fps = 1e3 / ms_per_step
 
     # ---- e2e: host buffers in, host result out, through the same public calls.  Every step copies ITS inputs from
-    # pinned host memory and reads ITS result back; the copies of step i+1 / i-1 run on their own streams while step
-    # i computes (double-buffered staging), as a serving loop would.  One event pair brackets all K steps including
-    # the first (un-overlapped) upload and the last readback.  No L2 flush here: the inputs arrive from the host.
-    s_cmp, s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    bev_stage = [torch.empty_like(bev_dev) for _ in range(2)]
-    preds_stage = [torch.empty((pipe.heads.cout, hw), dtype=torch.float32, device=device) for _ in range(2)]
-    preds_hosts = [preds_host, torch.empty_like(preds_host).pin_memory()]
+    # pinned host memory into its input buffer and reads ITS result back; the copies run on their own streams so
+    # that step i+1's upload and step i-1's readback overlap step i, as a serving loop would.  One event pair
+    # brackets all K steps including the first (un-overlapped) upload and the last readback.
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    preds_stage = [torch.empty((pipe.heads.cout, hw), dtype=torch.float32, device=device) for _ in range(INFLIGHT)]
+    preds_hosts = [preds_host] + [torch.empty_like(preds_host).pin_memory() for _ in range(INFLIGHT - 1)]
 
     def e2e_run(k):
         ev = lambda: torch.cuda.Event()
-        copied, stage_free, ego_done, d2h_done = [None, None], [None, None], [None, None], [None, None]
+        copied, enc_done = [None] * R, [None] * R
+        ego_done, d2h_done = [None] * INFLIGHT, [None] * INFLIGHT
+        main = torch.cuda.current_stream()
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.current_stream().synchronize()
-        start.record(s_cmp)
+        main.synchronize()
+        start.record(main)
         s_h2d.wait_event(start)
+        for st in streams:
+            st.wait_event(start)
 
         def upload(i):
-            bidx = i & 1
+            r = i % R
             with torch.cuda.stream(s_h2d):
-                if stage_free[bidx] is not None:
-                    s_h2d.wait_event(stage_free[bidx])
-                bev_stage[bidx].copy_(bev_host, non_blocking=True)
-                copied[bidx] = ev()
-                copied[bidx].record(s_h2d)
+                if enc_done[r] is not None:
+                    s_h2d.wait_event(enc_done[r])          # the graph that read this buffer R steps ago is done
+                bev_pool[r].copy_(bev_host, non_blocking=True)
+                copied[r] = ev()
+                copied[r].record(s_h2d)
 
         upload(0)
         for i in range(k):
-            bidx = i & 1
+            r, sl = i % R, i % INFLIGHT
             if i + 1 < k:
                 upload(i + 1)
-            with torch.cuda.stream(s_cmp):
-                s_cmp.wait_event(copied[bidx])
-                bev_dev.copy_(bev_stage[bidx], non_blocking=True)
-                stage_free[bidx] = ev()
-                stage_free[bidx].record(s_cmp)
-                p = step(bev_dev)
+            st = streams[sl]
+            with torch.cuda.stream(st):
+                st.wait_event(copied[r])
+                p = step(i)
+                enc_done[r] = ev()
+                enc_done[r].record(st)
                 if rank == 0:
-                    if d2h_done[bidx] is not None:
-                        s_cmp.wait_event(d2h_done[bidx])
-                    preds_stage[bidx].copy_(p, non_blocking=True)
-                ego_done[bidx] = ev()
-                ego_done[bidx].record(s_cmp)
+                    if d2h_done[sl] is not None:
+                        st.wait_event(d2h_done[sl])
+                    preds_stage[sl].copy_(p, non_blocking=True)
+                ego_done[sl] = ev()
+                ego_done[sl].record(st)
             if rank == 0:
                 with torch.cuda.stream(s_d2h):
-                    s_d2h.wait_event(ego_done[bidx])
-                    preds_hosts[bidx].copy_(preds_stage[bidx], non_blocking=True)
-                    d2h_done[bidx] = ev()
-                    d2h_done[bidx].record(s_d2h)
-        if rank == 0:
-            for d in d2h_done:
-                if d is not None:
-                    s_cmp.wait_event(d)
-        end.record(s_cmp)
+                    s_d2h.wait_event(ego_done[sl])
+                    preds_hosts[sl].copy_(preds_stage[sl], non_blocking=True)
+                    d2h_done[sl] = ev()
+                    d2h_done[sl].record(s_d2h)
+        for st in streams:
+            main.wait_stream(st)
+        main.wait_stream(s_d2h)
+        end.record(main)
         torch.cuda.synchronize()
         return start.elapsed_time(end)
 
@@ -389,6 +428,8 @@ def main():
     sync_all()
     e2e_ms = e2e_run(args.steps)
     sync_all()
+    for r in range(1, R):                    # the e2e loop uploaded frame 0 into every pool buffer: restore the pool
+        bev_pool[r].copy_(torch.roll(bev0, shifts=(3 * r, 5 * r), dims=(1, 2)))
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -396,7 +437,7 @@ def main():
 
     # the frame's result as a checksum: integers travel between the GPUs and every output pixel is computed by the
     # same arithmetic whatever the tiling, so this must be identical for every --gpus N
-    p = step(bev_dev)
+    p = step(0)
     preds_sha1 = None
     if rank == 0:
         import hashlib
@@ -473,7 +514,8 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": int(preds_host.numel() * 4)},
                 "gpu_launches": int(launches), "clocks": summarize_clocks(samples), "preds_sha1": preds_sha1,
-                "phases_ms_rank0": phases, "roofline": roof,
+                "phases_ms_rank0": phases,
+                "latency_ms_one_frame_at_a_time": serial_ms / args.steps, "roofline": roof,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -325,15 +325,16 @@ class Plan:
         check(_lib.lib().qv2x_plan_out_shape(self._h, h, w, byref(ho), byref(wo), byref(c)))
         return ho.value, wo.value, c.value
 
-    def workspace(self, n, h, w, device):
-        key = (n, h, w, str(device))
+    def workspace(self, n, h, w, device, slot=0):
+        """Scratch activations of one forward; `slot` separates frames that are in flight concurrently."""
+        key = (n, h, w, str(device), slot)
         if key not in self._ws:
             nbytes = ctypes.c_size_t()
             check(_lib.lib().qv2x_plan_workspace_bytes(self._h, n, h, w, byref(nbytes)))
             self._ws[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
         return self._ws[key]
 
-    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, dump_step: int = -1, acc_dump=None):
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, dump_step: int = -1, acc_dump=None, slot=0):
         """x uint8 NHWC [n, H, W, C0] -> uint8 NHWC [n, ho, wo, C_last]."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
         n, h, w, c = x.shape
@@ -341,7 +342,7 @@ class Plan:
         ho, wo, co = self.out_shape(h, w)
         if out is None:
             out = torch.empty((n, ho, wo, co), dtype=torch.uint8, device=x.device)
-        ws = self.workspace(n, h, w, x.device)
+        ws = self.workspace(n, h, w, x.device, slot)
         check(_lib.lib().qv2x_plan_forward(self._h, n, h, w, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()),
                                            c_void_p(ws.data_ptr()), ws.numel(), dump_step,
                                            None if acc_dump is None else c_void_p(acc_dump.data_ptr()),

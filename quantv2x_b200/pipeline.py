@@ -45,36 +45,37 @@ class CollabPipeline:
                                       "row); pass inputs_m1['bev_u8'] (uint8 [n, H, W, 64]) instead")
         return pillar.forward(inp)
 
-    def encode_buffers(self, n):
-        if n not in self._enc_buf:
+    def encode_buffers(self, n, slot=0):
+        """Buffers of the agent-side stage; `slot` separates frames that are in flight concurrently."""
+        if (n, slot) not in self._enc_buf:
             d = self.device
-            self._enc_buf[n] = dict(
+            self._enc_buf[(n, slot)] = dict(
                 feat=torch.empty((n, self.ho, self.wo, self.c_feat), dtype=torch.uint8, device=d),
                 codes=torch.empty((self.codebook.levels, self.codebook.m, n * self.hw), dtype=torch.uint8, device=d))
-        return self._enc_buf[n]
+        return self._enc_buf[(n, slot)]
 
-    def encode_agents(self, bev_u8: torch.Tensor) -> torch.Tensor:
+    def encode_agents(self, bev_u8: torch.Tensor, slot=0) -> torch.Tensor:
         """bev_u8 uint8 [n, H, W, C_bev] -> codes uint8 [levels, m, n*hw] (agent-major rows)."""
         n = bev_u8.shape[0]
-        b = self.encode_buffers(n)
-        self.fused.forward_u8(bev_u8, out=b["feat"])
+        b = self.encode_buffers(n, slot)
+        self.fused.forward_u8(bev_u8, out=b["feat"], slot=slot)
         self.codebook.encode(b["feat"], self.feat_delta, out=b["codes"])
         return b["codes"]
 
     # ------------------------------------------------------------------ ego side
-    def ego_buffers(self, n):
-        if n not in self._ego_buf:
+    def ego_buffers(self, n, slot=0):
+        if (n, slot) not in self._ego_buf:
             d = self.device
-            self._ego_buf[n] = dict(
+            self._ego_buf[(n, slot)] = dict(
                 feat=torch.empty((n, self.ho, self.wo, self.c_feat), dtype=torch.float32, device=d),
                 fused=torch.empty((self.ho, self.wo, self.c_feat), dtype=torch.float32, device=d),
                 preds=torch.empty((self.heads.cout, self.hw), dtype=torch.float32, device=d))
-        return self._ego_buf[n]
+        return self._ego_buf[(n, slot)]
 
-    def decode_fuse_heads(self, codes: torch.Tensor, affine: torch.Tensor) -> torch.Tensor:
+    def decode_fuse_heads(self, codes: torch.Tensor, affine: torch.Tensor, slot=0) -> torch.Tensor:
         """codes uint8 [levels, m, n*hw]; affine CUDA float32 [n, 2, 3] -> preds float32 [Cout, hw]."""
         n = codes.shape[-1] // self.hw
-        b = self.ego_buffers(n)
+        b = self.ego_buffers(n, slot)
         self.codebook.decode(codes, out=b["feat"].view(n * self.hw, self.c_feat))
         E.fuse(b["feat"], affine, self.fusion_mode, out=b["fused"])
         self.heads.forward(b["fused"], out=b["preds"])
@@ -104,8 +105,8 @@ class CollabPipeline:
             rects.append((cy0, max(cy1, cy0), cx0, max(cx1, cx0)))
         return rects
 
-    def ego_tile_buffers(self, n, tile):
-        key = (n, tuple(tile))
+    def ego_tile_buffers(self, n, tile, slot=0):
+        key = (n, tuple(tile), slot)
         if key not in self._ego_buf:
             d = self.device
             tp = (tile[1] - tile[0]) * (tile[3] - tile[2])
@@ -115,12 +116,13 @@ class CollabPipeline:
                 preds=torch.empty((self.heads.cout, tp), dtype=torch.float32, device=d))
         return self._ego_buf[key]
 
-    def decode_fuse_heads_tile(self, codes: torch.Tensor, affine: torch.Tensor, affine_host, tile) -> torch.Tensor:
+    def decode_fuse_heads_tile(self, codes: torch.Tensor, affine: torch.Tensor, affine_host, tile,
+                               slot=0) -> torch.Tensor:
         """The ego stage for ONE output tile (y0, y1, x0, x1): decode only the source rectangles the tile samples
         from, warp + fuse the tile, run the heads on it.  Returns compact preds [Cout, tile_pixels].  Per-pixel
         arithmetic is identical to decode_fuse_heads, so tiles assembled from several GPUs equal the 1-GPU result."""
         n = codes.shape[-1] // self.hw
-        b = self.ego_tile_buffers(n, tile)
+        b = self.ego_tile_buffers(n, tile, slot)
         rects = self.source_rects(affine_host, tile)
         self.codebook.decode_regions(codes, self.wo, [a * self.hw for a in range(n)], rects,
                                      b["feat"].view(n * self.hw, self.c_feat))
@@ -144,13 +146,13 @@ class CollabPipeline:
             out = fn()
         return g, out
 
-    def capture_encode(self, bev_static: torch.Tensor):
+    def capture_encode(self, bev_static: torch.Tensor, slot=0):
         """Graph of encode_agents over a STATIC input buffer; returns (graph, codes tensor it writes)."""
-        return self._capture(lambda: self.encode_agents(bev_static))
+        return self._capture(lambda: self.encode_agents(bev_static, slot))
 
-    def capture_ego(self, codes_static: torch.Tensor, affine_static: torch.Tensor):
+    def capture_ego(self, codes_static: torch.Tensor, affine_static: torch.Tensor, slot=0):
         """Graph of decode_fuse_heads over STATIC code / pose buffers; returns (graph, preds tensor it writes)."""
-        return self._capture(lambda: self.decode_fuse_heads(codes_static, affine_static))
+        return self._capture(lambda: self.decode_fuse_heads(codes_static, affine_static, slot))
 
     def split_preds(self, preds: torch.Tensor, n_cls: int, n_reg: int, n_dir: int):
         """[Cout, hw] -> dict of NCHW tensors as the reference model returns them (batch 1)."""
