@@ -2,10 +2,10 @@
 //
 // Reference semantics (opencood/quant/quant_layer.py:391-410 with :132-148): fake-quant weight ->
 // conv (+bias) -> folded BN = identity -> ReLU -> fake-quant activation.  Restated on integers
-// (SURVEY Appendix A.1); normative fp32 operation order, every operation rounded separately (no FMA):
+// (SURVEY Appendix A.1); normative fp32 operation order (the scale-and-bias step is ONE fused multiply-add):
 //     t_g = float( acc_g[p,n] - zpw_g[n] * S_g[p] )                     (int32 exact, then RN convert)
 //     v   = gs[0]*t_0  (+ gs[1]*t_1 + gs[2]*t_2, left to right)
-//     y   = v * cs[n] + bias[n] ;  y = max(y, 0) if relu
+//     y   = fma(v, cs[n], bias[n]) ;  y = max(y, 0) if relu                 (one rounding)
 //     q   = clamp( rint(y / delta_out) + zp_out, 0, qmax )              (true division, half-to-even)
 // S_g[p] is the sum of the group's input bytes over the receptive field of p (zero padding adds 0
 // because the activation zero-point is 0 after ReLU); it is rebuilt from per-pixel channel sums
@@ -15,7 +15,7 @@
 
 namespace qv2x {
 
-template <int G>
+template <int G, bool DIGITS = false, bool FAST8 = true>
 struct RequantEpilogue {
     // epilogue warps per TMEM lane quadrant: more warps hide the latencies of the (ALU-pipe bound) requant math
     static constexpr int col_split(int) { return 2; }   // (4 was measured: spills and no gain -- not latency bound)
@@ -31,8 +31,9 @@ struct RequantEpilogue {
     int relu;
     float qmax, delta_out, zp_out;
     float rdelta;                         // fl(1 / delta_out)
-    int fast8;                            // 8-bit output, zero-point 0, ReLU: saturating fast path
-    int digits;                           // G == 3 digit GEMM reduced in the order mid, lo, hi (see accum)
+    // FAST8: 8-bit output, zero-point 0, ReLU -- the saturating fast path (a template parameter, so that the
+    // generic path's W inline divisions do not bloat the hot kernels)
+    // DIGITS (G == 3): digit GEMM reduced in the order mid, lo, hi and combined on integers (see accum)
     float gscale[kMaxGroups];
     const float* cscale;                  // [N_total]
     const float* bias;                    // [N_total]
@@ -202,15 +203,16 @@ struct RequantEpilogue {
     template <int W>
     __device__ __forceinline__ void accum(const Tile& ts, const IgemmGeom& g, int grp, int n0, const int32_t (&acc)[W],
                                           float (&v)[W]) const {
-        if (G == 3 && digits) {
+        if constexpr (G == 3 && DIGITS) {
             // 24-bit fixed-point weights as three signed byte digits, groups arrive in the order mid, lo, hi:
             //   v = fl32( 65536 * hi + fl32(256 * mid + lo) )     (256 * mid + lo is exact in int32, hi exact in fp32)
             // the running "sum" holds the raw mid accumulator (as bits) between the first two groups
             if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook: dumped in hi, mid, lo order
                 const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
                 const int dg = (grp == 0) ? 1 : (grp == 1 ? 2 : 0);
+                int32_t* dp = acc_dump + (dg * gstride + ts.mrow) * n_total + n0;
 #pragma unroll
-                for (int j = 0; j < W; ++j) acc_dump[(dg * gstride + ts.mrow) * n_total + n0 + j] = acc[j];
+                for (int j = 0; j < W; j += 4) st_global_v4(dp + j, acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
             }
 #pragma unroll
             for (int j = 0; j < W; ++j) {
@@ -237,8 +239,9 @@ struct RequantEpilogue {
         }
         if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
             const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+            int32_t* dp = acc_dump + (grp * gstride + ts.mrow) * n_total + n0;
 #pragma unroll
-            for (int j = 0; j < W; ++j) acc_dump[(grp * gstride + ts.mrow) * n_total + n0 + j] = t[j];
+            for (int j = 0; j < W; j += 4) st_global_v4(dp + j, t[j], t[j + 1], t[j + 2], t[j + 3]);
         }
         float gs = 1.f;
 #pragma unroll
@@ -267,9 +270,10 @@ struct RequantEpilogue {
             cs[4 * v4 + 0] = c.x, cs[4 * v4 + 1] = c.y, cs[4 * v4 + 2] = c.z, cs[4 * v4 + 3] = c.w;
             bs[4 * v4 + 0] = b.x, bs[4 * v4 + 1] = b.y, bs[4 * v4 + 2] = b.z, bs[4 * v4 + 3] = b.w;
         }
-        if (fast8) {
-            // q = sat_u8(rint(y / delta)) for an 8-bit output with zero-point 0 (ReLU is subsumed by the clamp),
-            // entirely on the FMA/ALU pipes:
+        if constexpr (FAST8) {
+            // q = sat_u8(rint(y / delta)), y = fma(v, cs, b), for an 8-bit output with zero-point 0 (ReLU is subsumed
+            // by the clamp), entirely on the FMA/ALU pipes and mostly in immediate-operand forms (which issue at
+            // twice the rate of three-register forms):
             //   t = y * fl(1/delta) lies within 5.4e-5 of the IEEE quotient for |q| < 300, so both round to the same
             //   integer unless t is within 1e-4 of a half-integer -- only then (~2e-4 of elements) the exact division
             //   runs.  The clamp is applied to t (to [-0.25, 255.25], which rounds to 0 / 255 and is never "near"),
@@ -279,7 +283,7 @@ struct RequantEpilogue {
             float worst = 0.f;
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                y[j] = __fadd_rn(__fmul_rn(v[j], cs[j]), bs[j]);
+                y[j] = fmaf(v[j], cs[j], bs[j]);
                 const float t = fminf(fmaxf(__fmul_rn(y[j], rdelta), -0.25f), 255.25f);
                 const float sft = __fadd_rn(t, 12582912.0f);
                 const float r = __fadd_rn(sft, -12582912.0f);
@@ -308,7 +312,7 @@ struct RequantEpilogue {
         } else {
 #pragma unroll
             for (int j = 0; j < W; ++j) {
-                float y = __fadd_rn(__fmul_rn(v[j], cs[j]), bs[j]);
+                float y = fmaf(v[j], cs[j], bs[j]);
                 if (relu) y = fmaxf(y, 0.f);
                 // A zero dividend would send the whole warp through the division's slow path: divide
                 // delta/delta instead and mask.

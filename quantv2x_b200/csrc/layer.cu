@@ -276,8 +276,6 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.delta_out = d.out_delta;
         e.zp_out = d.out_zero_point;
         e.rdelta = 1.0f / d.out_delta;
-        e.fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) ? 1 : 0;
-        e.digits = (d.kind == 1 && d.cin <= 256) ? 1 : 0;
         for (int i = 0; i < 3; ++i) {
             e.gscale[i] = L->gscale[i];
             e.zpw[i] = (L->use_zp && i < L->groups) ? L->d_zpw : nullptr;
@@ -290,14 +288,22 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.acc_dump = d_acc_dump;
         e.n_total = L->n_total;
     };
-    if (L->groups == 1) {
-        RequantEpilogue<1> e{};
-        fill(e);
-        return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
+    const bool fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu);
+    const bool digits = (d.kind == 1 && d.cin <= 256);        // digit GEMM with packed integer recombination
+#define QV2X_RUN(GG, DG, F8)                                                     \
+    {                                                                            \
+        RequantEpilogue<GG, DG, F8> e{};                                         \
+        fill(e);                                                                 \
+        return dispatch_igemm<GG>(block_n, L->bk, tmA, tmB, g, e, stream);       \
     }
-    RequantEpilogue<3> e{};
-    fill(e);
-    return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
+    if (L->groups == 1) {
+        if (fast8) QV2X_RUN(1, false, true) else QV2X_RUN(1, false, false)
+    }
+    if (digits) {
+        if (fast8) QV2X_RUN(3, true, true) else QV2X_RUN(3, true, false)
+    }
+    if (fast8) QV2X_RUN(3, false, true) else QV2X_RUN(3, false, false)
+#undef QV2X_RUN
 }
 
 }  // extern "C"

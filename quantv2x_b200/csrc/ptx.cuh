@@ -159,6 +159,29 @@ __device__ __forceinline__ void ldg_nc_f8(const float* p, float (&v)[8]) {
                  : "l"(p));
 }
 
+// ---------------------------------------------------------------- packed fp32 pairs (sm_100 FFMA2 / FADD2)
+// Two IEEE fp32 operations per instruction, each lane-half rounded separately: the requant epilogue is bound by
+// instruction issue, and these halve its FMA-pipe share.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---------------------------------------------------------------- cp.async (LDGSTS), 4-byte elements
 // Copies 4 bytes global -> shared without a register round trip (the issuing warp does not stall on the load);
 // `valid == false` writes zero instead (src-size 0).
