@@ -25,6 +25,9 @@ __device__ __forceinline__ double i2d_exact(int x) {
     return __hiloint2double(0x43300000, x ^ 0x80000000) - 4503601774854144.0;
 }
 
+// FAST: fp32 filter with float64 fallback (one step per level); MSEG: segments per level as a compile-time constant
+// (0 = run-time m).  Both are template parameters so that the hot loop carries no code of the other variants.
+template <bool FAST, int MSEG>
 struct EncodeEpilogue {
     static constexpr int col_split(int) { return 2; }   // two epilogue warps per row quadrant, merged per level
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
@@ -49,12 +52,14 @@ struct EncodeEpilogue {
     //   the scores are first evaluated in fp32 with a rigorous error bound eps(row); if the best score beats the
     //   runner-up by more than 2*eps the fp32 argmin IS the float64 argmin, otherwise (~1e-4 of rows) the warp
     //   re-reads the accumulators and evaluates the level in float64 exactly as the slow path does.
-    int fast, pack16;
+    int pack16;
     const float* d32;             // float(delta * sc[j])
     const float* g32;             // float(g0[j])
     const float* btab32;          // float(btab), same layout
     float dmax[kMaxLevels];       // max_j |d32[j]| of the level
     float cabs[kMaxLevels];       // max_j |g0[j]| + sum_{j<l} max |B_{l,j}|
+
+    __device__ __forceinline__ int nseg() const { return MSEG > 0 ? MSEG : m; }
 
     struct Tile {
         long long r;
@@ -90,8 +95,8 @@ struct EncodeEpilogue {
     __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int c0,
                                           const int32_t (*acc)[W]) const {
         static_assert(W == 16, "the encode epilogue works on 16-column chunks");
-        if (fast) chunk_fast(ts, step, c0, acc);
-        else chunk_exact(ts, g, tc, step, c0, acc);
+        if constexpr (FAST) chunk_fast(ts, step, c0, acc);
+        else chunk_exact<16>(ts, g, tc, step, c0, acc);
     }
 
     // fp32 scores of 16 columns + running (best, runner-up, index) and max |V| of the row
@@ -129,7 +134,7 @@ struct EncodeEpilogue {
             if (jl < l) {
 #pragma unroll
                 for (int s2 = 0; s2 < kMaxSeg; ++s2) {
-                    if (s2 < m) {
+                    if (s2 < nseg()) {
                         const float* bp =
                             btab32 + boff[l][jl] + (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0;
 #pragma unroll
@@ -178,7 +183,7 @@ struct EncodeEpilogue {
                 if (jl < l) {
 #pragma unroll
                     for (int s2 = 0; s2 < kMaxSeg; ++s2)
-                        if (s2 < m) {
+                        if (s2 < nseg()) {
                             const double* nx = btab + boff[l][jl] +
                                                (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0 + 16;
                             asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
@@ -200,7 +205,7 @@ struct EncodeEpilogue {
             if (jl < l) {
 #pragma unroll
                 for (int s2 = 0; s2 < kMaxSeg; ++s2) {
-                    if (s2 < m) {
+                    if (s2 < nseg()) {
                         const double* bp = btab + boff[l][jl] +
                                            (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl + n0;
 #pragma unroll
@@ -230,6 +235,20 @@ struct EncodeEpilogue {
             if (s == seg) ts.best[s] = best, ts.bidx[s] = bidx;
     }
 
+    // The float64 evaluation of one level for this warp (rare path of the fp32 filter).
+    __device__ __forceinline__ void redo_level_exact(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step,
+                                                  const TmemView& tv) const {
+#pragma unroll
+        for (int s = 0; s < kMaxSeg; ++s) ts.best[s] = INFINITY, ts.bidx[s] = 0;
+        for (int c0 = tv.c_begin; c0 < tv.c_end; c0 += 16) {
+            uint32_t acc[3][16];
+#pragma unroll
+            for (int grp = 0; grp < 3; ++grp) tmem_ld_x16(tv.addr[grp] + c0, acc[grp]);
+            tmem_ld_wait();
+            chunk_exact<16>(ts, g, tc, step, c0, reinterpret_cast<const int32_t(*)[16]>(acc));
+        }
+    }
+
     static constexpr bool kHoldSlots = true;     // the level's accumulators may be re-read in step_end
     static constexpr float kEpsRel = 9.5367431640625e-07f;   // 2^-20 = 16 ulp(fp32): see the bound in step_end
 
@@ -239,7 +258,7 @@ struct EncodeEpilogue {
         const int l = step_level[step];
         const int bar_id = 1 + quad;
         bool exact_merge = true;
-        if (fast) {
+        if constexpr (FAST) {
             // ---- merge the fp32 candidates of the two column halves and test the gap.
             // Error bound of one fp32 score against the float64 evaluation: conversions of the digit accumulators
             // (<= 2 roundings), two fma roundings, the rounded parameters d32 / g32 / btab32 and the l additions
@@ -255,14 +274,14 @@ struct EncodeEpilogue {
             if (part == 1) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m) fc[s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
+                    if (s < nseg()) fc[s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
             }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             if (part == 0) {
                 bool unsafe = false;
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m) {
+                    if (s < nseg()) {
                         const FCand o = fc[s];
                         const float b0 = ts.fbest[s];
                         const float best = fminf(b0, o.best);
@@ -281,21 +300,13 @@ struct EncodeEpilogue {
             if (exact_merge) {
                 // rare: some row of this quadrant sits in a near-tie -- evaluate the level exactly for all 32 rows
                 // (the accumulators are still in TMEM because the slots are released only after step_end)
-#pragma unroll
-                for (int s = 0; s < kMaxSeg; ++s) ts.best[s] = INFINITY, ts.bidx[s] = 0;
-                for (int c0 = tv.c_begin; c0 < tv.c_end; c0 += 16) {
-                    uint32_t acc[3][16];
-#pragma unroll
-                    for (int grp = 0; grp < 3; ++grp) tmem_ld_x16(tv.addr[grp] + c0, acc[grp]);
-                    tmem_ld_wait();
-                    chunk_exact<16>(ts, g, tc, step, c0, reinterpret_cast<const int32_t(*)[16]>(acc));
-                }
+                redo_level_exact(ts, g, tc, step, tv);
                 // part 0 may still be reading fc[] above when part 1 starts overwriting the slots below
                 asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             } else {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m && part == 1) ts.bidx[s] = fc[s].idx;
+                    if (s < nseg() && part == 1) ts.bidx[s] = fc[s].idx;
             }
         }
         struct Cand {
@@ -310,13 +321,13 @@ struct EncodeEpilogue {
             if (part == 1) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
+                    if (s < nseg()) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
             }
             asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
             if (part == 0) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m) {
+                    if (s < nseg()) {
                         const double ob = cand[s].best;
                         const int oi = cand[s].idx;
                         if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s])) ts.bidx[s] = oi;   // ties -> lowest
@@ -327,12 +338,12 @@ struct EncodeEpilogue {
             if (part == 1) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < m) ts.bidx[s] = cand[s].idx;
+                    if (s < nseg()) ts.bidx[s] = cand[s].idx;
             }
         }
 #pragma unroll
         for (int s = 0; s < kMaxSeg; ++s) {
-            if (s < m) {
+            if (s < nseg()) {
                 const int code = ts.bidx[s];
 #pragma unroll
                 for (int ll = 0; ll < kMaxLevels; ++ll)
@@ -794,64 +805,68 @@ int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t*
     g.cblocks = cb->C / cb->bk;
     g.idesc = make_idesc_i8(cb->block_n, true);
     g.n_steps = cb->n_steps;
-    EncodeEpilogue e{};
+    const bool fast = cb->fast && !(g_debug_flags & 64);       // debug 64: force the float64 path
+    auto run = [&](auto e) -> int {
     e.levels = cb->levels;
-    e.m = cb->m;
-    int step = 0;
-    for (int l = 0; l < cb->levels; ++l) {
-        e.k[l] = cb->k[l];
-        e.n_level[l] = cb->n_level[l];
-        e.colbase[l] = cb->colbase[l];
-        for (int j = 0; j < kMaxLevels; ++j) e.boff[l][j] = cb->boff[l][j];
-        const int spl = cb->n_level[l] / cb->block_n;
-        for (int c = 0; c < spl; ++c, ++step) {
-            g.step_row_base[step] = cb->rowbase[l] + c * cb->block_n;
-            g.step_group_stride[step] = cb->n_level[l];
-            e.step_level[step] = l;
-            e.step_col0[step] = c * cb->block_n;
-            e.step_last[step] = (c == spl - 1);
-        }
-    }
-    if (delta != cb->cached_delta) {
-        auto* mcb = const_cast<qv2x_codebook*>(cb);
-        std::vector<float> d32(cb->h_sc.size());
-        std::vector<double> dsc(cb->h_sc.size());
-        for (size_t i = 0; i < d32.size(); ++i) {
-            dsc[i] = static_cast<double>(delta) * cb->h_sc[i];       // one float64 rounding, as the oracle does
-            d32[i] = static_cast<float>(dsc[i]);
-        }
-        QV2X_CUDA_OK(cudaMemcpy(cb->d_dsc, dsc.data(), dsc.size() * sizeof(double), cudaMemcpyHostToDevice));
+        e.m = cb->m;
+        int step = 0;
         for (int l = 0; l < cb->levels; ++l) {
-            float mx = 0.f;
-            for (int n = 0; n < cb->n_level[l]; ++n) mx = std::max(mx, std::fabs(d32[cb->colbase[l] + n]));
-            mcb->dmax[l] = mx;
+            e.k[l] = cb->k[l];
+            e.n_level[l] = cb->n_level[l];
+            e.colbase[l] = cb->colbase[l];
+            for (int j = 0; j < kMaxLevels; ++j) e.boff[l][j] = cb->boff[l][j];
+            const int spl = cb->n_level[l] / cb->block_n;
+            for (int c = 0; c < spl; ++c, ++step) {
+                g.step_row_base[step] = cb->rowbase[l] + c * cb->block_n;
+                g.step_group_stride[step] = cb->n_level[l];
+                e.step_level[step] = l;
+                e.step_col0[step] = c * cb->block_n;
+                e.step_last[step] = (c == spl - 1);
+            }
         }
-        QV2X_CUDA_OK(cudaMemcpy(cb->d_d32, d32.data(), d32.size() * sizeof(float), cudaMemcpyHostToDevice));
-        mcb->cached_delta = delta;
-    }
-    e.fast = (cb->fast && !(g_debug_flags & 64)) ? 1 : 0;      // debug 64: force the float64 path
-    e.pack16 = (cb->C <= 256) ? 1 : 0;
-    e.d32 = cb->d_d32;
-    e.g32 = cb->d_g32;
-    e.btab32 = cb->d_btab32;
-    for (int l = 0; l < cb->levels; ++l) {
-        e.dmax[l] = cb->dmax[l];
-        e.cabs[l] = cb->cabs[l];
-    }
-    e.delta = static_cast<double>(delta);
-    e.dsc = cb->d_dsc;
-    e.g0 = cb->d_g0;
-    e.btab = cb->d_btab;
-    e.codes = d_codes;
-    e.rows = rows;
-    CUtensorMap tmA, tmB;
-    int rc = make_act_tmap(&tmA, d_feat, 1, 1, static_cast<int>(rows), feat_cstride, 128, 1, 1, cb->bk);
-    if (rc) return rc;
-    int total_rows = 0;
-    for (int l = 0; l < cb->levels; ++l) total_rows += 3 * cb->n_level[l];
-    rc = make_weight_tmap(&tmB, cb->d_digits, total_rows, cb->C, cb->block_n, cb->bk);
-    if (rc) return rc;
-    return dispatch_igemm<3>(cb->block_n, cb->bk, tmA, tmB, g, e, stream);
+        if (delta != cb->cached_delta) {
+            auto* mcb = const_cast<qv2x_codebook*>(cb);
+            std::vector<float> d32(cb->h_sc.size());
+            std::vector<double> dsc(cb->h_sc.size());
+            for (size_t i = 0; i < d32.size(); ++i) {
+                dsc[i] = static_cast<double>(delta) * cb->h_sc[i];       // one float64 rounding, as the oracle does
+                d32[i] = static_cast<float>(dsc[i]);
+            }
+            QV2X_CUDA_OK(cudaMemcpy(cb->d_dsc, dsc.data(), dsc.size() * sizeof(double), cudaMemcpyHostToDevice));
+            for (int l = 0; l < cb->levels; ++l) {
+                float mx = 0.f;
+                for (int n = 0; n < cb->n_level[l]; ++n) mx = std::max(mx, std::fabs(d32[cb->colbase[l] + n]));
+                mcb->dmax[l] = mx;
+            }
+            QV2X_CUDA_OK(cudaMemcpy(cb->d_d32, d32.data(), d32.size() * sizeof(float), cudaMemcpyHostToDevice));
+            mcb->cached_delta = delta;
+        }
+        e.pack16 = (cb->C <= 256) ? 1 : 0;
+        e.d32 = cb->d_d32;
+        e.g32 = cb->d_g32;
+        e.btab32 = cb->d_btab32;
+        for (int l = 0; l < cb->levels; ++l) {
+            e.dmax[l] = cb->dmax[l];
+            e.cabs[l] = cb->cabs[l];
+        }
+        e.delta = static_cast<double>(delta);
+        e.dsc = cb->d_dsc;
+        e.g0 = cb->d_g0;
+        e.btab = cb->d_btab;
+        e.codes = d_codes;
+        e.rows = rows;
+        CUtensorMap tmA, tmB;
+        int rc = make_act_tmap(&tmA, d_feat, 1, 1, static_cast<int>(rows), feat_cstride, 128, 1, 1, cb->bk);
+        if (rc) return rc;
+        int total_rows = 0;
+        for (int l = 0; l < cb->levels; ++l) total_rows += 3 * cb->n_level[l];
+        rc = make_weight_tmap(&tmB, cb->d_digits, total_rows, cb->C, cb->block_n, cb->bk);
+        if (rc) return rc;
+        return dispatch_igemm<3>(cb->block_n, cb->bk, tmA, tmB, g, e, stream);
+    };
+    if (cb->m == 1) return fast ? run(EncodeEpilogue<true, 1>{}) : run(EncodeEpilogue<false, 1>{});
+    if (cb->m == 2) return fast ? run(EncodeEpilogue<true, 2>{}) : run(EncodeEpilogue<false, 2>{});
+    return fast ? run(EncodeEpilogue<true, 0>{}) : run(EncodeEpilogue<false, 0>{});
 }
 
 // Shared launcher of the two decode entry points.
