@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace qv2x {
 
@@ -162,66 +163,96 @@ static void launch_fuse(int n, int grid, int threads, cudaStream_t stream, const
 }
 
 // ------------------------------------------------------------------------------------------ heads
-// out[o][p] = bias[o] + sum_k x[p][k] * w[o][k]; CTA = 128 pixels x 72 outputs, thread = 4 pixels x 9 outputs.
-constexpr int kHeadsPix = 128, kHeadsOut = 72, kHeadsPitchPad = 4;
+// out[o][p] = bias[o] + sum_k x[p][k] * w[o][k] (k ascending, one fma per term: the same order for every pixel, so
+// results do not depend on how the map is tiled).  Persistent CTAs: the k-major weight matrix [C][72] is staged in
+// shared memory once, pixel tiles of 64 x C are double-buffered with cp.async so that the next tile's HBM read
+// overlaps the current tile's math.  Warp w owns outputs 8w..8w+7, lane l pixels l and l+32.  The inner product
+// runs on packed fp32 pairs (FFMA2: two IEEE fp32 fmas per instruction, the pixel value as the broadcast operand).
+constexpr int kHeadsPix = 64, kHeadsOut = 72, kHeadsPitchPad = 4, kHeadsThreads = 288;
 
-__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                    const float* __restrict__ bias, float* __restrict__ out,
-                                                    long long npix, int C, int cout) {
-    extern __shared__ float hsm[];
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+}
+
+__global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __restrict__ x, const float* __restrict__ wt,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              long long npix, int C, int cout) {
+    extern __shared__ float4 hsm4[];
+    float* hsm = reinterpret_cast<float*>(hsm4);
     const int pitch = C + kHeadsPitchPad;
-    float* xs = hsm;                           // [128][pitch]
-    float* ws = hsm + kHeadsPix * pitch;       // [72][pitch]
+    float* ws = hsm;                                   // [C][72]   k-major, outputs contiguous (pairs for FFMA2)
+    float* xs0 = hsm + C * kHeadsOut;                  // 2 x [64][pitch] pixel-major
     const int tid = threadIdx.x;
-    const long long p0 = static_cast<long long>(blockIdx.x) * kHeadsPix;
     const int vec = C / 4;
-    for (int idx = tid; idx < kHeadsOut * vec; idx += 256) {
-        const int o = idx / vec, v = idx - o * vec;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (o < cout) val = __ldg(reinterpret_cast<const float4*>(w + static_cast<long long>(o) * C) + v);
-        *reinterpret_cast<float4*>(ws + o * pitch + 4 * v) = val;
-    }
-    for (int idx = tid; idx < kHeadsPix * vec; idx += 256) {
-        const int pp = idx / vec, v = idx - pp * vec;
-        float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p0 + pp < npix) val = __ldg(reinterpret_cast<const float4*>(x + (p0 + pp) * C) + v);
-        *reinterpret_cast<float4*>(xs + pp * pitch + 4 * v) = val;
-    }
-    __syncthreads();
-    const int pg = tid & 31, og = tid >> 5;    // pixels pg + 32*i, outputs og*9 + j
-    float acc[4][9];
+    const long long ntiles = (npix + kHeadsPix - 1) / kHeadsPix;
+
+    auto load_tile = [&](long long t, int buf) {
+        const long long p0 = t * kHeadsPix;
+        const uint32_t dst = smem_u32(xs0 + buf * kHeadsPix * pitch);
+        for (int idx = tid; idx < kHeadsPix * vec; idx += kHeadsThreads) {
+            const int pp = idx / vec, v = idx - pp * vec;
+            const bool ok = (p0 + pp < npix);
+            cp_async_16(dst + (pp * pitch + 4 * v) * 4, ok ? x + (p0 + pp) * C + 4 * v : x, ok);
+        }
+    };
+    for (int idx = tid; idx < C * kHeadsOut / 4; idx += kHeadsThreads)
+        cp_async_16(smem_u32(ws) + idx * 16, wt + idx * 4, true);
+    if (blockIdx.x < ntiles) load_tile(blockIdx.x, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const int pg = tid & 31, og = tid >> 5;    // pixels pg, pg + 32; outputs og*8 + 2*j, og*8 + 2*j + 1
+    int buf = 0;
+    for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, buf ^= 1) {
+        if (t + gridDim.x < ntiles) load_tile(t + gridDim.x, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");       // everything but the tile just requested
+        __syncthreads();
+        const float* xs = xs0 + buf * kHeadsPix * pitch;
+        f32x2 acc[2][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-        for (int j = 0; j < 9; ++j) acc[i][j] = 0.f;
-    for (int k = 0; k < C; k += 4) {
-        float4 xv[4], wv[9];
+            for (int j = 0; j < 4; ++j) acc[i][j] = pack2(0.f, 0.f);
+        for (int k = 0; k < C; k += 4) {
+            float4 xv[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (pg + 32 * i) * pitch + k);
+            for (int i = 0; i < 2; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (pg + 32 * i) * pitch + k);
 #pragma unroll
-        for (int j = 0; j < 9; ++j) wv[j] = *reinterpret_cast<const float4*>(ws + (og * 9 + j) * pitch + k);
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w01 = *reinterpret_cast<const float4*>(ws + (k + kk) * kHeadsOut + og * 8);
+                const float4 w23 = *reinterpret_cast<const float4*>(ws + (k + kk) * kHeadsOut + og * 8 + 4);
+                const f32x2 wp[4] = {pack2(w01.x, w01.y), pack2(w01.z, w01.w), pack2(w23.x, w23.y),
+                                     pack2(w23.z, w23.w)};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 2; ++i) {
+                    const float xk = (kk == 0) ? xv[i].x : (kk == 1) ? xv[i].y : (kk == 2) ? xv[i].z : xv[i].w;
+                    const f32x2 xx = pack2(xk, xk);
 #pragma unroll
-            for (int j = 0; j < 9; ++j) {
-                acc[i][j] = fmaf(xv[i].x, wv[j].x, acc[i][j]);
-                acc[i][j] = fmaf(xv[i].y, wv[j].y, acc[i][j]);
-                acc[i][j] = fmaf(xv[i].z, wv[j].z, acc[i][j]);
-                acc[i][j] = fmaf(xv[i].w, wv[j].w, acc[i][j]);
-            }
-    }
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-        const int o = og * 9 + j;
-        if (o < cout) {
-            const float b = bias ? __ldg(bias + o) : 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long pp = p0 + pg + 32 * i;
-                if (pp < npix) out[static_cast<long long>(o) * npix + pp] = acc[i][j] + b;
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma2(xx, wp[j], acc[i][j]);
+                }
             }
         }
+        const long long p0 = t * kHeadsPix;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int o = og * 8 + 2 * j + h;
+                if (o < cout) {
+                    const float b = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const long long pp = p0 + pg + 32 * i;
+                        float lo, hi;
+                        unpack2(acc[i][j], lo, hi);
+                        if (pp < npix) out[static_cast<long long>(o) * npix + pp] = (h == 0 ? lo : hi) + b;
+                    }
+                }
+            }
+        }
+        __syncthreads();          // everyone is done with this buffer before the next iteration refills it
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // ------------------------------------------------------------------------------------------ layout converters
@@ -337,7 +368,11 @@ int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x
     auto h = new qv2x_heads();
     h->cin = cin;
     h->cout = cout;
-    int rc = upload(&h->d_w, w, static_cast<size_t>(cin) * cout);
+    // k-major, padded to 72 outputs: wt[k][o] = w[o][k] (what the kernel stages in shared memory)
+    std::vector<float> wt(static_cast<size_t>(cin) * kHeadsOut, 0.f);
+    for (int o = 0; o < cout; ++o)
+        for (int k = 0; k < cin; ++k) wt[static_cast<size_t>(k) * kHeadsOut + o] = w[static_cast<size_t>(o) * cin + k];
+    int rc = upload(&h->d_w, wt.data(), wt.size());
     if (!rc && bias) rc = upload(&h->d_b, bias, static_cast<size_t>(cout));
     if (rc) {
         cudaFree(h->d_w);
@@ -359,14 +394,15 @@ int qv2x_heads_forward(const qv2x_heads* h, long long pixels, const float* d_x, 
     QV2X_REQUIRE(h && d_x && d_out, "qv2x_heads_forward: null argument");
     if (pixels <= 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int smem = (kHeadsPix + kHeadsOut) * (h->cin + kHeadsPitchPad) * static_cast<int>(sizeof(float));
+    const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) * static_cast<int>(sizeof(float));
     static bool attr = false;
     if (!attr) {
         QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
-    const int grid = static_cast<int>((pixels + kHeadsPix - 1) / kHeadsPix);
-    heads_kernel<<<grid, 256, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout);
+    const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
+    const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
+    heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
