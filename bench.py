@@ -231,6 +231,7 @@ def main():
     preds_host = torch.empty((pipe.heads.cout, hw), dtype=torch.float32).pin_memory()
 
     from quantv2x_b200.distributed import all_gather_code_planes, gather_pred_tiles, rank_tile
+    from quantv2x_b200.engine import push_planes
 
     # ---- frames in flight and input rotation.
     # INFLIGHT frames are processed concurrently on their own streams and buffer sets (a serving loop pipelines
@@ -259,9 +260,31 @@ def main():
     g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
     recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT
     tile = rank_tile(rank, world, pipe.ho, pipe.wo) if world > 1 else None
+    # Multi-GPU exchange: peer-memory stores from our own kernels + two device barriers (PeerExchange); NCCL
+    # all-gather / gather only if the symmetric-memory mapping cannot be set up on this box.
+    px = None
+    if world > 1 and not os.environ.get("QV2X_NCCL_EXCHANGE"):
+        try:
+            from quantv2x_b200.distributed import PeerExchange
+            px = PeerExchange(device, levels, m, N_AGENTS * hw, pipe.heads.cout, hw, slots=INFLIGHT)
+        except Exception as exc:          # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] peer-memory exchange unavailable ({type(exc).__name__}: {exc}); using NCCL", file=sys.stderr)
+            px = None
+        ok = torch.tensor([1 if px is not None else 0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            px = None
+    config["exchange"] = "none (1 GPU)" if world == 1 else ("peer-memory stores + device barriers" if px else "NCCL all_gather + gather")
     for sl in range(INFLIGHT):
         if world == 1:
             g_ego[sl], preds_dev[sl] = pipe.capture_ego(codes_local[sl], aff, slot=sl)
+        elif px is not None:
+            codes_full[sl] = px.codes_full(sl)
+            g_ego[sl], _ = pipe._capture(
+                lambda sl=sl: pipe.decode_fuse_heads_tile_to(codes_full[sl], aff, aff_host, tile, px.preds_ptr(0, sl),
+                                                             slot=sl))
+            preds_dev[sl] = px.preds_full(sl)
         else:
             recv_codes[sl] = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
             codes_full[sl] = torch.zeros((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device)
@@ -281,8 +304,21 @@ def main():
         if world == 1:
             g_ego[sl].replay()
             return preds_dev[sl]
-        codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
+        exchange_codes(sl)
         g_ego[sl].replay()
+        return collect_preds(sl)
+
+    def exchange_codes(sl):
+        if px is not None:
+            push_planes(codes_local[sl], N_AGENTS * hw, rank * per * hw, px.code_ptrs(sl))
+            px.barrier(sl)              # every rank's planes have landed in this rank's buffer
+        else:
+            codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
+
+    def collect_preds(sl):
+        if px is not None:
+            px.barrier(sl)              # every rank's head tile has landed in the ego rank's buffer
+            return preds_dev[sl] if rank == 0 else None
         return gather_pred_tiles(preds_dev[sl], pipe.ho, pipe.wo, dst=0, recv=recv_preds[sl])
 
     def phase_times(k=10):
@@ -299,11 +335,11 @@ def main():
                 g_ego[sl].replay()
                 evs[2].record()
             else:
-                codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
+                exchange_codes(sl)
                 evs[2].record()
                 g_ego[sl].replay()
                 evs[3].record()
-                gather_pred_tiles(preds_dev[sl], pipe.ho, pipe.wo, dst=0, recv=recv_preds[sl])
+                collect_preds(sl)
                 evs[4].record()
             torch.cuda.synchronize()
             for j in range(len(names)):

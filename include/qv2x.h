@@ -168,6 +168,19 @@ typedef struct qv2x_heads qv2x_heads;
 int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out);
 void qv2x_heads_destroy(qv2x_heads* heads);
 int qv2x_heads_forward(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, void* stream);
+/* Same, for a tile of a larger map: the input is compact (pixels = tile_h * tile_w, row-major), output o of pixel
+ * (ty, tx) is stored at d_out[o * out_pixels + ty * out_w + tx].  d_out may point INTO another GPU's peer-mapped
+ * buffer (multi-GPU: every rank writes its tile of the head maps straight into the ego rank's result). */
+int qv2x_heads_forward_tile(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, int tile_w,
+                            long long out_w, long long out_pixels, void* stream);
+
+/* Multi-GPU exchange of the code planes without a collective: stores d_local ([planes][rows_local] bytes) into the
+ * code buffer of every peer: peer p receives plane i at peer_bases[p] + i * dst_plane_stride + dst_row0.
+ * peer_bases is a HOST array of n_peers (<= 8) device pointers (peer-mapped; this rank's own buffer included).
+ * Replaces the all-gather of reference-side int64 code lists (heter_pyramid_collab_codebook_mc_encdec.py:120-123
+ * keeps them in host lists; the reference has no multi-GPU path). */
+int qv2x_push_planes(const uint8_t* d_local, int planes, long long rows_local, long long dst_plane_stride,
+                     long long dst_row0, void* const* peer_bases, int n_peers, void* stream);
 
 /* Layout / quantization converters for the module boundaries of the drop-in wrappers (the reference
  * passes float32 NCHW between modules; the kernels work on uint8 / float32 pixel-major tensors).

@@ -149,6 +149,9 @@ def _declare_tiles(lib):
                                    c_int, c_int, c_void_p]
     lib.qv2x_codebook_decode_regions.argtypes = [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                  c_void_p, c_void_p]
+    lib.qv2x_heads_forward_tile.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_longlong, c_longlong,
+                                            c_void_p]
+    lib.qv2x_push_planes.argtypes = [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_void_p, c_int, c_void_p]
     lib.qv2x_set_debug_flags.argtypes = [c_int]
     lib.qv2x_set_debug_flags.restype = None
     lib.qv2x_debug_trace.argtypes = [c_void_p]

@@ -176,7 +176,8 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool 
 
 __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __restrict__ x, const float* __restrict__ wt,
                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                              long long npix, int C, int cout) {
+                                                              long long npix, int C, int cout, int tile_w,
+                                                              long long out_w, long long out_npix) {
     extern __shared__ float4 hsm4[];
     float* hsm = reinterpret_cast<float*>(hsm4);
     const int pitch = C + kHeadsPitchPad;
@@ -233,6 +234,15 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
             }
         }
         const long long p0 = t * kHeadsPix;
+        // pixel pp of the (compact, tile_w wide) input lands at row pp / tile_w, column pp % tile_w of an out_w wide
+        // map (out_w == tile_w: the plain [cout][npix] layout)
+        long long off[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const long long pp = p0 + pg + 32 * i;
+            const int ty = static_cast<int>(pp / tile_w);
+            off[i] = (pp < npix) ? ty * out_w + (pp - static_cast<long long>(ty) * tile_w) : -1;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -242,10 +252,9 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
                     const float b = bias ? __ldg(bias + o) : 0.f;
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
-                        const long long pp = p0 + pg + 32 * i;
                         float lo, hi;
                         unpack2(acc[i][j], lo, hi);
-                        if (pp < npix) out[static_cast<long long>(o) * npix + pp] = (h == 0 ? lo : hi) + b;
+                        if (off[i] >= 0) out[static_cast<long long>(o) * out_npix + off[i]] = (h == 0 ? lo : hi) + b;
                     }
                 }
             }
@@ -391,7 +400,14 @@ void qv2x_heads_destroy(qv2x_heads* h) {
 }
 
 int qv2x_heads_forward(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, void* stream_) {
+    return qv2x_heads_forward_tile(h, pixels, d_x, d_out, static_cast<int>(std::min<long long>(pixels, 1 << 30)),
+                                   pixels, pixels, stream_);
+}
+
+int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, int tile_w,
+                            long long out_w, long long out_pixels, void* stream_) {
     QV2X_REQUIRE(h && d_x && d_out, "qv2x_heads_forward: null argument");
+    QV2X_REQUIRE(tile_w >= 1 && out_w >= tile_w && out_pixels >= 1, "bad output tile geometry");
     if (pixels <= 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) * static_cast<int>(sizeof(float));
@@ -402,7 +418,8 @@ int qv2x_heads_forward(const qv2x_heads* h, long long pixels, const float* d_x, 
     }
     const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
     const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
-    heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout);
+    heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout, tile_w,
+                                                        out_w, out_pixels);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -76,3 +76,50 @@ def gather_pred_tiles(preds_tile: torch.Tensor, h: int, w: int, dst: int = 0, re
     th, tw = h // gy, w // gx
     full = recv.view(gy, gx, cout, th, tw).permute(2, 0, 3, 1, 4).reshape(cout, h * w)
     return full.contiguous()
+
+
+class PeerExchange:
+    """Peer-mapped (symmetric) buffers for the multi-GPU frame: every rank's kernels store their code planes straight
+    into every peer's code buffer and their tile of the head maps straight into the ego rank's result, so the step has
+    no collective -- only two device-side barriers.  torch's symmetric-memory allocator provides the mapping and the
+    barrier (plumbing); the stores are libqv2x kernels (qv2x_push_planes, qv2x_heads_forward_tile).
+
+    One buffer set per in-flight slot: [levels*m*rows_total bytes of codes | cout*hw float32 head maps]."""
+
+    def __init__(self, device, levels: int, m: int, rows_total: int, cout: int, hw: int, slots: int = 1):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        group = dist.group.WORLD
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.levels, self.m, self.rows_total, self.cout, self.hw = levels, m, rows_total, cout, hw
+        self.code_bytes = (levels * m * rows_total + 255) // 256 * 256
+        self.slot_bytes = self.code_bytes + cout * hw * 4
+        try:
+            symm_mem.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.buf = symm_mem.empty(slots * self.slot_bytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.hdl = symm_mem.rendezvous(self.buf, group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        assert len(self.ptrs) == self.world and self.ptrs[self.rank] == self.buf.data_ptr()
+
+    def codes_full(self, slot: int) -> torch.Tensor:
+        """This rank's copy of ALL agents' code planes, uint8 [levels, m, rows_total]."""
+        o = slot * self.slot_bytes
+        return self.buf[o:o + self.levels * self.m * self.rows_total].view(self.levels, self.m, self.rows_total)
+
+    def preds_full(self, slot: int) -> torch.Tensor:
+        """This rank's head-map buffer float32 [cout, hw] (complete on the ego rank after the second barrier)."""
+        o = slot * self.slot_bytes + self.code_bytes
+        return self.buf[o:o + self.cout * self.hw * 4].view(torch.float32).view(self.cout, self.hw)
+
+    def code_ptrs(self, slot: int):
+        return [p + slot * self.slot_bytes for p in self.ptrs]
+
+    def preds_ptr(self, rank: int, slot: int) -> int:
+        return self.ptrs[rank] + slot * self.slot_bytes + self.code_bytes
+
+    def barrier(self, slot: int):
+        """Device-side barrier of all ranks on the current stream (one signal channel per slot)."""
+        self.hdl.barrier(channel=slot)

@@ -254,6 +254,24 @@ class HeadsEngine:
         return out
 
 
+def heads_forward_tile(heads: "HeadsEngine", x: torch.Tensor, out_ptr: int, tile_w: int, out_w: int, out_pixels: int):
+    """Heads on a compact tile x float32 [tile_pixels, Cin]; output o of tile pixel (ty, tx) goes to
+    out_ptr[o * out_pixels + ty * out_w + tx] (out_ptr: raw device address, possibly in a peer GPU's memory)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == heads.cin
+    pixels = x.numel() // heads.cin
+    check(_lib.lib().qv2x_heads_forward_tile(heads._h, pixels, c_void_p(x.data_ptr()), c_void_p(out_ptr), tile_w, out_w,
+                                             out_pixels, _stream_ptr()))
+
+
+def push_planes(codes: torch.Tensor, dst_plane_stride: int, dst_row0: int, peer_ptrs):
+    """Store codes uint8 [levels, m, rows_local] into every peer's code buffer (see qv2x_push_planes)."""
+    assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+    planes, rows_local = codes.shape[0] * codes.shape[1], codes.shape[2]
+    arr = (c_void_p * len(peer_ptrs))(*[c_void_p(int(p)) for p in peer_ptrs])
+    check(_lib.lib().qv2x_push_planes(c_void_p(codes.data_ptr()), planes, rows_local, dst_plane_stride, dst_row0, arr,
+                                      len(peer_ptrs), _stream_ptr()))
+
+
 def quantize_nchw_to_nhwc_u8(x: torch.Tensor, delta: float, zero_point: float = 0.0, bits: int = 8,
                              out: torch.Tensor | None = None, out_cbase: int = 0) -> torch.Tensor:
     """float32 NCHW -> uint8 NHWC activation codes (module-boundary converter)."""

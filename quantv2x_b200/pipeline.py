@@ -130,6 +130,20 @@ class CollabPipeline:
         self.heads.forward(b["fused"], out=b["preds"])
         return b["preds"]
 
+    def decode_fuse_heads_tile_to(self, codes: torch.Tensor, affine: torch.Tensor, affine_host, tile, out_ptr: int,
+                                  slot=0) -> None:
+        """As decode_fuse_heads_tile, but the head maps of the tile are stored at their place in a FULL
+        [Cout, ho*wo] float32 map that starts at the raw device address `out_ptr` -- possibly the ego GPU's
+        peer-mapped result buffer (distributed.PeerExchange), which makes the gather of head tiles unnecessary."""
+        n = codes.shape[-1] // self.hw
+        b = self.ego_tile_buffers(n, tile, slot)
+        rects = self.source_rects(affine_host, tile)
+        self.codebook.decode_regions(codes, self.wo, [a * self.hw for a in range(n)], rects,
+                                     b["feat"].view(n * self.hw, self.c_feat))
+        E.fuse_tile(b["feat"], affine, self.fusion_mode, tile, b["fused"])
+        y0, _, x0, x1 = tile
+        E.heads_forward_tile(self.heads, b["fused"], out_ptr + 4 * (y0 * self.wo + x0), x1 - x0, self.wo, self.hw)
+
     # ------------------------------------------------------------------ CUDA graphs
     def _capture(self, fn):
         """Capture `fn` (library launches on static buffers) into a CUDA graph: one launch replays the ~25 kernels

@@ -101,3 +101,36 @@ def test_tiled_ego_stage_equals_whole(cuda_device):
                 out[r] = pipe.decode_fuse_heads_tile(codes, aff_d, aff, rank_tile(r, world, ho, wo))
             full = out.view(gy, gx, 72, th, tw).permute(2, 0, 3, 1, 4).reshape(72, ho * wo)
             assert torch.equal(full, whole), f"{mode}, {world} tiles: tiled ego stage differs from the whole frame"
+
+
+def test_push_planes_and_heads_tile_addressing(cuda_device):
+    """The two kernels of the peer-memory exchange, exercised on one GPU (the 'peers' are local buffers):
+    qv2x_push_planes must place every plane at its agent-major offset in every destination, and
+    qv2x_heads_forward_tile must store a tile's head maps at their place in the full map, bit-identical to the
+    compact result."""
+    from quantv2x_b200 import engine as E
+
+    rng = np.random.default_rng(5)
+    planes, rows_local, world, rank = 6, 35200, 4, 2
+    codes = torch.from_numpy(rng.integers(0, 256, size=(3, 2, rows_local), dtype=np.uint8)).to(cuda_device)
+    dsts = [torch.zeros((planes, world * rows_local), dtype=torch.uint8, device=cuda_device) for _ in range(3)]
+    E.push_planes(codes, world * rows_local, rank * rows_local, [d.data_ptr() for d in dsts])
+    torch.cuda.synchronize()
+    for d in dsts:
+        got = d.cpu().numpy()
+        assert np.array_equal(got[:, rank * rows_local:(rank + 1) * rows_local], codes.cpu().numpy().reshape(planes, -1))
+        assert got[:, :rank * rows_local].max() == 0 and got[:, (rank + 1) * rows_local:].max() == 0
+
+    ho, wo, C = 20, 48, 256
+    hd = E.HeadsEngine(rng.normal(size=(72, C)).astype(np.float32) / 16, rng.normal(size=72).astype(np.float32))
+    y0, y1, x0, x1 = 10, 20, 12, 24
+    x = torch.from_numpy(rng.normal(size=((y1 - y0) * (x1 - x0), C)).astype(np.float32)).to(cuda_device)
+    compact = hd.forward(x)                                            # [72, tile_pixels]
+    full = torch.full((72, ho * wo), -7.0, dtype=torch.float32, device=cuda_device)
+    E.heads_forward_tile(hd, x, full.data_ptr() + 4 * (y0 * wo + x0), x1 - x0, wo, ho * wo)
+    torch.cuda.synchronize()
+    f = full.view(72, ho, wo)
+    assert torch.equal(f[:, y0:y1, x0:x1].reshape(72, -1), compact)
+    mask = torch.ones((ho, wo), dtype=torch.bool, device=cuda_device)
+    mask[y0:y1, x0:x1] = False
+    assert bool((f[:, mask] == -7.0).all()), "stores outside the tile"
