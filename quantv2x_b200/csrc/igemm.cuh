@@ -79,7 +79,8 @@ struct IgemmCfg {
     static constexpr int kATile = kASub * TPS;
     static constexpr int kBTile = kBSub * TPS;
     static constexpr int kStageBytes = kATile + kBTile;
-    static constexpr int kStagesRaw = (188 * 1024) / kStageBytes;
+    // 227 KB per CTA minus alignment slack, barriers, the epilogue / side-input scratch and the halo buffers
+    static constexpr int kStagesRaw = (227 * 1024 - 1024 - 256 - kEpiSmemBytes - kHaloSmemBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > MAX_STAGES ? MAX_STAGES : kStagesRaw;
     static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
     static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiSmemBytes + kHaloSmemBytes;
