@@ -174,6 +174,36 @@ int qv2x_heads_forward(const qv2x_heads* heads, long long pixels, const float* d
 int qv2x_heads_forward_tile(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, int tile_w,
                             long long out_w, long long out_pixels, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PointPillars front end: pillars -> decorated points -> quantized Linear(10 -> 64) ->
+ * pre-ReLU activation quantizer -> ReLU -> block activation quantizer -> max over the pillar's points -> scatter
+ * into the uint8 NHWC BEV map, in one kernel.  Replaces QuantPointPillar.forward
+ * (opencood/quant/quant_block.py:611-630, 666-741) + PointPillarScatter.forward
+ * (opencood/models/sub_modules/point_pillar_scatter.py:19-75).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_pillar qv2x_pillar;
+typedef struct {
+    int n_feat;            /* decorated point features: 10 (use_absolute_xyz, no distance) */
+    int cout;              /* PFN output channels: 64 */
+    int max_points;        /* points per pillar: 32 */
+    int nx, ny;            /* BEV grid (cells along x / y) */
+    float voxel_size[3];   /* voxel_x, voxel_y, voxel_z */
+    float offset[3];       /* x_offset, y_offset, z_offset (cell centre of cell 0) */
+    int has_pre_quant;     /* the Linear's own activation quantizer (applied before the ReLU) is active */
+    float pre_delta, pre_zero_point;
+    int pre_bits;
+    float out_delta, out_zero_point;   /* the PFN block's post-ReLU quantizer = the BEV grid's scale */
+    int out_bits;
+} qv2x_pillar_desc;
+/* w_hat: HOST float [cout][n_feat], the fake-quantized (de-quantized) weights with BN folded, exactly the tensor the
+ * reference multiplies with (weight_quantizer(weight)); bias: HOST float [cout] or NULL. */
+int qv2x_pillar_create(const qv2x_pillar_desc* desc, const float* w_hat, const float* bias, qv2x_pillar** out);
+void qv2x_pillar_destroy(qv2x_pillar* p);
+/* d_points float [n_pillars][32][4] (padded points zero), d_coords int32 [n_pillars][4] = (batch, z, y, x),
+ * d_num_points int32 [n_pillars]; d_bev uint8 [batch][ny][nx][cout] is cleared and filled (empty cells = code 0). */
+int qv2x_pillar_forward(const qv2x_pillar* p, int n_pillars, const float* d_points, const int* d_coords,
+                        const int* d_num_points, int batch, uint8_t* d_bev, void* stream);
+
 /* Multi-GPU exchange of the code planes without a collective: stores d_local ([planes][rows_local] bytes) into the
  * code buffer of every peer: peer p receives plane i at peer_bases[p] + i * dst_plane_stride + dst_row0.
  * peer_bases is a HOST array of n_peers (<= 8) device pointers (peer-mapped; this rank's own buffer included).

@@ -86,6 +86,22 @@ def exported_symbols():
     return sorted(set(re.findall(r"\b(qv2x_[a-z0-9_]+)\s*\(", text)))
 
 
+class PillarDesc(ctypes.Structure):
+    """Mirror of qv2x_pillar_desc (include/qv2x.h)."""
+
+    _fields_ = [("n_feat", c_int), ("cout", c_int), ("max_points", c_int), ("nx", c_int), ("ny", c_int),
+                ("voxel_size", c_float * 3), ("offset", c_float * 3), ("has_pre_quant", c_int),
+                ("pre_delta", c_float), ("pre_zero_point", c_float), ("pre_bits", c_int),
+                ("out_delta", c_float), ("out_zero_point", c_float), ("out_bits", c_int)]
+
+
+def _declare_pillar(lib):
+    lib.qv2x_pillar_create.argtypes = [POINTER(PillarDesc), c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.qv2x_pillar_destroy.argtypes = [c_void_p]
+    lib.qv2x_pillar_destroy.restype = None
+    lib.qv2x_pillar_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+
+
 class CodebookDesc(ctypes.Structure):
     """Mirror of qv2x_codebook_desc (include/qv2x.h)."""
 
@@ -159,3 +175,4 @@ def _declare_tiles(lib):
 
 
 _DECLARERS.append(_declare_tiles)
+_DECLARERS.append(_declare_pillar)

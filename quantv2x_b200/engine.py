@@ -254,6 +254,61 @@ class HeadsEngine:
         return out
 
 
+class PillarEngine:
+    """libqv2x handle of the quantized PointPillars front end (qv2x_pillar_*): pillars -> uint8 NHWC BEV map."""
+
+    def __init__(self, w_hat: np.ndarray, bias, *, nx: int, ny: int, voxel_size, offset, pre_quant, out_quant):
+        """w_hat float32 [64, 10] fake-quantized weights (BN folded); bias [64] or None;
+        pre_quant: None or (delta, zero_point, bits) of the Linear's own (pre-ReLU) activation quantizer;
+        out_quant: (delta, zero_point, bits) of the PFN block's post-ReLU quantizer."""
+        from ._lib import PillarDesc
+
+        w_hat = np.ascontiguousarray(w_hat, dtype=np.float32)
+        d = PillarDesc()
+        d.cout, d.n_feat, d.max_points = int(w_hat.shape[0]), int(w_hat.shape[1]), 32
+        d.nx, d.ny = int(nx), int(ny)
+        for i in range(3):
+            d.voxel_size[i], d.offset[i] = float(voxel_size[i]), float(offset[i])
+        d.has_pre_quant = 0 if pre_quant is None else 1
+        if pre_quant is not None:
+            d.pre_delta, d.pre_zero_point, d.pre_bits = float(pre_quant[0]), float(pre_quant[1]), int(pre_quant[2])
+        else:
+            d.pre_delta, d.pre_zero_point, d.pre_bits = 1.0, 0.0, 8
+        d.out_delta, d.out_zero_point, d.out_bits = float(out_quant[0]), float(out_quant[1]), int(out_quant[2])
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        self.nx, self.ny, self.cout = d.nx, d.ny, d.cout
+        self.out_delta = float(out_quant[0])
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_pillar_create(byref(d), _np_ptr(w_hat), None if b is None else _np_ptr(b),
+                                            byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_pillar_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward(self, voxel_features: torch.Tensor, voxel_coords: torch.Tensor, voxel_num_points: torch.Tensor,
+                batch: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """voxel_features float32 [M, 32, 4], voxel_coords int [M, 4] (batch, z, y, x), voxel_num_points int [M]
+        (CUDA tensors) -> uint8 BEV codes [batch, ny, nx, 64]."""
+        assert voxel_features.is_cuda and voxel_features.dim() == 3 and voxel_features.shape[1:] == (32, 4)
+        f = voxel_features.to(torch.float32).contiguous()
+        c = voxel_coords.to(torch.int32).contiguous()
+        n = voxel_num_points.to(torch.int32).contiguous()
+        if out is None:
+            out = torch.empty((batch, self.ny, self.nx, self.cout), dtype=torch.uint8, device=f.device)
+        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+        assert tuple(out.shape) == (batch, self.ny, self.nx, self.cout)
+        check(_lib.lib().qv2x_pillar_forward(self._h, int(f.shape[0]), c_void_p(f.data_ptr()), c_void_p(c.data_ptr()),
+                                             c_void_p(n.data_ptr()), int(batch), c_void_p(out.data_ptr()),
+                                             _stream_ptr()))
+        return out
+
+
 def heads_forward_tile(heads: "HeadsEngine", x: torch.Tensor, out_ptr: int, tile_w: int, out_w: int, out_pixels: int):
     """Heads on a compact tile x float32 [tile_pixels, Cin]; output o of tile pixel (ty, tx) goes to
     out_ptr[o * out_pixels + ty * out_w + tx] (out_ptr: raw device address, possibly in a peer GPU's memory)."""

@@ -170,6 +170,41 @@ def build_modality_engines(backbone: QuantBaseBEVBackbone, shrinker: QuantDownsa
 # ---------------------------------------------------------------------------------------------------
 # model level
 # ---------------------------------------------------------------------------------------------------
+def pillar_spec(enc) -> dict:
+    """Plain-numpy description of a calibrated QuantPointPillar (reference quant_block.py:589-741): the
+    fake-quantized Linear weights (BN folded), both activation quantizers and the grid geometry."""
+    vfe = enc.pillar_vfe
+    if len(vfe.pfn_layers) != 1 or not vfe.pfn_layers[0].last_vfe or not vfe.use_absolute_xyz or vfe.with_distance:
+        raise NotImplementedError("the pillar kernel covers the single-layer PFN with absolute xyz and no distance "
+                                  "feature (the configuration of every yaml of the hot path)")
+    pfn = vfe.pfn_layers[0]
+    lin = pfn.linear
+    with torch.no_grad():
+        w_hat = lin.weight_quantizer(lin.weight) if lin.use_weight_quant else lin.org_weight
+    pre = None
+    if lin.use_act_quant and not lin.disable_act_quant:
+        aq = lin.act_quantizer
+        pre = (_scalar(aq.delta), _scalar(aq.zero_point), int(aq.n_bits))
+    oq = pfn.act_quantizer
+    out_q = (_scalar(oq.delta), _scalar(oq.zero_point), int(oq.n_bits))
+    if not pfn.use_act_quant:
+        raise NotImplementedError("the BEV map must lie on the PFN block's activation grid (use_act_quant)")
+    return dict(w_hat=w_hat.detach().cpu().numpy().astype(np.float32).copy(),
+                bias=None if lin.bias is None else lin.bias.detach().cpu().numpy().astype(np.float32).copy(),
+                nx=int(enc.scatter.nx), ny=int(enc.scatter.ny),
+                voxel_size=(float(vfe.voxel_x), float(vfe.voxel_y), float(vfe.voxel_z)),
+                offset=(float(vfe.x_offset), float(vfe.y_offset), float(vfe.z_offset)), pre_quant=pre, out_quant=out_q)
+
+
+def build_pillar_engine(enc):
+    """libqv2x engine of a calibrated QuantPointPillar."""
+    from .engine import PillarEngine
+
+    sp = pillar_spec(enc)
+    return PillarEngine(sp["w_hat"], sp["bias"], nx=sp["nx"], ny=sp["ny"], voxel_size=sp["voxel_size"],
+                        offset=sp["offset"], pre_quant=sp["pre_quant"], out_quant=sp["out_quant"])
+
+
 def attach_engines(qmodel, bev_delta: float | None = None, device=None):
     """Build every libqv2x engine of a calibrated ``QuantModel(HeterBaselineCollabCodebookMC)`` and attach them:
     block-level engines to the quantized backbone / shrinker wrappers (module-boundary drop-in) and a
@@ -199,6 +234,12 @@ def attach_engines(qmodel, bev_delta: float | None = None, device=None):
                               heads_from_quant_modules(model.cls_head, model.reg_head, model.dir_head),
                               model.fusion_method, (H, W), device)
         pipe.bev_delta = d_in
+        # pillar-level input: the PFN + scatter kernel, when the encoder is quantized, calibrated, and its output
+        # grid is the one the backbone engine was built for
+        if isinstance(enc, QuantPointPillar):
+            oq = enc.pillar_vfe.pfn_layers[-1].act_quantizer
+            if getattr(oq, "inited", False) and abs(enc.bev_delta() - d_in) <= 1e-6 * abs(d_in):
+                pipe.pillar_engine = build_pillar_engine(enc)
         model._pipelines[name] = pipe
     return model
 

@@ -41,9 +41,14 @@ class CollabPipeline:
             return inp["bev_u8"]
         pillar = getattr(self, "pillar_engine", None)
         if pillar is None:
-            raise NotImplementedError("pillar-level input needs the PFN + scatter engine (SURVEY 8(f)-1, a 'next' "
-                                      "row); pass inputs_m1['bev_u8'] (uint8 [n, H, W, 64]) instead")
-        return pillar.forward(inp)
+            raise RuntimeError("pillar-level input needs the PFN + scatter engine: attach_engines() builds it when "
+                               "the PointPillar encoder is quantized and calibrated; otherwise pass "
+                               "inputs_m1['bev_u8'] (uint8 [n, H, W, 64])")
+        n = len(data_dict["agent_modality_list"]) if "agent_modality_list" in data_dict else int(
+            data_dict["record_len"].sum())
+        dev = self.device
+        return pillar.forward(inp["voxel_features"].to(dev), inp["voxel_coords"].to(dev),
+                              inp["voxel_num_points"].to(dev), n)
 
     def encode_buffers(self, n, slot=0):
         """Buffers of the agent-side stage; `slot` separates frames that are in flight concurrently."""
