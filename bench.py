@@ -57,7 +57,7 @@ def build_calibrated_model(device, fusion, w_bits, seed=1234):
 
     from quantv2x_b200 import yaml_utils
     from quantv2x_b200.quant import QuantModel, set_weight_quantize_params
-    from quantv2x_b200.synthetic import seeded_init, synthetic_bev
+    from quantv2x_b200.synthetic import seeded_init
 
     hypes = yaml_utils.load_yaml(yaml_utils.default_config(fusion))
     torch.manual_seed(seed)
@@ -69,20 +69,27 @@ def build_calibrated_model(device, fusion, w_bits, seed=1234):
     q.disable_network_output_quantization()
     q.to(device)
     set_weight_quantize_params(q)
-    # BEV-level calibration: one synthetic agent on the uint8 grid bev_delta (what the PFN block would emit)
-    bev_delta = 0.05
-    bev = synthetic_bev(0, 1, BEV_H, BEV_W, BEV_C, PILLARS)
-    x = torch.from_numpy(bev.astype(np.float32) * np.float32(bev_delta)).permute(0, 3, 1, 2).contiguous().to(device)
+    # Pillar-level calibration (SURVEY 8(d) recipe): one synthetic agent's pillars through the float fake-quant
+    # model -- PointPillar encoder included, so the BEV grid's scale is the PFN block's own quantizer
+    from quantv2x_b200.synthetic import synthetic_pillars
+    enc_args = hypes["model"]["args"]["m1"]["encoder_args"]
+    vf, vc, vn = synthetic_pillars(99, 1, enc_args["lidar_range"], enc_args["voxel_size"], PILLARS)
+    data = {"inputs_m1": {"voxel_features": torch.from_numpy(vf).to(device),
+                          "voxel_coords": torch.from_numpy(vc).to(device),
+                          "voxel_num_points": torch.from_numpy(vn).to(device)},
+            "agent_modality_list": ["m1"], "pairwise_t_matrix": torch.eye(4).view(1, 1, 1, 4, 4).repeat(1, 5, 5, 1, 1),
+            "record_len": torch.tensor([1])}
     mods = [m for m in q.modules() if hasattr(m, "act_quantizer")]
     q.set_quant_state(True, True)
     for m in mods:
         m.act_quantizer.set_inited(False)
     with torch.no_grad():
-        feat = q.model.backbone_m1(x)
-        q.model.shrinker_m1(feat)
+        q.model.calibration_forward(data)
     for m in mods:
         m.act_quantizer.set_inited(True)
     q.set_quant_state(True, True)
+    bev_delta = q.model.encoder_m1.bev_delta()
+    q.hypes = hypes
     return q, bev_delta
 
 
@@ -204,7 +211,7 @@ def main():
 
     from quantv2x_b200 import _lib
     from quantv2x_b200.export import attach_engines, export_spec
-    from quantv2x_b200.synthetic import synthetic_bev, synthetic_poses
+    from quantv2x_b200.synthetic import synthetic_poses
     from quantv2x_b200.collab_model import normalize_pairwise_tfm
 
     if not torch.cuda.is_available():
@@ -222,8 +229,24 @@ def main():
     attach_engines(q, bev_delta=bev_delta, device=device)
     pipe = q.model._pipelines["m1"]
 
-    bev_all = synthetic_bev(0, N_AGENTS, BEV_H, BEV_W, BEV_C, PILLARS)
-    bev_host = torch.from_numpy(bev_all[rank * per:(rank + 1) * per]).pin_memory()
+    # this rank's agents as PILLARS in the reference's dict schema (voxel_features / voxel_coords / voxel_num_points);
+    # the frame starts at the PointPillars front end (qv2x_pillar_forward), as the reference model does
+    from quantv2x_b200.synthetic import synthetic_pillars
+    enc_args = q.hypes["model"]["args"]["m1"]["encoder_args"]
+    pillar = getattr(pipe, "pillar_engine", None)
+    if pillar is None:
+        raise SystemExit("the calibrated PointPillar encoder did not yield a pillar engine")
+
+    def pillar_set(seed):
+        """(features [per*P, 32, 4] f32, coords [per*P, 4] i32 with LOCAL agent index, num_points [per*P] i32), host."""
+        vf, vc, vn = synthetic_pillars(seed, N_AGENTS, enc_args["lidar_range"], enc_args["voxel_size"], PILLARS)
+        sel = (vc[:, 0] >= rank * per) & (vc[:, 0] < (rank + 1) * per)
+        vc = vc[sel].copy()
+        vc[:, 0] -= rank * per
+        return (torch.from_numpy(np.ascontiguousarray(vf[sel])), torch.from_numpy(vc),
+                torch.from_numpy(np.ascontiguousarray(vn[sel])))
+
+    pil_host = tuple(t.pin_memory() for t in pillar_set(0))
     poses = torch.from_numpy(synthetic_poses(N_AGENTS)).float()
     aff = normalize_pairwise_tfm(poses, 80.0, 281.6, 1)[0, 0, :N_AGENTS].contiguous().to(device)
     aff_host = aff.cpu().numpy()
@@ -239,14 +262,29 @@ def main():
     # path.  The input of step i is buffer i % R of a pool of R distinct frames whose total size exceeds the 126 MB
     # L2, so no step finds its input in L2 (this replaces the flush buffer, which would serialise the pipeline).
     INFLIGHT = 2
-    in_bytes = per * BEV_H * BEV_W * BEV_C
+    in_bytes = sum(int(t.numel()) * t.element_size() for t in pil_host)
     R = max(INFLIGHT, -(-(140 * 1024 * 1024) // in_bytes))
     R += R % INFLIGHT
-    bev0 = bev_host.to(device)
-    bev_pool = [bev0] + [torch.roll(bev0, shifts=(3 * r, 5 * r), dims=(1, 2)).contiguous() for r in range(1, R)]
+    pil_pool = [tuple(t.to(device) for t in pil_host)]
+    for r in range(1, R):
+        # distinct frames of the same statistics: the point clouds of frame 0, every pillar moved to another cell
+        f0, c0, n0 = pil_pool[0]
+        shift_y, shift_x = 3 * r, 5 * r
+        c = c0.clone()
+        dy = (c[:, 2] + shift_y) % BEV_H - c[:, 2]
+        dx = (c[:, 3] + shift_x) % BEV_W - c[:, 3]
+        c[:, 2] += dy
+        c[:, 3] += dx
+        f = f0.clone()
+        live = (torch.arange(32, device=device)[None, :] < n0[:, None]).to(f.dtype)
+        f[:, :, 0] += dx[:, None].to(f.dtype) * enc_args["voxel_size"][0] * live
+        f[:, :, 1] += dy[:, None].to(f.dtype) * enc_args["voxel_size"][1] * live
+        pil_pool.append((f, c, n0.clone()))
+    bev_slot = [torch.empty((per, BEV_H, BEV_W, BEV_C), dtype=torch.uint8, device=device) for _ in range(INFLIGHT)]
     config["inflight"] = INFLIGHT
-    config["l2"] = (f"the input of step i is buffer i % {R} of {R} distinct frames ({R * in_bytes / 2**20:.0f} MB per rank, "
-                    "more than the 126 MB L2); no flush between steps because frames are pipelined")
+    config["input"] = f"pillars [{per}x{PILLARS}, 32, 4] f32 + coords + point counts per rank ({in_bytes / 2**20:.1f} MB per step)"
+    config["l2"] = (f"the input of step i is pillar set i % {R} of {R} distinct frames ({R * in_bytes / 2**20:.0f} MB per "
+                    "rank, more than the 126 MB L2); no flush between steps because frames are pipelined")
 
     # CUDA graphs over static buffers: one replay per stage instead of ~25 launches (collectives stay outside).
     #   1 GPU : encode graph (8 agents) -> ego graph (decode + warp/fuse + heads on the whole map)
@@ -255,7 +293,9 @@ def main():
     lc0 = _lib.lib().qv2x_launch_count()
     g_enc, codes_local = [None] * R, [None] * INFLIGHT
     for r in range(R):
-        g_enc[r], codes_local[r % INFLIGHT] = pipe.capture_encode(bev_pool[r], slot=r % INFLIGHT)
+        g_enc[r], codes_local[r % INFLIGHT] = pipe._capture(
+            lambda r=r: pipe.encode_agents(pillar.forward(*pil_pool[r], per, out=bev_slot[r % INFLIGHT]),
+                                           slot=r % INFLIGHT))
     lc1 = _lib.lib().qv2x_launch_count()
     g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
     recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT
@@ -426,7 +466,8 @@ def main():
             with torch.cuda.stream(s_h2d):
                 if enc_done[r] is not None:
                     s_h2d.wait_event(enc_done[r])          # the graph that read this buffer R steps ago is done
-                bev_pool[r].copy_(bev_host, non_blocking=True)
+                for dst, src in zip(pil_pool[r], pil_host):
+                    dst.copy_(src, non_blocking=True)
                 copied[r] = ev()
                 copied[r].record(s_h2d)
 
@@ -464,8 +505,6 @@ def main():
     sync_all()
     e2e_ms = e2e_run(args.steps)
     sync_all()
-    for r in range(1, R):                    # the e2e loop uploaded frame 0 into every pool buffer: restore the pool
-        bev_pool[r].copy_(torch.roll(bev0, shifts=(3 * r, 5 * r), dims=(1, 2)))
     t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -542,7 +581,7 @@ def main():
         cpu = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
-        h2d = int(bev_host.numel()) * world
+        h2d = in_bytes * world
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "u8 (int8 tensor cores, int32 accumulate)",

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "host_common.h"
+#include "ptx.cuh"
 
 namespace qv2x {
 
@@ -41,13 +42,12 @@ __global__ void __launch_bounds__(256) pillar_bev_kernel(const float4* __restric
     __shared__ __align__(16) float s_f[8][kPillarPoints][kPillarFeatPad];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // this lane's two output channels: weights and bias stay in registers for the whole kernel
-    float w0[kPillarFeat], w1[kPillarFeat];
+    // (as packed fp32 pairs: one FFMA2 advances both outputs, the point feature is the broadcast operand)
+    f32x2 wp[kPillarFeat];
 #pragma unroll
-    for (int c = 0; c < kPillarFeat; ++c) {
-        w0[c] = __ldg(w + lane * kPillarFeatPad + c);
-        w1[c] = __ldg(w + (lane + 32) * kPillarFeatPad + c);
-    }
-    const float b0 = __ldg(bias + lane), b1 = __ldg(bias + lane + 32);
+    for (int c = 0; c < kPillarFeat; ++c)
+        wp[c] = pack2(__ldg(w + lane * kPillarFeatPad + c), __ldg(w + (lane + 32) * kPillarFeatPad + c));
+    const f32x2 bp = pack2(__ldg(bias + lane), __ldg(bias + lane + 32));
     const int warps = (gridDim.x * blockDim.x) >> 5;
     for (int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < n_pillars; m += warps) {
         const float4 pt = __ldg(pts + static_cast<long long>(m) * kPillarPoints + lane);
@@ -85,12 +85,11 @@ __global__ void __launch_bounds__(256) pillar_bev_kernel(const float4* __restric
             const float4* src = reinterpret_cast<const float4*>(&s_f[wib][q][0]);     // broadcast reads
             const float4 a = src[0], b = src[1], c = src[2];
             const float g[kPillarFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
-            float u0 = b0, u1 = b1;
+            f32x2 u = bp;
 #pragma unroll
-            for (int k = 0; k < kPillarFeat; ++k) {
-                u0 = fmaf(g[k], w0[k], u0);
-                u1 = fmaf(g[k], w1[k], u1);
-            }
+            for (int k = 0; k < kPillarFeat; ++k) u = fma2(pack2(g[k], g[k]), wp[k], u);
+            float u0, u1;
+            unpack2(u, u0, u1);
             y0 = fmaxf(y0, u0);
             y1 = fmaxf(y1, u1);
         }
