@@ -261,7 +261,7 @@ def main():
     # frames: frame i+1's backbone overlaps frame i's exchange + ego stage); every frame still runs the complete
     # path.  The input of step i is buffer i % R of a pool of R distinct frames whose total size exceeds the 126 MB
     # L2, so no step finds its input in L2 (this replaces the flush buffer, which would serialise the pipeline).
-    INFLIGHT = 2
+    INFLIGHT = int(os.environ.get("QV2X_INFLIGHT", "2" if world == 1 else "4"))     # short per-rank stages: deeper pipeline
     in_bytes = sum(int(t.numel()) * t.element_size() for t in pil_host)
     R = max(INFLIGHT, -(-(140 * 1024 * 1024) // in_bytes))
     R += R % INFLIGHT
