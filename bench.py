@@ -559,7 +559,11 @@ def main():
                 "achieved": ach0, "peak": peak, "unit": "TOP/s (int8)", "frac": ach0 / peak,
                 "peak_source": "live cuBLASLt int8 GEMM 8192^3 (torch._int_mm), best of 10 -- MEASURED_PEAKS.json "
                                "has no int8 entry; its bf16 burst figure x2 is the nominal ratio",
-                "traffic": None, "us_per_launch": k0_ms * 1e3,
+                # dram__bytes_read + dram__bytes_write of this kernel from `ncu --set full` (profiles/r1_ncu_shrink0_final.txt:
+                # 62.9 MB for 4 agents; algorithmic 13.5 MB in + 9 MB out + 0.9 MB weights per agent -- the output
+                # mostly stays in L2 for the next layer), scaled to this rank's agent count
+                "traffic": 15.73e6 * per, "traffic_unit": "bytes per launch (ncu, scaled by agents)",
+                "us_per_launch": k0_ms * 1e3,
                 "other_kernels": [{"kernel": "igemm_kernel<256,128,1,RequantEpilogue<1>> (shrinker conv3x3 256->256)",
                                    "achieved": ach1, "frac": ach1 / peak, "us_per_launch": k1_ms * 1e3}],
                 "step_tensor_frac": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * per / (ms_per_step * 1e-3) / 1e12 / peak}
