@@ -170,7 +170,8 @@ def cpu_reference_frames_per_s(spec, n_agents, steps, warmup, budget_s=60.0):
             break
     t = float(np.median(times))
     sample = (f"{a} agent backbone+shrinker+encode timed and scaled x{n_agents // a}, plus the full {n_agents}-agent "
-              f"ego stage; {len(times)} timed frame(s), torch {torch.__version__} CPU fp32 fake-quant")
+              f"ego stage; starts at the BEV map (PointPillars front end not included); {len(times)} timed frame(s), "
+              f"torch {torch.__version__} CPU fp32 fake-quant")
     return 1.0 / t, cores, sample, t
 
 
@@ -180,7 +181,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"ego+7 agents ({N_AGENTS}), BEV {BEV_W}x{BEV_H}x{BEV_C} uint8, {PILLARS} pillars/agent, "
+    config = {"workload": f"ego+7 agents ({N_AGENTS}), {PILLARS} pillars x 32 points per agent -> BEV {BEV_W}x{BEV_H}x{BEV_C} uint8, "
                           f"W{args.w_bits}A8 backbone+shrinker, codebook m=1 k=128 x3 levels, {args.fusion} fusion, "
                           "heads 72 ch; SURVEY 8(d)",
               "agents": N_AGENTS, "agents_per_gpu": N_AGENTS // max(world, 1), "parallelism": f"agents/{world}gpu",
