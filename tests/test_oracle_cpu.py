@@ -1,5 +1,6 @@
 """CPU tests of the oracle itself (no GPU): internal consistency of the restatements."""
 import numpy as np
+import pytest
 
 from oracle import codebook_oracle as co
 from oracle import int_oracle
@@ -71,3 +72,37 @@ def test_library_exports_all_symbols():
     for n in names:
         assert hasattr(handle, n), f"libqv2x.so does not export {n}"
     assert _lib.lib().qv2x_version() >= 100
+
+
+def test_c_abi_error_convention_without_gpu():
+    """Argument validation happens before any CUDA call: a bad descriptor returns QV2X_ERR_INVALID (-1), leaves the
+    output handle untouched and sets a message -- the ctypes shim turns that into an exception (the reference's own
+    error behaviour is a Python exception).  No compute call is made."""
+    import ctypes
+    from ctypes import byref, c_void_p
+
+    from quantv2x_b200 import _lib
+
+    L = _lib.lib()
+    # pillar front end: only the 10 -> 64 / 32-point configuration exists
+    d = _lib.PillarDesc()
+    d.n_feat, d.cout, d.max_points, d.nx, d.ny = 9, 64, 32, 704, 200
+    d.out_delta, d.out_bits, d.pre_bits, d.pre_delta = 0.05, 8, 8, 0.1
+    w = (ctypes.c_float * 640)()
+    h = c_void_p()
+    rc = L.qv2x_pillar_create(byref(d), w, None, byref(h))
+    assert rc == -1 and not h.value
+    assert b"10 decorated features" in L.qv2x_last_error()
+    with pytest.raises(_lib.Qv2xError):
+        _lib.check(rc)
+    # quantized layer: unsupported kernel size
+    ld = _lib.LayerDesc()
+    ld.kind, ld.cin, ld.cout, ld.ksize, ld.stride, ld.pad = 0, 64, 64, 5, 1, 2
+    ld.w_bits, ld.relu, ld.n_in_groups, ld.out_delta, ld.out_bits = 8, 1, 1, 0.1, 8
+    buf = (ctypes.c_uint8 * 16)()
+    fl = (ctypes.c_float * 64)()
+    rc = L.qv2x_layer_create(byref(ld), buf, fl, fl, fl, byref(h))
+    assert rc == -1 and b"ksize" in L.qv2x_last_error()
+    # null arguments
+    assert L.qv2x_fuse(1, 2, 4, 4, 256, None, None, None, None) == -1
+    assert L.qv2x_push_planes(None, 3, 16, 16, 0, None, 1, None) == -1
