@@ -428,7 +428,9 @@ def main():
         th = threading.Thread(target=clock_sampler, args=(stop, samples, local_rank), daemon=True)
         th.start()
     sync_all()
+    torch.cuda.nvtx.range_push("timed")          # ncu --nvtx --nvtx-include "timed/" lists exactly these launches
     total_ms = run_steps(args.steps, INFLIGHT)
+    torch.cuda.nvtx.range_pop()
     sync_all()
     serial_ms = run_steps(args.steps, 1)          # one frame at a time: the single-frame latency
     sync_all()
