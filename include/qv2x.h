@@ -204,6 +204,37 @@ void qv2x_pillar_destroy(qv2x_pillar* p);
 int qv2x_pillar_forward(const qv2x_pillar* p, int n_pillars, const float* d_points, const int* d_coords,
                         const int* d_num_points, int batch, uint8_t* d_bev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Detection post-processing on the GPU: sigmoid / max over classes / score threshold, box decode
+ * against the anchors, BEV corners, rotated NMS (top-k by score, greedy), range mask.  Replaces
+ * VoxelPostprocessor3Heads.post_process (opencood/data_utils/post_processor/voxel_postprocessor_3heads.py:318-477)
+ * with nms_rotated (opencood/utils/box_utils_mc.py:665-710), which the reference runs on the CPU with shapely.
+ * Anchors are generated on the fly: class c, rotation r, cell (y, x) has centre
+ * (anchor_x0[c] + x * anchor_dx[c], anchor_y0[c] + y * anchor_dy[c], anchor_z[c]), size anchor_hwl[c], yaw
+ * anchor_rot[r]; anchor index = ((y * W + x) * n_classes + c) * n_rotations + r, as the reference flattens them.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_postprocess qv2x_postprocess;
+typedef struct {
+    int H, W;                       /* head-map size */
+    int n_classes, n_rotations;     /* anchors per cell = n_classes * n_rotations */
+    double anchor_x0[4], anchor_y0[4], anchor_dx[4], anchor_dy[4], anchor_z[4];
+    double anchor_hwl[4][3];
+    double anchor_rot[4];
+    double score_threshold;
+    float nms_threshold;
+    double range_lo[2], range_hi[2];   /* a box is kept only if all four BEV corners lie inside */
+    int max_candidates;             /* capacity for anchors above the score threshold (excess is dropped) */
+    int top;                        /* candidates that enter NMS (reference: 1000; at most 1024) */
+} qv2x_postprocess_desc;
+int qv2x_postprocess_create(const qv2x_postprocess_desc* desc, qv2x_postprocess** out);
+void qv2x_postprocess_destroy(qv2x_postprocess* p);
+/* d_preds float32 [n_cls*A + 7*A + ...][H*W] channel-major head maps (cls first, then reg), A = anchors per cell.
+ * Outputs (device, capacity `top` boxes): d_corners double [K][4][2], d_scores double [K], d_labels int [K]
+ * (1-based class), d_boxes double [K][7] (x, y, z, h, w, l, yaw), *d_n_out = K, in NMS pick order.
+ * d_n_candidates (nullable): anchors that passed the score threshold (may exceed max_candidates). */
+int qv2x_postprocess_forward(const qv2x_postprocess* p, const float* d_preds, double* d_corners, double* d_scores,
+                             int* d_labels, double* d_boxes, int* d_n_out, int* d_n_candidates, void* stream);
+
 /* Multi-GPU exchange of the code planes without a collective: stores d_local ([planes][rows_local] bytes) into the
  * code buffer of every peer: peer p receives plane i at peer_bases[p] + i * dst_plane_stride + dst_row0.
  * peer_bases is a HOST array of n_peers (<= 8) device pointers (peer-mapped; this rank's own buffer included).

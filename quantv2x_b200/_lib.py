@@ -102,6 +102,25 @@ def _declare_pillar(lib):
     lib.qv2x_pillar_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
 
 
+class PostprocessDesc(ctypes.Structure):
+    """Mirror of qv2x_postprocess_desc (include/qv2x.h)."""
+
+    _fields_ = [("H", c_int), ("W", c_int), ("n_classes", c_int), ("n_rotations", c_int),
+                ("anchor_x0", ctypes.c_double * 4), ("anchor_y0", ctypes.c_double * 4),
+                ("anchor_dx", ctypes.c_double * 4), ("anchor_dy", ctypes.c_double * 4),
+                ("anchor_z", ctypes.c_double * 4), ("anchor_hwl", (ctypes.c_double * 3) * 4),
+                ("anchor_rot", ctypes.c_double * 4), ("score_threshold", ctypes.c_double),
+                ("nms_threshold", c_float), ("range_lo", ctypes.c_double * 2), ("range_hi", ctypes.c_double * 2),
+                ("max_candidates", c_int), ("top", c_int)]
+
+
+def _declare_postprocess(lib):
+    lib.qv2x_postprocess_create.argtypes = [POINTER(PostprocessDesc), POINTER(c_void_p)]
+    lib.qv2x_postprocess_destroy.argtypes = [c_void_p]
+    lib.qv2x_postprocess_destroy.restype = None
+    lib.qv2x_postprocess_forward.argtypes = [c_void_p] + [c_void_p] * 8
+
+
 class CodebookDesc(ctypes.Structure):
     """Mirror of qv2x_codebook_desc (include/qv2x.h)."""
 
@@ -176,3 +195,4 @@ def _declare_tiles(lib):
 
 _DECLARERS.append(_declare_tiles)
 _DECLARERS.append(_declare_pillar)
+_DECLARERS.append(_declare_postprocess)

@@ -309,6 +309,80 @@ class PillarEngine:
         return out
 
 
+class PostProcessEngine:
+    """libqv2x handle of the GPU detection post-processing (qv2x_postprocess_*).
+
+    anchor_cfg: the yaml's anchor generator config list (one dict per class: anchor_sizes [[l, w, h]],
+    anchor_rotations, anchor_bottom_heights, align_center, feature_map_stride), as
+    VoxelPostprocessor3Heads.generate_anchor_box reads it; lidar_range / grid_wh as in the yaml."""
+
+    def __init__(self, anchor_cfg, lidar_range, grid_wh, *, score_threshold: float, nms_threshold: float,
+                 box_range, max_candidates: int = 8192, top: int = 1000):
+        from ._lib import PostprocessDesc
+
+        d = PostprocessDesc()
+        strides = {c["feature_map_stride"] for c in anchor_cfg}
+        rots = [tuple(c["anchor_rotations"]) for c in anchor_cfg]
+        if len(strides) != 1 or len(set(rots)) != 1:
+            raise NotImplementedError("all classes must share the feature-map stride and the rotation list")
+        st = strides.pop()
+        d.W, d.H = int(grid_wh[0] // st), int(grid_wh[1] // st)
+        d.n_classes, d.n_rotations = len(anchor_cfg), len(rots[0])
+        for c, cfg in enumerate(anchor_cfg):
+            if len(cfg["anchor_sizes"]) != 1 or len(cfg["anchor_bottom_heights"]) != 1:
+                raise NotImplementedError("one anchor size and one bottom height per class")
+            if cfg["align_center"]:
+                xs, ys = (lidar_range[3] - lidar_range[0]) / d.W, (lidar_range[4] - lidar_range[1]) / d.H
+                xo, yo = xs / 2, ys / 2
+            else:
+                xs, ys = (lidar_range[3] - lidar_range[0]) / (d.W - 1), (lidar_range[4] - lidar_range[1]) / (d.H - 1)
+                xo, yo = 0.0, 0.0
+            d.anchor_x0[c], d.anchor_y0[c] = lidar_range[0] + xo, lidar_range[1] + yo
+            d.anchor_dx[c], d.anchor_dy[c] = xs, ys
+            d.anchor_z[c] = cfg["anchor_bottom_heights"][0]
+            l, w, h = cfg["anchor_sizes"][0]
+            d.anchor_hwl[c][0], d.anchor_hwl[c][1], d.anchor_hwl[c][2] = h, w, l
+        for r, v in enumerate(rots[0]):
+            d.anchor_rot[r] = v
+        d.score_threshold, d.nms_threshold = float(score_threshold), float(nms_threshold)
+        d.range_lo[0], d.range_lo[1] = box_range[0], box_range[1]
+        d.range_hi[0], d.range_hi[1] = box_range[3], box_range[4]
+        d.max_candidates, d.top = int(max_candidates), int(top)
+        self.top, self.hw = int(top), d.H * d.W
+        self.channels = d.n_classes * d.n_classes * d.n_rotations + 7 * d.n_classes * d.n_rotations
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_postprocess_create(byref(d), byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_postprocess_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward(self, preds: torch.Tensor):
+        """preds float32 [>= cls + reg channels, H*W] (channel-major head maps, cls first then reg) ->
+        (corners [K, 4, 2], scores [K], labels [K], boxes [K, 7]) float64 / int32 CUDA tensors in NMS pick order."""
+        assert preds.is_cuda and preds.dtype == torch.float32 and preds.is_contiguous()
+        p = preds.reshape(preds.shape[0] if preds.dim() == 2 else -1, self.hw) if preds.dim() != 2 else preds
+        assert p.shape[1] == self.hw and p.shape[0] >= self.channels
+        dev = preds.device
+        corners = torch.empty((self.top, 4, 2), dtype=torch.float64, device=dev)
+        scores = torch.empty((self.top,), dtype=torch.float64, device=dev)
+        labels = torch.empty((self.top,), dtype=torch.int32, device=dev)
+        boxes = torch.empty((self.top, 7), dtype=torch.float64, device=dev)
+        n = torch.zeros((2,), dtype=torch.int32, device=dev)
+        check(_lib.lib().qv2x_postprocess_forward(self._h, c_void_p(p.data_ptr()), c_void_p(corners.data_ptr()),
+                                                  c_void_p(scores.data_ptr()), c_void_p(labels.data_ptr()),
+                                                  c_void_p(boxes.data_ptr()), c_void_p(n.data_ptr()),
+                                                  c_void_p(n.data_ptr() + 4), _stream_ptr()))
+        k = int(n[0].item())
+        self.last_candidates = int(n[1].item())
+        return corners[:k], scores[:k], labels[:k], boxes[:k]
+
+
 def heads_forward_tile(heads: "HeadsEngine", x: torch.Tensor, out_ptr: int, tile_w: int, out_w: int, out_pixels: int):
     """Heads on a compact tile x float32 [tile_pixels, Cin]; output o of tile pixel (ty, tx) goes to
     out_ptr[o * out_pixels + ty * out_w + tx] (out_ptr: raw device address, possibly in a peer GPU's memory)."""
