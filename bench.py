@@ -46,11 +46,14 @@ def parse():
     ap.add_argument("--fusion", default="att", choices=["att", "max"])
     ap.add_argument("--w-bits", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    # parity / sweep configurations of BASELINE.json (the default is the metric's configuration)
+    ap.add_argument("--agents", type=int, default=8, help="agents in the frame (ego included): 2, 4 or 8")
+    ap.add_argument("--dict-size", type=int, default=0, help="codebook size k (0 = the yaml's 128)")
     return ap.parse_args()
 
 
 # ----------------------------------------------------------------------------------------------- model
-def build_calibrated_model(device, fusion, w_bits, seed=1234):
+def build_calibrated_model(device, fusion, w_bits, seed=1234, dict_size=0):
     """Seeded float model from the yaml -> QuantModel -> weight qparams -> one calibration forward (float path,
     on `device`) -> frozen W8A8.  Returns (qmodel, bev_delta)."""
     import torch
@@ -60,6 +63,8 @@ def build_calibrated_model(device, fusion, w_bits, seed=1234):
     from quantv2x_b200.synthetic import seeded_init
 
     hypes = yaml_utils.load_yaml(yaml_utils.default_config(fusion))
+    if dict_size:
+        hypes["model"]["args"]["codebook"]["dict_size"] = int(dict_size)
     torch.manual_seed(seed)
     model = yaml_utils.create_model(hypes).eval()
     seeded_init(model, seed)
@@ -177,12 +182,17 @@ def cpu_reference_frames_per_s(spec, n_agents, steps, warmup, budget_s=60.0):
 
 # ----------------------------------------------------------------------------------------------- main
 def main():
+    global N_AGENTS, METRIC
     args = parse()
+    if args.agents != 8 or args.dict_size or args.w_bits != 8 or args.fusion != "att":
+        N_AGENTS = args.agents
+        METRIC = (f"W{args.w_bits}A8 fused BEV frames/s (ego + {N_AGENTS - 1} agents, PointPillars V2X-Real 704x200, "
+                  f"codebook m=1 k={args.dict_size or 128}, {args.fusion} fusion)")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": f"ego+7 agents ({N_AGENTS}), {PILLARS} pillars x 32 points per agent -> BEV {BEV_W}x{BEV_H}x{BEV_C} uint8, "
-                          f"W{args.w_bits}A8 backbone+shrinker, codebook m=1 k=128 x3 levels, {args.fusion} fusion, "
+    config = {"workload": f"ego+{N_AGENTS - 1} agents ({N_AGENTS}), {PILLARS} pillars x 32 points per agent -> BEV {BEV_W}x{BEV_H}x{BEV_C} uint8, "
+                          f"W{args.w_bits}A8 backbone+shrinker, codebook m=1 k={args.dict_size or 128} x3 levels, {args.fusion} fusion, "
                           "heads 72 ch; SURVEY 8(d)",
               "agents": N_AGENTS, "agents_per_gpu": N_AGENTS // max(world, 1), "parallelism": f"agents/{world}gpu",
               "l2": "per-frame working set (72 MB inputs + ~45 MB activations per agent) exceeds the 126 MB L2; a "
@@ -194,7 +204,7 @@ def main():
         import torch
 
         from quantv2x_b200.export import export_spec
-        q, bev_delta = build_calibrated_model(torch.device("cpu"), args.fusion, args.w_bits)
+        q, bev_delta = build_calibrated_model(torch.device("cpu"), args.fusion, args.w_bits, dict_size=args.dict_size)
         spec = export_spec(q, bev_delta)
         fps, cores, sample, t = cpu_reference_frames_per_s(spec, N_AGENTS, args.steps, min(args.warmup, 1),
                                                             budget_s=120.0)
@@ -226,7 +236,7 @@ def main():
     assert N_AGENTS % world == 0, "agent count must divide over the GPUs"
     per = N_AGENTS // world
 
-    q, bev_delta = build_calibrated_model(device, args.fusion, args.w_bits)
+    q, bev_delta = build_calibrated_model(device, args.fusion, args.w_bits, dict_size=args.dict_size)
     attach_engines(q, bev_delta=bev_delta, device=device)
     pipe = q.model._pipelines["m1"]
 
