@@ -49,6 +49,11 @@ class QLayer:
         assert w_delta.size == w_int.shape[0] and w_zp.size == w_int.shape[0]
         b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
         self.desc = d
+        # everything needed to rebuild the layer (quantv2x_b200.serialize)
+        self.spec = dict(kind=int(kind), w_int=w_int, w_delta=w_delta, w_zp=w_zp, bias=b, ksize=int(ksize),
+                         stride=int(stride), pad=int(pad), w_bits=int(w_bits), relu=bool(relu),
+                         in_delta=np.asarray(in_delta, np.float32), out_delta=float(out_delta), out_zp=float(out_zp),
+                         out_bits=int(out_bits))
         self._h = c_void_p()
         check(_lib.lib().qv2x_layer_create(byref(d), _np_ptr(w_int), _np_ptr(w_delta), _np_ptr(w_zp),
                                             None if b is None else _np_ptr(b), byref(self._h)))
@@ -123,6 +128,7 @@ class CodebookEngine:
 
         levels = len(codebooks)
         cbs = [np.ascontiguousarray(c, dtype=np.float32) for c in codebooks]
+        self.spec = dict(codebooks=cbs, heads=heads)          # quantv2x_b200.serialize
         m, _, dseg = cbs[0].shape
         d = CodebookDesc()
         d.channel, d.m, d.levels = int(m * dseg), int(m), int(levels)
@@ -230,6 +236,7 @@ class HeadsEngine:
         w = np.ascontiguousarray(w, dtype=np.float32)
         self.cout, self.cin = w.shape
         b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        self.spec = dict(w=w, bias=b)                         # quantv2x_b200.serialize
         self._h = c_void_p()
         check(_lib.lib().qv2x_heads_create(self.cin, self.cout, _np_ptr(w), None if b is None else _np_ptr(b),
                                             byref(self._h)))
@@ -264,6 +271,9 @@ class PillarEngine:
         from ._lib import PillarDesc
 
         w_hat = np.ascontiguousarray(w_hat, dtype=np.float32)
+        self.spec = dict(w_hat=w_hat, bias=None if bias is None else np.ascontiguousarray(bias, dtype=np.float32),
+                         nx=int(nx), ny=int(ny), voxel_size=tuple(float(v) for v in voxel_size),
+                         offset=tuple(float(v) for v in offset), pre_quant=pre_quant, out_quant=out_quant)
         d = PillarDesc()
         d.cout, d.n_feat, d.max_points = int(w_hat.shape[0]), int(w_hat.shape[1]), 32
         d.nx, d.ny = int(nx), int(ny)
@@ -449,6 +459,7 @@ class Plan:
         from ._lib import PlanStep
 
         self.layers = [s[0] for s in steps]          # keep the layers alive
+        self.wiring = [(int(ib), int(ic), int(ob), int(oc)) for (_, ib, ic, ob, oc) in steps]
         arr = (PlanStep * len(steps))()
         for i, (layer, ib, ic, ob, oc) in enumerate(steps):
             arr[i].layer, arr[i].in_buf, arr[i].in_cbase, arr[i].out_buf, arr[i].out_cbase = layer._h, ib, ic, ob, oc

@@ -106,3 +106,25 @@ def test_c_abi_error_convention_without_gpu():
     # null arguments
     assert L.qv2x_fuse(1, 2, 4, 4, 256, None, None, None, None) == -1
     assert L.qv2x_push_planes(None, 3, 16, 16, 0, None, 1, None) == -1
+
+
+def test_wire_format_roundtrip():
+    """pack_codes / unpack_codes: exact round trip for every codebook size, the packed size is
+    ceil(log2 k) bits per code, ragged row counts and corrupt messages are handled."""
+    from quantv2x_b200.serialize import pack_codes, unpack_codes
+
+    rng = np.random.default_rng(0)
+    for k, rows, m in [(128, 35200, 1), (64, 1001, 2), (256, 77, 1), (16, 5, 4), (128, 0, 1)]:
+        codes = rng.integers(0, k, size=(3, m, rows), dtype=np.uint8)
+        msg = pack_codes(codes, k)
+        bits = int(np.ceil(np.log2(k)))
+        assert len(msg) == 24 + (3 * m * rows * bits + 7) // 8
+        back, k2 = unpack_codes(msg)
+        assert k2 == k and back.dtype == np.uint8 and np.array_equal(back, codes)
+    assert len(pack_codes(np.zeros((3, 1, 35200), np.uint8), 128)) == 24 + 92400        # 92.4 KB per agent
+    with pytest.raises(ValueError):
+        pack_codes(np.full((1, 1, 4), 200, np.uint8), 128)
+    with pytest.raises(ValueError):
+        unpack_codes(b"XXXX" + bytes(40))
+    with pytest.raises(ValueError):
+        unpack_codes(pack_codes(np.zeros((3, 1, 100), np.uint8), 128)[:-3])
