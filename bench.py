@@ -581,11 +581,55 @@ def main():
                                    "achieved": ach1, "frac": ach1 / peak, "us_per_launch": k1_ms * 1e3}],
                 "step_tensor_frac": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * per / (ms_per_step * 1e-3) / 1e12 / peak}
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if os.path.exists(peaks_file):
             try:
-                roof["bf16_tflops_measured"] = json.load(open(peaks_file)).get("bf16_tflops")
+                pk = json.load(open(peaks_file))
+                roof["bf16_tflops_measured"] = pk.get("bf16_tflops")
+                if pk.get("hbm_gbs"):
+                    hbm_peak, hbm_src = float(pk["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"
             except Exception:
                 pass
+        # HBM-bound kernels of the ego stage (whole map, all agents), timed alone on cold inputs: the decode gather
+        # writes N x 36 MB of features from 3 code bytes per row; the fuse kernel reads them once and writes 36 MB
+        from quantv2x_b200 import engine as E
+        n_all = N_AGENTS
+        codes_all = torch.randint(0, pipe.codebook.k[0], (levels, m, n_all * hw), dtype=torch.uint8, device=device)
+        eb = pipe.ego_buffers(n_all, slot=99)
+        cold = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+
+        def time_cold(fn, reps=10):
+            tot = 0.0
+            for _ in range(reps):
+                cold.fill_(1)                       # evict the inputs from L2
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            return tot / reps
+
+        feat_flat = eb["feat"].view(n_all * hw, pipe.c_feat)
+        for _ in range(2):
+            pipe.codebook.decode(codes_all, out=feat_flat)
+            E.fuse(eb["feat"], aff, pipe.fusion_mode, out=eb["fused"])
+        dec_ms = time_cold(lambda: pipe.codebook.decode(codes_all, out=feat_flat))
+        fuse_ms = time_cold(lambda: E.fuse(eb["feat"], aff, pipe.fusion_mode, out=eb["fused"]))
+        row_bytes = pipe.c_feat * 4
+        dec_bytes = n_all * hw * (row_bytes + levels * m)
+        fuse_bytes = (n_all + 1) * hw * row_bytes
+        roof["hbm_kernels"] = [
+            {"kernel": "codebook_decode_kernel (table gather from shared memory)", "bound": "hbm",
+             "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": dec_bytes / (dec_ms * 1e-3) / 1e9 / hbm_peak, "us_per_launch": dec_ms * 1e3,
+             "algorithmic_bytes": dec_bytes},
+            {"kernel": f"fuse_kernel ({pipe.fusion_mode}, warp + fuse, {n_all} agents)", "bound": "hbm",
+             "achieved": fuse_bytes / (fuse_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": fuse_bytes / (fuse_ms * 1e-3) / 1e9 / hbm_peak, "us_per_launch": fuse_ms * 1e3,
+             "algorithmic_bytes": fuse_bytes}]
+        roof["hbm_peak_source"] = hbm_src
+        del cold, codes_all
 
     if rank == 0:
         stop.set()
