@@ -47,9 +47,13 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
         const int i = p.y0 + ti, j = p.x0 + static_cast<int>(pix - static_cast<long long>(ti) * p.tw);
         const float xn = (2.f * j + 1.f) / p.W - 1.f;
         const float yn = (2.f * i + 1.f) / p.H - 1.f;
-        float4 xa[NA][VPL];
-#pragma unroll
-        for (int a = 0; a < NA; ++a) {
+        // Sampling geometry: lane a (< NA) works out agent a's four tap offsets and weights ONCE; the other lanes
+        // receive them by shuffle (every lane computing all NA agents' geometry was a third of the kernel's
+        // instructions).  Out-of-image taps get a clamped offset and weight 0.
+        float tw_[4] = {0.f, 0.f, 0.f, 0.f};
+        int to_[4] = {0, 0, 0, 0};
+        if (lane < NA) {
+            const int a = lane;
             const float xs = am[a][0] * xn + am[a][1] * yn + am[a][2];
             const float ys = am[a][3] * xn + am[a][4] * yn + am[a][5];
             const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
@@ -59,17 +63,26 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
             const float fy = fminf(fmaxf(floorf(iy), -2.f), static_cast<float>(p.H) + 1.f);
             const float tx = ix - fx, ty = iy - fy;
             const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
-            const float4* base = reinterpret_cast<const float4*>(feat + static_cast<long long>(a) * npix * p.C);
-            float4 s[4][VPL];
-            float w[4];
 #pragma unroll
             for (int tap = 0; tap < 4; ++tap) {
                 const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
                 const bool inb = (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H);
                 const float wt = ((tap & 1) ? tx : 1.f - tx) * ((tap >> 1) ? ty : 1.f - ty);
-                w[tap] = inb ? wt : 0.f;
+                tw_[tap] = inb ? wt : 0.f;
                 const int xc = min(max(xx, 0), p.W - 1), yc = min(max(yy, 0), p.H - 1);
-                const float4* src = base + (static_cast<long long>(yc) * p.W + xc) * vec;
+                to_[tap] = (yc * p.W + xc) * vec;                    // float4 offset inside the agent's map
+            }
+        }
+        float4 xa[NA][VPL];
+#pragma unroll
+        for (int a = 0; a < NA; ++a) {
+            const float4* base = reinterpret_cast<const float4*>(feat + static_cast<long long>(a) * npix * p.C);
+            float4 s[4][VPL];
+            float w[4];
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                w[tap] = __shfl_sync(0xffffffffu, tw_[tap], a);
+                const float4* src = base + __shfl_sync(0xffffffffu, to_[tap], a);
 #pragma unroll
                 for (int t = 0; t < VPL; ++t) {
                     const int v = lane + 32 * t;
