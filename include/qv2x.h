@@ -1,7 +1,8 @@
 /*
  * qv2x.h -- C ABI of libqv2x.so: the B200 (sm_100a) fast path for QuantV2X's fully quantized
- * intermediate-fusion inference (quantized BEV backbone convs -> codebook encode -> [indices on the
- * wire] -> codebook decode -> ego-side max / attention fusion -> detection heads).
+ * intermediate-fusion inference (pillars -> PointPillars front end -> quantized BEV backbone convs -> codebook
+ * encode -> [indices on the wire / in peer memory] -> codebook decode -> ego-side max / attention fusion ->
+ * detection heads -> post-processing).
  *
  * Every entry point replaces one PyTorch call site of the reference (paths relative to the reference
  * repository root); the reference has no FFI of its own -- the binding a maintainer adds is the
@@ -43,7 +44,8 @@ int qv2x_device_check(int device);
 /* Number of kernels this library has launched since load (all threads); bench.py reports it. */
 long long qv2x_launch_count(void);
 /* Bring-up / profiling knobs for the igemm kernels (0 = normal operation): 1 skip the epilogue math and stores,
- * 2 skip MMA issue, 4 skip activation (A) loads, 8 skip weight (B) loads.  Results are garbage when non-zero. */
+ * 2 skip MMA issue, 4 skip activation (A) loads, 8 skip weight (B) loads, 16 skip the output stores only (results are
+ * garbage with any of these); 64 forces the float64 path of the codebook encoder (results unchanged). */
 void qv2x_set_debug_flags(int flags);
 /* Bring-up: when d_buf != NULL the conv kernels record clock64 stamps per CTA / tile / role into
  * d_buf[grid][32 tiles][16 slots] (int64, device memory owned by the caller); NULL switches it off. */
