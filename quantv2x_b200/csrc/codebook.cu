@@ -49,7 +49,7 @@ struct EncodeEpilogue {
     long long rows;
     // fp32 filter (fast != 0; needs one step per level so that the level's accumulators are still in TMEM when a
     // row turns out to need the exact evaluation):
-    //   the scores are first evaluated in fp32 with a rigorous error bound eps(row); if the best score beats the
+    //   the scores are first evaluated in fp32 with a rigorous error bound eps(row) (levels <= 3); if the best score beats the
     //   runner-up by more than 2*eps the fp32 argmin IS the float64 argmin, otherwise (~1e-4 of rows) the warp
     //   re-reads the accumulators and evaluates the level in float64 exactly as the slow path does.
     int pack16;
@@ -120,10 +120,18 @@ struct EncodeEpilogue {
                     const int j = 4 * q + e;
                     const float hi = __int2float_rn(acc[0][j]);
                     // |256 * mid + lo| < 2^31 when the reduction has at most 256 terms (pack16)
-                    const float lo = pack16 ? __int2float_rn(acc[1][j] * 256 + acc[2][j])
-                                            : fmaf(__int2float_rn(acc[1][j]), 256.f, __int2float_rn(acc[2][j]));
+                    float lo, lo_mag;
+                    if (pack16) {
+                        lo = __int2float_rn(acc[1][j] * 256 + acc[2][j]);
+                        lo_mag = fabsf(lo);
+                    } else {
+                        const float md = __int2float_rn(acc[1][j]), l2 = __int2float_rn(acc[2][j]);
+                        lo = fmaf(md, 256.f, l2);
+                        lo_mag = fmaf(fabsf(md), 256.f, fabsf(l2));
+                    }
                     const float vf = fmaf(hi, 65536.f, lo);
-                    vm = fmaxf(vm, fabsf(vf));
+                    // the error bound needs the magnitude of the PARTS (the high and low digits may cancel in vf)
+                    vm = fmaxf(vm, fmaf(fabsf(hi), 65536.f, lo_mag));
                     sc16[j] = fmaf(vf, dd[e], gg[e]);
                 }
             }
@@ -260,10 +268,13 @@ struct EncodeEpilogue {
         bool exact_merge = true;
         if constexpr (FAST) {
             // ---- merge the fp32 candidates of the two column halves and test the gap.
-            // Error bound of one fp32 score against the float64 evaluation: conversions of the digit accumulators
-            // (<= 2 roundings), two fma roundings, the rounded parameters d32 / g32 / btab32 and the l additions
-            // add up to less than 10 * 2^-24 * T with T = max|V| * max|d| + max|g0| + sum max|B| >= every partial
-            // sum; kEpsRel = 16 * 2^-24 leaves margin.  best + eps < second - eps  =>  same argmin in float64.
+            // Error bound of one fp32 score against the float64 evaluation.  With P = 65536 |hi| + |256 mid + lo| (the
+            // magnitude of the digit parts, >= |V| even when they cancel): the conversion of the low part and the
+            // fma that forms V cost <= 2^-23 P; the rounded d32, the score fma, the rounded g32 and each rounded
+            // cross term with its addition cost <= 2^-24 of a partial sum each.  Every partial sum is <= T =
+            // max P * max|d| + max|g0| + sum max|B|, so the total is below (6 + 2 l) 2^-24 T <= 10 * 2^-24 T for the
+            // l <= 2 earlier levels; kEpsRel = 16 * 2^-24 leaves margin.  best + eps < second - eps  =>  same argmin
+            // in float64.  (vmax holds max P over the row's columns.)
             struct FCand {
                 float best, second;
                 int idx;
