@@ -72,6 +72,8 @@ typedef struct {
     float out_delta;     /* this layer's act_quantizer.delta */
     float out_zero_point;/* this layer's act_quantizer.zero_point (0 after ReLU) */
     int out_bits;        /* act_quantizer.n_bits (<= 8) */
+    int groups;          /* nn.Conv2d groups (0 or 1 = dense).  > 1: w_int is [cout][cin/groups][k][k] (the ResNeXt
+                            convs of the pyramid backbone, resblock.py:94); conv only */
 } qv2x_layer_desc;
 
 /* w_int: the integer weight grid round(w/delta)+zp clamped to [0, 2^w_bits-1], in PyTorch layout
@@ -95,6 +97,26 @@ int qv2x_layer_needs_rowsum(const qv2x_layer* layer);
 int qv2x_layer_forward(const qv2x_layer* layer, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
                        int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride,
                        int out_cbase, int32_t* d_rowsum_out, int32_t* d_acc_dump, void* stream);
+/* Residual-block forms (reference QuantBasicBlock / QuantBottleneck.forward, opencood/quant/quant_block.py:88-97,
+ * 124-134; the convs built with disable_act_quant=True, :79-86, :113-122):
+ *   - shortcut: `out += residual` before the block's ReLU and act_quantizer.  Either the block input on its
+ *     quantizer's grid (d_res_u8 codes, value = res_delta * code) or the FP32 output of the downsample conv
+ *     (d_res_f32); both NHWC over the layer's OUTPUT pixels, row pitch res_cstride elements, first channel res_cbase.
+ *   - d_out_f32: the layer has no act_quantizer (downsample conv, single_head_i): y (after the ReLU if desc.relu) is
+ *     written as FP32 NHWC with row pitch out_f32_cstride; d_y may be NULL and d_rowsum_out must be.
+ * extra == NULL is qv2x_layer_forward. */
+typedef struct {
+    const uint8_t* d_res_u8;
+    const float* d_res_f32;
+    float res_delta;
+    int res_cstride, res_cbase;
+    float* d_out_f32;
+    int out_f32_cstride;
+} qv2x_layer_extra;
+int qv2x_layer_forward_ex(const qv2x_layer* layer, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
+                          int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride,
+                          int out_cbase, int32_t* d_rowsum_out, int32_t* d_acc_dump, const qv2x_layer_extra* extra,
+                          void* stream);
 /* Output extent of a layer for a given input extent. */
 int qv2x_layer_out_shape(const qv2x_layer* layer, int hi, int wi, int* ho, int* wo);
 
@@ -160,6 +182,16 @@ int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, 
 /* Same, restricted to the output tile rows [y0, y1) x columns [x0, x1); d_out is compact [(y1-y0)*(x1-x0)][C]. */
 int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine,
                    float* d_out, int y0, int y1, int x0, int x1, void* stream);
+/* uint8 codes -> float32 values fl(delta * code), same (NHWC) layout; n elements, a multiple of 16. */
+int qv2x_dequant_u8(const uint8_t* d_x, long long n, float delta, float* d_out, void* stream);
+/* Score-weighted fusion of one pyramid level = reference weighted_fuse (opencood/models/fuse_modules/
+ * pyramid_fuse.py:17-62) with the score preparation of QuantPyramidFusion.forward_collab
+ * (opencood/quant/quant_block.py:516-539) folded in.  d_score: [n_agents][H][W] float32; score_is_logit = 1: the
+ * occupancy logits of single_head_i, the kernel applies sigmoid(.) + 1e-4; 0: ready-made scores (e.g. after the
+ * camera crop mask).  Scores are warped like the features; a warped score of exactly 0 excludes the agent;
+ * out = sum_j softmax_j(score_j) x_j, or 0 where every agent is excluded.  Layouts as qv2x_fuse. */
+int qv2x_fuse_weighted(int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
+                       int score_is_logit, const float* d_affine, float* d_out, void* stream);
 
 /* Detection heads = the three 1x1 convs cls_head / reg_head / dir_head (reference
  * heter_model_baseline_mc.py:137-142) concatenated along the output channel; weights are the de-quantized

@@ -6,6 +6,8 @@ Follows
                                 (F.affine_grid + F.grid_sample, bilinear, zeros padding, align_corners=False)
   * MaxFusion.forward           opencood/models/fuse_modules/fusion_in_one.py:87-124
   * AttFusion.forward           opencood/models/fuse_modules/fusion_in_one.py:126-151 (+ ScaledDotProductAttention :14-45)
+  * weighted_fuse               opencood/models/fuse_modules/pyramid_fuse.py:17-62, with the score preparation of
+                                QuantPyramidFusion.forward_collab (opencood/quant/quant_block.py:516-539)
 Pinned against the reference's torch implementation by tests/golden/fusion_*.npz.
 """
 from __future__ import annotations
@@ -66,6 +68,22 @@ def att_fusion(feat, aff):
     score = score - score.max(axis=0, keepdims=True)
     p = np.exp(score)
     p = p / p.sum(axis=0, keepdims=True)
+    return (p[..., None] * x).sum(axis=0)
+
+
+def weighted_fusion(feat, score, aff, score_is_logit=True):
+    """feat [N, H, W, C], score [N, H, W] (occupancy logits, or scores), aff [N, 2, 3] -> [H, W, C]."""
+    s = np.asarray(score, np.float64)
+    if score_is_logit:
+        s = 1.0 / (1.0 + np.exp(-s)) + np.float64(np.float32(1e-4))
+    x = warp(feat, aff)                                   # [N, H, W, C]
+    ws = warp(s[..., None], aff)[..., 0]                  # [N, H, W]
+    ws = np.where(ws == 0.0, -np.inf, ws)
+    mx = ws.max(axis=0, keepdims=True)
+    with np.errstate(invalid="ignore"):
+        p = np.exp(ws - mx)
+        p = p / p.sum(axis=0, keepdims=True)
+    p = np.where(np.isnan(p), 0.0, p)                     # every agent excluded -> 0
     return (p[..., None] * x).sum(axis=0)
 
 

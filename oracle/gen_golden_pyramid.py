@@ -1,0 +1,124 @@
+"""Generates tests/golden/fusion_weighted.npz and tests/golden/pyramid_blocks.npz by running the UNMODIFIED reference `weighted_fuse`
+(opencood/models/fuse_modules/pyramid_fuse.py:17-62) with the score preparation of
+QuantPyramidFusion.forward_collab (opencood/quant/quant_block.py:516-520) on seeded inputs, at the three pyramid
+level shapes (C = 64 / 128 / 256 on H, H/2, H/4), and the reference QuantBottleneck (opencood/quant/quant_block.py:
+100-134) over seeded ResNeXt blocks (tests/pyramid_cases.py).  Build container only:  python oracle/gen_golden_pyramid.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shim  # noqa: E402
+
+ref_shim.install()
+from opencood.models.fuse_modules.pyramid_fuse import weighted_fuse  # noqa: E402
+from opencood.utils.transformation_utils import normalize_pairwise_tfm  # noqa: E402
+
+from opencood.models.sub_modules.resblock import Bottleneck  # noqa: E402
+from opencood.quant.quant_block import QuantBottleneck  # noqa: E402
+from opencood.quant.quant_layer import UniformAffineQuantizer  # noqa: E402
+
+from quantv2x_b200.synthetic import synthetic_poses  # noqa: E402
+from tests.pyramid_cases import BLOCK_CASES, GROUPS, IN_DELTA, block_tensors  # noqa: E402
+
+WQ = dict(n_bits=8, channel_wise=True, scale_method="minmax")
+AQ = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def main():
+    rng = np.random.default_rng(21)
+    out = {}
+    N = 4
+    poses = synthetic_poses(N)
+    # one far-away agent: every tap falls outside its map, so its warped score is exactly 0 everywhere
+    poses[0, 0, 3, 0, 3] = 500.0
+    aff = normalize_pairwise_tfm(torch.from_numpy(poses).float(), 80.0, 281.6, 1)
+    out["poses"] = poses
+    out["affine"] = aff.numpy().astype(np.float32)
+    for lvl, (C, H, W) in enumerate([(64, 16, 24), (128, 8, 12), (256, 4, 6)]):
+        feat = (rng.standard_normal((N, C, H, W)) * (rng.random((N, C, H, W)) > 0.3)).astype(np.float32)
+        occ = (rng.standard_normal((N, 1, H, W)) * 3).astype(np.float32)
+        with torch.no_grad():
+            score = torch.sigmoid(torch.from_numpy(occ)) + 1e-4
+            fused = weighted_fuse(torch.from_numpy(feat), score, torch.tensor([N]), aff, False)[0]
+        out[f"l{lvl}.feat"] = feat
+        out[f"l{lvl}.occ"] = occ
+        out[f"l{lvl}.fused"] = fused.numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "fusion_weighted.npz"), **out)
+    print("fusion_weighted.npz", os.path.getsize(os.path.join(OUT, "fusion_weighted.npz")))
+
+
+def with_bias(conv, wb):
+    m = torch.nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
+                        groups=conv.groups, bias=True)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(wb[0]))
+        m.bias.copy_(torch.from_numpy(wb[1]))
+    return m
+
+
+def gen_blocks():
+    out = {}
+    Bottleneck.expansion = 1                                   # as PyramidFusion.__init__ sets it (pyramid_fuse.py:71)
+    for idx, (name, inplanes, planes, stride, H, W) in enumerate(BLOCK_CASES):
+        t, q_in = block_tensors(idx)
+        down = None
+        if "down" in t:
+            down = torch.nn.Sequential(torch.nn.Conv2d(inplanes, planes, 1, stride=stride, bias=False),
+                                       torch.nn.Identity())
+        # BN is folded into the convs before quantization (quant_model.py:14), i.e. the norm layers are identities
+        b = Bottleneck(inplanes, planes, stride, down, groups=GROUPS, base_width=4, norm_layer=torch.nn.Identity)
+        b.conv1, b.conv2, b.conv3 = with_bias(b.conv1, t["conv1"]), with_bias(b.conv2, t["conv2"]), with_bias(b.conv3, t["conv3"])
+        if down is not None:
+            b.downsample[0] = with_bias(b.downsample[0], t["down"])
+        qb = QuantBottleneck(b, WQ, AQ).eval()
+        qb.set_quant_state(True, True)
+        quantizers = [m for m in qb.modules() if isinstance(m, UniformAffineQuantizer)]
+        x = torch.from_numpy(q_in.astype(np.float32) * IN_DELTA)
+        taps = {}
+        hooks = [getattr(qb, n).register_forward_hook(lambda m, i, o, n=n: taps.__setitem__(n, o.detach().clone()))
+                 for n in ("conv1", "conv2", "conv3")]
+        if down is not None:
+            hooks.append(qb.downsample.register_forward_hook(lambda m, i, o: taps.__setitem__("down", o.detach().clone())))
+        with torch.no_grad():
+            for q in quantizers:
+                q.set_inited(False)
+            qb(x)
+            for q in quantizers:
+                q.set_inited(True)
+            y = qb(x)
+        for h in hooks:
+            h.remove()
+        out[f"{name}.q_in"] = q_in
+        names = ["conv1", "conv2", "conv3"] + (["down"] if down is not None else [])
+        for n in names:
+            m = qb.downsample if n == "down" else getattr(qb, n)
+            out[f"{name}.{n}.w_delta"] = m.weight_quantizer.delta.detach().numpy().astype(np.float32).reshape(-1)
+            out[f"{name}.{n}.w_zp"] = m.weight_quantizer.zero_point.detach().numpy().astype(np.float32).reshape(-1)
+        for n, q, val in (("conv1", qb.conv1.act_quantizer, taps["conv1"]), ("conv2", qb.conv2.act_quantizer, taps["conv2"]),
+                          ("out", qb.act_quantizer, y)):
+            d, z = float(q.delta), float(q.zero_point)
+            assert z == 0.0
+            codes = torch.round(val / d)
+            assert float((codes * d - val).abs().max()) < 1e-4 * d
+            out[f"{name}.{n}.act_delta"] = np.float32(d)
+            out[f"{name}.{n}.codes"] = codes.numpy().astype(np.uint8)
+        out[f"{name}.conv3.out"] = taps["conv3"].numpy().astype(np.float32)       # FP32, no quantizer
+        if down is not None:
+            out[f"{name}.down.out"] = taps["down"].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "pyramid_blocks.npz"), **out)
+    print("pyramid_blocks.npz", os.path.getsize(os.path.join(OUT, "pyramid_blocks.npz")))
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    main()
+    gen_blocks()

@@ -35,6 +35,21 @@ class LayerDesc(ctypes.Structure):
         ("out_delta", c_float),
         ("out_zero_point", c_float),
         ("out_bits", c_int),
+        ("groups", c_int),
+    ]
+
+
+class LayerExtra(ctypes.Structure):
+    """Mirror of qv2x_layer_extra (include/qv2x.h): shortcut input and FP32 output of residual-block convs."""
+
+    _fields_ = [
+        ("d_res_u8", c_void_p),
+        ("d_res_f32", c_void_p),
+        ("res_delta", c_float),
+        ("res_cstride", c_int),
+        ("res_cbase", c_int),
+        ("d_out_f32", c_void_p),
+        ("out_f32_cstride", c_int),
     ]
 
 
@@ -187,6 +202,11 @@ def _declare_tiles(lib):
     lib.qv2x_heads_forward_tile.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_longlong, c_longlong,
                                             c_void_p]
     lib.qv2x_push_planes.argtypes = [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_void_p, c_int, c_void_p]
+    lib.qv2x_layer_forward_ex.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, POINTER(c_void_p),
+                                          c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(LayerExtra), c_void_p]
+    lib.qv2x_dequant_u8.argtypes = [c_void_p, c_longlong, c_float, c_void_p, c_void_p]
+    lib.qv2x_fuse_weighted.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                       c_void_p]
     lib.qv2x_set_debug_flags.argtypes = [c_int]
     lib.qv2x_set_debug_flags.restype = None
     lib.qv2x_debug_trace.argtypes = [c_void_p]

@@ -52,9 +52,39 @@ __global__ void push_planes_kernel(const uint8_t* __restrict__ local, int planes
     }
 }
 
+// uint8 NHWC codes -> float32 NHWC values fl(delta * code): 16 codes in, four float4 out per thread.
+__global__ void dequant_u8_kernel(const uint4* __restrict__ x, long long n_vec, float delta, float4* __restrict__ out) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const uint4 v = __ldg(x + i);
+        const unsigned w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            out[4 * i + k] = make_float4(__fmul_rn(static_cast<float>(w[k] & 0xffu), delta),
+                                         __fmul_rn(static_cast<float>((w[k] >> 8) & 0xffu), delta),
+                                         __fmul_rn(static_cast<float>((w[k] >> 16) & 0xffu), delta),
+                                         __fmul_rn(static_cast<float>(w[k] >> 24), delta));
+    }
+}
+
 }  // namespace qv2x
 
 using namespace qv2x;
+
+extern "C" int qv2x_dequant_u8(const uint8_t* d_x, long long n, float delta, float* d_out, void* stream_) {
+    QV2X_REQUIRE(d_x && d_out && n >= 0 && n % 16 == 0, "qv2x_dequant_u8: null argument or n not a multiple of 16");
+    QV2X_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0,
+                 "qv2x_dequant_u8: pointers must be 16-byte aligned");
+    if (n == 0) return 0;
+    const long long n_vec = n / 16;
+    const int threads = 256;
+    const int grid = static_cast<int>(std::min<long long>((n_vec + threads - 1) / threads, num_sms() * 16LL));
+    dequant_u8_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        reinterpret_cast<const uint4*>(d_x), n_vec, delta, reinterpret_cast<float4*>(d_out));
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 extern "C" int qv2x_push_planes(const uint8_t* d_local, int planes, long long rows_local, long long dst_plane_stride,
                                 long long dst_row0, void* const* peer_bases, int n_peers, void* stream_) {

@@ -7,6 +7,10 @@
 //     v   = gs[0]*t_0  (+ gs[1]*t_1 + gs[2]*t_2, left to right)
 //     y   = fma(v, cs[n], bias[n]) ;  y = max(y, 0) if relu                 (one rounding)
 //     q   = clamp( rint(y / delta_out) + zp_out, 0, qmax )              (true division, half-to-even)
+// Residual blocks (QuantBasicBlock / QuantBottleneck.forward, opencood/quant/quant_block.py:88-97, 124-134): the last
+// conv of a block has no quantizer of its own; `out += residual` comes before the ReLU and the block's quantizer:
+//     y   = fma(v, cs, bias) + r ,   r = fl(res_delta * code) for an identity shortcut (the block input, on its
+//           quantizer's grid) or the FP32 output of the downsample conv (which is this epilogue with out_f32 set).
 // S_g[p] is the sum of the group's input bytes over the receptive field of p (zero padding adds 0
 // because the activation zero-point is 0 after ReLU); it is rebuilt from per-pixel channel sums
 // ("rowsums") that the producing layer's epilogue emitted, so the tensor pipe does no extra work.
@@ -43,6 +47,13 @@ struct RequantEpilogue {
     int32_t* rowsum_out;                  // [n_img*Hout*Wout] (atomically accumulated) or nullptr
     int32_t* acc_dump;                    // [G][n_img*Ho*Wo][N_total] zero-point-corrected accumulators, or nullptr
     int n_total;
+    // generic (FAST8 == false) path only: shortcut added before the ReLU, FP32 output without a quantizer
+    const uint8_t* res_u8;                // [n_img*Hout*Wout][res_cstride] codes at channel res_cbase, scale res_delta
+    const float* res_f32;                 // [n_img*Hout*Wout][res_cstride] floats at channel res_cbase
+    float res_delta;
+    int res_cstride, res_cbase;
+    float* out_f32;                       // [n_img*Hout*Wout][out_f32_cstride]: y after the (optional) ReLU, no codes
+    int out_f32_cstride;
 
     struct Tile {
         int32_t S[G];
@@ -310,9 +321,49 @@ struct RequantEpilogue {
                 rsum = __dp4a(packed[w], 0x01010101u, static_cast<unsigned>(rsum));
             }
         } else {
+            const bool live = (ts.opix >= 0);
+            float radd[W];
+#pragma unroll
+            for (int j = 0; j < W; ++j) radd[j] = 0.f;
+            const bool has_res = (res_u8 != nullptr) || (res_f32 != nullptr);
+            if (has_res && live) {
+                const long long ro = ts.opix * res_cstride + res_cbase + (n0 - ts.ch_off);
+                if (res_u8 != nullptr) {
+#pragma unroll
+                    for (int w = 0; w < W / 4; ++w) {
+                        const uint32_t rb = __ldg(reinterpret_cast<const uint32_t*>(res_u8 + ro) + w);
+#pragma unroll
+                        for (int b = 0; b < 4; ++b)
+                            radd[4 * w + b] = __fmul_rn(static_cast<float>((rb >> (8 * b)) & 0xffu), res_delta);
+                    }
+                } else {
+#pragma unroll
+                    for (int w = 0; w < W / 4; ++w) {
+                        const float4 rf = __ldg(reinterpret_cast<const float4*>(res_f32 + ro) + w);
+                        radd[4 * w + 0] = rf.x, radd[4 * w + 1] = rf.y, radd[4 * w + 2] = rf.z, radd[4 * w + 3] = rf.w;
+                    }
+                }
+            }
+            if (out_f32 != nullptr) {               // no output quantizer (downsample conv, occupancy head)
+                float yo[W];
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    float y = fmaf(v[j], cs[j], bs[j]);
+                    if (has_res) y = __fadd_rn(y, radd[j]);
+                    yo[j] = relu ? fmaxf(y, 0.f) : y;
+                }
+                if (live && !(debug & 16)) {
+                    float4* dst = reinterpret_cast<float4*>(out_f32 + ts.opix * out_f32_cstride + (n0 - ts.ch_off));
+#pragma unroll
+                    for (int w = 0; w < W / 4; ++w)
+                        dst[w] = make_float4(yo[4 * w], yo[4 * w + 1], yo[4 * w + 2], yo[4 * w + 3]);
+                }
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 float y = fmaf(v[j], cs[j], bs[j]);
+                if (has_res) y = __fadd_rn(y, radd[j]);
                 if (relu) y = fmaxf(y, 0.f);
                 // A zero dividend would send the whole warp through the division's slow path: divide
                 // delta/delta instead and mask.

@@ -6,6 +6,10 @@
 //   max    : reference MaxFusion.forward  (opencood/models/fuse_modules/fusion_in_one.py:87-124)
 //   att    : reference AttFusion.forward  (fusion_in_one.py:126-151) -- only the ego query row is kept by the
 //            reference (`[0, ...]`), so only that row is computed: out = sum_j softmax_j(x0.xj/sqrt(C)) xj
+//   weighted : reference weighted_fuse (opencood/models/fuse_modules/pyramid_fuse.py:17-62) as called per pyramid level
+//            by QuantPyramidFusion.forward_collab (opencood/quant/quant_block.py:516-539): the per-agent occupancy
+//            score sigmoid(occ) + 1e-4 is warped like the features, a warped score of exactly 0 (no tap inside the
+//            agent's map) excludes the agent, out = sum_j softmax_j(score_j) x_j
 //   heads  : cls/reg/dir 1x1 convs with fake-quant weights on FP32 features (quant_model.py:129-136)
 #include <algorithm>
 #include <cmath>
@@ -23,6 +27,8 @@ struct FuseParams {
     int y0, x0, th, tw;         // output tile (rows [y0, y0+th), columns [x0, x0+tw)); the result is stored compactly
     const float* aff;           // DEVICE [n][6]: row-major 2x3, normalized coordinates (ego <- agent j)
     float inv_sqrt_c;
+    const float* score;         // MODE 2: DEVICE [n][H][W] occupancy logits (score_is_logit) or ready-made scores
+    int score_is_logit;
 };
 
 // One warp per output pixel; lane owns float4 chunks v = lane + 32*t of the channel vector.
@@ -52,6 +58,7 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
         // instructions).  Out-of-image taps get a clamped offset and weight 0.
         float tw_[4] = {0.f, 0.f, 0.f, 0.f};
         int to_[4] = {0, 0, 0, 0};
+        float wscore = 0.f;                                          // MODE 2: agent `lane`'s warped score
         if (lane < NA) {
             const int a = lane;
             const float xs = am[a][0] * xn + am[a][1] * yn + am[a][2];
@@ -71,6 +78,11 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
                 tw_[tap] = inb ? wt : 0.f;
                 const int xc = min(max(xx, 0), p.W - 1), yc = min(max(yy, 0), p.H - 1);
                 to_[tap] = (yc * p.W + xc) * vec;                    // float4 offset inside the agent's map
+                if (MODE == 2) {
+                    float sv = __ldg(p.score + static_cast<long long>(a) * npix + yc * p.W + xc);
+                    if (p.score_is_logit) sv = 1.f / (1.f + expf(-sv)) + 1e-4f;
+                    wscore = fmaf(tw_[tap], sv, wscore);
+                }
             }
         }
         float4 xa[NA][VPL];
@@ -114,6 +126,34 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
                     o[t].y = fmaxf(o[t].y, xa[a][t].y);
                     o[t].z = fmaxf(o[t].z, xa[a][t].z);
                     o[t].w = fmaxf(o[t].w, xa[a][t].w);
+                }
+            }
+        } else if (MODE == 2) {
+            float sc[NA];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const float sv = __shfl_sync(0xffffffffu, wscore, a);
+                sc[a] = (sv == 0.f) ? -INFINITY : sv;              // masked_fill_(scores == 0, -inf)
+                mx = fmaxf(mx, sc[a]);
+            }
+            float den = 0.f;
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                sc[a] = (mx == -INFINITY) ? 0.f : expf(sc[a] - mx);  // all agents excluded: softmax NaN -> 0
+                den += sc[a];
+            }
+#pragma unroll
+            for (int t = 0; t < VPL; ++t) o[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int a = 0; a < NA; ++a) {
+                const float w = den > 0.f ? sc[a] / den : 0.f;
+#pragma unroll
+                for (int t = 0; t < VPL; ++t) {
+                    o[t].x += w * xa[a][t].x;
+                    o[t].y += w * xa[a][t].y;
+                    o[t].z += w * xa[a][t].z;
+                    o[t].w += w * xa[a][t].w;
                 }
             }
         } else {
@@ -344,11 +384,29 @@ int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, 
     return qv2x_fuse_tile(mode, n_agents, H, W, C, d_feat, d_affine, d_out, 0, H, 0, W, stream_);
 }
 
+static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
+                     int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
+                     void* stream_);
+
 int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine,
                    float* d_out, int y0, int y1, int x0, int x1, void* stream_) {
+    QV2X_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (max) or 1 (attention)");
+    return fuse_impl(mode, n_agents, H, W, C, d_feat, nullptr, 0, d_affine, d_out, y0, y1, x0, x1, stream_);
+}
+
+int qv2x_fuse_weighted(int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
+                       int score_is_logit, const float* d_affine, float* d_out, void* stream_) {
+    QV2X_REQUIRE(d_score, "qv2x_fuse_weighted: null score map");
+    return fuse_impl(2, n_agents, H, W, C, d_feat, d_score, score_is_logit, d_affine, d_out, 0, H, 0, W, stream_);
+}
+
+}  // extern "C"
+
+static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
+                     int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
+                     void* stream_) {
     QV2X_REQUIRE(d_feat && d_affine && d_out, "qv2x_fuse: null argument");
     QV2X_REQUIRE(0 <= y0 && y0 < y1 && y1 <= H && 0 <= x0 && x0 < x1 && x1 <= W, "bad output tile");
-    QV2X_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (max) or 1 (attention)");
     QV2X_REQUIRE(n_agents >= 1 && n_agents <= kMaxAgents, "n_agents must be 1..%d", kMaxAgents);
     QV2X_REQUIRE(C % 4 == 0 && C <= 512, "C must be a multiple of 4 and <= 512");
     QV2X_REQUIRE(H > 0 && W > 0, "empty feature map");
@@ -364,6 +422,8 @@ int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_f
     p.th = y1 - y0;
     p.tw = x1 - x0;
     p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(C));
+    p.score = d_score;
+    p.score_is_logit = score_is_logit;
     const long long npix = static_cast<long long>(p.th) * p.tw;
     const int threads = 256;
     const int grid = static_cast<int>(std::min<long long>((npix * 32 + threads - 1) / threads,
@@ -373,15 +433,21 @@ int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_f
         if (vpl == 1) launch_fuse<0, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else if (vpl == 2) launch_fuse<0, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else launch_fuse<0, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
-    } else {
+    } else if (mode == 1) {
         if (vpl == 1) launch_fuse<1, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else if (vpl == 2) launch_fuse<1, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else launch_fuse<1, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
+    } else {
+        if (vpl == 1) launch_fuse<2, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else if (vpl == 2) launch_fuse<2, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else launch_fuse<2, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
     }
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
+
+extern "C" {
 
 int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out) {
     QV2X_REQUIRE(w && out, "qv2x_heads_create: null argument");

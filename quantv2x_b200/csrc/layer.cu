@@ -35,6 +35,9 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
     QV2X_REQUIRE(d.w_bits >= 2 && d.w_bits <= 8 && d.out_bits >= 2 && d.out_bits <= 8, "bit widths must be 2..8");
     QV2X_REQUIRE(d.n_in_groups == 1 || d.n_in_groups == 3, "n_in_groups must be 1 or 3");
     QV2X_REQUIRE(d.out_delta > 0.f, "out_delta must be positive");
+    const int wg = d.groups > 1 ? d.groups : 1;       // nn.Conv2d(groups=...)
+    QV2X_REQUIRE(wg == 1 || (d.kind == 0 && d.n_in_groups == 1 && d.cin % wg == 0 && d.cout % wg == 0),
+                 "grouped weights: conv only, one input scale, channels divisible by groups");
     auto L = new qv2x_layer();
     L->d = d;
     std::vector<uint8_t> wpack;
@@ -61,15 +64,22 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
         cscale.resize(d.cout);
         biasv.resize(d.cout);
         zpw.resize(d.cout);
+        // Grouped weights ([cout][cin/groups][k][k], ResNeXt convs of the pyramid backbone) run as the dense GEMM of
+        // the block-diagonal matrix: an off-group entry is the channel's zero-point, i.e. a real weight of exactly 0,
+        // so every integer accumulator equals the grouped convolution's.  (Groups of 4-16 channels are far below
+        // the 32-byte K step of the tensor pipe; the dense form costs `groups` x the MACs at full tensor rate.)
+        const int cin_g = d.cin / wg, cout_g = d.cout / wg;
         for (int co = 0; co < d.cout; ++co) {
             const int zp = static_cast<int>(w_zero_point[co]);
             zpw[co] = zp;
             // G=1: y = float(acc) * fl(in_delta * w_delta[c]);  G=3: y = (sum_g in_delta[g]*acc_g) * w_delta[c]
             cscale[co] = (L->groups == 1) ? d.in_delta[0] * w_delta[co] : w_delta[co];
             biasv[co] = bias ? bias[co] : 0.f;
+            const int ci0 = (co / cout_g) * cin_g;
             for (int ci = 0; ci < d.cin; ++ci)
                 for (int t = 0; t < taps; ++t) {
-                    const int w = w_int[(static_cast<size_t>(co) * d.cin + ci) * taps + t];
+                    const bool in_group = (ci >= ci0 && ci < ci0 + cin_g);
+                    const int w = in_group ? w_int[(static_cast<size_t>(co) * cin_g + (ci - ci0)) * taps + t] : zp;
                     const int v = L->b_signed ? (w - zp) : w;
                     wpack[static_cast<size_t>(co) * L->k_total + static_cast<size_t>(t) * d.cin + ci] =
                         static_cast<uint8_t>(v & 0xff);
@@ -165,12 +175,37 @@ int qv2x_layer_out_shape(const qv2x_layer* L, int hi, int wi, int* ho, int* wo) 
 int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
                        int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride, int out_cbase,
                        int32_t* d_rowsum_out, int32_t* d_acc_dump, void* stream_) {
-    QV2X_REQUIRE(L && d_x && d_y, "qv2x_layer_forward: null argument");
+    return qv2x_layer_forward_ex(L, n_img, hi, wi, d_x, in_cstride, in_cbase, d_rowsum_in, d_y, out_cstride, out_cbase,
+                                 d_rowsum_out, d_acc_dump, nullptr, stream_);
+}
+
+int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const uint8_t* d_x, int in_cstride,
+                          int in_cbase, const int32_t* const* d_rowsum_in, uint8_t* d_y, int out_cstride,
+                          int out_cbase, int32_t* d_rowsum_out, int32_t* d_acc_dump, const qv2x_layer_extra* ex,
+                          void* stream_) {
+    QV2X_REQUIRE(L && d_x, "qv2x_layer_forward: null argument");
+    const bool f32_out = ex && ex->d_out_f32;
+    const bool has_res = ex && (ex->d_res_u8 || ex->d_res_f32);
+    QV2X_REQUIRE(d_y || f32_out, "qv2x_layer_forward: null output");
+    if (ex) {
+        QV2X_REQUIRE(!(ex->d_res_u8 && ex->d_res_f32), "one shortcut at most");
+        QV2X_REQUIRE(!ex->d_res_u8 || (ex->res_cstride % 4 == 0 && ex->res_cbase % 4 == 0 && ex->res_delta > 0.f &&
+                                       (reinterpret_cast<uintptr_t>(ex->d_res_u8) & 3) == 0),
+                     "code shortcut: 4-byte aligned, positive scale");
+        QV2X_REQUIRE(!ex->d_res_f32 || (ex->res_cstride % 4 == 0 && ex->res_cbase % 4 == 0 &&
+                                        (reinterpret_cast<uintptr_t>(ex->d_res_f32) & 15) == 0),
+                     "FP32 shortcut: 16-byte aligned rows");
+        QV2X_REQUIRE(!f32_out || (ex->out_f32_cstride % 4 == 0 && ex->out_f32_cstride >= L->d.cout &&
+                                  (reinterpret_cast<uintptr_t>(ex->d_out_f32) & 15) == 0),
+                     "FP32 output: 16-byte aligned rows of at least cout floats");
+    }
+    if (!d_y) d_y = reinterpret_cast<uint8_t*>(ex->d_out_f32);    // never written on the FP32-output path
     QV2X_REQUIRE(n_img > 0 && hi > 0 && wi > 0, "empty input (n_img=%d hi=%d wi=%d)", n_img, hi, wi);
     QV2X_REQUIRE(in_cstride % 16 == 0 && in_cbase % 16 == 0 && out_cstride % 16 == 0 && out_cbase % 16 == 0,
                  "channel strides / bases must be multiples of 16 bytes");
     QV2X_REQUIRE((reinterpret_cast<uintptr_t>(d_x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_y) & 15) == 0,
                  "activation pointers must be 16-byte aligned");
+    QV2X_REQUIRE(!(f32_out && d_rowsum_out), "an FP32 output has no code sums");
     QV2X_REQUIRE(!L->use_zp || d_rowsum_in, "this layer needs d_rowsum_in (see qv2x_layer_needs_rowsum)");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const qv2x_layer_desc& d = L->d;
@@ -287,8 +322,16 @@ int qv2x_layer_forward(const qv2x_layer* L, int n_img, int hi, int wi, const uin
         e.rowsum_out = d_rowsum_out;
         e.acc_dump = d_acc_dump;
         e.n_total = L->n_total;
+        e.res_u8 = ex ? ex->d_res_u8 : nullptr;
+        e.res_f32 = ex ? ex->d_res_f32 : nullptr;
+        e.res_delta = ex ? ex->res_delta : 0.f;
+        e.res_cstride = ex ? ex->res_cstride : 0;
+        e.res_cbase = ex ? ex->res_cbase : 0;
+        e.out_f32 = ex ? ex->d_out_f32 : nullptr;
+        e.out_f32_cstride = ex ? ex->out_f32_cstride : 0;
     };
-    const bool fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu);
+    // shortcuts and FP32 outputs live in the generic epilogue only
+    const bool fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) && !has_res && !f32_out;
     const bool digits = (d.kind == 1 && d.cin <= 256);        // digit GEMM with packed integer recombination
 #define QV2X_RUN(GG, DG, F8)                                                     \
     {                                                                            \

@@ -29,15 +29,16 @@ class QLayer:
     """
 
     def __init__(self, *, kind, w_int, w_delta, w_zp, bias, ksize, stride, pad, w_bits, relu, in_delta,
-                 out_delta, out_zp=0.0, out_bits=8):
+                 out_delta, out_zp=0.0, out_bits=8, groups=1):
         w_int = np.ascontiguousarray(w_int, dtype=np.uint8)
         w_delta = np.ascontiguousarray(w_delta, dtype=np.float32).reshape(-1)
         w_zp = np.ascontiguousarray(w_zp, dtype=np.float32).reshape(-1)
         in_delta = [float(v) for v in np.atleast_1d(np.asarray(in_delta, dtype=np.float32))]
         d = LayerDesc()
         d.kind = int(kind)
+        d.groups = int(groups)
         if kind == 0:
-            d.cout, d.cin = int(w_int.shape[0]), int(w_int.shape[1])
+            d.cout, d.cin = int(w_int.shape[0]), int(w_int.shape[1]) * int(groups)   # [cout][cin/groups][k][k]
         else:
             d.cin, d.cout = int(w_int.shape[0]), int(w_int.shape[1])
         d.ksize, d.stride, d.pad = int(ksize), int(stride), int(pad)
@@ -53,7 +54,7 @@ class QLayer:
         self.spec = dict(kind=int(kind), w_int=w_int, w_delta=w_delta, w_zp=w_zp, bias=b, ksize=int(ksize),
                          stride=int(stride), pad=int(pad), w_bits=int(w_bits), relu=bool(relu),
                          in_delta=np.asarray(in_delta, np.float32), out_delta=float(out_delta), out_zp=float(out_zp),
-                         out_bits=int(out_bits))
+                         out_bits=int(out_bits), groups=int(groups))
         self._h = c_void_p()
         check(_lib.lib().qv2x_layer_create(byref(d), _np_ptr(w_int), _np_ptr(w_delta), _np_ptr(w_zp),
                                             None if b is None else _np_ptr(b), byref(self._h)))
@@ -77,15 +78,36 @@ class QLayer:
         return ho.value, wo.value
 
     def forward(self, x: torch.Tensor, *, in_cbase=0, rowsum_in=None, out=None, out_cbase=0, rowsum_out=None,
-                acc_dump=None):
-        """x: uint8 NHWC [n, H, W, Cstride] on the GPU.  Returns the uint8 NHWC output tensor."""
+                acc_dump=None, residual=None, res_delta=None, res_cbase=0, out_f32=None):
+        """x: uint8 NHWC [n, H, W, Cstride] on the GPU.  Returns the uint8 NHWC output tensor.
+
+        Residual-block forms (reference QuantBottleneck.forward, quant_block.py:124-134): ``residual`` is added before
+        the ReLU and the output quantizer -- uint8 NHWC codes with scale ``res_delta`` (identity shortcut) or a float32
+        NHWC tensor (the downsample conv's output); ``out_f32`` (float32 NHWC [n, Ho, Wo, >= cout]) makes this a
+        layer without an output quantizer and is returned instead of codes."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
         n, hi, wi, cs = x.shape
         ho, wo = self.out_shape(hi, wi)
-        if out is None:
+        extra = None
+        if residual is not None or out_f32 is not None:
+            extra = _lib.LayerExtra()
+            if residual is not None:
+                assert residual.is_cuda and residual.is_contiguous() and tuple(residual.shape[:3]) == (n, ho, wo)
+                if residual.dtype == torch.uint8:
+                    extra.d_res_u8, extra.res_delta = residual.data_ptr(), float(res_delta)
+                else:
+                    assert residual.dtype == torch.float32
+                    extra.d_res_f32 = residual.data_ptr()
+                extra.res_cstride, extra.res_cbase = residual.shape[3], int(res_cbase)
+            if out_f32 is not None:
+                assert out_f32.is_cuda and out_f32.dtype == torch.float32 and out_f32.is_contiguous()
+                assert tuple(out_f32.shape[:3]) == (n, ho, wo) and rowsum_out is None
+                extra.d_out_f32, extra.out_f32_cstride = out_f32.data_ptr(), out_f32.shape[3]
+        if out is None and out_f32 is None:
             out = torch.empty((n, ho, wo, self.cout), dtype=torch.uint8, device=x.device)
-        assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
-        assert tuple(out.shape[:3]) == (n, ho, wo)
+        if out is not None:
+            assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
+            assert tuple(out.shape[:3]) == (n, ho, wo)
         rs_arr = None
         if self.needs_rowsum:
             if rowsum_in is None:
@@ -93,12 +115,13 @@ class QLayer:
                 cg = self.cin // g
                 rowsum_in = [rowsum_u8(x, in_cbase + i * cg, cg) for i in range(g)]
             rs_arr = (c_void_p * len(rowsum_in))(*[c_void_p(t.data_ptr()) for t in rowsum_in])
-        check(_lib.lib().qv2x_layer_forward(
+        check(_lib.lib().qv2x_layer_forward_ex(
             self._h, n, hi, wi, c_void_p(x.data_ptr()), cs, in_cbase, rs_arr,
-            c_void_p(out.data_ptr()), out.shape[3], out_cbase,
+            None if out is None else c_void_p(out.data_ptr()), 16 if out is None else out.shape[3], out_cbase,
             None if rowsum_out is None else c_void_p(rowsum_out.data_ptr()),
-            None if acc_dump is None else c_void_p(acc_dump.data_ptr()), _stream_ptr()))
-        return out
+            None if acc_dump is None else c_void_p(acc_dump.data_ptr()),
+            None if extra is None else byref(extra), _stream_ptr()))
+        return out if out_f32 is None else out_f32
 
 
 def rowsum_u8(x: torch.Tensor, cbase: int, c: int, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -226,6 +249,26 @@ def fuse(feat: torch.Tensor, affine, mode: str, out: torch.Tensor | None = None)
         out = torch.empty((h, w, c), dtype=torch.float32, device=feat.device)
     check(_lib.lib().qv2x_fuse({"max": 0, "att": 1}[mode], n, h, w, c, c_void_p(feat.data_ptr()),
                                c_void_p(aff.data_ptr()), c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def fuse_weighted(feat: torch.Tensor, score: torch.Tensor, affine, score_is_logit: bool = True,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+    """Score-weighted fusion of one pyramid level (reference weighted_fuse, pyramid_fuse.py:17-62).
+    feat float32 [N, H, W, C] pixel-major (agent 0 = ego); score float32 [N, H, W]: the occupancy logits
+    (score_is_logit, the kernel applies sigmoid + 1e-4 as quant_block.py:520 does) or ready-made scores;
+    affine [N, 2, 3] normalized.  Returns float32 [H, W, C]."""
+    assert feat.is_cuda and feat.dtype == torch.float32 and feat.is_contiguous() and feat.dim() == 4
+    n, h, w, c = feat.shape
+    assert score.is_cuda and score.dtype == torch.float32 and score.is_contiguous() and score.numel() == n * h * w
+    if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
+        affine = torch.as_tensor(np.asarray(affine, dtype=np.float32)).to(feat.device)
+    aff = affine.to(torch.float32).reshape(n, 6).contiguous()
+    if out is None:
+        out = torch.empty((h, w, c), dtype=torch.float32, device=feat.device)
+    check(_lib.lib().qv2x_fuse_weighted(n, h, w, c, c_void_p(feat.data_ptr()), c_void_p(score.data_ptr()),
+                                        1 if score_is_logit else 0, c_void_p(aff.data_ptr()),
+                                        c_void_p(out.data_ptr()), _stream_ptr()))
     return out
 
 
@@ -430,6 +473,16 @@ def dequant_nhwc_u8_to_nchw_f32(x: torch.Tensor, delta: float, zero_point: float
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     check(_lib.lib().qv2x_dequant_nhwc_u8_to_nchw_f32(c_void_p(x.data_ptr()), n, c, h * w, float(delta),
                                                       float(zero_point), c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
+def dequantize_u8(x: torch.Tensor, delta: float, out: torch.Tensor | None = None) -> torch.Tensor:
+    """uint8 codes -> float32 fl(delta * code), same shape / layout."""
+    assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.numel() % 16 == 0
+    if out is None:
+        out = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    check(_lib.lib().qv2x_dequant_u8(c_void_p(x.data_ptr()), x.numel(), float(delta), c_void_p(out.data_ptr()),
+                                     _stream_ptr()))
     return out
 
 

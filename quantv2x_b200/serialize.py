@@ -90,7 +90,8 @@ def load_pipeline(path: str, device):
         layers.append(E.QLayer(kind=m("kind"), w_int=g("w_int"), w_delta=g("w_delta"), w_zp=g("w_zp"),
                                bias=g("bias") if m("has_bias") else None, ksize=m("ksize"), stride=m("stride"),
                                pad=m("pad"), w_bits=m("w_bits"), relu=m("relu"), in_delta=g("in_delta"),
-                               out_delta=m("out_delta"), out_zp=m("out_zp"), out_bits=m("out_bits")))
+                               out_delta=m("out_delta"), out_zp=m("out_zp"), out_bits=m("out_bits"),
+                               groups=meta.get(f"layer{i}.groups", 1)))
     steps = [(layers[i],) + tuple(w) for i, w in enumerate(meta["plan.wiring"])]
     plan = E.Plan(steps, meta["plan.buf_channels"])
     fused = BlockEngine(plan, meta["in_deltas"], meta["in_group_channels"], meta["out_deltas"],

@@ -34,6 +34,54 @@ def test_fuse(cuda_device, mode, shape):
     np.testing.assert_allclose(out, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
 
 
+def test_weighted_fuse_vs_reference_golden(cuda_device):
+    """Pyramid-level fusion through the module mirror of weighted_fuse, against the outputs of the
+    reference itself (tests/golden/fusion_weighted.npz) at the three level shapes; tolerance 1e-4 * max|x|."""
+    import os
+
+    from quantv2x_b200.fusion_modules import weighted_fuse
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fusion_weighted.npz"))
+    aff = torch.from_numpy(g["affine"]).to(cuda_device)
+    for lvl in range(3):
+        feat = torch.from_numpy(g[f"l{lvl}.feat"]).to(cuda_device)
+        occ = torch.from_numpy(g[f"l{lvl}.occ"]).to(cuda_device)
+        rl = torch.tensor([feat.shape[0]])
+        ref = g[f"l{lvl}.fused"]
+        out = weighted_fuse(feat, occ, rl, aff, False, score_is_logit=True)[0].cpu().numpy()
+        np.testing.assert_allclose(out, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+        out2 = weighted_fuse(feat, torch.sigmoid(occ) + 1e-4, rl, aff, False)[0].cpu().numpy()
+        np.testing.assert_allclose(out2, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(1, 12, 20, 64), (5, 25, 44, 128), (8, 10, 16, 256), (2, 9, 7, 512)])
+def test_weighted_fuse_vs_oracle(cuda_device, shape):
+    from quantv2x_b200.engine import fuse_weighted
+
+    n, H, W, C = shape
+    rng = np.random.default_rng(n * 77 + H)
+    feat = rng.standard_normal((n, H, W, C)).astype(np.float32)
+    occ = (rng.standard_normal((n, H, W)) * 3).astype(np.float32)
+    aff = make_affines(n, rng)
+    ref = fo.weighted_fusion(feat, occ, aff)
+    out = fuse_weighted(torch.from_numpy(feat).to(cuda_device), torch.from_numpy(occ).to(cuda_device), aff)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+    # ready-made scores with an exact zero region (the camera crop mask case): those pixels drop the agent.
+    # (Only for a rotated agent: with the identity warp the sample points sit exactly on pixel centres, where
+    # "warped score == 0" depends on the last ulp of the sampling coordinate in any implementation.)
+    if n > 1:
+        score = (1.0 / (1.0 + np.exp(-occ.astype(np.float64))) + 1e-4).astype(np.float32)
+        score[n - 1, : H // 2] = 0.0
+        ref = fo.weighted_fusion(feat, score, aff, score_is_logit=False)
+        out = fuse_weighted(torch.from_numpy(feat).to(cuda_device), torch.from_numpy(score).to(cuda_device), aff,
+                            score_is_logit=False)
+        np.testing.assert_allclose(out.cpu().numpy(), ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+    # every agent out of range -> zeros
+    far = np.tile(np.array([[1.0, 0.0, 9.0], [0.0, 1.0, 0.0]], np.float32), (n, 1, 1))
+    z = fuse_weighted(torch.from_numpy(feat).to(cuda_device), torch.from_numpy(occ).to(cuda_device), far)
+    assert not z.any()
+
+
 def test_heads(cuda_device):
     from quantv2x_b200.engine import HeadsEngine
 

@@ -1,0 +1,99 @@
+"""GPU parity of the pyramid-fusion building blocks: ResNeXt bottleneck blocks (grouped 3x3 as a
+block-diagonal int8 GEMM, shortcut + block quantizer fused into the last conv's epilogue, FP32 downsample conv),
+occupancy head and the per-level score-weighted fusion.  Integer outputs are bit-exact against oracle/int_oracle.py,
+which tests/test_golden_cpu.py pins to the reference's QuantBottleneck."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fusion_oracle as fo
+from oracle import int_oracle
+from tests.pyramid_cases import BLOCK_CASES, IN_DELTA
+from tests.test_golden_cpu import GOLD, block_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("idx", [0, 1], ids=[c[0] for c in BLOCK_CASES])
+def test_bottleneck_block_bit_exact(cuda_device, idx):
+    from quantv2x_b200.pyramid import BottleneckEngine
+
+    g = np.load(os.path.join(GOLD, "pyramid_blocks.npz"))
+    name, p, x = block_params(g, idx)
+    ref = int_oracle.bottleneck_oracle(x, IN_DELTA, p)
+    eng = BottleneckEngine(p, IN_DELTA)
+    taps = {}
+    xd = torch.from_numpy(np.ascontiguousarray(x)).to(cuda_device)
+    out, rs = eng.forward(xd, want_rowsum=True, taps=taps)
+    assert np.array_equal(taps["q1"].cpu().numpy(), ref["q1"])
+    assert np.array_equal(taps["q2"].cpu().numpy(), ref["q2"])
+    if "down" in p:
+        assert np.array_equal(taps["res"].cpu().numpy(), ref["res"])          # FP32 output: same fma, bit-exact
+    assert np.array_equal(out.cpu().numpy(), ref["out"])
+    assert np.array_equal(rs.cpu().numpy(), ref["out"].astype(np.int64).sum(-1))
+    # and against the reference block itself: <= 1 LSB on < 1 % of the codes (free-running over three convs)
+    d = np.abs(out.cpu().numpy().astype(np.int64) - g[f"{name}.out.codes"].transpose(0, 2, 3, 1).astype(np.int64))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-2
+
+
+def test_bottleneck_chain_and_larger_map(cuda_device):
+    """Two chained blocks (down then identity) on a map that spans several tiles, W4 weights on the grouped conv."""
+    from quantv2x_b200.pyramid import BottleneckEngine
+
+    rng = np.random.default_rng(11)
+    n, H, W = 2, 50, 88
+
+    def qconv(cout, cin_g, k, bits=8):
+        w = rng.normal(0, np.sqrt(2.0 / (cin_g * k * k)), size=(cout, cin_g, k, k)).astype(np.float32)
+        d, z = int_oracle.weight_qparams_minmax(w, bits)
+        return dict(w_int=int_oracle.weight_int_grid(w, d, z, bits), w_delta=d, w_zp=z, w_bits=bits,
+                    bias=rng.uniform(-0.2, 0.2, size=cout).astype(np.float32))
+
+    def block(inpl, planes, stride, down):
+        width = 2 * planes
+        p = dict(stride=stride, groups=32, out_delta=np.float32(0.05), conv1=qconv(width, inpl, 1),
+                 conv2=qconv(width, width // 32, 3, 4), conv3=qconv(planes, width, 1))
+        p["conv1"]["act_delta"], p["conv2"]["act_delta"] = np.float32(0.03), np.float32(0.04)
+        if down:
+            p["down"] = qconv(planes, inpl, 1)
+        return p
+
+    pa, pb = block(64, 128, 2, True), block(128, 128, 1, False)
+    x = rng.integers(0, 256, size=(n, H, W, 64)).astype(np.uint8)
+    x[rng.random(x.shape) > 0.5] = 0
+    ra = int_oracle.bottleneck_oracle(x, IN_DELTA, pa)
+    rb = int_oracle.bottleneck_oracle(ra["out"], pa["out_delta"], pb)
+    ea, eb = BottleneckEngine(pa, IN_DELTA), BottleneckEngine(pb, float(pa["out_delta"]))
+    ya, rsa = ea.forward(torch.from_numpy(x).to(cuda_device), want_rowsum=True)
+    yb = eb.forward(ya, rowsum=rsa)
+    assert ra["out"].std() > 3 and rb["out"].std() > 3
+    assert np.array_equal(ya.cpu().numpy(), ra["out"])
+    assert np.array_equal(yb.cpu().numpy(), rb["out"])
+
+
+def test_occupancy_head_and_level_fusion(cuda_device):
+    """single_head_i (1x1 conv to one channel, FP32 logits) bit-exact against the oracle's fma, then one level of
+    forward_collab from codes: dequantize -> warp features and scores -> softmax over agents."""
+    from quantv2x_b200.pyramid import OccupancyHead, weighted_fuse_level
+    from tests.test_fusion_gpu import make_affines
+
+    rng = np.random.default_rng(5)
+    n, H, W, C = 3, 20, 36, 128
+    delta = np.float32(0.021)
+    codes = rng.integers(0, 256, size=(n, H, W, C)).astype(np.uint8)
+    codes[rng.random(codes.shape) > 0.5] = 0
+    w = rng.normal(0, 0.1, size=(1, C, 1, 1)).astype(np.float32)
+    wd, wz = int_oracle.weight_qparams_minmax(w, 8)
+    w_int = int_oracle.weight_int_grid(w, wd, wz, 8)
+    bias = np.array([-0.3], np.float32)
+    _, occ_ref = int_oracle.conv_oracle(codes, w_int, wd, wz, bias, delta, None, stride=1, pad=0, relu=False)
+    head = OccupancyHead(w_int, wd, wz, bias, float(delta))
+    cd = torch.from_numpy(codes).to(cuda_device)
+    occ = head.forward(cd)
+    assert np.array_equal(occ.cpu().numpy(), occ_ref[..., 0])
+    aff = make_affines(n, rng)
+    fused = weighted_fuse_level(cd, float(delta), occ, aff).cpu().numpy()
+    ref = fo.weighted_fusion(codes.astype(np.float32) * delta, occ_ref[..., 0], aff)
+    np.testing.assert_allclose(fused, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
