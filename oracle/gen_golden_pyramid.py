@@ -25,7 +25,8 @@ from opencood.quant.quant_block import QuantBottleneck  # noqa: E402
 from opencood.quant.quant_layer import UniformAffineQuantizer  # noqa: E402
 
 from quantv2x_b200.synthetic import synthetic_poses  # noqa: E402
-from tests.pyramid_cases import BLOCK_CASES, GROUPS, IN_DELTA, block_tensors  # noqa: E402
+from tests.pyramid_cases import (BLOCK_CASES, GROUPS, IN_DELTA, PYRAMID_AGENTS, PYRAMID_CFG, PYRAMID_H,  # noqa: E402
+                                 PYRAMID_W, block_tensors, pyramid_tensors)
 
 WQ = dict(n_bits=8, channel_wise=True, scale_method="minmax")
 AQ = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
@@ -118,7 +119,76 @@ def gen_blocks():
     print("pyramid_blocks.npz", os.path.getsize(os.path.join(OUT, "pyramid_blocks.npz")))
 
 
+def gen_backbone():
+    """QuantPyramidFusion.forward_collab (quant_block.py:504-541) of a small ResNeXt pyramid backbone: per-level
+    codes of every agent, occupancy logits and fused features."""
+    import opencood.quant.quant_block as qblock
+    from opencood.models.fuse_modules.pyramid_fuse import PyramidFusion
+
+    t, x = pyramid_tensors()
+    pf = PyramidFusion(dict(PYRAMID_CFG), 64).eval()
+    ident = torch.nn.Identity()
+    for li, nb in enumerate(PYRAMID_CFG["layer_nums"]):
+        for bi in range(nb):
+            b, tb = getattr(pf.resnet, f"layer{li}")[bi], t[f"l{li}.b{bi}"]
+            b.conv1, b.conv2, b.conv3 = with_bias(b.conv1, tb["conv1"]), with_bias(b.conv2, tb["conv2"]), with_bias(b.conv3, tb["conv3"])
+            b.bn1 = b.bn2 = b.bn3 = ident                      # BN folded before quantization (quant_model.py:14)
+            assert (b.downsample is not None) == ("down" in tb) and b.conv2.groups == GROUPS
+            if b.downsample is not None:
+                b.downsample[0], b.downsample[1] = with_bias(b.downsample[0], tb["down"]), ident
+        setattr(pf, f"single_head_{li}", with_bias(getattr(pf, f"single_head_{li}"), t[f"head{li}"]))
+    q = qblock.QuantPyramidFusion(pf, WQ, AQ).eval()
+    for m in q.modules():                                      # as QuantModel.set_quant_state (quant_model.py:107-110)
+        if isinstance(m, (qblock.QuantModule, qblock.BaseQuantBlock)):
+            m.set_quant_state(True, True)
+    quantizers = [m for m in q.modules() if isinstance(m, UniformAffineQuantizer)]
+    poses = synthetic_poses(PYRAMID_AGENTS)
+    aff = normalize_pairwise_tfm(torch.from_numpy(poses).float(), 80.0, 281.6, 1)
+    rl = torch.tensor([PYRAMID_AGENTS])
+    fused_rec, feat_rec = [], {}
+    orig_fuse = qblock.weighted_fuse
+
+    def rec_fuse(xx, score, record_len, affine, align):
+        o = orig_fuse(xx, score, record_len, affine, align)
+        fused_rec.append(o.detach().clone())
+        return o
+
+    qblock.weighted_fuse = rec_fuse
+    hooks = [getattr(q.resnet, f"layer{li}").register_forward_hook(lambda m, i, o, li=li: feat_rec.__setitem__(li, o.detach().clone()))
+             for li in range(3)]
+    # the deblocks after the fusion are not part of this fixture: keep forward_collab from running them on FP32
+    q.decode_multiscale_feature = lambda feats: feats[0]
+    with torch.no_grad():
+        xt = torch.from_numpy(x)
+        for m in quantizers:
+            m.set_inited(False)
+        q.forward_collab(xt, rl, aff)
+        for m in quantizers:
+            m.set_inited(True)
+        fused_rec.clear()
+        _, occ_list = q.forward_collab(xt, rl, aff)
+    qblock.weighted_fuse = orig_fuse
+    for h in hooks:
+        h.remove()
+    out = {"poses": poses, "affine": aff.numpy().astype(np.float32)}
+    for li, nb in enumerate(PYRAMID_CFG["layer_nums"]):
+        for bi in range(nb):
+            b = getattr(q.resnet, f"layer{li}")[bi]
+            for n, aq in (("conv1", b.conv1.act_quantizer), ("conv2", b.conv2.act_quantizer), ("out", b.act_quantizer)):
+                assert float(aq.zero_point) == 0.0
+                out[f"l{li}.b{bi}.{n}.act_delta"] = np.float32(float(aq.delta))
+        d = float(getattr(q.resnet, f"layer{li}")[-1].act_quantizer.delta)
+        codes = torch.round(feat_rec[li] / d)
+        assert float((codes * d - feat_rec[li]).abs().max()) < 1e-4 * d
+        out[f"l{li}.codes"] = codes.numpy().astype(np.uint8)
+        out[f"l{li}.occ"] = occ_list[li].numpy().astype(np.float32)
+        out[f"l{li}.fused"] = fused_rec[li][0].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "pyramid_backbone.npz"), **out)
+    print("pyramid_backbone.npz", os.path.getsize(os.path.join(OUT, "pyramid_backbone.npz")))
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     main()
     gen_blocks()
+    gen_backbone()

@@ -9,8 +9,13 @@
 * ``OccupancyHead`` -- ``single_head_i`` (1x1 conv to one channel, no quantizer; quant_block.py:474-478).
 * ``weighted_fuse_level`` -- score-weighted fusion of one level from codes + occupancy logits.
 
-What is not here yet: the first block of stage 0 reads the FP32 (off-grid) decoded features, and the stage / deblock
-wiring of ``QuantPyramidFusion.forward_collab``; see DESIGN.md section 1.
+* ``FirstBottleneckEngine`` -- the block that reads the FP32 (off-grid) decoded features: its first 1x1 conv is an
+  FP32 GEMM (QuantModule quantizes outputs only, quant_layer.py:391-410), the shortcut is the FP32 input itself.
+* ``PyramidBackboneEngine`` -- ``QuantPyramidFusion.forward_collab`` (quant_block.py:504-541) up to the fused
+  per-level features: ResNeXt stages over every agent's map, occupancy heads, per-level fusion.
+
+What is not here yet: the deblocks that follow the fusion (transposed convs on the FP32 fused maps) and the model
+driver around them; see DESIGN.md section 1.
 """
 from __future__ import annotations
 
@@ -74,6 +79,50 @@ class BottleneckEngine:
         return (out, rs_out) if want_rowsum else out
 
 
+class FirstBottleneckEngine:
+    """The first block of stage 0 (64 -> 64 channels, stride 1, identity shortcut) on FP32 input features.  conv1 runs
+    on the FP32 GEMM kernel of the detection heads (bias first, one fma per input channel in ascending order), in
+    column chunks of 64, and its output is quantized by the NCHW -> NHWC converter (the clamp at 0 is the ReLU)."""
+
+    def __init__(self, params: dict):
+        p = params
+        assert "down" not in p and int(p["stride"]) == 1
+        c1 = p["conv1"]
+        self.d1, d2 = float(c1["act_delta"]), float(p["conv2"]["act_delta"])
+        self.out_delta = float(p["out_delta"])
+        w_hat = ((np.asarray(c1["w_int"], np.float32) - np.asarray(c1["w_zp"], np.float32).reshape(-1, 1, 1, 1))
+                 * np.asarray(c1["w_delta"], np.float32).reshape(-1, 1, 1, 1)).reshape(c1["w_int"].shape[0], -1)
+        bias = np.zeros(w_hat.shape[0], np.float32) if c1.get("bias") is None else np.asarray(c1["bias"], np.float32)
+        self.width, self.cin = w_hat.shape
+        assert self.width % 64 == 0
+        self.conv1 = [E.HeadsEngine(w_hat[o:o + 64], bias[o:o + 64]) for o in range(0, self.width, 64)]
+        self.conv2 = _layer(p["conv2"], ksize=3, stride=1, pad=1, relu=True, in_delta=self.d1, out_delta=d2,
+                            groups=int(p["groups"]))
+        self.conv3 = _layer(p["conv3"], ksize=1, stride=1, pad=0, relu=True, in_delta=d2, out_delta=self.out_delta)
+        self.cout = self.conv3.cout
+        assert self.cout == self.cin, "identity shortcut"
+
+    def forward(self, x: torch.Tensor, want_rowsum: bool = False, taps: dict | None = None, q1_override=None):
+        """x float32 NHWC [n, H, W, cin] -> uint8 NHWC [n, H, W, cout] (scale out_delta)."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin
+        n, h, w, _ = x.shape
+        dev = x.device
+        planar = torch.empty((self.width, n * h * w), dtype=torch.float32, device=dev)
+        for i, eng in enumerate(self.conv1):
+            eng.forward(x, out=planar[64 * i:64 * (i + 1)])
+        q1 = E.quantize_nchw_to_nhwc_u8(planar.view(1, self.width, n * h, w), self.d1).view(n, h, w, self.width)
+        if taps is not None:
+            taps["q1_first"] = q1
+        if q1_override is not None:            # test hook: teacher-force the only FP32-accumulated codes
+            q1 = q1_override
+        rs1 = E.rowsum_u8(q1, 0, self.width)
+        rs2 = torch.zeros((n, h, w), dtype=torch.int32, device=dev)
+        q2 = self.conv2.forward(q1, rowsum_in=[rs1], rowsum_out=rs2)
+        rs_out = torch.zeros((n, h, w), dtype=torch.int32, device=dev) if want_rowsum else None
+        out = self.conv3.forward(q2, rowsum_in=[rs2], residual=x, rowsum_out=rs_out)
+        return (out, rs_out) if want_rowsum else out
+
+
 class OccupancyHead:
     """``single_head_i``: nn.Conv2d(C, 1, 1) wrapped in a QuantModule whose output feeds sigmoid directly
     (quant_block.py:474-478, 516-520).  The one real output channel is padded to the 64-column tile of the GEMM
@@ -106,3 +155,44 @@ def weighted_fuse_level(codes: torch.Tensor, delta: float, occ: torch.Tensor, af
     -> fused float32 [H, W, C]."""
     feat = E.dequantize_u8(codes, delta)
     return E.fuse_weighted(feat, occ, affine, score_is_logit=True)
+
+
+class PyramidBackboneEngine:
+    """``QuantPyramidFusion.forward_collab`` (quant_block.py:504-541) up to the fused per-level features.
+
+    params: ``'l{i}.b{j}'`` -> bottleneck dicts (see BottleneckEngine) and ``'head{i}'`` -> dict(w_int, w_delta, w_zp,
+    bias) of ``single_head_i``; layer_nums: blocks per stage."""
+
+    def __init__(self, params: dict, layer_nums):
+        self.stages, self.heads, self.deltas = [], [], []
+        delta = None
+        for li, nb in enumerate(layer_nums):
+            blocks = []
+            for bi in range(nb):
+                p = params[f"l{li}.b{bi}"]
+                blk = FirstBottleneckEngine(p) if delta is None else BottleneckEngine(p, delta)
+                delta = blk.out_delta
+                blocks.append(blk)
+            self.stages.append(blocks)
+            self.deltas.append(delta)
+            h = params[f"head{li}"]
+            self.heads.append(OccupancyHead(h["w_int"], h["w_delta"], h["w_zp"], h.get("bias"), delta))
+
+    def forward_collab(self, x: torch.Tensor, affine, taps: dict | None = None, q1_override=None):
+        """x float32 NHWC [N, H, W, 64] decoded features of the N agents in range (agent 0 = ego); affine [N, 2, 3]
+        = normalize_pairwise_tfm(...)[b][0, :N].  Returns the fused float32 [h_i, w_i, C_i] map of every level."""
+        if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
+            affine = torch.as_tensor(np.asarray(affine, dtype=np.float32)).to(x.device)
+        fused = []
+        cur, rs = x, None
+        for li, blocks in enumerate(self.stages):
+            for blk in blocks:
+                if isinstance(blk, FirstBottleneckEngine):
+                    cur, rs = blk.forward(cur, want_rowsum=True, taps=taps, q1_override=q1_override)
+                else:
+                    cur, rs = blk.forward(cur, rowsum=rs, want_rowsum=True)
+            occ = self.heads[li].forward(cur, rowsum=rs)
+            fused.append(weighted_fuse_level(cur, self.deltas[li], occ, affine))
+            if taps is not None:
+                taps[f"l{li}.codes"], taps[f"l{li}.occ"] = cur, occ
+        return fused

@@ -29,3 +29,41 @@ def block_tensors(idx):
     q_in = rng.integers(0, 256, size=(2, inplanes, H, W)).astype(np.uint8)
     q_in[rng.random(q_in.shape) > 0.6] = 0
     return t, q_in
+
+
+# ------------------------------------------------------------------------------------------ small pyramid backbone
+# HEAL's pyramid backbone scaled down in depth and map size, same widths / strides / grouping
+# (hypes_yaml/.../pyramid configs: layer_nums [3, 5, 8], layer_strides [1, 2, 2], num_filters [64, 128, 256]).
+PYRAMID_CFG = dict(layer_nums=[2, 2, 1], layer_strides=[1, 2, 2], num_filters=[64, 128, 256],
+                   upsample_strides=[1, 2, 4], num_upsample_filter=[128, 128, 128], inplanes=64, resnext=True,
+                   stage="collab")
+PYRAMID_AGENTS, PYRAMID_H, PYRAMID_W = 3, 24, 32
+
+
+def pyramid_tensors(seed=900):
+    """Float weights of every conv of the ResNeXt pyramid backbone + occupancy heads, and the FP32 input features
+    [N, 64, H, W] (what the codebook decoder hands to the backbone: off the quantization grid, any sign)."""
+    rng = np.random.default_rng(seed)
+
+    def conv(cout, cin_g, k, gain=1.0):
+        w = rng.normal(0, gain * np.sqrt(2.0 / (cin_g * k * k)), size=(cout, cin_g, k, k)).astype(np.float32)
+        b = rng.uniform(-0.2, 0.2, size=cout).astype(np.float32)
+        return w, b
+
+    t = {}
+    inpl = PYRAMID_CFG["inplanes"]
+    for li, (nb, stride, planes) in enumerate(zip(PYRAMID_CFG["layer_nums"], PYRAMID_CFG["layer_strides"],
+                                                  PYRAMID_CFG["num_filters"])):
+        width = 2 * planes
+        for bi in range(nb):
+            s = stride if bi == 0 else 1
+            blk = {"conv1": conv(width, inpl, 1), "conv2": conv(width, width // GROUPS, 3),
+                   "conv3": conv(planes, width, 1, 0.5), "stride": s}
+            if bi == 0 and (s != 1 or inpl != planes):
+                blk["down"] = conv(planes, inpl, 1)
+            t[f"l{li}.b{bi}"] = blk
+            inpl = planes
+        t[f"head{li}"] = conv(1, planes, 1)
+    x = (rng.standard_normal((PYRAMID_AGENTS, 64, PYRAMID_H, PYRAMID_W)) * 1.5).astype(np.float32)
+    x[rng.random(x.shape) > 0.7] = 0
+    return t, x

@@ -97,3 +97,38 @@ def test_occupancy_head_and_level_fusion(cuda_device):
     fused = weighted_fuse_level(cd, float(delta), occ, aff).cpu().numpy()
     ref = fo.weighted_fusion(codes.astype(np.float32) * delta, occ_ref[..., 0], aff)
     np.testing.assert_allclose(fused, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+
+def test_pyramid_backbone_collab(cuda_device):
+    """QuantPyramidFusion.forward_collab up to the fused level features on the small seeded backbone: the first
+    conv (FP32 GEMM on the decoded features) within 1 LSB of the oracle on < 0.1 % of the codes; with those codes
+    teacher-forced, every level's codes and occupancy logits bit-exact and the fused maps within 1e-4; free-running,
+    within the drift of the reference fixture (tests/golden/pyramid_backbone.npz)."""
+    from oracle import pyramid_oracle
+    from quantv2x_b200.pyramid import PyramidBackboneEngine
+    from tests.pyramid_cases import PYRAMID_AGENTS, PYRAMID_CFG
+    from tests.test_golden_cpu import pyramid_params
+
+    g = np.load(os.path.join(GOLD, "pyramid_backbone.npz"))
+    P, x = pyramid_params(g)
+    aff = g["affine"][0, 0, :PYRAMID_AGENTS]
+    nums = PYRAMID_CFG["layer_nums"]
+    eng = PyramidBackboneEngine(P, nums)
+    xd = torch.from_numpy(x).to(cuda_device)
+    taps = {}
+    fused = eng.forward_collab(xd, aff, taps=taps)
+    q1_gpu = taps["q1_first"].cpu().numpy()
+    levels, q1_ref = pyramid_oracle.backbone_collab(x, P, aff, nums, q1_override=q1_gpu)
+    d = np.abs(q1_gpu.astype(np.int64) - q1_ref.astype(np.int64))
+    assert q1_ref.std() > 3 and d.max() <= 1 and (d > 0).mean() < 1e-3, (d.max(), (d > 0).mean())
+    for li, lv in enumerate(levels):
+        assert np.array_equal(taps[f"l{li}.codes"].cpu().numpy(), lv["codes"]), li
+        assert np.array_equal(taps[f"l{li}.occ"].cpu().numpy(), lv["occ"]), li
+        np.testing.assert_allclose(fused[li].cpu().numpy(), lv["fused"], atol=1e-4 * np.abs(lv["fused"]).max(),
+                                   rtol=1e-4)
+        # against the reference itself (free-running): same bounds as the CPU oracle test
+        ref = g[f"l{li}.codes"].transpose(0, 2, 3, 1)
+        dr = np.abs(taps[f"l{li}.codes"].cpu().numpy().astype(np.int64) - ref.astype(np.int64))
+        assert dr.max() <= 2 and (dr > 0).mean() < 3e-2 and (dr > 1).mean() < 1e-3
+        fr = g[f"l{li}.fused"].transpose(1, 2, 0)
+        np.testing.assert_allclose(fused[li].cpu().numpy(), fr, atol=2e-2 * np.abs(fr).max())

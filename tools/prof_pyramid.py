@@ -1,0 +1,112 @@
+"""Times the pyramid-backbone building blocks at HEAL's full shape: N agents x 200x704x64 decoded
+features -> ResNeXt stages [3, 5, 8] blocks (64/128/256 channels, strides 1/2/2, 32 groups) -> occupancy heads ->
+per-level weighted fusion.  Random weights, fixed activation scales (timing only).  Writes one JSON object.
+
+    python tools/prof_pyramid.py [--agents 8] [--out gpurun_out/pyramid_times.json]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from quantv2x_b200 import engine as E  # noqa: E402
+from quantv2x_b200.pyramid import PyramidBackboneEngine  # noqa: E402
+
+
+def qconv(rng, cout, cin_g, k):
+    w = rng.normal(0, np.sqrt(2.0 / (cin_g * k * k)), size=(cout, cin_g, k, k)).astype(np.float32)
+    flat = w.reshape(cout, -1)
+    lo, hi = np.minimum(flat.min(1), 0), np.maximum(flat.max(1), 0)
+    d = ((hi - lo) / 255).astype(np.float32)
+    z = np.round(-lo / d).astype(np.float32)
+    wi = np.clip(np.round(w / d.reshape(-1, 1, 1, 1)) + z.reshape(-1, 1, 1, 1), 0, 255).astype(np.uint8)
+    return dict(w_int=wi, w_delta=d, w_zp=z, bias=rng.uniform(-0.1, 0.1, size=cout).astype(np.float32))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--agents", type=int, default=8)
+    ap.add_argument("--layers", type=int, nargs=3, default=[3, 5, 8])
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--out", default="gpurun_out/pyramid_times.json")
+    a = ap.parse_args()
+    rng = np.random.default_rng(0)
+    P, inpl = {}, 64
+    for li, (nb, stride, planes) in enumerate(zip(a.layers, [1, 2, 2], [64, 128, 256])):
+        width = 2 * planes
+        for bi in range(nb):
+            s = stride if bi == 0 else 1
+            p = dict(stride=s, groups=32, out_delta=0.05, conv1=qconv(rng, width, inpl, 1),
+                     conv2=qconv(rng, width, width // 32, 3), conv3=qconv(rng, planes, width, 1))
+            p["conv1"]["act_delta"], p["conv2"]["act_delta"] = 0.03, 0.04
+            if bi == 0 and (s != 1 or inpl != planes):
+                p["down"] = qconv(rng, planes, inpl, 1)
+            P[f"l{li}.b{bi}"] = p
+            inpl = planes
+        P[f"head{li}"] = qconv(rng, 1, planes, 1)
+    dev = torch.device("cuda:0")
+    eng = PyramidBackboneEngine(P, a.layers)
+    n, H, W = a.agents, 200, 704
+    x = (torch.randn((n, H, W, 64), device=dev) * 1.5) * (torch.rand((n, H, W, 64), device=dev) > 0.5)
+    aff = np.tile(np.array([[1, 0, 0], [0, 1, 0]], np.float32), (n, 1, 1))
+    for j in range(1, n):
+        aff[j] = [[0.99, -0.05, 0.02 * j], [0.6, 0.99, -0.03 * j]]
+    affd = torch.from_numpy(aff).to(dev)
+
+    def timed(fn, iters):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
+
+    res = {"agents": n, "map": [H, W], "layers": a.layers}
+    res["forward_collab_ms"] = timed(lambda: eng.forward_collab(x, affd), a.iters)
+    # per-piece: stage inputs captured once
+    cur, rs = x, None
+    stage_ms, ops = [], []
+    for li, blocks in enumerate(eng.stages):
+        inp, inrs = cur, rs
+
+        def run_stage(inp=inp, inrs=inrs, blocks=blocks):
+            c, r = inp, inrs
+            for b in blocks:
+                c, r = b.forward(c, want_rowsum=True) if r is None else b.forward(c, rowsum=r, want_rowsum=True)
+            return c, r
+
+        stage_ms.append(timed(run_stage, a.iters))
+        cur, rs = run_stage()
+        h, w, c = cur.shape[1:]
+        # int8 MACs of the stage as executed (grouped 3x3 as the dense block-diagonal GEMM)
+        width = 2 * c
+        macs = 0
+        for bi, b in enumerate(blocks):
+            cin = b.cin
+            macs += n * h * w * (cin * width + 9 * width * width + width * c + (cin * c if getattr(b, "down", None) else 0))
+        ops.append(2 * macs)
+        occ = eng.heads[li].forward(cur, rowsum=rs)
+        res[f"level{li}_head_ms"] = timed(lambda: eng.heads[li].forward(cur, rowsum=rs), a.iters)
+        res[f"level{li}_fuse_ms"] = timed(lambda: eng_fuse(cur, eng.deltas[li], occ, affd), a.iters)
+    res["stage_ms"] = stage_ms
+    res["stage_dense_int8_tops"] = [o / (t * 1e-3) / 1e12 for o, t in zip(ops, stage_ms)]
+    os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
+    with open(a.out, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res))
+
+
+def eng_fuse(codes, delta, occ, aff):
+    from quantv2x_b200.pyramid import weighted_fuse_level
+    return weighted_fuse_level(codes, delta, occ, aff)
+
+
+if __name__ == "__main__":
+    main()
