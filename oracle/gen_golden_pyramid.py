@@ -137,6 +137,12 @@ def gen_backbone():
             if b.downsample is not None:
                 b.downsample[0], b.downsample[1] = with_bias(b.downsample[0], tb["down"]), ident
         setattr(pf, f"single_head_{li}", with_bias(getattr(pf, f"single_head_{li}"), t[f"head{li}"]))
+        up = pf.deblocks[li][0]
+        nu = torch.nn.ConvTranspose2d(up.in_channels, up.out_channels, up.kernel_size, stride=up.stride, bias=True)
+        with torch.no_grad():
+            nu.weight.copy_(torch.from_numpy(t[f"up{li}"][0]))
+            nu.bias.copy_(torch.from_numpy(t[f"up{li}"][1]))
+        pf.deblocks[li][0], pf.deblocks[li][1] = nu, ident
     q = qblock.QuantPyramidFusion(pf, WQ, AQ).eval()
     for m in q.modules():                                      # as QuantModel.set_quant_state (quant_model.py:107-110)
         if isinstance(m, (qblock.QuantModule, qblock.BaseQuantBlock)):
@@ -156,8 +162,6 @@ def gen_backbone():
     qblock.weighted_fuse = rec_fuse
     hooks = [getattr(q.resnet, f"layer{li}").register_forward_hook(lambda m, i, o, li=li: feat_rec.__setitem__(li, o.detach().clone()))
              for li in range(3)]
-    # the deblocks after the fusion are not part of this fixture: keep forward_collab from running them on FP32
-    q.decode_multiscale_feature = lambda feats: feats[0]
     with torch.no_grad():
         xt = torch.from_numpy(x)
         for m in quantizers:
@@ -166,7 +170,7 @@ def gen_backbone():
         for m in quantizers:
             m.set_inited(True)
         fused_rec.clear()
-        _, occ_list = q.forward_collab(xt, rl, aff)
+        final, occ_list = q.forward_collab(xt, rl, aff)
     qblock.weighted_fuse = orig_fuse
     for h in hooks:
         h.remove()
@@ -183,6 +187,15 @@ def gen_backbone():
         out[f"l{li}.codes"] = codes.numpy().astype(np.uint8)
         out[f"l{li}.occ"] = occ_list[li].numpy().astype(np.float32)
         out[f"l{li}.fused"] = fused_rec[li][0].numpy().astype(np.float32)
+        # the deblock of this level: its 128 channels of the final [1, 384, H, W] feature, on its own grid
+        aq = q.deblocks[li][0].act_quantizer
+        du = float(aq.delta)
+        assert float(aq.zero_point) == 0.0
+        part = final[0, 128 * li:128 * (li + 1)]
+        cu = torch.round(part / du)
+        assert float((cu * du - part).abs().max()) < 1e-4 * du
+        out[f"up{li}.act_delta"] = np.float32(du)
+        out[f"up{li}.codes"] = cu.numpy().astype(np.uint8)
     np.savez_compressed(os.path.join(OUT, "pyramid_backbone.npz"), **out)
     print("pyramid_backbone.npz", os.path.getsize(os.path.join(OUT, "pyramid_backbone.npz")))
 

@@ -3,7 +3,9 @@ QuantPyramidFusion.forward_collab (opencood/quant/quant_block.py:504-541), up to
 
   FP32 decoded features -> ResNeXt stages of QuantBottleneck blocks (quant_block.py:100-134; the very first conv
   reads the FP32 features, QuantModule quantizes outputs only: quant_layer.py:391-410) -> per level: single_head_i
-  occupancy logits (quant_block.py:516-518) -> weighted_fuse (pyramid_fuse.py:17-62).
+  occupancy logits (quant_block.py:516-518) -> weighted_fuse (pyramid_fuse.py:17-62) -> decode_multiscale_feature
+  (quant_block.py:441-458): one ConvTranspose2d (kernel = stride) + ReLU + quantizer per level on the FP32 fused map,
+  concatenated along the channels.
 
 Integer layers follow oracle/int_oracle.py; the FP32-input 1x1 conv follows the order of the product's FP32 GEMM
 (bias first, then one fma per input channel in ascending order).  Pinned against the reference by
@@ -69,3 +71,24 @@ def backbone_collab(x, P, aff, layer_nums, q1_override=None):
         fused = fusion_oracle.weighted_fusion(cur.astype(f32) * cur_delta, occ[..., 0], aff)
         levels.append(dict(codes=cur, delta=cur_delta, occ=occ[..., 0], fused=fused))
     return levels, q1_first
+
+
+def deblock_f32(fused, up):
+    """QuantModule(ConvTranspose2d(cin, cout, s, stride=s)) + ReLU + act quantizer on an FP32 map (quant_block.py:
+    389-396).  fused float32 [h, w, cin]; up: w_int [cin, cout, s, s], w_delta / w_zp per cin (dim 0 of a transposed
+    conv weight, quant_layer.py:325-335), bias [cout], act_delta, stride.  Returns codes uint8 [h*s, w*s, cout]:
+    y = bias, then one fma per input channel in ascending order (the FP32 GEMM's order), ReLU + quantize."""
+    s = int(up["stride"])
+    w_hat = (up["w_int"].astype(f32) - np.asarray(up["w_zp"], f32).reshape(-1, 1, 1, 1)) * np.asarray(up["w_delta"], f32).reshape(-1, 1, 1, 1)
+    cin, cout = w_hat.shape[:2]
+    h, w, _ = fused.shape
+    rows = w_hat.transpose(2, 3, 1, 0).reshape(s * s * cout, cin)          # row (dy*s + dx)*cout + co
+    y = conv1x1_f32(np.asarray(fused, f32), rows, np.tile(np.asarray(up["bias"], f32), s * s))
+    q = quantize(y, up["act_delta"])                                        # [h, w, s*s*cout]
+    return q.reshape(h, w, s, s, cout).transpose(0, 2, 1, 3, 4).reshape(h * s, w * s, cout)
+
+
+def decode_multiscale(fused_levels, P):
+    """[fused_0, fused_1, ...] -> codes uint8 [H, W, sum cout] and the per-level scales."""
+    parts = [deblock_f32(f, P[f"up{li}"]) for li, f in enumerate(fused_levels)]
+    return np.concatenate(parts, axis=-1), [f32(P[f"up{li}"]["act_delta"]) for li in range(len(parts))]

@@ -14,8 +14,12 @@
 * ``PyramidBackboneEngine`` -- ``QuantPyramidFusion.forward_collab`` (quant_block.py:504-541) up to the fused
   per-level features: ResNeXt stages over every agent's map, occupancy heads, per-level fusion.
 
-What is not here yet: the deblocks that follow the fusion (transposed convs on the FP32 fused maps) and the model
-driver around them; see DESIGN.md section 1.
+* ``DeblockF32`` / ``PyramidBackboneEngine.decode_multiscale_feature`` -- the deblocks after the fusion
+  (quant_block.py:441-458): transposed convs (kernel = stride) on the FP32 fused maps as FP32 GEMMs, quantized and
+  concatenated into the uint8 [H, W, 384] input of the shrink conv (three scales, as the att/max path's concat).
+
+What is not here yet: the model driver of the pyramid model (shrink header + heads are the kernels of the att/max
+path); see DESIGN.md section 3.8.
 """
 from __future__ import annotations
 
@@ -157,6 +161,38 @@ def weighted_fuse_level(codes: torch.Tensor, delta: float, occ: torch.Tensor, af
     return E.fuse_weighted(feat, occ, affine, score_is_logit=True)
 
 
+class DeblockF32:
+    """QuantModule(ConvTranspose2d(cin, cout, s, stride=s)) + ReLU + act quantizer on an FP32 input (the fused map of
+    a level is off every quantization grid).  Output pixel (y*s + dy, x*s + dx) is a 1x1 conv of input pixel (y, x)
+    with the weight slice [:, :, dy, dx]: one FP32 GEMM with s*s*cout columns (64-column chunks of the heads kernel),
+    then the quantizing converter and a pixel shuffle."""
+
+    def __init__(self, up: dict):
+        self.s = int(up["stride"])
+        self.delta = float(up["act_delta"])
+        w_hat = ((np.asarray(up["w_int"], np.float32) - np.asarray(up["w_zp"], np.float32).reshape(-1, 1, 1, 1))
+                 * np.asarray(up["w_delta"], np.float32).reshape(-1, 1, 1, 1))         # [cin, cout, s, s]
+        self.cin, self.cout = w_hat.shape[:2]
+        rows = np.ascontiguousarray(w_hat.transpose(2, 3, 1, 0).reshape(self.s * self.s * self.cout, self.cin))
+        b = np.zeros(self.cout, np.float32) if up.get("bias") is None else np.asarray(up["bias"], np.float32)
+        bias = np.tile(b, self.s * self.s)
+        assert rows.shape[0] % 64 == 0
+        self.gemm = [E.HeadsEngine(rows[o:o + 64], bias[o:o + 64]) for o in range(0, rows.shape[0], 64)]
+
+    def forward(self, fused: torch.Tensor, out: torch.Tensor, out_cbase: int = 0) -> torch.Tensor:
+        """fused float32 [h, w, cin] -> codes written to out[:, :, out_cbase : out_cbase + cout] (uint8 [h*s, w*s, C])."""
+        assert fused.is_cuda and fused.dtype == torch.float32 and fused.is_contiguous() and fused.shape[-1] == self.cin
+        h, w, _ = fused.shape
+        s, n_col = self.s, self.s * self.s * self.cout
+        planar = torch.empty((n_col, h * w), dtype=torch.float32, device=fused.device)
+        for i, eng in enumerate(self.gemm):
+            eng.forward(fused, out=planar[64 * i:64 * (i + 1)])
+        q = E.quantize_nchw_to_nhwc_u8(planar.view(1, n_col, h, w), self.delta)        # [1, h, w, s*s*cout]
+        q = q.view(h, w, s, s, self.cout).permute(0, 2, 1, 3, 4).reshape(h * s, w * s, self.cout)
+        out[:, :, out_cbase:out_cbase + self.cout].copy_(q)
+        return out
+
+
 class PyramidBackboneEngine:
     """``QuantPyramidFusion.forward_collab`` (quant_block.py:504-541) up to the fused per-level features.
 
@@ -177,6 +213,8 @@ class PyramidBackboneEngine:
             self.deltas.append(delta)
             h = params[f"head{li}"]
             self.heads.append(OccupancyHead(h["w_int"], h["w_delta"], h["w_zp"], h.get("bias"), delta))
+        self.deblocks = [DeblockF32(params[f"up{li}"]) for li in range(len(layer_nums)) if f"up{li}" in params]
+        self.up_deltas = [d.delta for d in self.deblocks]
 
     def forward_collab(self, x: torch.Tensor, affine, taps: dict | None = None, q1_override=None):
         """x float32 NHWC [N, H, W, 64] decoded features of the N agents in range (agent 0 = ego); affine [N, 2, 3]
@@ -196,3 +234,15 @@ class PyramidBackboneEngine:
             if taps is not None:
                 taps[f"l{li}.codes"], taps[f"l{li}.occ"] = cur, occ
         return fused
+
+    def decode_multiscale_feature(self, fused):
+        """The deblocks + channel concat of QuantResNetBEVBackbone.decode_multiscale_feature (quant_block.py:441-458):
+        fused level maps -> uint8 codes [1, H, W, sum cout] (level i's channels carry scale up_deltas[i])."""
+        assert len(self.deblocks) == len(fused)
+        h, w = fused[0].shape[0] * self.deblocks[0].s, fused[0].shape[1] * self.deblocks[0].s
+        cat = torch.empty((h, w, sum(d.cout for d in self.deblocks)), dtype=torch.uint8, device=fused[0].device)
+        base = 0
+        for d, f in zip(self.deblocks, fused):
+            d.forward(f, cat, base)
+            base += d.cout
+        return cat.unsqueeze(0)

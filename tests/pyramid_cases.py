@@ -66,4 +66,9 @@ def pyramid_tensors(seed=900):
         t[f"head{li}"] = conv(1, planes, 1)
     x = (rng.standard_normal((PYRAMID_AGENTS, 64, PYRAMID_H, PYRAMID_W)) * 1.5).astype(np.float32)
     x[rng.random(x.shape) > 0.7] = 0
+    # deblocks (ConvTranspose2d, kernel = stride, BN folded): weight [cin, cout, s, s]
+    for li, (cin, cout, s) in enumerate(zip(PYRAMID_CFG["num_filters"], PYRAMID_CFG["num_upsample_filter"],
+                                            PYRAMID_CFG["upsample_strides"])):
+        w = rng.normal(0, np.sqrt(2.0 / cin), size=(cin, cout, s, s)).astype(np.float32)
+        t[f"up{li}"] = (w, rng.uniform(-0.2, 0.2, size=cout).astype(np.float32))
     return t, x

@@ -132,3 +132,13 @@ def test_pyramid_backbone_collab(cuda_device):
         assert dr.max() <= 2 and (dr > 0).mean() < 3e-2 and (dr > 1).mean() < 1e-3
         fr = g[f"l{li}.fused"].transpose(1, 2, 0)
         np.testing.assert_allclose(fused[li].cpu().numpy(), fr, atol=2e-2 * np.abs(fr).max())
+    # deblocks + concat (decode_multiscale_feature): the oracle teacher-forced with the GPU's fused maps -- FP32 GEMM
+    # in the documented order -> within 1 LSB on < 0.1 % of the codes; and within the drift bounds of the reference
+    cat = eng.decode_multiscale_feature(fused)[0].cpu().numpy()
+    cat_ref, deltas = pyramid_oracle.decode_multiscale([f.cpu().numpy() for f in fused], P)
+    assert cat.shape == cat_ref.shape and [float(v) for v in deltas] == eng.up_deltas
+    dc = np.abs(cat.astype(np.int64) - cat_ref.astype(np.int64))
+    assert cat_ref.std() > 3 and dc.max() <= 1 and (dc > 0).mean() < 1e-3, (dc.max(), (dc > 0).mean())
+    gold = np.concatenate([g[f"up{li}.codes"] for li in range(3)]).transpose(1, 2, 0)
+    dg = np.abs(cat.astype(np.int64) - gold.astype(np.int64))
+    assert dg.max() <= 3 and (dg > 0).mean() < 5e-2 and (dg > 1).mean() < 2e-3

@@ -48,6 +48,10 @@ def main():
             P[f"l{li}.b{bi}"] = p
             inpl = planes
         P[f"head{li}"] = qconv(rng, 1, planes, 1)
+        up_s = [1, 2, 4][li]
+        up = qconv(rng, planes, 128, up_s)            # ConvTranspose2d weight [cin, cout, s, s], per-cin scales
+        up.update(act_delta=0.03, stride=up_s)
+        P[f"up{li}"] = up
     dev = torch.device("cuda:0")
     eng = PyramidBackboneEngine(P, a.layers)
     n, H, W = a.agents, 200, 704
@@ -95,6 +99,8 @@ def main():
         occ = eng.heads[li].forward(cur, rowsum=rs)
         res[f"level{li}_head_ms"] = timed(lambda: eng.heads[li].forward(cur, rowsum=rs), a.iters)
         res[f"level{li}_fuse_ms"] = timed(lambda: eng_fuse(cur, eng.deltas[li], occ, affd), a.iters)
+    fused = eng.forward_collab(x, affd)
+    res["deblocks_ms"] = timed(lambda: eng.decode_multiscale_feature(fused), a.iters)
     res["stage_ms"] = stage_ms
     res["stage_dense_int8_tops"] = [o / (t * 1e-3) / 1e12 for o, t in zip(ops, stage_ms)]
     os.makedirs(os.path.dirname(a.out) or ".", exist_ok=True)
