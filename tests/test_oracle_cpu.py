@@ -103,9 +103,33 @@ def test_c_abi_error_convention_without_gpu():
     fl = (ctypes.c_float * 64)()
     rc = L.qv2x_layer_create(byref(ld), buf, fl, fl, fl, byref(h))
     assert rc == -1 and b"ksize" in L.qv2x_last_error()
+    # grouped weights: channels must divide, conv only
+    ld.ksize, ld.pad, ld.groups, ld.cin, ld.cout = 3, 1, 32, 80, 64
+    rc = L.qv2x_layer_create(byref(ld), buf, fl, fl, fl, byref(h))
+    assert rc == -1 and b"grouped" in L.qv2x_last_error()
+    ld.kind, ld.ksize, ld.stride, ld.pad, ld.cin, ld.cout = 1, 2, 2, 0, 64, 64
+    assert L.qv2x_layer_create(byref(ld), buf, fl, fl, fl, byref(h)) == -1 and b"grouped" in L.qv2x_last_error()
     # null arguments
     assert L.qv2x_fuse(1, 2, 4, 4, 256, None, None, None, None) == -1
     assert L.qv2x_push_planes(None, 3, 16, 16, 0, None, 1, None) == -1
+    assert L.qv2x_fuse_weighted(2, 4, 4, 64, None, None, 1, None, None, None) == -1
+    assert b"score" in L.qv2x_last_error()
+    assert L.qv2x_dequant_u8(None, 16, 0.1, None, None) == -1
+    assert L.qv2x_layer_forward_ex(None, 1, 4, 4, None, 64, 0, None, None, 64, 0, None, None, None, None) == -1
+
+
+def test_weighted_fuse_module_host_logic():
+    """The mirror of weighted_fuse refuses what the kernel does not implement instead of falling back."""
+    import torch
+
+    from quantv2x_b200.fusion_modules import weighted_fuse
+
+    x, sc = torch.zeros(2, 8, 4, 4), torch.ones(2, 1, 4, 4)
+    aff = torch.zeros(1, 2, 2, 2, 3)
+    with pytest.raises(NotImplementedError):
+        weighted_fuse(x, sc, torch.tensor([2]), aff, align_corners=True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        weighted_fuse(x, sc, torch.tensor([2]), aff, False)
 
 
 def test_wire_format_roundtrip():
