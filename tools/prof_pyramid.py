@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--layers", type=int, nargs=3, default=[3, 5, 8])
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/pyramid_times.json")
+    ap.add_argument("--once", action="store_true",
+                    help="one warm-up pass, then ONE pass inside the NVTX range 'timed' (for an ncu launch list: "
+                         "ncu --nvtx --nvtx-include 'timed/' --metrics gpu__time_duration.sum --clock-control none)")
     a = ap.parse_args()
     rng = np.random.default_rng(0)
     P, inpl = {}, 64
@@ -60,6 +63,15 @@ def main():
     for j in range(1, n):
         aff[j] = [[0.99, -0.05, 0.02 * j], [0.6, 0.99, -0.03 * j]]
     affd = torch.from_numpy(aff).to(dev)
+
+    if a.once:
+        eng.decode_multiscale_feature(eng.forward_collab(x, affd))
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_push("timed")
+        eng.decode_multiscale_feature(eng.forward_collab(x, affd))
+        torch.cuda.synchronize()
+        torch.cuda.nvtx.range_pop()
+        return
 
     def timed(fn, iters):
         fn()
