@@ -25,8 +25,8 @@ from opencood.quant.quant_block import QuantBottleneck  # noqa: E402
 from opencood.quant.quant_layer import UniformAffineQuantizer  # noqa: E402
 
 from quantv2x_b200.synthetic import synthetic_poses  # noqa: E402
-from tests.pyramid_cases import (BLOCK_CASES, GROUPS, IN_DELTA, PYRAMID_AGENTS, PYRAMID_CFG, PYRAMID_H,  # noqa: E402
-                                 PYRAMID_W, block_tensors, pyramid_tensors)
+from tests.pyramid_cases import (BLOCK_CASES, GROUPS, IN_DELTA, PYRAMID_AGENTS, PYRAMID_CFG,  # noqa: E402
+                                 block_tensors, pyramid_tensors)
 
 WQ = dict(n_bits=8, channel_wise=True, scale_method="minmax")
 AQ = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)

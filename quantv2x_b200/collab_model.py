@@ -11,7 +11,6 @@ from __future__ import annotations
 
 from collections import Counter
 
-import numpy as np
 import torch
 import torch.nn as nn
 

@@ -3,7 +3,6 @@ usage: python tools/prof_encode.py [agents] [--debug=N] [--k=128]"""
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -3,7 +3,6 @@ usage: python tools/prof_layer.py [shrink1|shrink0|s0|s1|s2|d0|d1|d2] [iters] [-
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -13,7 +13,6 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from quantv2x_b200 import engine as E  # noqa: E402
 from quantv2x_b200.pyramid import PyramidBackboneEngine  # noqa: E402
 
 

@@ -3,7 +3,6 @@ usage: python tools/trace_layer.py [shrink1|shrink0|s0|s1|s2] [cta]"""
 import os
 import sys
 
-import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
