@@ -128,9 +128,195 @@ class QuantDownsampleConv(BaseQuantBlock):
         return x
 
 
+# --------------------------------------------------------------------------------------------------
+# Pyramid-fusion backbone: reference quant_block.py:100-134 (QuantBottleneck), :337-385
+# (QuantResNetModified), :462-549 (QuantPyramidFusion).  The torch bodies below are the calibration path; after
+# calibration ``export_params`` hands the integer parameters to quantv2x_b200.pyramid.PyramidBackboneEngine and
+# ``attach_engine`` makes ``forward_collab`` run there.
+# --------------------------------------------------------------------------------------------------
+from ..pyramid_modules import Bottleneck, PyramidFusion, ResNeXtStages, weighted_fuse_torch  # noqa: E402
+
+
+def _conv_params(qm: QuantModule):
+    w_int, w_delta, w_zp = qm.integer_weight()
+    bias = None if qm.bias is None else qm.bias.detach().float().cpu().numpy()
+    return dict(w_int=w_int, w_delta=w_delta, w_zp=w_zp, bias=bias, w_bits=int(qm.weight_quantizer.n_bits))
+
+
+def _act_delta(q) -> float:
+    if float(q.zero_point) != 0.0:
+        raise ValueError("the integer path needs activation zero-points of 0 (post-ReLU quantizers)")
+    return float(q.delta)
+
+
+class QuantBottleneck(BaseQuantBlock):
+    """conv1 / conv2 with their own ReLU + quantizer, conv3 (and the downsample conv) without: the shortcut is added
+    first, then the block's ReLU and quantizer."""
+
+    def __init__(self, bottleneck: Bottleneck, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        from .quant_layer import UniformAffineQuantizer
+
+        self.conv1 = QuantModule(bottleneck.conv1, weight_quant_params, act_quant_params)
+        self.conv1.norm_function, self.conv1.activation_function = bottleneck.bn1, bottleneck.relu
+        self.conv2 = QuantModule(bottleneck.conv2, weight_quant_params, act_quant_params)
+        self.conv2.norm_function, self.conv2.activation_function = bottleneck.bn2, bottleneck.relu
+        self.conv3 = QuantModule(bottleneck.conv3, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.conv3.norm_function = bottleneck.bn3
+        self.downsample = None
+        if bottleneck.downsample is not None:
+            self.downsample = QuantModule(bottleneck.downsample[0], weight_quant_params, act_quant_params,
+                                          disable_act_quant=True)
+            self.downsample.norm_function = bottleneck.downsample[1]
+        self.activation_function = bottleneck.relu
+        self.act_quantizer = UniformAffineQuantizer(**act_quant_params)
+        self.stride = bottleneck.stride
+        self.groups = bottleneck.conv2.groups
+
+    def forward(self, x):
+        residual = x if self.downsample is None else self.downsample(x)
+        out = self.conv3(self.conv2(self.conv1(x)))
+        out = self.activation_function(out + residual)
+        if self.use_act_quant:
+            out = self.act_quantizer(out)
+        return out
+
+    def export_params(self) -> dict:
+        """The dict quantv2x_b200.pyramid.BottleneckEngine takes."""
+        p = dict(stride=int(self.stride), groups=int(self.groups), out_delta=_act_delta(self.act_quantizer))
+        for n in ("conv1", "conv2", "conv3"):
+            p[n] = _conv_params(getattr(self, n))
+        p["conv1"]["act_delta"] = _act_delta(self.conv1.act_quantizer)
+        p["conv2"]["act_delta"] = _act_delta(self.conv2.act_quantizer)
+        if self.downsample is not None:
+            p["down"] = _conv_params(self.downsample)
+        return p
+
+
+class QuantResNeXtStages(BaseQuantBlock):
+    def __init__(self, stages: ResNeXtStages, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.layernum = stages.layernum
+        for i in range(self.layernum):
+            setattr(self, f"layer{i}", nn.Sequential(*[QuantBottleneck(b, weight_quant_params, act_quant_params)
+                                                        for b in getattr(stages, f"layer{i}")]))
+
+    def forward(self, x):
+        feats = []
+        for i in range(self.layernum):
+            x = getattr(self, f"layer{i}")(x)
+            feats.append(x)
+        return feats
+
+
+class QuantPyramidFusion(BaseQuantBlock):
+    def __init__(self, pyramid_fusion: PyramidFusion, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.model_cfg = pyramid_fusion.model_cfg
+        self.stage = pyramid_fusion.stage
+        self.align_corners = pyramid_fusion.align_corners
+        self.num_levels = pyramid_fusion.num_levels
+        self.num_bev_features = pyramid_fusion.num_bev_features
+        self.resnet = QuantResNeXtStages(pyramid_fusion.resnet, weight_quant_params, act_quant_params)
+        self.deblocks = nn.ModuleList()
+        for deblock in pyramid_fusion.deblocks:
+            qm = QuantModule(deblock[0], weight_quant_params, act_quant_params)
+            qm.norm_function, qm.activation_function = deblock[1], deblock[2]
+            self.deblocks.append(nn.Sequential(qm))
+        for i in range(self.num_levels):
+            setattr(self, f"single_head_{i}", QuantModule(getattr(pyramid_fusion, f"single_head_{i}"),
+                                                          weight_quant_params, act_quant_params))
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        super().set_quant_state(weight_quant, act_quant)
+        for m in self.modules():                      # the nested blocks own quantizers too
+            if isinstance(m, BaseQuantBlock) and m is not self:
+                m.use_weight_quant, m.use_act_quant = weight_quant, act_quant
+
+    def get_multiscale_feature(self, spatial_features):
+        return self.resnet(spatial_features)
+
+    def decode_multiscale_feature(self, x):
+        ups = [self.deblocks[i](x[i]) if len(self.deblocks) > 0 else x[i] for i in range(self.num_levels)]
+        return torch.cat(ups, dim=1) if len(ups) > 1 else ups[0]
+
+    def forward_single(self, spatial_features):
+        feats = self.get_multiscale_feature(spatial_features)
+        occ = [getattr(self, f"single_head_{i}")(feats[i]) for i in range(self.num_levels)]
+        return self.decode_multiscale_feature(feats), occ
+
+    def forward_collab(self, spatial_features, record_len, affine_matrix, agent_modality_list=None, cam_crop_info=None):
+        if cam_crop_info:
+            raise NotImplementedError("the camera crop mask is not built (LiDAR agents only)")
+        if self.engine_ready():
+            return self._run_engine_collab(spatial_features, record_len, affine_matrix)
+        return self.forward_collab_float(spatial_features, record_len, affine_matrix)
+
+    def forward_collab_float(self, spatial_features, record_len, affine_matrix):
+        """The reference's fake-quant torch body (calibration, and the float side of parity tests)."""
+        feats = self.get_multiscale_feature(spatial_features)
+        fused, occ = [], []
+        for i in range(self.num_levels):
+            o = getattr(self, f"single_head_{i}")(feats[i])
+            occ.append(o)
+            fused.append(weighted_fuse_torch(feats[i], torch.sigmoid(o) + 1e-4, record_len, affine_matrix))
+        return self.decode_multiscale_feature(fused), occ
+
+    def forward(self, spatial_features, record_len=None, affine_matrix=None, agent_modality_list=None,
+                cam_crop_info=None):
+        if self.stage == "single":
+            return self.forward_single(spatial_features)
+        if record_len is None or affine_matrix is None:
+            raise ValueError("record_len and affine_matrix are required for forward_collab()")
+        return self.forward_collab(spatial_features, record_len, affine_matrix, agent_modality_list, cam_crop_info)
+
+    # ------------------------------------------------------------------ engine hand-off
+    def layer_nums(self):
+        return [len(getattr(self.resnet, f"layer{i}")) for i in range(self.num_levels)]
+
+    def export_params(self) -> dict:
+        """The dict quantv2x_b200.pyramid.PyramidBackboneEngine takes (every quantizer must be calibrated)."""
+        P = {}
+        for li in range(self.num_levels):
+            for bi, blk in enumerate(getattr(self.resnet, f"layer{li}")):
+                P[f"l{li}.b{bi}"] = blk.export_params()
+            P[f"head{li}"] = _conv_params(getattr(self, f"single_head_{li}"))
+            if len(self.deblocks) > 0:
+                qm = self.deblocks[li][0]
+                up = _conv_params(qm)
+                up.update(act_delta=_act_delta(qm.act_quantizer), stride=int(qm.fwd_kwargs["stride"][0]))
+                P[f"up{li}"] = up
+        return P
+
+    def _run_engine_collab(self, x, record_len, affine_matrix):
+        """forward_collab on libqv2x: NCHW FP32 in, the reference's NCHW FP32 tensors out (drop-in boundary)."""
+        if self._engine is None:
+            raise RuntimeError("QuantPyramidFusion: quantized inference requested but no libqv2x engine is attached; "
+                               "call attach_engine(PyramidBackboneEngine(self.export_params(), self.layer_nums())) "
+                               "after calibration (there is no CPU fallback)")
+        from .. import engine as E
+
+        eng, outs, occs, start = self._engine, [], None, 0
+        for b, n in enumerate(int(v) for v in record_len):
+            xb = E.nchw_to_nhwc_f32(x[start:start + n].contiguous().float())
+            taps = {}
+            fused = eng.forward_collab(xb, affine_matrix[b][0, :n].to(x.device, torch.float32).contiguous(), taps=taps)
+            cat = eng.decode_multiscale_feature(fused)                               # uint8 [1, H, W, sum cout]
+            parts, base = [], 0
+            for d in eng.deblocks:
+                parts.append(E.dequant_nhwc_u8_to_nchw_f32(cat[..., base:base + d.cout].contiguous(), d.delta))
+                base += d.cout
+            outs.append(torch.cat(parts, dim=1))
+            occ_b = [taps[f"l{i}.occ"].unsqueeze(1) for i in range(self.num_levels)]
+            occs = occ_b if occs is None else [torch.cat([a, c]) for a, c in zip(occs, occ_b)]
+            start += n
+        return torch.cat(outs), occs
+
+
 opencood_specials = {
     BaseBEVBackbone: QuantBaseBEVBackbone,
     DownsampleConv: QuantDownsampleConv,
+    PyramidFusion: QuantPyramidFusion,
 }
 
 # modules the reference keeps in FP32 by attribute name (quant_block.py:1599-1615)

@@ -142,3 +142,27 @@ def test_pyramid_backbone_collab(cuda_device):
     gold = np.concatenate([g[f"up{li}.codes"] for li in range(3)]).transpose(1, 2, 0)
     dg = np.abs(cat.astype(np.int64) - gold.astype(np.int64))
     assert dg.max() <= 3 and (dg > 0).mean() < 5e-2 and (dg > 1).mean() < 2e-3
+
+
+def test_quant_pyramid_fusion_module_on_engine(cuda_device):
+    """The drop-in module: QuantPyramidFusion calibrated in torch, exported, engine attached -> forward_collab returns
+    the reference's tensors (NCHW FP32 [1, 384, H, W] on the deblocks' grids + occupancy maps) within the free-running
+    drift bounds of the fake-quant float body."""
+    from quantv2x_b200.pyramid import PyramidBackboneEngine
+    from tests.pyramid_cases import PYRAMID_AGENTS, pyramid_tensors
+    from tests.test_golden_cpu import build_pyramid_mirror
+
+    q, g, final, occ = build_pyramid_mirror()
+    q.attach_engine(PyramidBackboneEngine(q.export_params(), q.layer_nums()))
+    _, x = pyramid_tensors()
+    out, occ_g = q.forward_collab(torch.from_numpy(x).to(cuda_device), torch.tensor([PYRAMID_AGENTS]),
+                                  torch.from_numpy(g["affine"]).to(cuda_device))
+    assert tuple(out.shape) == tuple(final.shape) and out.dtype == torch.float32
+    for li in range(3):
+        d = float(q.deblocks[li][0].act_quantizer.delta)
+        a = torch.round(out[0, 128 * li:128 * (li + 1)].cpu() / d).numpy().astype(np.int64)
+        b = torch.round(final[0, 128 * li:128 * (li + 1)] / d).numpy().astype(np.int64)
+        dd = np.abs(a - b)
+        assert dd.max() <= 3 and (dd > 0).mean() < 5e-2 and (dd > 1).mean() < 2e-3, (li, dd.max(), (dd > 0).mean())
+        assert tuple(occ_g[li].shape) == tuple(occ[li].shape)
+        np.testing.assert_allclose(occ_g[li].cpu().numpy(), occ[li].numpy(), atol=2e-2 * float(occ[li].abs().max()))
