@@ -19,7 +19,7 @@
 
 namespace qv2x {
 
-template <int G, bool DIGITS = false, bool FAST8 = true>
+template <int G, bool DIGITS = false, bool FAST8 = true, bool RES = false>
 struct RequantEpilogue {
     // epilogue warps per TMEM lane quadrant: more warps hide the latencies of the (ALU-pipe bound) requant math
     static constexpr int col_split(int) { return 2; }   // (4 was measured: spills and no gain -- not latency bound)
@@ -47,7 +47,7 @@ struct RequantEpilogue {
     int32_t* rowsum_out;                  // [n_img*Hout*Wout] (atomically accumulated) or nullptr
     int32_t* acc_dump;                    // [G][n_img*Ho*Wo][N_total] zero-point-corrected accumulators, or nullptr
     int n_total;
-    // generic (FAST8 == false) path only: shortcut added before the ReLU, FP32 output without a quantizer
+    // shortcut added before the ReLU (generic path, or FAST8 with RES); FP32 output without a quantizer (generic only)
     const uint8_t* res_u8;                // [n_img*Hout*Wout][res_cstride] codes at channel res_cbase, scale res_delta
     const float* res_f32;                 // [n_img*Hout*Wout][res_cstride] floats at channel res_cbase
     float res_delta;
@@ -266,6 +266,34 @@ struct RequantEpilogue {
         }
     }
 
+    // The shortcut of a residual block for W consecutive channels of this row: fl(res_delta * code) from the block's
+    // uint8 input, or the FP32 output of the downsample conv.  Returns false (and zeros) when the layer has none.
+    template <int W>
+    __device__ __forceinline__ bool load_res(const Tile& ts, int n0, float (&radd)[W]) const {
+#pragma unroll
+        for (int j = 0; j < W; ++j) radd[j] = 0.f;
+        const bool has_res = (res_u8 != nullptr) || (res_f32 != nullptr);
+        if (has_res && ts.opix >= 0) {
+            const long long ro = ts.opix * res_cstride + res_cbase + (n0 - ts.ch_off);
+            if (res_u8 != nullptr) {
+#pragma unroll
+                for (int w = 0; w < W / 4; ++w) {
+                    const uint32_t rb = __ldg(reinterpret_cast<const uint32_t*>(res_u8 + ro) + w);
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        radd[4 * w + b] = __fmul_rn(static_cast<float>((rb >> (8 * b)) & 0xffu), res_delta);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < W / 4; ++w) {
+                    const float4 rf = __ldg(reinterpret_cast<const float4*>(res_f32 + ro) + w);
+                    radd[4 * w + 0] = rf.x, radd[4 * w + 1] = rf.y, radd[4 * w + 2] = rf.z, radd[4 * w + 3] = rf.w;
+                }
+            }
+        }
+        return has_res;
+    }
+
     // v (the scaled accumulator sum) -> bias, ReLU, output quantization, packed store of W bytes.
     template <int W>
     __device__ __forceinline__ void finish(Tile& ts, int n0, const float (&v)[W]) const {
@@ -292,9 +320,12 @@ struct RequantEpilogue {
             uint32_t bits[W];
             float y[W];
             float worst = 0.f;
+            float radd[W];
+            if constexpr (RES) load_res<W>(ts, n0, radd);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 y[j] = fmaf(v[j], cs[j], bs[j]);
+                if constexpr (RES) y[j] = __fadd_rn(y[j], radd[j]);
                 const float t = fminf(fmaxf(__fmul_rn(y[j], rdelta), -0.25f), 255.25f);
                 const float sft = __fadd_rn(t, 12582912.0f);
                 const float r = __fadd_rn(sft, -12582912.0f);
@@ -323,27 +354,7 @@ struct RequantEpilogue {
         } else {
             const bool live = (ts.opix >= 0);
             float radd[W];
-#pragma unroll
-            for (int j = 0; j < W; ++j) radd[j] = 0.f;
-            const bool has_res = (res_u8 != nullptr) || (res_f32 != nullptr);
-            if (has_res && live) {
-                const long long ro = ts.opix * res_cstride + res_cbase + (n0 - ts.ch_off);
-                if (res_u8 != nullptr) {
-#pragma unroll
-                    for (int w = 0; w < W / 4; ++w) {
-                        const uint32_t rb = __ldg(reinterpret_cast<const uint32_t*>(res_u8 + ro) + w);
-#pragma unroll
-                        for (int b = 0; b < 4; ++b)
-                            radd[4 * w + b] = __fmul_rn(static_cast<float>((rb >> (8 * b)) & 0xffu), res_delta);
-                    }
-                } else {
-#pragma unroll
-                    for (int w = 0; w < W / 4; ++w) {
-                        const float4 rf = __ldg(reinterpret_cast<const float4*>(res_f32 + ro) + w);
-                        radd[4 * w + 0] = rf.x, radd[4 * w + 1] = rf.y, radd[4 * w + 2] = rf.z, radd[4 * w + 3] = rf.w;
-                    }
-                }
-            }
+            const bool has_res = load_res<W>(ts, n0, radd);
             if (out_f32 != nullptr) {               // no output quantizer (downsample conv, occupancy head)
                 float yo[W];
 #pragma unroll

@@ -330,8 +330,9 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         e.out_f32 = ex ? ex->d_out_f32 : nullptr;
         e.out_f32_cstride = ex ? ex->out_f32_cstride : 0;
     };
-    // shortcuts and FP32 outputs live in the generic epilogue only
-    const bool fast8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) && !has_res && !f32_out;
+    // FP32 outputs live in the generic epilogue only; a shortcut has a saturating fast variant for one input group
+    const bool sat8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) && !f32_out;
+    const bool fast8 = sat8 && !has_res;
     const bool digits = (d.kind == 1 && d.cin <= 256);        // digit GEMM with packed integer recombination
 #define QV2X_RUN(GG, DG, F8)                                                     \
     {                                                                            \
@@ -340,6 +341,11 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         return dispatch_igemm<GG>(block_n, L->bk, tmA, tmB, g, e, stream);       \
     }
     if (L->groups == 1) {
+        if (sat8 && has_res) {
+            RequantEpilogue<1, false, true, true> e{};
+            fill(e);
+            return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
+        }
         if (fast8) QV2X_RUN(1, false, true) else QV2X_RUN(1, false, false)
     }
     if (digits) {
