@@ -60,6 +60,28 @@ def test_deconv_oracle_matches_fakequant_float():
     assert diff.max() <= 1 and (diff > 0).mean() < 1e-3
 
 
+def test_grouped_conv_equals_block_diagonal_dense():
+    """The identity behind qv2x_layer_desc.groups: a grouped conv is the dense conv of the block-diagonal weight whose
+    off-group entries are the channel's zero-point (real weight 0) -- same int accumulators, same codes."""
+    rng = np.random.default_rng(8)
+    groups, cin, cout = 8, 64, 64
+    w = rng.normal(0, 0.1, size=(cout, cin // groups, 3, 3)).astype(np.float32)
+    d, z = int_oracle.weight_qparams_minmax(w, 8)
+    wi = int_oracle.weight_int_grid(w, d, z, 8)
+    dense = np.empty((cout, cin, 3, 3), np.uint8)
+    dense[:] = z.astype(np.uint8).reshape(-1, 1, 1, 1)
+    cg, og = cin // groups, cout // groups
+    for co in range(cout):
+        g0 = (co // og) * cg
+        dense[co, g0:g0 + cg] = wi[co]
+    x = rng.integers(0, 256, size=(1, 9, 11, cin)).astype(np.uint8)
+    b = rng.uniform(-0.1, 0.1, size=cout).astype(np.float32)
+    for stride in (1, 2):
+        a1, q1 = int_oracle.conv_oracle(x, wi, d, z, b, 0.05, 0.07, stride=stride, pad=1, groups=groups)
+        a2, q2 = int_oracle.conv_oracle(x, dense, d, z, b, 0.05, 0.07, stride=stride, pad=1)
+        assert np.array_equal(a1, a2) and np.array_equal(q1, q2) and q1.std() > 3
+
+
 def test_library_exports_all_symbols():
     """The C-ABI library loads without a GPU and exports every symbol include/qv2x.h declares."""
     import ctypes
