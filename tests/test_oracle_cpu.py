@@ -82,6 +82,55 @@ def test_grouped_conv_equals_block_diagonal_dense():
         assert np.array_equal(a1, a2) and np.array_equal(q1, q2) and q1.std() > 3
 
 
+def test_encode_filter_error_bound_holds():
+    """The fp32 filter of the codebook encoder (csrc/codebook.cu, chunk_fast / step_end) accepts a row without the
+    float64 pass when best + eps < second - eps with eps = 2^-20 * (max P * max|d| + max|g0| + sum max|B|),
+    P = 65536 |hi| + |256 mid + lo|.  Restated here in numpy fp32 (same operations, same order) and checked against
+    the float64 score on random and adversarial accumulators: digit cancellation (65536 hi ~ -(256 mid + lo)), huge
+    and tiny scales, both digit-recombination variants."""
+    rng = np.random.default_rng(2024)
+    n, cols = 4000, 64
+    f32, fma = np.float32, int_oracle.fma32
+    for pack16 in (True, False):
+        for case in range(4):
+            hi = rng.integers(-2 ** 23, 2 ** 23, size=(n, cols))
+            mid = rng.integers(-2 ** 22, 2 ** 22, size=(n, cols))
+            lo = rng.integers(-2 ** 23, 2 ** 23, size=(n, cols))
+            if case == 1:                        # the high digit cancels the low part almost exactly
+                hi = rng.integers(-2 ** 14, 2 ** 14, size=(n, cols))
+                t12 = -hi * 65536 + rng.integers(-300, 300, size=(n, cols))
+                mid, lo = t12 >> 8, t12 & 255
+            elif case == 2:                      # small accumulators, constants dominate
+                hi, mid, lo = hi >> 20, mid >> 14, lo >> 10
+            d = rng.normal(size=cols) * 10.0 ** rng.uniform(-12, -4)
+            g0 = rng.normal(size=cols) * 10.0 ** rng.uniform(-3, 3)
+            B = [rng.normal(size=(n, cols)) * 10.0 ** rng.uniform(-3, 3) for _ in range(2 if case != 3 else 0)]
+            V = hi * 65536 + mid * 256 + lo                                     # exact (int64)
+            exact = V.astype(np.float64) * d + g0
+            for b in B:
+                exact = exact + b
+            hif = hi.astype(f32)
+            if pack16:
+                lof = (mid * 256 + lo).astype(f32)
+                lo_mag = np.abs(lof)
+            else:
+                mf, l2 = mid.astype(f32), lo.astype(f32)
+                lof = fma(mf, f32(256), l2)
+                lo_mag = fma(np.abs(mf), f32(256), np.abs(l2))
+            vf = fma(hif, f32(65536), lof)
+            P = fma(np.abs(hif), f32(65536), lo_mag)
+            d32, g32 = d.astype(f32), g0.astype(f32)
+            sc = fma(vf, d32, g32)
+            for b in B:
+                sc = sc + b.astype(f32)
+            vmax = P.max(axis=1)
+            cabs = np.nextafter(f32((np.abs(g0).max() + sum(np.abs(b).max() for b in B)) * (1 + 1e-6)), f32(np.inf))
+            eps = f32(2.0 ** -20) * fma(vmax, np.abs(d32).max(), cabs)
+            err = np.abs(sc.astype(np.float64) - exact).max(axis=1)
+            assert (err <= eps.astype(np.float64)).all(), (pack16, case, float((err / eps).max()))
+            assert (err / eps).max() < 0.7            # the margin the comment in the kernel claims (10/16)
+
+
 def test_library_exports_all_symbols():
     """The C-ABI library loads without a GPU and exports every symbol include/qv2x.h declares."""
     import ctypes
