@@ -131,6 +131,36 @@ def test_encode_filter_error_bound_holds():
             assert (err / eps).max() < 0.7            # the margin the comment in the kernel claims (10/16)
 
 
+def test_saturating_requant_fast_path_is_exact():
+    """The 8-bit / ReLU epilogue (csrc/epilogue_requant.cuh, FAST8) replaces q = clip(rint(y / delta), 0, 255) by a
+    multiply with fl(1/delta), a clamp, the 1.5 * 2^23 magic-number rounding and -- only for elements within 1e-4 of a
+    rounding boundary -- the true division.  Restated in numpy fp32 and compared with the normative form over
+    log-uniform scales, the whole output range and points placed right at the half-integer boundaries."""
+    rng = np.random.default_rng(77)
+    f32 = np.float32
+    magic = f32(12582912.0)
+    n_fallback = n_total = 0
+    for _ in range(40):
+        delta = f32(10.0 ** rng.uniform(-4, 1))
+        rdelta = f32(1.0) / delta
+        k = rng.integers(-40, 300, size=200000)
+        frac = np.where(rng.random(k.size) < 0.5, 0.5 + rng.normal(0, 3e-5, k.size), rng.random(k.size))
+        y = ((k + frac) * np.float64(delta)).astype(f32)
+        y[:1000] = (rng.integers(0, 256, 1000) + 0.5).astype(f32) * delta          # as close to a tie as fp32 gets
+        want = np.clip(np.rint(np.maximum(y, f32(0)) / delta), 0, 255).astype(np.int64)
+        t = np.minimum(np.maximum(y * rdelta, f32(-0.25)), f32(255.25)).astype(f32)
+        sft = (t + magic).astype(f32)
+        r = (sft - magic).astype(f32)
+        near = np.abs((t - r).astype(f32)) > f32(0.4999)
+        fast = (sft.view(np.uint32) & 0xFF).astype(np.int64)
+        exact = np.clip(np.rint(y / delta), 0, 255).astype(np.int64)
+        got = np.where(near, exact, fast)
+        assert np.array_equal(got, want), (float(delta), int((got != want).sum()))
+        n_fallback += int(near.sum())
+        n_total += y.size
+    assert 0 < n_fallback < 0.6 * n_total          # both branches were exercised
+
+
 def test_library_exports_all_symbols():
     """The C-ABI library loads without a GPU and exports every symbol include/qv2x.h declares."""
     import ctypes
