@@ -9,7 +9,11 @@ Follows the reference's VoxelPostprocessor3Heads:
   nms_rotated           opencood/utils/box_utils_mc.py:665-710 (top-1000, greedy, IoU > thresh suppressed)
 The reference computes polygon IoU with shapely==2.0.0 / GEOS (requirements.txt:13), which is absent here and
 on the GPU box; the IoU of two convex quadrilaterals is restated with Sutherland-Hodgman clipping + the shoelace
-formula (parity unpinned at that third-party boundary -- both sides of the check use this same function).
+formula.  Pinning: tests/golden/postprocess.npz (oracle/gen_golden_postprocess.py) holds the outputs of the
+reference's own generate_anchor_box / post_process run with a stand-in for shapely's Polygon built on this same
+clip -- it pins anchors, score / label selection, box decoding, corner order, NMS order and the range mask, but not
+the polygon AREA arithmetic, which tests/test_golden_cpu.py::test_polygon_iou_closed_forms checks against closed
+forms (parity with GEOS itself stays unpinned at that third-party boundary).
 """
 from __future__ import annotations
 

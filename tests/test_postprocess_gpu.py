@@ -8,15 +8,9 @@ import torch
 
 from oracle import postprocess_oracle as pp
 from tests.test_golden_cpu import GOLD
+from tests.test_golden_cpu import POST_CFG as CFG
 
 pytestmark = pytest.mark.gpu
-
-CFG = [dict(anchor_sizes=[[3.9, 1.6, 1.56]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-1.78],
-            align_center=True, feature_map_stride=2),
-       dict(anchor_sizes=[[0.8, 0.6, 1.73]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-0.6],
-            align_center=True, feature_map_stride=2),
-       dict(anchor_sizes=[[8, 3, 3]], anchor_rotations=[0, 1.57], anchor_bottom_heights=[-1.78],
-            align_center=True, feature_map_stride=2)]
 
 
 def _compare(preds, lidar_range, grid_wh, thr, nms, box_range, cuda_device):
