@@ -377,16 +377,16 @@ struct qv2x_heads {
     float* d_b = nullptr;
 };
 
+static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
+                     int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
+                     void* stream_);
+
 extern "C" {
 
 int qv2x_fuse(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine, float* d_out,
               void* stream_) {
     return qv2x_fuse_tile(mode, n_agents, H, W, C, d_feat, d_affine, d_out, 0, H, 0, W, stream_);
 }
-
-static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
-                     int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
-                     void* stream_);
 
 int qv2x_fuse_tile(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_affine,
                    float* d_out, int y0, int y1, int x0, int x1, void* stream_) {
