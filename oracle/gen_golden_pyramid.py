@@ -20,13 +20,13 @@ ref_shim.install()
 from opencood.models.fuse_modules.pyramid_fuse import weighted_fuse  # noqa: E402
 from opencood.utils.transformation_utils import normalize_pairwise_tfm  # noqa: E402
 
-from opencood.models.sub_modules.resblock import Bottleneck  # noqa: E402
-from opencood.quant.quant_block import QuantBottleneck  # noqa: E402
+from opencood.models.sub_modules.resblock import BasicBlock, Bottleneck  # noqa: E402
+from opencood.quant.quant_block import QuantBasicBlock, QuantBottleneck  # noqa: E402
 from opencood.quant.quant_layer import UniformAffineQuantizer  # noqa: E402
 
 from quantv2x_b200.synthetic import synthetic_poses  # noqa: E402
-from tests.pyramid_cases import (BLOCK_CASES, GROUPS, IN_DELTA, PYRAMID_AGENTS, PYRAMID_CFG,  # noqa: E402
-                                 block_tensors, pyramid_tensors)
+from tests.pyramid_cases import (BASIC_CASES, BLOCK_CASES, GROUPS, IN_DELTA, PYRAMID_AGENTS, PYRAMID_CFG,  # noqa: E402
+                                 basic_tensors, block_tensors, pyramid_tensors)
 
 WQ = dict(n_bits=8, channel_wise=True, scale_method="minmax")
 AQ = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
@@ -119,6 +119,50 @@ def gen_blocks():
     print("pyramid_blocks.npz", os.path.getsize(os.path.join(OUT, "pyramid_blocks.npz")))
 
 
+def gen_basic_blocks():
+    """QuantBasicBlock (quant_block.py:68-97) over the seeded two-conv blocks -> tests/golden/basic_blocks.npz."""
+    out = {}
+    for idx, (name, inplanes, planes, stride, H, W) in enumerate(BASIC_CASES):
+        t, q_in = basic_tensors(idx)
+        down = None
+        if "down" in t:
+            down = torch.nn.Sequential(torch.nn.Conv2d(inplanes, planes, 1, stride=stride, bias=False),
+                                       torch.nn.Identity())
+        b = BasicBlock(inplanes, planes, stride, down, norm_layer=torch.nn.Identity)
+        b.conv1, b.conv2 = with_bias(b.conv1, t["conv1"]), with_bias(b.conv2, t["conv2"])
+        if down is not None:
+            b.downsample[0] = with_bias(b.downsample[0], t["down"])
+        qb = QuantBasicBlock(b, WQ, AQ).eval()
+        qb.set_quant_state(True, True)
+        quantizers = [m for m in qb.modules() if isinstance(m, UniformAffineQuantizer)]
+        x = torch.from_numpy(q_in.astype(np.float32) * IN_DELTA)
+        taps = {}
+        hooks = [qb.conv1.register_forward_hook(lambda m, i, o: taps.__setitem__("conv1", o.detach().clone()))]
+        if down is not None:
+            hooks.append(qb.downsample.register_forward_hook(lambda m, i, o: taps.__setitem__("down", o.detach().clone())))
+        with torch.no_grad():
+            for q in quantizers:
+                q.set_inited(False)
+            qb(x)
+            for q in quantizers:
+                q.set_inited(True)
+            y = qb(x)
+        for h in hooks:
+            h.remove()
+        out[f"{name}.q_in"] = q_in
+        for n, q, val in (("conv1", qb.conv1.act_quantizer, taps["conv1"]), ("out", qb.act_quantizer, y)):
+            d = float(q.delta)
+            assert float(q.zero_point) == 0.0
+            codes = torch.round(val / d)
+            assert float((codes * d - val).abs().max()) < 1e-4 * d
+            out[f"{name}.{n}.act_delta"] = np.float32(d)
+            out[f"{name}.{n}.codes"] = codes.numpy().astype(np.uint8)
+        if down is not None:
+            out[f"{name}.down.out"] = taps["down"].numpy().astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "basic_blocks.npz"), **out)
+    print("basic_blocks.npz", os.path.getsize(os.path.join(OUT, "basic_blocks.npz")))
+
+
 def gen_backbone():
     """QuantPyramidFusion.forward_collab (quant_block.py:504-541) of a small ResNeXt pyramid backbone: per-level
     codes of every agent, occupancy logits and fused features."""
@@ -204,4 +248,5 @@ if __name__ == "__main__":
     torch.manual_seed(0)
     main()
     gen_blocks()
+    gen_basic_blocks()
     gen_backbone()

@@ -6,6 +6,7 @@
   before the ReLU and the block's quantizer; the optional 1x1 strided downsample conv writes FP32 (it has no
   quantizer) and is that shortcut.  Activations stay uint8 NHWC; per-pixel code sums travel with them so no layer
   re-reads its input to correct for the weight zero-points.
+* ``BasicBlockEngine`` -- ``QuantBasicBlock`` (two 3x3 convs; the agent-side ResNetBEVBackbone of the pyramid models).
 * ``OccupancyHead`` -- ``single_head_i`` (1x1 conv to one channel, no quantizer; quant_block.py:474-478).
 * ``weighted_fuse_level`` -- score-weighted fusion of one level from codes + occupancy logits.
 
@@ -80,6 +81,48 @@ class BottleneckEngine:
             out = self.conv3.forward(q2, rowsum_in=[rs2], residual=x, res_delta=self.in_delta, rowsum_out=rs_out)
         if taps is not None:
             taps.update(q1=q1, q2=q2, res=res)
+        return (out, rs_out) if want_rowsum else out
+
+
+class BasicBlockEngine:
+    """One calibrated ``QuantBasicBlock`` (quant_block.py:68-97; the agent-side ResNetBEVBackbone of the pyramid
+    models) as two int8 3x3 convs, the second with the shortcut in its epilogue; the optional strided 1x1 downsample
+    conv writes the FP32 shortcut.  params: ``conv1`` / ``conv2`` (/ ``down``), ``conv1.act_delta``, ``out_delta``,
+    ``stride``."""
+
+    def __init__(self, params: dict, in_delta: float):
+        p = params
+        self.in_delta, self.out_delta = float(in_delta), float(p["out_delta"])
+        self.stride = int(p["stride"])
+        d1 = float(p["conv1"]["act_delta"])
+        self.conv1 = _layer(p["conv1"], ksize=3, stride=self.stride, pad=1, relu=True, in_delta=in_delta, out_delta=d1)
+        self.conv2 = _layer(p["conv2"], ksize=3, stride=1, pad=1, relu=True, in_delta=d1, out_delta=self.out_delta)
+        self.down = None
+        if "down" in p:
+            self.down = _layer(p["down"], ksize=1, stride=self.stride, pad=0, relu=False, in_delta=in_delta,
+                               out_delta=1.0)
+        self.cin, self.cout = self.conv1.cin, self.conv2.cout
+
+    def forward(self, x: torch.Tensor, rowsum: torch.Tensor | None = None, want_rowsum: bool = False,
+                taps: dict | None = None):
+        """x uint8 NHWC [n, H, W, cin] (scale in_delta) -> uint8 NHWC [n, Ho, Wo, cout] (scale out_delta)."""
+        n, h, w, _ = x.shape
+        dev = x.device
+        if rowsum is None:
+            rowsum = E.rowsum_u8(x, 0, self.cin)
+        ho, wo = self.conv1.out_shape(h, w)
+        rs1 = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev)
+        q1 = self.conv1.forward(x, rowsum_in=[rowsum], rowsum_out=rs1)
+        rs_out = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev) if want_rowsum else None
+        if self.down is not None:
+            res = torch.empty((n, ho, wo, self.cout), dtype=torch.float32, device=dev)
+            self.down.forward(x, rowsum_in=[rowsum], out_f32=res)
+            out = self.conv2.forward(q1, rowsum_in=[rs1], residual=res, rowsum_out=rs_out)
+        else:
+            res = None
+            out = self.conv2.forward(q1, rowsum_in=[rs1], residual=x, res_delta=self.in_delta, rowsum_out=rs_out)
+        if taps is not None:
+            taps.update(q1=q1, res=res)
         return (out, rs_out) if want_rowsum else out
 
 

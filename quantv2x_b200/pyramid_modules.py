@@ -1,6 +1,7 @@
 """FP32 PyTorch definitions of the pyramid-fusion backbone, so that reference checkpoints load
 unchanged (same parameter names and shapes) and PTQ calibration has a float model to observe:
 
+* ``BasicBlock``                    -- resblock.py:19-64, the block of the agent-side ResNetBEVBackbone
 * ``Bottleneck`` / ``ResNeXtStages`` -- the ResNeXt trunk ``ResNetModified(Bottleneck, groups=32, width_per_group=4)``
   with ``Bottleneck.expansion = 1`` (opencood/models/sub_modules/resblock.py:67-122, 125-235 as configured by
   opencood/models/fuse_modules/pyramid_fuse.py:69-77)
@@ -15,6 +16,29 @@ from __future__ import annotations
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+
+class BasicBlock(nn.Module):
+    """Two 3x3 convs with the shortcut added before the last ReLU (the agent-side ResNetBEVBackbone of the pyramid
+    models: opencood/models/sub_modules/resblock.py:19-64, base_bev_backbone_resnet.py:40-45)."""
+
+    expansion = 1
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, 3, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        shortcut = x if self.downsample is None else self.downsample(x)
+        out = self.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return self.relu(out + shortcut)
 
 
 class Bottleneck(nn.Module):

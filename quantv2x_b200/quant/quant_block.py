@@ -134,7 +134,7 @@ class QuantDownsampleConv(BaseQuantBlock):
 # calibration ``export_params`` hands the integer parameters to quantv2x_b200.pyramid.PyramidBackboneEngine and
 # ``attach_engine`` makes ``forward_collab`` run there.
 # --------------------------------------------------------------------------------------------------
-from ..pyramid_modules import Bottleneck, PyramidFusion, ResNeXtStages, weighted_fuse_torch  # noqa: E402
+from ..pyramid_modules import BasicBlock, Bottleneck, PyramidFusion, ResNeXtStages, weighted_fuse_torch  # noqa: E402
 
 
 def _conv_params(qm: QuantModule):
@@ -147,6 +147,44 @@ def _act_delta(q) -> float:
     if float(q.zero_point) != 0.0:
         raise ValueError("the integer path needs activation zero-points of 0 (post-ReLU quantizers)")
     return float(q.delta)
+
+
+class QuantBasicBlock(BaseQuantBlock):
+    """Mirror of the reference QuantBasicBlock (quant_block.py:68-97): conv1 with ReLU + quantizer, conv2 (and the
+    downsample conv) without; shortcut, ReLU and the block's quantizer follow."""
+
+    def __init__(self, basic_block: BasicBlock, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        from .quant_layer import UniformAffineQuantizer
+
+        self.conv1 = QuantModule(basic_block.conv1, weight_quant_params, act_quant_params)
+        self.conv1.norm_function, self.conv1.activation_function = basic_block.bn1, basic_block.relu
+        self.conv2 = QuantModule(basic_block.conv2, weight_quant_params, act_quant_params, disable_act_quant=True)
+        self.conv2.norm_function = basic_block.bn2
+        self.downsample = None
+        if basic_block.downsample is not None:
+            self.downsample = QuantModule(basic_block.downsample[0], weight_quant_params, act_quant_params,
+                                          disable_act_quant=True)
+            self.downsample.norm_function = basic_block.downsample[1]
+        self.activation_function = basic_block.relu
+        self.act_quantizer = UniformAffineQuantizer(**act_quant_params)
+        self.stride = basic_block.stride
+
+    def forward(self, x):
+        residual = x if self.downsample is None else self.downsample(x)
+        out = self.activation_function(self.conv2(self.conv1(x)) + residual)
+        if self.use_act_quant:
+            out = self.act_quantizer(out)
+        return out
+
+    def export_params(self) -> dict:
+        """The dict quantv2x_b200.pyramid.BasicBlockEngine takes."""
+        p = dict(stride=int(self.stride), out_delta=_act_delta(self.act_quantizer),
+                 conv1=_conv_params(self.conv1), conv2=_conv_params(self.conv2))
+        p["conv1"]["act_delta"] = _act_delta(self.conv1.act_quantizer)
+        if self.downsample is not None:
+            p["down"] = _conv_params(self.downsample)
+        return p
 
 
 class QuantBottleneck(BaseQuantBlock):

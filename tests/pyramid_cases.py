@@ -10,6 +10,27 @@ BLOCK_CASES = [
     ("bneck_down_s2", 64, 128, 2, 12, 16),         # first block of stage 1: strided 3x3 + 1x1 stride-2 downsample
 ]
 IN_DELTA = np.float32(0.047)
+# BasicBlock (two 3x3 convs) of the agent-side ResNetBEVBackbone: name, inplanes, planes, stride, H, W
+BASIC_CASES = [
+    ("basic_identity", 64, 64, 1, 10, 12),
+    ("basic_down_s2", 64, 128, 2, 11, 16),         # odd height: (H - 1) // 2 + 1 output rows on both branches
+]
+
+
+def basic_tensors(idx):
+    name, inplanes, planes, stride, H, W = BASIC_CASES[idx]
+    rng = np.random.default_rng(700 + idx)
+
+    def conv(cout, cin, k, gain=1.0):
+        w = rng.normal(0, gain * np.sqrt(2.0 / (cin * k * k)), size=(cout, cin, k, k)).astype(np.float32)
+        return w, rng.uniform(-0.2, 0.2, size=cout).astype(np.float32)
+
+    t = {"conv1": conv(planes, inplanes, 3), "conv2": conv(planes, planes, 3, 0.5)}
+    if stride != 1 or inplanes != planes:
+        t["down"] = conv(planes, inplanes, 1)
+    q_in = rng.integers(0, 256, size=(2, inplanes, H, W)).astype(np.uint8)
+    q_in[rng.random(q_in.shape) > 0.6] = 0
+    return t, q_in
 
 
 def block_tensors(idx):

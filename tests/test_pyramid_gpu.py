@@ -166,3 +166,25 @@ def test_quant_pyramid_fusion_module_on_engine(cuda_device):
         assert dd.max() <= 3 and (dd > 0).mean() < 5e-2 and (dd > 1).mean() < 2e-3, (li, dd.max(), (dd > 0).mean())
         assert tuple(occ_g[li].shape) == tuple(occ[li].shape)
         np.testing.assert_allclose(occ_g[li].cpu().numpy(), occ[li].numpy(), atol=2e-2 * float(occ[li].abs().max()))
+
+
+@pytest.mark.parametrize("idx", [0, 1], ids=["basic_identity", "basic_down_s2"])
+def test_basic_block_bit_exact(cuda_device, idx):
+    """QuantBasicBlock on the engine (two 3x3 int8 convs, shortcut in the second conv's epilogue, FP32 strided 1x1
+    downsample): every tensor bit-exact against the integer oracle, and within 1 LSB on < 1 % of the reference block."""
+    from quantv2x_b200.pyramid import BasicBlockEngine
+    from tests.test_golden_cpu import basic_params
+
+    g = np.load(os.path.join(GOLD, "basic_blocks.npz"))
+    name, p, x = basic_params(g, idx)
+    ref = int_oracle.basicblock_oracle(x, IN_DELTA, p)
+    eng = BasicBlockEngine(p, IN_DELTA)
+    taps = {}
+    out, rs = eng.forward(torch.from_numpy(np.ascontiguousarray(x)).to(cuda_device), want_rowsum=True, taps=taps)
+    assert np.array_equal(taps["q1"].cpu().numpy(), ref["q1"])
+    if "down" in p:
+        assert np.array_equal(taps["res"].cpu().numpy(), ref["res"])
+    assert np.array_equal(out.cpu().numpy(), ref["out"])
+    assert np.array_equal(rs.cpu().numpy(), ref["out"].astype(np.int64).sum(-1))
+    d = np.abs(out.cpu().numpy().astype(np.int64) - g[f"{name}.out.codes"].transpose(0, 2, 3, 1).astype(np.int64))
+    assert d.max() <= 1 and (d > 0).mean() < 1e-2
