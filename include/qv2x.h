@@ -147,7 +147,11 @@ int qv2x_codebook_create(const qv2x_codebook_desc* desc, const float* const* cod
 void qv2x_codebook_destroy(qv2x_codebook* cb);
 
 /* encode: d_feat [rows][feat_cstride] uint8 activation codes (first C channels used) with scale `delta`
- * (x = delta * q, zero-point 0) -> d_codes [levels][m][rows] uint8.  argmin ties resolve to the lowest index. */
+ * (x = delta * q, zero-point 0) -> d_codes [levels][m][rows] uint8.  argmin ties resolve to the lowest index.
+ * `delta` is the static scale of the shrinker's output quantizer: the per-column score scales delta * sc[j] are
+ * cached in the handle for the last delta seen.  A call with a DIFFERENT delta rewrites that cache with a
+ * synchronous copy -- the one exception to "handles are immutable after create": such a call must not overlap
+ * encodes of the same handle still in flight on other streams (use one handle per scale instead). */
 int qv2x_codebook_encode(const qv2x_codebook* cb, long long rows, const uint8_t* d_feat, int feat_cstride,
                          float delta, uint8_t* d_codes, void* stream);
 /* decode: d_codes [levels][m][rows] -> d_out [rows][C] float32 (pixel-major). */
