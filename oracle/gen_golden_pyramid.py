@@ -244,8 +244,27 @@ def gen_backbone():
     print("pyramid_backbone.npz", os.path.getsize(os.path.join(OUT, "pyramid_backbone.npz")))
 
 
+def gen_state_dict_layout():
+    """Parameter / buffer names and shapes of the reference PyramidFusion and BasicBlock, so that the test can check
+    that reference checkpoints load into quantv2x_b200.pyramid_modules unchanged."""
+    import json
+
+    from opencood.models.fuse_modules.pyramid_fuse import PyramidFusion
+
+    out = {}
+    for tag, nums in (("small", PYRAMID_CFG["layer_nums"]), ("heal", [3, 5, 8])):
+        cfg = dict(PYRAMID_CFG, layer_nums=nums)
+        out[f"pyramid_fusion.{tag}"] = {k: list(v.shape) for k, v in PyramidFusion(cfg, 64).state_dict().items()}
+    down = torch.nn.Sequential(torch.nn.Conv2d(64, 128, 1, stride=2, bias=False), torch.nn.BatchNorm2d(128))
+    out["basic_block"] = {k: list(v.shape) for k, v in BasicBlock(64, 128, 2, down).state_dict().items()}
+    with open(os.path.join(OUT, "pyramid_state_dict_layout.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    print("pyramid_state_dict_layout.json", {k: len(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
+    gen_state_dict_layout()
     main()
     gen_blocks()
     gen_basic_blocks()
