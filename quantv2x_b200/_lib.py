@@ -11,7 +11,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqv2x.so")
+# QV2X_LIB selects another build of the same library (the bring-up build with role traces, `make debug`)
+LIB_PATH = os.environ.get("QV2X_LIB") or os.path.join(_HERE, "libqv2x.so")
 
 
 class Qv2xError(RuntimeError):

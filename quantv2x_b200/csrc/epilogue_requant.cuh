@@ -19,6 +19,98 @@
 
 namespace qv2x {
 
+// ------------------------------------------------------------------------------------------------------------
+// Receptive-field sums S_g[row] of a tile, rebuilt by a side warp from the producing layer's per-pixel channel sums:
+// the (th-1)*stride+taps_h by (tw-1)*stride+taps_w window of sums is fetched once with cp.async (zero outside the
+// image), then every tile row adds its taps from shared memory -- ~10x fewer global loads than taps x rows.
+// Shared by the float and the fixed-point requant epilogues.
+struct SideHalo {
+    static constexpr int kHaloInts = 1024;   // >= (2*127+3)*3, the widest halo (stride 2, 128 x 1 tile box)
+    // Per-lane constants of the side warp, computed once per kernel: which halo elements the lane fetches and
+    // where its four tile rows start inside the halo.  (A single warp runs this code, so every instruction it does
+    // NOT execute per tile is latency taken off the tile period.)
+    static constexpr int kFlat = 8;          // halos of up to 32 * kFlat elements take the unrolled path
+    int hw, hh, n;
+    int hoff[4];
+    int hy[kFlat], hx[kFlat];
+
+    __device__ __forceinline__ void init(const IgemmGeom& g, int lane) {
+        hw = (g.tw - 1) * g.stride + g.taps_w;
+        hh = (g.th - 1) * g.stride + g.taps_h;
+        n = hw * hh;
+#pragma unroll
+        for (int j = 0; j < kFlat; ++j) {
+            const int e = lane + 32 * j;
+            hy[j] = e / hw;
+            hx[j] = e - hy[j] * hw;
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4; ++rr) {
+            const int row = lane + 32 * rr;
+            const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;      // tw is a power of two
+            hoff[rr] = ly * g.stride * hw + lx * g.stride;
+        }
+    }
+
+    // s_S[grp * 128 + row] for grp < G; rowsum_in[grp] == nullptr -> zeros
+    template <int G>
+    __device__ __forceinline__ void stage(const IgemmGeom& g, const TileCoord& tc, int lane, int32_t* s_S,
+                                          int32_t* halo, const int32_t* const (&rowsum_in)[kMaxGroups]) const {
+        const int ix0 = tc.tx * g.tw * g.stride - g.pad, iy0 = tc.ty * g.th * g.stride - g.pad;
+        const uint32_t halo_s = smem_u32(halo);
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp) {
+            const int32_t* rs = rowsum_in[grp];
+            if (rs == nullptr) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = 0;
+                continue;
+            }
+            rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
+            __syncwarp();                                   // the previous group's readers are done with the halo
+            if (n <= 32 * kFlat) {
+#pragma unroll
+                for (int j = 0; j < kFlat; ++j) {
+                    const int e = lane + 32 * j;
+                    if (e < n) {
+                        const int iy = iy0 + hy[j], ix = ix0 + hx[j];
+                        const bool ok = (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi);
+                        cp_async_4(halo_s + 4 * e, ok ? rs + iy * g.Wi + ix : rs, ok);
+                    }
+                }
+            } else {
+                for (int y = 0; y < hh; ++y) {
+                    const int iy = iy0 + y;
+                    const bool yok = (iy >= 0 && iy < g.Hi);
+                    for (int x = lane; x < hw; x += 32) {
+                        const int ix = ix0 + x;
+                        const bool ok = yok && ix >= 0 && ix < g.Wi;
+                        cp_async_4(halo_s + 4 * (y * hw + x), ok ? rs + iy * g.Wi + ix : rs, ok);
+                    }
+                }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int32_t* h0 = halo + hoff[rr];
+                int32_t sum = 0;
+                if (g.taps == 9) {
+                    const int32_t *h1 = h0 + hw, *h2 = h1 + hw;
+                    sum = ((h0[0] + h0[1]) + (h0[2] + h1[0])) + ((h1[1] + h1[2]) + (h2[0] + h2[1])) + h2[2];
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx)
+                            if (ky < g.taps_h && kx < g.taps_w) sum += h0[ky * hw + kx];
+                }
+                s_S[grp * kTileM + lane + 32 * rr] = sum;     // rows outside the image are never stored
+            }
+        }
+    }
+};
+
 template <int G, bool DIGITS = false, bool FAST8 = true, bool RES = false>
 struct RequantEpilogue {
     // epilogue warps per TMEM lane quadrant: more warps hide the latencies of the (ALU-pipe bound) requant math
@@ -70,34 +162,9 @@ struct RequantEpilogue {
     // rebuilt from the producing layer's per-pixel channel sums.
     static constexpr int kSlotS = 3072;
 
-    static constexpr int kHaloInts = 1024;   // >= (2*127+3)*3, the widest halo (stride 2, 128 x 1 tile box)
-
-    // Per-lane constants of the side warp, computed once per kernel: which halo elements the lane fetches and
-    // where its four tile rows start inside the halo.  (A single warp runs this code, so every instruction it does
-    // NOT execute per tile is latency taken off the tile period.)
-    static constexpr int kFlat = 8;          // halos of up to 32 * kFlat elements take the unrolled path
-    struct Side {
-        int hw, hh, n;
-        int hoff[4];
-        int hy[kFlat], hx[kFlat];
-    };
-    __device__ __forceinline__ void side_init(Side& sd, const IgemmGeom& g, int lane) const {
-        sd.hw = (g.tw - 1) * g.stride + g.taps_w;
-        sd.hh = (g.th - 1) * g.stride + g.taps_h;
-        sd.n = sd.hw * sd.hh;
-#pragma unroll
-        for (int j = 0; j < kFlat; ++j) {
-            const int e = lane + 32 * j;
-            sd.hy[j] = e / sd.hw;
-            sd.hx[j] = e - sd.hy[j] * sd.hw;
-        }
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr) {
-            const int row = lane + 32 * rr;
-            const int lx = row & (g.tw - 1), ly = row >> g.tw_shift;      // tw is a power of two
-            sd.hoff[rr] = ly * g.stride * sd.hw + lx * g.stride;
-        }
-    }
+    static constexpr int kHaloInts = SideHalo::kHaloInts;
+    using Side = SideHalo;
+    __device__ __forceinline__ void side_init(Side& sd, const IgemmGeom& g, int lane) const { sd.init(g, lane); }
 
     __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
                                               int32_t* halo, int& staged_nt, const Side& sd) const {
@@ -114,63 +181,7 @@ struct RequantEpilogue {
             }
             staged_nt = tc.nt;
         }
-        // Receptive-field sums through a halo in shared memory: the (th-1)*stride+taps_h by (tw-1)*stride+taps_w
-        // window of per-pixel sums is loaded once (zero outside the image), then every tile row adds its taps from
-        // shared memory.  ~10x fewer global loads than taps x rows.
-        int32_t* s_S = reinterpret_cast<int32_t*>(slot + kSlotS);
-        const int hw = sd.hw;
-        const int ix0 = tc.tx * g.tw * g.stride - g.pad, iy0 = tc.ty * g.th * g.stride - g.pad;
-        const uint32_t halo_s = smem_u32(halo);
-#pragma unroll
-        for (int grp = 0; grp < G; ++grp) {
-            const int32_t* rs = rowsum_in[grp];
-            if (rs == nullptr) {
-#pragma unroll
-                for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = 0;
-                continue;
-            }
-            rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
-            __syncwarp();                                   // the previous group's readers are done with the halo
-            if (sd.n <= 32 * kFlat) {
-#pragma unroll
-                for (int j = 0; j < kFlat; ++j) {
-                    const int e = lane + 32 * j;
-                    if (e < sd.n) {
-                        const int iy = iy0 + sd.hy[j], ix = ix0 + sd.hx[j];
-                        const bool ok = (iy >= 0 && iy < g.Hi && ix >= 0 && ix < g.Wi);
-                        cp_async_4(halo_s + 4 * e, ok ? rs + iy * g.Wi + ix : rs, ok);
-                    }
-                }
-            } else {
-                for (int hy = 0; hy < sd.hh; ++hy) {
-                    const int iy = iy0 + hy;
-                    const bool yok = (iy >= 0 && iy < g.Hi);
-                    for (int hx = lane; hx < hw; hx += 32) {
-                        const int ix = ix0 + hx;
-                        const bool ok = yok && ix >= 0 && ix < g.Wi;
-                        cp_async_4(halo_s + 4 * (hy * hw + hx), ok ? rs + iy * g.Wi + ix : rs, ok);
-                    }
-                }
-            }
-            cp_async_wait_all();
-            __syncwarp();
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int32_t* h0 = halo + sd.hoff[rr];
-                int32_t sum = 0;
-                if (g.taps == 9) {
-                    const int32_t *h1 = h0 + hw, *h2 = h1 + hw;
-                    sum = ((h0[0] + h0[1]) + (h0[2] + h1[0])) + ((h1[1] + h1[2]) + (h2[0] + h2[1])) + h2[2];
-                } else {
-#pragma unroll
-                    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx)
-                            if (ky < g.taps_h && kx < g.taps_w) sum += h0[ky * hw + kx];
-                }
-                s_S[grp * kTileM + lane + 32 * rr] = sum;     // rows outside the image are never stored
-            }
-        }
+        sd.template stage<G>(g, tc, lane, reinterpret_cast<int32_t*>(slot + kSlotS), halo, rowsum_in);
         cp_async_wait_all();                       // the parameter copies, when no group waited for them
     }
 

@@ -59,14 +59,30 @@ struct IgemmGeom {
     int n_steps;
     int step_row_base[kMaxSteps];
     int step_group_stride[kMaxSteps];
+    // HALO mainloop (3x3 stride-1 convs): the (th+2) x (tw+2) input window of a tile is loaded ONCE per channel block
+    // and all nine taps read it through shifted shared-memory descriptors; B (weights) is either streamed one
+    // (tap, channel block) stage at a time or, when the whole [BLOCK_N x K] slice fits, loaded once per CTA.
+    int a_slots, b_stages, b_resident;
 };
 
+// Role timelines (qv2x_debug_trace) and role knock-outs (qv2x_set_debug_flags) are bring-up instruments: they cost
+// constant loads, branches and R2UR moves inside the single-thread TMA / MMA issue loops, which is exactly what paces
+// the short layers (profiles/r2_exp_mma_rate.log), so the product build compiles them out.
+#ifdef QV2X_IGEMM_DEBUG
+constexpr bool kIgemmDebug = true;
+#else
+constexpr bool kIgemmDebug = false;
+#endif
 constexpr int kTraceTiles = 32;
 __device__ __forceinline__ void trace_stamp(const IgemmGeom& g, int tile_local, int slot) {
-    if (g.trace != nullptr && tile_local < kTraceTiles)
-        g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tile_local) * 16 + slot] = clock64();
+    if constexpr (kIgemmDebug) {
+        if (g.trace != nullptr && tile_local < kTraceTiles)
+            g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tile_local) * 16 + slot] = clock64();
+    }
 }
+__device__ __forceinline__ int dbg_flags(const IgemmGeom& g) { return kIgemmDebug ? g.debug : 0; }
 
+constexpr int kBarrierBytes = 1024;    // mbarriers + the TMEM base address
 constexpr int kEpiSmemBytes = 10240;   // two side-input slots / epilogue scratch
 constexpr int kHaloSmemBytes = 8192;   // two halo buffers, one per side warp   // scratch handed to the epilogue functor (cross-warp merges)
 
@@ -80,10 +96,27 @@ struct IgemmCfg {
     static constexpr int kBTile = kBSub * TPS;
     static constexpr int kStageBytes = kATile + kBTile;
     // 227 KB per CTA minus alignment slack, barriers, the epilogue / side-input scratch and the halo buffers
-    static constexpr int kStagesRaw = (227 * 1024 - 1024 - 256 - kEpiSmemBytes - kHaloSmemBytes) / kStageBytes;
+    static constexpr int kStagesRaw = (227 * 1024 - 1024 - kBarrierBytes - kEpiSmemBytes - kHaloSmemBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > MAX_STAGES ? MAX_STAGES : kStagesRaw;
     static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiSmemBytes + kHaloSmemBytes;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + kBarrierBytes + kEpiSmemBytes + kHaloSmemBytes;
+};
+
+// Shared-memory budget of the HALO mainloop: A slots hold one 18 x 10 pixel window of CB channel bytes (rounded up to
+// the swizzle pattern), B stages one tap x CB bytes of K for BLOCK_N output columns.  Ring depths are chosen at launch.
+constexpr int kHaloTileW = 8, kHaloTileH = 16;     // output pixel box of a tile: 8-row operand groups = 8 pixels in x
+constexpr int kHaloW = kHaloTileW + 2, kHaloH = kHaloTileH + 2;
+constexpr int kHaloMaxBStages = 32, kHaloMaxASlots = 4;
+template <int BLOCK_N, int CB>
+struct HaloCfg {
+    static constexpr int kABytes = kHaloW * kHaloH * CB;                       // bytes one TMA box delivers
+    static constexpr int kASlot = (kABytes + 1023) / 1024 * 1024;
+    static constexpr int kBStage = BLOCK_N * CB;
+    static constexpr int kSlots = (512 / BLOCK_N) > 4 ? 4 : (512 / BLOCK_N);
+    static constexpr int kRingBudget = 227 * 1024 - 1024 - kBarrierBytes - kEpiSmemBytes - kHaloSmemBytes;
+    static constexpr int smem_bytes(int a_slots, int b_stages) {
+        return a_slots * kASlot + b_stages * kBStage + 1024 + kBarrierBytes + kEpiSmemBytes + kHaloSmemBytes;
+    }
 };
 
 struct TileCoord {
@@ -137,29 +170,36 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 template <class Epi, int BLOCK_N>
 constexpr int igemm_threads() { return (4 + 4 * Epi::col_split(BLOCK_N)) * 32; }
 
-template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1>
+template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1, bool HALO = false, bool BRES = false, bool SRING = false>
 __global__ void __launch_bounds__(igemm_threads<Epi, BLOCK_N>(), 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
              const Epi epi) {
     using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages, TPS>;
-    constexpr int kStages = Cfg::kStages;
+    using HCfg = HaloCfg<BLOCK_N, BK>;
+    constexpr int kStages = HALO ? kHaloMaxBStages : Cfg::kStages;   // barrier slots (HALO: ring depth is g.b_stages)
     constexpr int kSlots = Cfg::kSlots;
     static_assert(G <= kSlots, "every group needs its own TMEM slot");
+    static_assert(!HALO || TPS == 1, "the HALO mainloop has one tap per B stage");
+    static_assert(!(BRES && SRING), "a static ring is a streamed-weights mode");
     constexpr int kColSplit = Epi::col_split(BLOCK_N);
     constexpr int kNumEpiWarps = 4 * kColSplit;
     static_assert(BLOCK_N % (16 * kColSplit) == 0, "BLOCK_N must split into 16-column-aligned parts");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    const int ring_bytes = HALO ? g.a_slots * HCfg::kASlot + g.b_stages * HCfg::kBStage : Cfg::kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ring_bytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tfull_bar = bars + 2 * kStages;
     uint64_t* tempty_bar = bars + 2 * kStages + kSlots;
     uint64_t* side_full = bars + 2 * kStages + 2 * kSlots;      // [2] side-input slots (warp 3 -> epilogue)
     uint64_t* side_empty = side_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(side_empty + 2);
-    uint8_t* epi_scratch = smem + kStages * Cfg::kStageBytes + 256;
+    uint64_t* afull_bar = side_empty + 2;                        // HALO: [kHaloMaxASlots] activation windows
+    uint64_t* aempty_bar = afull_bar + kHaloMaxASlots;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aempty_bar + kHaloMaxASlots);
+    static_assert((2 * kHaloMaxBStages + 2 * 4 + 4 + 2 * kHaloMaxASlots) * 8 + 4 <= kBarrierBytes, "barrier area");
+    uint8_t* epi_scratch = smem + ring_bytes + kBarrierBytes;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -181,6 +221,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_init(smem_u32(&side_full[i]), 1);
             mbar_init(smem_u32(&side_empty[i]), kNumEpiWarps);
         }
+        if constexpr (HALO) {
+            for (int i = 0; i < kHaloMaxASlots; ++i) {
+                mbar_init(smem_u32(&afull_bar[i]), 1);
+                mbar_init(smem_u32(&aempty_bar[i]), 1);
+            }
+        }
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_ptr), 512);
@@ -196,12 +242,179 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // values, so they live in uniform registers) and elect one lane only for the instructions that must be issued
     // once.  All addressing is incremental: a single thread's dependent integer chain (divisions, 64-bit
     // descriptor assembly) between two TMA / MMA instructions was what paced these roles before.
-    if (warp == 0) {
+    if (HALO && warp == 0) {
+        // ------------------------------------------------------------ TMA producer, HALO mainloop
+        // Two independent streams from one warp: activation windows (ONE 4-D box per (tile, group, channel block) = the
+        // tile's 18 x 10 pixel input window, zero fill outside the image = conv padding) and -- unless the weights are
+        // resident -- B stages, one per tap.  Windows are prefetched as far ahead as free slots allow: while the
+        // B stream waits for a free stage the warp keeps polling the window ring, so a window is requested the moment
+        // its slot is released instead of after the previous group's nine B stages (one L2 round trip too late).
+        const bool leader = elect_one();
+        const uint32_t a_base = smem_u32(smem);
+        const uint32_t b_base = a_base + g.a_slots * HCfg::kASlot;
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
+        const uint32_t a_slots = g.a_slots, b_stages = g.b_stages;
+        const int n_grp_cb = G * g.cblocks;
+        if (BRES && leader) {
+            // every CTA keeps one column tile (the grid is a multiple of n_tiles): its whole B slice is loaded once
+            const int ncol0 = static_cast<int>(blockIdx.x % g.n_tiles) * BLOCK_N;
+            int kb = 0;
+            for (int grp = 0; grp < G; ++grp)
+                for (int cb = 0; cb < g.cblocks; ++cb)
+                    for (int tap = 0; tap < 9; ++tap, ++kb) {
+                        const uint32_t fb = full0 + 8 * kb;
+                        mbar_expect_tx(fb, HCfg::kBStage);
+                        tma_load_2d(b_base + kb * HCfg::kBStage, &tmB, fb,
+                                    g.b_k_base[grp] + tap * g.b_k_tap_stride + cb * BK, g.b_row_base[grp] + ncol0);
+                    }
+        }
+        // window stream cursor
+        int a_t = blockIdx.x, a_gc = 0, a_x0 = 0, a_y0 = 0, a_img = 0;
+        uint32_t sa = 0, aph = 0;
+        long long a_issued = 0;                 // windows requested so far
+        auto a_tile = [&]() {
+            const TileCoord tc = decode_tile(g, a_t);
+            a_x0 = tc.tx * kHaloTileW - g.pad;
+            a_y0 = tc.ty * kHaloTileH - g.pad;
+            a_img = tc.img;
+        };
+        if (a_t < total_tiles) a_tile();
+        auto a_issue = [&]() {                  // request the next window into slot sa (which must be free)
+            if (leader) {
+                const uint32_t fb = afull0 + 8 * sa;
+                const int grp = (G == 1) ? 0 : a_gc / g.cblocks;
+                const int cb = (G == 1) ? a_gc : a_gc - grp * g.cblocks;
+                mbar_expect_tx(fb, HCfg::kABytes);
+                tma_load_4d(a_base + sa * HCfg::kASlot, &tmA, fb, g.a_c_base[grp] + cb * BK, a_x0, a_y0, a_img);
+            }
+            if (++sa == a_slots) sa = 0, aph ^= 1;
+            ++a_issued;
+            if (++a_gc == n_grp_cb) {
+                a_gc = 0;
+                a_t += gridDim.x;
+                if (a_t < total_tiles) a_tile();
+            }
+        };
+        if constexpr (BRES) {
+            while (a_t < total_tiles) {
+                mbar_wait(aempty0 + 8 * sa, aph ^ 1);
+                a_issue();
+            }
+        } else {
+            uint32_t sb = 0, bph = 0;
+            long long b_group = 0;              // (tile, group, channel block) index of the B stream
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int ncol0 = (t - g.fd_ntiles.div(t) * g.n_tiles) * BLOCK_N;
+                for (int grp = 0; grp < G; ++grp) {
+                    const int brow = g.b_row_base[grp] + ncol0;
+                    for (int cb = 0; cb < g.cblocks; ++cb, ++b_group) {
+                        // the consumer needs this group's window before its first tap: never let B run ahead of it
+                        while (a_issued <= b_group) {
+                            mbar_wait(aempty0 + 8 * sa, aph ^ 1);
+                            a_issue();
+                        }
+                        int bk = g.b_k_base[grp] + cb * BK;
+                        for (int tap = 0; tap < 9; ++tap, bk += g.b_k_tap_stride) {
+                            while (!mbar_try_wait(empty0 + 8 * sb, bph ^ 1)) {
+                                if (a_t < total_tiles && mbar_try_wait(aempty0 + 8 * sa, aph ^ 1)) a_issue();
+                            }
+                            if (leader) {
+                                const uint32_t fb = full0 + 8 * sb;
+                                mbar_expect_tx(fb, HCfg::kBStage);
+                                tma_load_2d(b_base + sb * HCfg::kBStage, &tmB, fb, bk, brow);
+                            }
+                            if (++sb == b_stages) sb = 0, bph ^= 1;
+                        }
+                        if (a_t < total_tiles && mbar_try_wait(aempty0 + 8 * sa, aph ^ 1)) a_issue();
+                    }
+                }
+            }
+        }
+    } else if (HALO && warp == 1) {
+        // ------------------------------------------------------------ MMA issuer, HALO mainloop
+        // Tap (ky, kx) of the window is the SAME shared-memory bytes read through a descriptor whose start address is
+        // moved by (ky * 10 + kx) pixels: 8-row operand groups are 8 consecutive window pixels, consecutive groups one
+        // window row (10 pixels) apart (stride byte offset), and the hardware swizzles on absolute address bits
+        // (profiles/r2_exp_shift_descriptor.log).  The nine taps are unrolled, so every descriptor is base + constant.
+        const bool leader = elect_one();
+        const uint32_t a_base = smem_u32(smem);
+        const uint32_t b_base = a_base + g.a_slots * HCfg::kASlot;
+        const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+        const uint32_t afull0 = smem_u32(&afull_bar[0]), aempty0 = smem_u32(&aempty_bar[0]);
+        const uint32_t tfull0 = smem_u32(&tfull_bar[0]), tempty0 = smem_u32(&tempty_bar[0]);
+        const uint64_t a_desc0 = umma_smem_desc_sbo(a_base, BK, kHaloW * BK);
+        const uint64_t b_desc0 = umma_smem_desc(b_base, BK);
+        const uint32_t a_slots = g.a_slots, b_stages = g.b_stages;
+        const int cblocks = g.cblocks;
+        const uint32_t idesc = g.idesc;
+        uint32_t sa = 0, aph = 0, sb = 0, bph = 0, slot = 0, tph = 0;
+        bool first = true;
+        int tl = 0;
+        // Every descriptor of a tap is a compile-time offset from two per-channel-block bases: the window slot and
+        // (weights resident) the block's first B stage, or (streamed, ring of exactly nine stages) the ring itself,
+        // so that tap t always lives in stage t.  The issuing thread executes ~20 instructions per tap; with a
+        // run-time stage index it was ~45 and paced every BLOCK_N <= 128 layer (profiles/r2_exp_mma_rate.log).
+        constexpr bool kStaticB = BRES || SRING;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+            if (leader) trace_stamp(g, tl, 2);
+            uint32_t kb0 = 0;                          // resident: first B stage of the (group, channel block)
+            for (int grp = 0; grp < G; ++grp) {
+                mbar_wait(tempty0 + 8 * slot, tph ^ 1);
+                tcgen05_fence_after();
+                if (leader && grp == 0) trace_stamp(g, tl, 3);
+                const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
+                for (int cb = 0; cb < cblocks; ++cb, kb0 += 9) {
+                    mbar_wait(afull0 + 8 * sa, aph);
+                    tcgen05_fence_after();
+                    if (leader && grp == 0 && cb == 0) trace_stamp(g, tl, 4);
+                    const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(sa * (HCfg::kASlot >> 4));
+                    const uint64_t b_desc_cb = b_desc0 + static_cast<uint64_t>(BRES ? kb0 * (HCfg::kBStage >> 4) : 0u);
+                    const uint32_t full_cb = full0 + (BRES ? 8 * kb0 : 0u);
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if constexpr (kStaticB) {
+                            if (!BRES || first) {
+                                mbar_wait(full_cb + 8 * tap, BRES ? 0u : bph);
+                                tcgen05_fence_after();
+                            }
+                        } else {
+                            mbar_wait(full0 + 8 * sb, bph);
+                            tcgen05_fence_after();
+                        }
+                        if (leader) {
+                            const uint64_t b_desc =
+                                kStaticB ? b_desc_cb + static_cast<uint64_t>(tap * (HCfg::kBStage >> 4))
+                                         : b_desc0 + static_cast<uint64_t>(sb * (HCfg::kBStage >> 4));
+#pragma unroll
+                            for (int k = 0; k < BK / 32; ++k)
+                                umma_i8(d_tmem, a_desc + ((((tap / 3) * kHaloW + (tap % 3)) * BK) >> 4) + 2 * k,
+                                        b_desc + 2 * k, idesc, (tap | k) != 0 ? 1u : static_cast<uint32_t>(cb));
+                            if constexpr (!BRES) umma_commit(kStaticB ? empty0 + 8 * tap : empty0 + 8 * sb);
+                        }
+                        __syncwarp();
+                        if constexpr (!kStaticB) {
+                            if (++sb == b_stages) sb = 0, bph ^= 1;
+                        }
+                    }
+                    if constexpr (SRING) bph ^= 1;
+                    if (leader) umma_commit(aempty0 + 8 * sa);
+                    __syncwarp();
+                    if (++sa == a_slots) sa = 0, aph ^= 1;
+                }
+                if (leader) umma_commit(tfull0 + 8 * slot);
+                __syncwarp();
+                if (++slot == kSlots) slot = 0, tph ^= 1;
+            }
+            if (leader) trace_stamp(g, tl, 5);
+            first = false;
+        }
+    } else if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         const bool leader = elect_one();
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
-        const uint32_t tx_bytes = ((g.debug & 4) ? 0 : Cfg::kATile) + ((g.debug & 8) ? 0 : Cfg::kBTile);
+        const uint32_t tx_bytes = ((dbg_flags(g) & 4) ? 0 : Cfg::kATile) + ((dbg_flags(g) & 8) ? 0 : Cfg::kBTile);
         uint32_t s = 0, ph = 0;
         int tl = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
@@ -219,7 +432,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     int b_k0 = g.b_k_base[grp];         // its K coordinate in B
                     for (int tap0 = 0; tap0 < g.taps; tap0 += TPS) {
                         for (int cb = 0; cb < g.cblocks; ++cb) {
-                            if (g.trace != nullptr) {
+                            if (kIgemmDebug && g.trace != nullptr) {
                                 const long long w0 = clock64();
                                 mbar_wait(empty0 + 8 * s, ph ^ 1);
                                 waited += clock64() - w0;
@@ -233,10 +446,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                 int kyi = ky, kxi = kx, bki = b_k0 + cb * BK;
 #pragma unroll
                                 for (int i = 0; i < TPS; ++i) {
-                                    if (!(g.debug & 4))
+                                    if (!(dbg_flags(g) & 4))
                                         tma_load_4d(st + i * Cfg::kASub, &tmA, fb, a_c0 + cb * BK, x0 + kxi, y0 + kyi,
                                                     tc.img);
-                                    if (!(g.debug & 8))
+                                    if (!(dbg_flags(g) & 8))
                                         tma_load_2d(st + Cfg::kATile + i * Cfg::kBSub, &tmB, fb, bki, brow);
                                     bki += g.b_k_tap_stride;
                                     if (++kxi == g.taps_w) kxi = 0, ++kyi;
@@ -254,7 +467,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (leader) {
                 trace_stamp(g, tl, 1);
-                if (g.trace != nullptr && tl < kTraceTiles)
+                if (kIgemmDebug && g.trace != nullptr && tl < kTraceTiles)
                     g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 14] = waited;
             }
         }
@@ -277,7 +490,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (leader && sg == 0) trace_stamp(g, tl, 3);
                 const uint32_t d_tmem = tmem_base + slot * BLOCK_N;
                 for (int kb = 0; kb < kblocks_per_group; ++kb) {
-                    if (g.trace != nullptr) {
+                    if (kIgemmDebug && g.trace != nullptr) {
                         const long long w0 = clock64();
                         mbar_wait(full0 + 8 * s, ph);
                         waited += clock64() - w0;
@@ -287,7 +500,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     tcgen05_fence_after();
                     if (leader) {
                         if (sg == 0 && kb == 0) trace_stamp(g, tl, 4);
-                        if (!(g.debug & 2)) {
+                        if (!(dbg_flags(g) & 2)) {
                             const uint64_t soff = static_cast<uint64_t>(s * (Cfg::kStageBytes >> 4));
 #pragma unroll
                             for (int i = 0; i < TPS; ++i) {
@@ -311,7 +524,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             if (leader) {
                 trace_stamp(g, tl, 5);
-                if (g.trace != nullptr && tl < kTraceTiles)
+                if (kIgemmDebug && g.trace != nullptr && tl < kTraceTiles)
                     g.trace[(static_cast<long long>(blockIdx.x) * kTraceTiles + tl) * 16 + 15] = waited;
             }
         }
@@ -376,7 +589,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         for (int c0 = 0; c0 < kColsPerWarp; c0 += 32) {
                             tmem_ld_wait();
                             tmem_ld_x16(tbase + c0 + 16, acc_b);
-                            if (!(g.debug & 1)) {
+                            if (!(dbg_flags(g) & 1)) {
                                 const int n0 = tc.nt * BLOCK_N + c_begin + c0;
                                 epi.template accum<16>(ts, g, grp, n0, reinterpret_cast<const int32_t(&)[16]>(acc_a),
                                                        vsum[c0 / 16]);
@@ -384,7 +597,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             }
                             tmem_ld_wait();
                             if (c0 + 32 < kColsPerWarp) tmem_ld_x16(tbase + c0 + 32, acc_a);
-                            if (!(g.debug & 1)) {
+                            if (!(dbg_flags(g) & 1)) {
                                 const int n0 = tc.nt * BLOCK_N + c_begin + c0 + 16;
                                 epi.template accum<16>(ts, g, grp, n0, reinterpret_cast<const int32_t(&)[16]>(acc_b),
                                                        vsum[c0 / 16 + 1]);
@@ -414,12 +627,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     for (int c0 = c_begin; c0 < c_end; c0 += 32) {
                         tmem_ld_wait();
                         tmem_ld_x16(tbase + c0 + 16, acc_b[0]);
-                        if (!(g.debug & 1))
+                        if (!(dbg_flags(g) & 1))
                             epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
                                                    reinterpret_cast<const int32_t(*)[16]>(acc_a));
                         tmem_ld_wait();
                         if (c0 + 32 < c_end) tmem_ld_x16(tbase + c0 + 32, acc_a[0]);
-                        if (!(g.debug & 1))
+                        if (!(dbg_flags(g) & 1))
                             epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0 + 16,
                                                    reinterpret_cast<const int32_t(*)[16]>(acc_b));
                     }
@@ -432,7 +645,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             tmem_ld_x16(tmem_base + lane_base + slot * BLOCK_N + c0, acc[grp]);
                         }
                         tmem_ld_wait();
-                        if (!(g.debug & 1))
+                        if (!(dbg_flags(g) & 1))
                             epi.template chunk<16>(ts, g, tc, step, tc.nt * BLOCK_N + c0,
                                                    reinterpret_cast<const int32_t(*)[16]>(acc));
                     }

@@ -2,8 +2,10 @@
 // Host side: weight packing, tile/launch selection, tensor maps.  Device side: igemm.cuh.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
+#include "epilogue_fixed.cuh"
 #include "epilogue_requant.cuh"
 #include "igemm_launch.cuh"
 
@@ -23,7 +25,49 @@ struct qv2x_layer {
     float* d_bias = nullptr;
     int32_t* d_zpw = nullptr;
     float gscale[3] = {1.f, 1.f, 1.f};
+    // fixed-point requantization (epilogue_fixed.cuh) when every column's parameters are representable
+    bool fixed_ok = false;
+    int32_t* d_mul[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_clo = nullptr;
+    int32_t* d_chi = nullptr;
 };
+
+namespace {
+// One output column of the fixed-point requantizer: M_g = rint(r_g * 2^sh), C = rint(bq * 2^(sh - c_off)) +
+// 2^(sh - c_off - 1) with its low 4 bits replaced by sh - sh_min.  Returns false when the column does not fit
+// (the layer then keeps the fp32 epilogue).  oracle/int_oracle.py::fixed_column is the same arithmetic.
+bool fixed_column(const double* r, int ng, double bq, int sh_min, int sh_max, int c_off, int32_t* M, int32_t* clo,
+                  int32_t* chi) {
+    double rmax = 0.0;
+    for (int g = 0; g < ng; ++g) {
+        if (!(r[g] >= 0.0) || !std::isfinite(r[g])) return false;
+        rmax = std::max(rmax, r[g]);
+    }
+    if (!(rmax > 0.0) || !std::isfinite(bq) || std::fabs(bq) >= 32768.0) return false;
+    int e = 0;
+    std::frexp(rmax, &e);
+    int sh = 31 - e;
+    if (sh < sh_min) return false;
+    if (sh > sh_max) sh = sh_max;
+    long long m[3] = {0, 0, 0};
+    for (;;) {
+        bool ok = true;
+        for (int g = 0; g < ng; ++g) {
+            m[g] = std::llrint(std::ldexp(r[g], sh));
+            if (m[g] >= (1LL << 31)) ok = false;
+        }
+        if (ok) break;
+        if (--sh < sh_min) return false;
+    }
+    const int cs = sh - c_off;
+    long long c = std::llrint(std::ldexp(bq, cs)) + (1LL << (cs - 1));
+    c = (c & ~15LL) | static_cast<long long>(sh - sh_min);
+    for (int g = 0; g < ng; ++g) M[g] = static_cast<int32_t>(m[g]);
+    *clo = static_cast<int32_t>(static_cast<uint32_t>(c & 0xffffffffLL));
+    *chi = static_cast<int32_t>(c >> 32);
+    return true;
+}
+}  // namespace
 
 extern "C" {
 
@@ -43,6 +87,8 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
     std::vector<uint8_t> wpack;
     std::vector<float> cscale, biasv;
     std::vector<int32_t> zpw;
+    std::vector<int32_t> fx_mul[3], fx_clo, fx_chi;
+    bool fx_ok = false;
 
     if (d.kind == 0) {
         QV2X_REQUIRE((d.ksize == 1 || d.ksize == 3) && (d.stride == 1 || d.stride == 2), "conv: ksize 1|3, stride 1|2");
@@ -86,6 +132,19 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
                 }
         }
         for (int g = 0; g < 3; ++g) L->gscale[g] = (L->groups == 1) ? 1.f : d.in_delta[g];
+        fx_ok = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu);
+        for (int g = 0; g < L->groups; ++g) fx_mul[g].resize(d.cout);
+        fx_clo.resize(d.cout);
+        fx_chi.resize(d.cout);
+        for (int co = 0; co < d.cout && fx_ok; ++co) {
+            double r[3];
+            for (int g = 0; g < L->groups; ++g)
+                r[g] = static_cast<double>(L->gscale[g]) * static_cast<double>(cscale[co]) / static_cast<double>(d.out_delta);
+            int32_t m[3];
+            fx_ok = fixed_column(r, L->groups, static_cast<double>(biasv[co]) / static_cast<double>(d.out_delta), 32, 47, 0,
+                                 m, &fx_clo[co], &fx_chi[co]);
+            for (int g = 0; g < L->groups && fx_ok; ++g) fx_mul[g][co] = m[g];
+        }
     } else {
         QV2X_REQUIRE(d.ksize == d.stride && (d.stride == 1 || d.stride == 2 || d.stride == 4),
                      "transposed conv: kernel == stride in {1,2,4}");
@@ -129,11 +188,28 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
         L->gscale[0] = 65536.f;
         L->gscale[1] = 256.f;
         L->gscale[2] = 1.f;
+        fx_ok = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu && d.cin <= 256);
+        fx_mul[0].resize(L->n_total);
+        fx_clo.resize(L->n_total);
+        fx_chi.resize(L->n_total);
+        for (int n = 0; n < L->n_total && fx_ok; ++n) {
+            const double r = static_cast<double>(cscale[n]) / static_cast<double>(d.out_delta);
+            fx_ok = fixed_column(&r, 1, static_cast<double>(biasv[n]) / static_cast<double>(d.out_delta), 48, 62, 16,
+                                 &fx_mul[0][n], &fx_clo[n], &fx_chi[n]);
+        }
     }
     int rc = upload(&L->d_w, wpack.data(), wpack.size());
     if (rc == 0) rc = upload(&L->d_cscale, cscale.data(), cscale.size());
     if (rc == 0) rc = upload(&L->d_bias, biasv.data(), biasv.size());
     if (rc == 0 && L->use_zp) rc = upload(&L->d_zpw, zpw.data(), zpw.size());
+    static const int env_fixed = getenv("QV2X_FIXED") ? atoi(getenv("QV2X_FIXED")) : 1;
+    if (rc == 0 && fx_ok && env_fixed) {
+        for (int g = 0; g < 3 && rc == 0; ++g)
+            if (!fx_mul[g].empty()) rc = upload(&L->d_mul[g], fx_mul[g].data(), fx_mul[g].size());
+        if (rc == 0) rc = upload(&L->d_clo, fx_clo.data(), fx_clo.size());
+        if (rc == 0) rc = upload(&L->d_chi, fx_chi.data(), fx_chi.size());
+        L->fixed_ok = (rc == 0);
+    }
     if (rc != 0) {
         qv2x_layer_destroy(L);
         return rc;
@@ -148,6 +224,9 @@ void qv2x_layer_destroy(qv2x_layer* L) {
     cudaFree(L->d_cscale);
     cudaFree(L->d_bias);
     cudaFree(L->d_zpw);
+    for (int g = 0; g < 3; ++g) cudaFree(L->d_mul[g]);
+    cudaFree(L->d_clo);
+    cudaFree(L->d_chi);
     delete L;
 }
 
@@ -259,7 +338,15 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         out_h = ho;
         out_w = wo;
     }
-    choose_tile_box(g.Ho, g.Wo, &g.tw, &g.th);
+    // 3x3 stride-1 convs take the HALO mainloop: fixed 8 x 16 pixel tiles, the input window loaded once per tile
+    static const int env_halo = getenv("QV2X_HALO") ? atoi(getenv("QV2X_HALO")) : 1;
+    const bool halo = env_halo && d.kind == 0 && d.ksize == 3 && d.stride == 1;
+    if (halo) {
+        g.tw = kHaloTileW;
+        g.th = kHaloTileH;
+    } else {
+        choose_tile_box(g.Ho, g.Wo, &g.tw, &g.th);
+    }
     g.tiles_x = (g.Wo + g.tw - 1) / g.tw;
     g.tiles_y = (g.Ho + g.th - 1) / g.th;
     {   // the side warp's halo of per-pixel input sums must fit its shared-memory buffer
@@ -286,12 +373,39 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
             }
         }
     }
+    HaloPlan hp{};
+    if (halo) {
+        // tile width and weights-resident mode by the cost model of plan_halo (QV2X_HALO_BN / QV2X_HALO_RES override
+        // it for experiments)
+        static const int env_bn = getenv("QV2X_HALO_BN") ? atoi(getenv("QV2X_HALO_BN")) : 0;
+        static const int env_res = getenv("QV2X_HALO_RES") ? atoi(getenv("QV2X_HALO_RES")) : -1;
+        const long long m_tiles = static_cast<long long>(n_img) * g.tiles_x * g.tiles_y;
+        hp.cost = -1;
+        for (int bn = 256; bn >= 64; bn >>= 1) {
+            if (L->n_total % bn != 0 || (bn == 256 && (L->groups != 1 || L->bk != 128))) continue;
+            if (env_bn && bn != env_bn && L->n_total % env_bn == 0 && !(env_bn == 256 && (L->groups != 1 || L->bk != 128)))
+                continue;
+            for (int res = 1; res >= 0; --res) {
+                if (env_res >= 0 && res != env_res) continue;
+                const HaloPlan c = plan_halo(bn, L->bk, L->groups, g.cblocks, m_tiles, L->n_total, res == 1, res);
+                if (c.cost < 0 || (res == 1 && !c.resident)) continue;
+                if (hp.cost < 0 || c.cost < hp.cost) hp = c;
+            }
+        }
+        if (hp.cost < 0) {   // a forced mode that does not fit: fall back to the streamed default
+            hp = plan_halo(L->block_n == 256 && L->bk != 128 ? 128 : L->block_n, L->bk, L->groups, g.cblocks, m_tiles,
+                           L->n_total, false, 0);
+        }
+        QV2X_REQUIRE(hp.cost >= 0, "no HALO configuration fits shared memory");
+        block_n = hp.block_n;
+    }
     g.block_n = block_n;
     g.n_tiles = L->n_total / block_n;
     g.idesc = make_idesc_i8(block_n, L->b_signed);
 
     CUtensorMap tmA, tmB;
-    int rc = make_act_tmap(&tmA, d_x, n_img, hi, wi, in_cstride, g.tw, g.th, g.stride, L->bk);
+    int rc = halo ? make_halo_tmap(&tmA, d_x, n_img, hi, wi, in_cstride, L->bk)
+                  : make_act_tmap(&tmA, d_x, n_img, hi, wi, in_cstride, g.tw, g.th, g.stride, L->bk);
     if (rc) return rc;
     rc = make_weight_tmap(&tmB, L->d_w, (d.kind == 0 ? 1 : 3) * L->n_total, L->k_total, block_n, L->bk);
     if (rc) return rc;
@@ -330,28 +444,69 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         e.out_f32 = ex ? ex->d_out_f32 : nullptr;
         e.out_f32_cstride = ex ? ex->out_f32_cstride : 0;
     };
+    // 8-bit / zero-point 0 / ReLU outputs without a shortcut requantize in 64-bit fixed point (epilogue_fixed.cuh)
+    if (L->fixed_ok && !f32_out && !has_res) {
+        auto fill_fx = [&](auto& e) {
+            e.up = (d.kind == 0) ? 1 : d.stride;
+            e.cout_sub = d.cout;
+            e.up_shift = (e.up == 4) ? 2 : (e.up == 2 ? 1 : 0);
+            e.debug = g_debug_flags;
+            e.fd_cout_sub = FastDiv(d.cout);
+            e.Hout = out_h;
+            e.Wout = out_w;
+            e.out_cstride = out_cstride;
+            e.out_cbase = out_cbase;
+            for (int i = 0; i < 3; ++i) {
+                e.mul[i] = L->d_mul[i];
+                e.rowsum_in[i] = (L->use_zp && i < L->groups) ? d_rowsum_in[i] : nullptr;
+            }
+            e.c_lo = L->d_clo;
+            e.c_hi = L->d_chi;
+            e.zpw = L->use_zp ? L->d_zpw : nullptr;
+            e.out = d_y;
+            e.rowsum_out = d_rowsum_out;
+            e.acc_dump = d_acc_dump;
+            e.n_total = L->n_total;
+        };
+        if (d.kind == 1) {
+            FixedEpilogue<3, true> e{};
+            fill_fx(e);
+            return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
+        }
+        if (L->groups == 1) {
+            FixedEpilogue<1> e{};
+            fill_fx(e);
+            if (halo) return dispatch_igemm_halo<1>(L->bk, tmA, tmB, g, e, hp, stream);
+            return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
+        }
+        FixedEpilogue<3> e{};
+        fill_fx(e);
+        if (halo) return dispatch_igemm_halo<3>(L->bk, tmA, tmB, g, e, hp, stream);
+        return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
+    }
     // FP32 outputs live in the generic epilogue only; a shortcut has a saturating fast variant for one input group
     const bool sat8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) && !f32_out;
-    const bool fast8 = sat8 && !has_res;
     const bool digits = (d.kind == 1 && d.cin <= 256);        // digit GEMM with packed integer recombination
+    // (the saturating 8-bit fast path of the fp32 epilogue survives only for residual blocks; plain 8-bit layers
+    // whose parameters do not fit the fixed-point requantizer take the generic fp32 path)
 #define QV2X_RUN(GG, DG, F8)                                                     \
     {                                                                            \
         RequantEpilogue<GG, DG, F8> e{};                                         \
         fill(e);                                                                 \
+        if (halo) return dispatch_igemm_halo<GG>(L->bk, tmA, tmB, g, e, hp, stream); \
         return dispatch_igemm<GG>(block_n, L->bk, tmA, tmB, g, e, stream);       \
     }
     if (L->groups == 1) {
         if (sat8 && has_res) {
             RequantEpilogue<1, false, true, true> e{};
             fill(e);
+            if (halo) return dispatch_igemm_halo<1>(L->bk, tmA, tmB, g, e, hp, stream);
             return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
         }
-        if (fast8) QV2X_RUN(1, false, true) else QV2X_RUN(1, false, false)
+        QV2X_RUN(1, false, false)
     }
-    if (digits) {
-        if (fast8) QV2X_RUN(3, true, true) else QV2X_RUN(3, true, false)
-    }
-    if (fast8) QV2X_RUN(3, false, true) else QV2X_RUN(3, false, false)
+    if (digits) QV2X_RUN(3, true, false)
+    QV2X_RUN(3, false, false)
 #undef QV2X_RUN
 }
 

@@ -116,6 +116,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t row_
     return d;
 }
 
+// The same with an explicit stride between 8-row groups (a pixel window read through a shifted descriptor: groups are
+// window rows, `sbo_bytes` apart; the start address need not be aligned to the swizzle pattern -- the hardware swizzles
+// on absolute shared-memory address bits, see tools/exp_shift.cu).
+__device__ __forceinline__ uint64_t umma_smem_desc_sbo(uint32_t saddr, uint32_t row_bytes, uint32_t sbo_bytes) {
+    const uint64_t layout = (row_bytes == 128) ? 2ull : 4ull;
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= layout << 61;
+    return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, 8-bit integer operands, int32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                         uint32_t accumulate) {

@@ -24,8 +24,10 @@ CFG = {
 
 
 def build(which, dev):
-    """Returns (run, ops): run() launches the layer once on static buffers; ops = 2*MACs per launch."""
+    """Returns (run, ops): run() launches the layer once on static buffers; ops = 2*MACs per launch.
+    QV2X_NIMG overrides the number of agents (default 4; the bench frame has 8)."""
     n, H, W, cin, cout, groups, kind, k = CFG[which]
+    n = int(os.environ.get("QV2X_NIMG", n))
     rng = np.random.default_rng(1)
     x = torch.from_numpy(make_input(rng, n, H, W, cin)).to(dev)
     if kind == 0:
