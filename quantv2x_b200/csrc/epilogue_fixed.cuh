@@ -12,11 +12,10 @@
 //         u = sum_g t_g * M_g[c] + C[c]                                      int64, exact
 //         q = clamp(u >> sh[c], 0, 255)                                      arithmetic shift = floor
 //       M_g[c] = rint(r_g * 2^sh),  r_g = gs_g * cs[c] / delta_out (double),  sh in [32, 47] so that max_g M_g < 2^31
-//       C[c]   = rint(bias[c] / delta_out * 2^sh) + 2^(sh-1)                 (round half up), low 4 bits := sh - 32
+//       C[c]   = rint(bias[c] / delta_out * 2^sh) + 2^(sh-1)                 (round half up)
 //     DIGITS (transposed convs: 24-bit fixed-point weights as three signed byte digits, K <= 256):
 //         w = 256 * acc_mid + acc_lo   (int32, exact)        u = acc_hi * M + ((w * M) >> 16) + C'
-//         q = clamp(u >> (sh - 16), 0, 255),  sh in [48, 62],  C' = rint(bias / delta_out * 2^(sh-16)) + 2^(sh-17),
-//         low 4 bits := sh - 48
+//         q = clamp(u >> (sh - 16), 0, 255),  sh in [48, 62],  C' = rint(bias / delta_out * 2^(sh-16)) + 2^(sh-17)
 // The host (qv2x_layer_create) derives M, C in double precision; layers whose parameters do not fit (r >= 0.5,
 // |bias / delta_out| >= 2^15) keep the fp32 epilogue -- the oracle applies the same rule.
 #pragma once
@@ -32,7 +31,15 @@ __device__ __forceinline__ uint32_t pack4_sat_u8(int x0, int x1, int x2, int x3)
     return d;
 }
 
-template <int G, bool DIGITS = false>
+__device__ __forceinline__ int2 lds_i2(uint32_t saddr) {
+    int2 v;
+    asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+
+// ZP: the weights carry a per-column zero-point (8-bit weights); DUMP: test hook that writes the zero-point-corrected
+// accumulators (a separate instantiation, so that the branch and its address arithmetic stay out of the hot kernels).
+template <int G, bool DIGITS = false, bool ZP = true, bool DUMP = false>
 struct FixedEpilogue {
     static constexpr int col_split(int) { return 2; }
     static constexpr int kMaxStages = 8;
@@ -45,27 +52,29 @@ struct FixedEpilogue {
     int debug;
     FastDiv fd_cout_sub;
     const int32_t* mul[kMaxGroups];       // [N_total] M_g (DIGITS: mul[0] only)
-    const int32_t* c_lo;                  // [N_total] low / high words of C
-    const int32_t* c_hi;
-    const int32_t* zpw;                   // [N_total] or nullptr (weights already zero-centred; always for DIGITS)
+    const int2* cadd;                     // [N_total] C as {low word, high word}
+    const int32_t* shr;                   // [N_total] sh - 32 (DIGITS: sh - 48): shift of the high word of u
+    const int32_t* zpw;                   // [N_total] (ZP only)
     const int32_t* rowsum_in[kMaxGroups];
     uint8_t* out;
     int32_t* rowsum_out;
-    int32_t* acc_dump;                    // as RequantEpilogue (DIGITS: dumped in hi, mid, lo order)
+    int32_t* acc_dump;                    // DUMP only (DIGITS: dumped in hi, mid, lo order)
     int n_total;
 
     struct Tile {
-        int32_t S[G];
+        int32_t negS[G];         // -S_g of this row
         long long opix, mrow;
         int rsum;
         uint32_t sm_par;
         int n_base, ch_off;
     };
-    // Side slot (kEpiSmemBytes / 2 = 5 KB): parameter arrays of kPar entries each: M_0 .. M_{G-1} | C_lo | C_hi | zpw,
+    // Side slot (kEpiSmemBytes / 2 = 6 KB): arrays of kPar columns: M_0 .. M_{G-1} (int32) | C (int2) | shift | zpw,
     // then S[G][128].  G = 1 tiles are up to 256 columns wide, G = 3 tiles up to 128.
     static constexpr int kPar = (G == 1) ? 256 : 128;
-    static constexpr int kNumArr = G + 3;
-    static constexpr int kSlotS = kNumArr * kPar * 4;
+    static constexpr int kOffC = G * kPar * 4;
+    static constexpr int kOffSh = kOffC + kPar * 8;
+    static constexpr int kOffZ = kOffSh + kPar * 4;
+    static constexpr int kSlotS = kOffZ + kPar * 4;
     static_assert(kSlotS + G * kTileM * 4 <= kEpiSmemBytes / 2, "side slot");
     static constexpr int kHaloInts = SideHalo::kHaloInts;
     using Side = SideHalo;
@@ -75,15 +84,15 @@ struct FixedEpilogue {
     __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
                                               int32_t* halo, int& staged_nt, const Side& sd) const {
         if (staged_nt != tc.nt) {
-            int32_t* s_p = reinterpret_cast<int32_t*>(slot);
+            const uint32_t sp = smem_u32(slot);
             const int n_base = tc.nt * g.block_n;
-            const bool has_zp = (zpw != nullptr);
             for (int i = lane; i < g.block_n; i += 32) {
 #pragma unroll
-                for (int q = 0; q < (DIGITS ? 1 : G); ++q) cp_async_4(smem_u32(s_p + q * kPar + i), mul[q] + n_base + i, true);
-                cp_async_4(smem_u32(s_p + G * kPar + i), c_lo + n_base + i, true);
-                cp_async_4(smem_u32(s_p + (G + 1) * kPar + i), c_hi + n_base + i, true);
-                cp_async_4(smem_u32(s_p + (G + 2) * kPar + i), has_zp ? zpw + n_base + i : c_lo, has_zp);
+                for (int q = 0; q < (DIGITS ? 1 : G); ++q) cp_async_4(sp + 4 * (q * kPar + i), mul[q] + n_base + i, true);
+                cp_async_4(sp + kOffC + 8 * i, &cadd[n_base + i].x, true);
+                cp_async_4(sp + kOffC + 8 * i + 4, &cadd[n_base + i].y, true);
+                cp_async_4(sp + kOffSh + 4 * i, shr + n_base + i, true);
+                if constexpr (ZP) cp_async_4(sp + kOffZ + 4 * i, zpw + n_base + i, true);
             }
             staged_nt = tc.nt;
         }
@@ -104,7 +113,7 @@ struct FixedEpilogue {
         ts.mrow = -1;
 #pragma unroll
         for (int grp = 0; grp < G; ++grp)
-            ts.S[grp] = *reinterpret_cast<const int32_t*>(slot + kSlotS + 4 * (grp * kTileM + row));
+            ts.negS[grp] = -*reinterpret_cast<const int32_t*>(slot + kSlotS + 4 * (grp * kTileM + row));
         if (!valid) return;
         ts.mrow = (static_cast<long long>(tc.img) * g.Ho + oy) * g.Wo + ox;
         int dy = 0, dx = 0;
@@ -117,12 +126,26 @@ struct FixedEpilogue {
     }
 
     template <int W>
-    __device__ __forceinline__ void load_par(const Tile& ts, int arr, int nl, int32_t (&v)[W]) const {
+    __device__ __forceinline__ void load_i32(uint32_t saddr, int32_t (&v)[W]) const {
 #pragma unroll
         for (int v4 = 0; v4 < W / 4; ++v4) {
-            const int4 z = lds_i4(ts.sm_par + 4 * (arr * kPar + nl) + 16 * v4);
+            const int4 z = lds_i4(saddr + 16 * v4);
             v[4 * v4 + 0] = z.x, v[4 * v4 + 1] = z.y, v[4 * v4 + 2] = z.z, v[4 * v4 + 3] = z.w;
         }
+    }
+    // C of W columns as ready-made 64-bit operands (even / odd register pairs straight out of LDS.128)
+    template <int W>
+    __device__ __forceinline__ void load_c(uint32_t saddr, long long (&c)[W]) const {
+#pragma unroll
+        for (int v2 = 0; v2 < W / 2; ++v2) {
+            const int4 z = lds_i4(saddr + 16 * v2);
+            asm("mov.b64 %0, {%1, %2};" : "=l"(c[2 * v2]) : "r"(z.x), "r"(z.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(c[2 * v2 + 1]) : "r"(z.z), "r"(z.w));
+        }
+    }
+    // high word of a * b + c (one IMAD.HI: its addend is a 64-bit register pair)
+    static __device__ __forceinline__ int32_t mad_hi64(int32_t a, int32_t b, long long c) {
+        return static_cast<int32_t>((static_cast<long long>(a) * b + c) >> 32);
     }
 
     // W consecutive columns [n0, n0 + W) of this thread's row, all G accumulator groups at once.
@@ -133,69 +156,72 @@ struct FixedEpilogue {
         (void)step;
         static_assert(W == 16, "chunk width");
         const int nl = n0 - ts.n_base;
-        int32_t clo[W], chi[W];
-        load_par<W>(ts, G, nl, clo);
-        load_par<W>(ts, G + 1, nl, chi);
+        long long c[W];
+        int32_t sh[W];
+        load_c<W>(ts.sm_par + kOffC + 8 * nl, c);
+        load_i32<W>(ts.sm_par + kOffSh + 4 * nl, sh);
         int q[W];
         if constexpr (DIGITS) {
             // groups arrive in the order mid, lo, hi (see qv2x_layer_forward)
-            if (acc_dump != nullptr && ts.mrow >= 0) {
-                const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+            if constexpr (DUMP) {
+                if (acc_dump != nullptr && ts.mrow >= 0) {
+                    const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
 #pragma unroll
-                for (int grp = 0; grp < 3; ++grp) {
-                    const int dg = (grp == 0) ? 1 : (grp == 1 ? 2 : 0);
-                    int32_t* dp = acc_dump + (dg * gstride + ts.mrow) * n_total + n0;
+                    for (int grp = 0; grp < 3; ++grp) {
+                        const int dg = (grp == 0) ? 1 : (grp == 1 ? 2 : 0);
+                        int32_t* dp = acc_dump + (dg * gstride + ts.mrow) * n_total + n0;
 #pragma unroll
-                    for (int j = 0; j < W; j += 4)
-                        st_global_v4(dp + j, acc[grp][j], acc[grp][j + 1], acc[grp][j + 2], acc[grp][j + 3]);
+                        for (int j = 0; j < W; j += 4)
+                            st_global_v4(dp + j, acc[grp][j], acc[grp][j + 1], acc[grp][j + 2], acc[grp][j + 3]);
+                    }
                 }
             }
             int32_t m[W];
-            load_par<W>(ts, 0, nl, m);
+            load_i32<W>(ts.sm_par + 4 * nl, m);
 #pragma unroll
             for (int j = 0; j < W; ++j) {
                 const int32_t w = acc[0][j] * 256 + acc[1][j];
                 const long long b = static_cast<long long>(w) * m[j];
-                const long long c = (static_cast<long long>(chi[j]) << 32) | static_cast<uint32_t>(clo[j]);
-                const long long u = static_cast<long long>(acc[2][j]) * m[j] + ((b >> 16) + c);
-                q[j] = static_cast<int32_t>(u >> 32) >> (clo[j] & 15);
+                q[j] = mad_hi64(acc[2][j], m[j], (b >> 16) + c[j]) >> sh[j];
             }
         } else {
             int32_t t[G][W];
-            if (zpw != nullptr) {
+            if constexpr (ZP) {
                 int32_t zw[W];
-                load_par<W>(ts, G + 2, nl, zw);
+                load_i32<W>(ts.sm_par + kOffZ + 4 * nl, zw);
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp)
 #pragma unroll
-                    for (int j = 0; j < W; ++j) t[grp][j] = acc[grp][j] - zw[j] * ts.S[grp];
+                    for (int j = 0; j < W; ++j) t[grp][j] = zw[j] * ts.negS[grp] + acc[grp][j];
             } else {
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp)
 #pragma unroll
                     for (int j = 0; j < W; ++j) t[grp][j] = acc[grp][j];
             }
-            if (acc_dump != nullptr && ts.mrow >= 0) {      // test hook, off the hot path
-                const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
+            if constexpr (DUMP) {
+                if (acc_dump != nullptr && ts.mrow >= 0) {
+                    const long long gstride = static_cast<long long>(g.n_img) * g.Ho * g.Wo;
 #pragma unroll
-                for (int grp = 0; grp < G; ++grp) {
-                    int32_t* dp = acc_dump + (grp * gstride + ts.mrow) * n_total + n0;
+                    for (int grp = 0; grp < G; ++grp) {
+                        int32_t* dp = acc_dump + (grp * gstride + ts.mrow) * n_total + n0;
 #pragma unroll
-                    for (int j = 0; j < W; j += 4) st_global_v4(dp + j, t[grp][j], t[grp][j + 1], t[grp][j + 2], t[grp][j + 3]);
+                        for (int j = 0; j < W; j += 4)
+                            st_global_v4(dp + j, t[grp][j], t[grp][j + 1], t[grp][j + 2], t[grp][j + 3]);
+                    }
                 }
             }
-            long long u[W];
 #pragma unroll
-            for (int j = 0; j < W; ++j) u[j] = (static_cast<long long>(chi[j]) << 32) | static_cast<uint32_t>(clo[j]);
-#pragma unroll
-            for (int grp = 0; grp < G; ++grp) {
+            for (int grp = 0; grp < G - 1; ++grp) {
                 int32_t m[W];
-                load_par<W>(ts, grp, nl, m);
+                load_i32<W>(ts.sm_par + 4 * (grp * kPar + nl), m);
 #pragma unroll
-                for (int j = 0; j < W; ++j) u[j] += static_cast<long long>(t[grp][j]) * m[j];
+                for (int j = 0; j < W; ++j) c[j] += static_cast<long long>(t[grp][j]) * m[j];
             }
+            int32_t m[W];
+            load_i32<W>(ts.sm_par + 4 * ((G - 1) * kPar + nl), m);
 #pragma unroll
-            for (int j = 0; j < W; ++j) q[j] = static_cast<int32_t>(u[j] >> 32) >> (clo[j] & 15);
+            for (int j = 0; j < W; ++j) q[j] = mad_hi64(t[G - 1][j], m[j], c[j]) >> sh[j];
         }
         uint32_t packed[W / 4];
         unsigned rsum = 0;
@@ -204,7 +230,7 @@ struct FixedEpilogue {
             packed[w] = pack4_sat_u8(q[4 * w], q[4 * w + 1], q[4 * w + 2], q[4 * w + 3]);
             rsum = __dp4a(packed[w], 0x01010101u, rsum);
         }
-        if (ts.opix >= 0 && !(debug & 16)) {
+        if (ts.opix >= 0) {
             st_global_v4(out + ts.opix * out_cstride + out_cbase + (n0 - ts.ch_off), packed[0], packed[1], packed[2],
                          packed[3]);
             ts.rsum += static_cast<int>(rsum);
@@ -218,6 +244,69 @@ struct FixedEpilogue {
         (void)g;
         (void)tc;
         if (rowsum_out != nullptr && ts.opix >= 0) atomicAdd(rowsum_out + ts.opix, ts.rsum);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// The same requantizer with its per-column parameters in the KERNEL-PARAMETER constant bank instead of shared memory.
+// While tcgen05.mma streams operands (128 B/clk for BLOCK_N <= 128) ordinary shared-memory loads are starved -- one
+// LDS wavefront takes ~74 cycles (profiles/r2_exp_smem_contention.log) -- and the ~20 parameter loads per 16-column chunk
+// were what paced every epilogue.  The column index is warp-uniform, so the constant cache serves it as a broadcast and
+// the shared-memory port is left to the tensor core.  Layers of up to 256 output columns (every conv of the model).
+template <int G>
+struct FixedTable {
+    int32_t mul[G][256];
+    int2 cadd[256];
+    int32_t shr[256];
+    int32_t zw[256];
+};
+
+template <int G, bool ZP = true>
+struct FixedEpilogueC : FixedEpilogue<G, false, ZP, false> {
+    using Base = FixedEpilogue<G, false, ZP, false>;
+    using Tile = typename Base::Tile;
+    using Side = typename Base::Side;
+    static constexpr bool kStaticCols = true;      // igemm.cuh: the column base of every chunk is a compile-time value
+    FixedTable<G> tab;
+
+    __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
+                                              int32_t* halo, int& staged_nt, const Side& sd) const {
+        (void)staged_nt;
+        sd.template stage<G>(g, tc, lane, reinterpret_cast<int32_t*>(slot + Base::kSlotS), halo, this->rowsum_in);
+    }
+
+    template <int W>
+    __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int n0,
+                                          const int32_t (*acc)[W]) const {
+        (void)g;
+        (void)tc;
+        (void)step;
+        static_assert(W == 16, "chunk width");
+        int q[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const int n = n0 + j;
+            long long u;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "r"(tab.cadd[n].x), "r"(tab.cadd[n].y));
+#pragma unroll
+            for (int grp = 0; grp < G; ++grp) {
+                const int32_t t = ZP ? tab.zw[n] * ts.negS[grp] + acc[grp][j] : acc[grp][j];
+                if (grp < G - 1) u += static_cast<long long>(t) * tab.mul[grp][n];
+                else q[j] = Base::mad_hi64(t, tab.mul[grp][n], u) >> tab.shr[n];
+            }
+        }
+        uint32_t packed[W / 4];
+        unsigned rsum = 0;
+#pragma unroll
+        for (int w = 0; w < W / 4; ++w) {
+            packed[w] = pack4_sat_u8(q[4 * w], q[4 * w + 1], q[4 * w + 2], q[4 * w + 3]);
+            rsum = __dp4a(packed[w], 0x01010101u, rsum);
+        }
+        if (ts.opix >= 0) {
+            st_global_v4(this->out + ts.opix * this->out_cstride + this->out_cbase + (n0 - ts.ch_off), packed[0],
+                         packed[1], packed[2], packed[3]);
+            ts.rsum += static_cast<int>(rsum);
+        }
     }
 };
 

@@ -16,6 +16,8 @@
 //               (deblocks with per-input-channel scales, folded codebook distance GEMM).
 // K is walked group-major, then tap-major, then BK-byte channel blocks.
 #pragma once
+#include <type_traits>
+
 #include "ptx.cuh"
 
 namespace qv2x {
@@ -83,7 +85,7 @@ __device__ __forceinline__ void trace_stamp(const IgemmGeom& g, int tile_local, 
 __device__ __forceinline__ int dbg_flags(const IgemmGeom& g) { return kIgemmDebug ? g.debug : 0; }
 
 constexpr int kBarrierBytes = 1024;    // mbarriers + the TMEM base address
-constexpr int kEpiSmemBytes = 10240;   // two side-input slots / epilogue scratch
+constexpr int kEpiSmemBytes = 12288;   // two side-input slots / epilogue scratch
 constexpr int kHaloSmemBytes = 8192;   // two halo buffers, one per side warp   // scratch handed to the epilogue functor (cross-warp merges)
 
 // TPS = taps per pipeline stage: layers with 64 input channels have only 64 bytes of K per tap, so three taps
@@ -167,13 +169,27 @@ __device__ __forceinline__ TileCoord decode_tile(const IgemmGeom& g, int t) {
 //                              uint8_t* scratch, const TmemView&) const;   -- scratch: kEpiSmemBytes of shared memory
 //     __device__ void end(Tile&, const IgemmGeom&, const TileCoord&) const;
 //   };
+// Calls f(integral_constant<int, I * STEP>) for the I < COUNT with v == I * STEP: turns a run-time column base into
+// a compile-time one (epilogues whose per-column parameters are immediate constant-bank operands).
+template <int I, int COUNT, int STEP, class F>
+__device__ __forceinline__ void dispatch_col(int v, F& f) {
+    if constexpr (I < COUNT) {
+        if (v == I * STEP) f(std::integral_constant<int, I * STEP>{});
+        else dispatch_col<I + 1, COUNT, STEP>(v, f);
+    }
+}
+template <class Epi, class = void>
+struct EpiStaticCols : std::false_type {};
+template <class Epi>
+struct EpiStaticCols<Epi, std::enable_if_t<Epi::kStaticCols>> : std::true_type {};
+
 template <class Epi, int BLOCK_N>
 constexpr int igemm_threads() { return (4 + 4 * Epi::col_split(BLOCK_N)) * 32; }
 
 template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1, bool HALO = false, bool BRES = false, bool SRING = false>
 __global__ void __launch_bounds__(igemm_threads<Epi, BLOCK_N>(), 1)
-igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const IgemmGeom g,
-             const Epi epi) {
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ IgemmGeom g, const __grid_constant__ Epi epi) {
     using Cfg = IgemmCfg<BLOCK_N, BK, Epi::kMaxStages, TPS>;
     using HCfg = HaloCfg<BLOCK_N, BK>;
     constexpr int kStages = HALO ? kHaloMaxBStages : Cfg::kStages;   // barrier slots (HALO: ring depth is g.b_stages)
@@ -371,13 +387,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t a_desc = a_desc0 + static_cast<uint64_t>(sa * (HCfg::kASlot >> 4));
                     const uint64_t b_desc_cb = b_desc0 + static_cast<uint64_t>(BRES ? kb0 * (HCfg::kBStage >> 4) : 0u);
                     const uint32_t full_cb = full0 + (BRES ? 8 * kb0 : 0u);
+                    if (BRES && !first) {
+                        // resident weights, steady state: nothing to wait for between taps -- all 9 x BK/32 MMAs of the
+                        // channel block are issued back to back from two descriptor bases
+                        if (leader) {
+#pragma unroll
+                            for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                                for (int k = 0; k < BK / 32; ++k)
+                                    umma_i8(d_tmem, a_desc + ((((tap / 3) * kHaloW + (tap % 3)) * BK) >> 4) + 2 * k,
+                                            b_desc_cb + (tap * (HCfg::kBStage >> 4) + 2 * k), idesc,
+                                            (tap | k) != 0 ? 1u : static_cast<uint32_t>(cb));
+                        }
+                        __syncwarp();
+                    } else {
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         if constexpr (kStaticB) {
-                            if (!BRES || first) {
-                                mbar_wait(full_cb + 8 * tap, BRES ? 0u : bph);
-                                tcgen05_fence_after();
-                            }
+                            mbar_wait(full_cb + 8 * tap, BRES ? 0u : bph);
+                            tcgen05_fence_after();
                         } else {
                             mbar_wait(full0 + 8 * sb, bph);
                             tcgen05_fence_after();
@@ -396,6 +424,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         if constexpr (!kStaticB) {
                             if (++sb == b_stages) sb = 0, bph ^= 1;
                         }
+                    }
                     }
                     if constexpr (SRING) bph ^= 1;
                     if (leader) umma_commit(aempty0 + 8 * sa);
@@ -619,7 +648,46 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 }
                 tcgen05_fence_after();
                 if (tracer && step == 0) trace_stamp(g, tl, part == 0 ? 8 : 12);
-                if constexpr (G == 1 && (kColsPerWarp % 32 == 0)) {
+                if constexpr (EpiStaticCols<Epi>::value) {
+                    // Per-column parameters are kernel-parameter constants: make the warp's column base a compile-time
+                    // value (one code copy per (column tile, part); a CTA only ever runs its own two), so that after
+                    // unrolling every parameter is an immediate constant-bank operand -- no load instruction at all.
+                    static_assert(kColsPerWarp % 32 == 0, "static columns work on 32-column pairs of chunks");
+                    auto cols = [&](auto col0_c) {
+                        constexpr int kCol0 = decltype(col0_c)::value;          // global column of the warp's first one
+                        constexpr int kLoc0 = kCol0 % BLOCK_N;                  // ... and its place inside the tile
+                        if constexpr (G == 1) {
+                            const uint32_t tbase = tmem_base + lane_base + (ac % kSlots) * BLOCK_N + kLoc0;
+                            uint32_t acc_a[1][16], acc_b[1][16];
+                            tmem_ld_x16(tbase, acc_a[0]);
+#pragma unroll
+                            for (int c = 0; c < kColsPerWarp; c += 32) {
+                                tmem_ld_wait();
+                                tmem_ld_x16(tbase + c + 16, acc_b[0]);
+                                epi.template chunk<16>(ts, g, tc, step, kCol0 + c,
+                                                       reinterpret_cast<const int32_t(*)[16]>(acc_a));
+                                tmem_ld_wait();
+                                if (c + 32 < kColsPerWarp) tmem_ld_x16(tbase + c + 32, acc_a[0]);
+                                epi.template chunk<16>(ts, g, tc, step, kCol0 + c + 16,
+                                                       reinterpret_cast<const int32_t(*)[16]>(acc_b));
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < kColsPerWarp; c += 16) {
+                                uint32_t acc[G][16];
+#pragma unroll
+                                for (int grp = 0; grp < G; ++grp) {
+                                    const uint32_t sl = (ac + grp) % kSlots;
+                                    tmem_ld_x16(tmem_base + lane_base + sl * BLOCK_N + kLoc0 + c, acc[grp]);
+                                }
+                                tmem_ld_wait();
+                                epi.template chunk<16>(ts, g, tc, step, kCol0 + c,
+                                                       reinterpret_cast<const int32_t(*)[16]>(acc));
+                            }
+                        }
+                    };
+                    dispatch_col<0, 256 / kColsPerWarp, kColsPerWarp>(tc.nt * BLOCK_N + c_begin, cols);
+                } else if constexpr (G == 1 && (kColsPerWarp % 32 == 0)) {
                     // software-pipelined TMEM reads: the load of chunk i+1 is in flight while chunk i is processed
                     const uint32_t tbase = tmem_base + lane_base + (ac % kSlots) * BLOCK_N;
                     uint32_t acc_a[1][16], acc_b[1][16];

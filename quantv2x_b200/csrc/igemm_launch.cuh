@@ -124,7 +124,9 @@ inline HaloPlan plan_halo(int bn, int bk, int groups, int cblocks, long long m_t
     const long long epi = 12LL * bn * (groups > 1 ? 2 : 1);
     const long long stream = resident ? 0 : (static_cast<long long>(kblocks) * b_stage + groups * cblocks * a_slot) / 60;
     const long long per_tile = std::max(std::max(mma, epi), stream);
-    hp.cost = rounds * per_tile + 3000 + (resident ? static_cast<long long>(kblocks) * b_stage / 60 : 0);
+    // (resident weights: the one-time load overlaps the first window; measured slightly ahead of streaming whenever
+    //  it fits and a CTA sees two or more tiles)
+    hp.cost = rounds * per_tile + 3000 + (resident ? (rounds >= 2 ? -1 : static_cast<long long>(kblocks) * b_stage / 60) : 0);
     return hp;
 }
 

@@ -5,9 +5,7 @@
 #include <cstdlib>
 #include <vector>
 
-#include "epilogue_fixed.cuh"
-#include "epilogue_requant.cuh"
-#include "igemm_launch.cuh"
+#include "layer_launch.h"
 
 
 
@@ -28,16 +26,19 @@ struct qv2x_layer {
     // fixed-point requantization (epilogue_fixed.cuh) when every column's parameters are representable
     bool fixed_ok = false;
     int32_t* d_mul[3] = {nullptr, nullptr, nullptr};
-    int32_t* d_clo = nullptr;
-    int32_t* d_chi = nullptr;
+    int2* d_cadd = nullptr;
+    int32_t* d_shr = nullptr;
+    // host copies of the same parameters: layers of up to 256 columns pass them through the kernel-parameter bank
+    std::vector<int32_t> h_mul[3], h_shr, h_zpw;
+    std::vector<int2> h_cadd;
 };
 
 namespace {
 // One output column of the fixed-point requantizer: M_g = rint(r_g * 2^sh), C = rint(bq * 2^(sh - c_off)) +
-// 2^(sh - c_off - 1) with its low 4 bits replaced by sh - sh_min.  Returns false when the column does not fit
+// 2^(sh - c_off - 1), shift of the high word = sh - sh_min.  Returns false when the column does not fit
 // (the layer then keeps the fp32 epilogue).  oracle/int_oracle.py::fixed_column is the same arithmetic.
-bool fixed_column(const double* r, int ng, double bq, int sh_min, int sh_max, int c_off, int32_t* M, int32_t* clo,
-                  int32_t* chi) {
+bool fixed_column(const double* r, int ng, double bq, int sh_min, int sh_max, int c_off, int32_t* M, int2* cadd,
+                  int32_t* shr) {
     double rmax = 0.0;
     for (int g = 0; g < ng; ++g) {
         if (!(r[g] >= 0.0) || !std::isfinite(r[g])) return false;
@@ -60,11 +61,11 @@ bool fixed_column(const double* r, int ng, double bq, int sh_min, int sh_max, in
         if (--sh < sh_min) return false;
     }
     const int cs = sh - c_off;
-    long long c = std::llrint(std::ldexp(bq, cs)) + (1LL << (cs - 1));
-    c = (c & ~15LL) | static_cast<long long>(sh - sh_min);
+    const long long c = std::llrint(std::ldexp(bq, cs)) + (1LL << (cs - 1));
     for (int g = 0; g < ng; ++g) M[g] = static_cast<int32_t>(m[g]);
-    *clo = static_cast<int32_t>(static_cast<uint32_t>(c & 0xffffffffLL));
-    *chi = static_cast<int32_t>(c >> 32);
+    cadd->x = static_cast<int32_t>(static_cast<uint32_t>(c & 0xffffffffLL));
+    cadd->y = static_cast<int32_t>(c >> 32);
+    *shr = sh - sh_min;
     return true;
 }
 }  // namespace
@@ -87,7 +88,8 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
     std::vector<uint8_t> wpack;
     std::vector<float> cscale, biasv;
     std::vector<int32_t> zpw;
-    std::vector<int32_t> fx_mul[3], fx_clo, fx_chi;
+    std::vector<int32_t> fx_mul[3], fx_shr;
+    std::vector<int2> fx_cadd;
     bool fx_ok = false;
 
     if (d.kind == 0) {
@@ -134,15 +136,15 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
         for (int g = 0; g < 3; ++g) L->gscale[g] = (L->groups == 1) ? 1.f : d.in_delta[g];
         fx_ok = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu);
         for (int g = 0; g < L->groups; ++g) fx_mul[g].resize(d.cout);
-        fx_clo.resize(d.cout);
-        fx_chi.resize(d.cout);
+        fx_cadd.resize(d.cout);
+        fx_shr.resize(d.cout);
         for (int co = 0; co < d.cout && fx_ok; ++co) {
             double r[3];
             for (int g = 0; g < L->groups; ++g)
                 r[g] = static_cast<double>(L->gscale[g]) * static_cast<double>(cscale[co]) / static_cast<double>(d.out_delta);
             int32_t m[3];
             fx_ok = fixed_column(r, L->groups, static_cast<double>(biasv[co]) / static_cast<double>(d.out_delta), 32, 47, 0,
-                                 m, &fx_clo[co], &fx_chi[co]);
+                                 m, &fx_cadd[co], &fx_shr[co]);
             for (int g = 0; g < L->groups && fx_ok; ++g) fx_mul[g][co] = m[g];
         }
     } else {
@@ -190,12 +192,12 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
         L->gscale[2] = 1.f;
         fx_ok = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu && d.cin <= 256);
         fx_mul[0].resize(L->n_total);
-        fx_clo.resize(L->n_total);
-        fx_chi.resize(L->n_total);
+        fx_cadd.resize(L->n_total);
+        fx_shr.resize(L->n_total);
         for (int n = 0; n < L->n_total && fx_ok; ++n) {
             const double r = static_cast<double>(cscale[n]) / static_cast<double>(d.out_delta);
             fx_ok = fixed_column(&r, 1, static_cast<double>(biasv[n]) / static_cast<double>(d.out_delta), 48, 62, 16,
-                                 &fx_mul[0][n], &fx_clo[n], &fx_chi[n]);
+                                 &fx_mul[0][n], &fx_cadd[n], &fx_shr[n]);
         }
     }
     int rc = upload(&L->d_w, wpack.data(), wpack.size());
@@ -206,9 +208,13 @@ int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const f
     if (rc == 0 && fx_ok && env_fixed) {
         for (int g = 0; g < 3 && rc == 0; ++g)
             if (!fx_mul[g].empty()) rc = upload(&L->d_mul[g], fx_mul[g].data(), fx_mul[g].size());
-        if (rc == 0) rc = upload(&L->d_clo, fx_clo.data(), fx_clo.size());
-        if (rc == 0) rc = upload(&L->d_chi, fx_chi.data(), fx_chi.size());
+        if (rc == 0) rc = upload(&L->d_cadd, fx_cadd.data(), fx_cadd.size());
+        if (rc == 0) rc = upload(&L->d_shr, fx_shr.data(), fx_shr.size());
         L->fixed_ok = (rc == 0);
+        for (int g = 0; g < 3; ++g) L->h_mul[g] = fx_mul[g];
+        L->h_cadd = fx_cadd;
+        L->h_shr = fx_shr;
+        L->h_zpw = zpw;
     }
     if (rc != 0) {
         qv2x_layer_destroy(L);
@@ -225,8 +231,8 @@ void qv2x_layer_destroy(qv2x_layer* L) {
     cudaFree(L->d_bias);
     cudaFree(L->d_zpw);
     for (int g = 0; g < 3; ++g) cudaFree(L->d_mul[g]);
-    cudaFree(L->d_clo);
-    cudaFree(L->d_chi);
+    cudaFree(L->d_cadd);
+    cudaFree(L->d_shr);
     delete L;
 }
 
@@ -409,6 +415,7 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
     if (rc) return rc;
     rc = make_weight_tmap(&tmB, L->d_w, (d.kind == 0 ? 1 : 3) * L->n_total, L->k_total, block_n, L->bk);
     if (rc) return rc;
+    LayerLaunch ctx{block_n, L->bk, halo, tmA, tmB, g, hp, stream};
 
     auto fill = [&](auto& e) {
         e.up = (d.kind == 0) ? 1 : d.stride;
@@ -445,7 +452,8 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         e.out_f32_cstride = ex ? ex->out_f32_cstride : 0;
     };
     // 8-bit / zero-point 0 / ReLU outputs without a shortcut requantize in 64-bit fixed point (epilogue_fixed.cuh)
-    if (L->fixed_ok && !f32_out && !has_res) {
+    static const int env_fixed_g3 = getenv("QV2X_FIXED_G3") ? atoi(getenv("QV2X_FIXED_G3")) : 1;
+    if (L->fixed_ok && !f32_out && !has_res && (env_fixed_g3 || d.kind == 1 || L->groups == 1)) {
         auto fill_fx = [&](auto& e) {
             e.up = (d.kind == 0) ? 1 : d.stride;
             e.cout_sub = d.cout;
@@ -460,29 +468,60 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
                 e.mul[i] = L->d_mul[i];
                 e.rowsum_in[i] = (L->use_zp && i < L->groups) ? d_rowsum_in[i] : nullptr;
             }
-            e.c_lo = L->d_clo;
-            e.c_hi = L->d_chi;
+            e.cadd = L->d_cadd;
+            e.shr = L->d_shr;
             e.zpw = L->use_zp ? L->d_zpw : nullptr;
             e.out = d_y;
             e.rowsum_out = d_rowsum_out;
             e.acc_dump = d_acc_dump;
             e.n_total = L->n_total;
         };
+#define QV2X_FX(GG, DG, ZPP, DMP)                                                          \
+    {                                                                                      \
+        FixedEpilogue<GG, DG, ZPP, DMP> e{};                                               \
+        fill_fx(e);                                                                        \
+        return run_layer(ctx, e);                                                          \
+    }
+        const bool dump = (d_acc_dump != nullptr);
+        static const int env_cpar = getenv("QV2X_CPAR") ? atoi(getenv("QV2X_CPAR")) : 1;
+        // (constant-bank parameters pay off for one-group layers whose tile spans all output columns: two code copies,
+        //  5 KB of constants; measured on s0 / s1 / s2 / shrinker, profiles/r2_sweep_epilogue_params.log)
+        if (d.kind == 0 && !dump && L->n_total <= 256 && env_cpar && L->groups == 1 && g.n_tiles == 1) {
+            auto fill_tab = [&](auto& e) {
+                fill_fx(e);
+                for (int n = 0; n < L->n_total; ++n) {
+                    for (int q = 0; q < L->groups; ++q) e.tab.mul[q][n] = L->h_mul[q][n];
+                    e.tab.cadd[n] = L->h_cadd[n];
+                    e.tab.shr[n] = L->h_shr[n];
+                    e.tab.zw[n] = L->use_zp ? L->h_zpw[n] : 0;
+                }
+            };
+#define QV2X_FXC(GG, ZPP)                 \
+    {                                     \
+        FixedEpilogueC<GG, ZPP> e{};      \
+        fill_tab(e);                      \
+        return run_layer(ctx, e);         \
+    }
+            if (L->groups == 1) {
+                if (L->use_zp) QV2X_FXC(1, true) else QV2X_FXC(1, false)
+            }
+            if (L->use_zp) QV2X_FXC(3, true) else QV2X_FXC(3, false)
+#undef QV2X_FXC
+        }
         if (d.kind == 1) {
-            FixedEpilogue<3, true> e{};
-            fill_fx(e);
-            return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
+            if (dump) QV2X_FX(3, true, false, true) else QV2X_FX(3, true, false, false)
         }
         if (L->groups == 1) {
-            FixedEpilogue<1> e{};
-            fill_fx(e);
-            if (halo) return dispatch_igemm_halo<1>(L->bk, tmA, tmB, g, e, hp, stream);
-            return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
+            if (dump) {
+                if (L->use_zp) QV2X_FX(1, false, true, true) else QV2X_FX(1, false, false, true)
+            }
+            if (L->use_zp) QV2X_FX(1, false, true, false) else QV2X_FX(1, false, false, false)
         }
-        FixedEpilogue<3> e{};
-        fill_fx(e);
-        if (halo) return dispatch_igemm_halo<3>(L->bk, tmA, tmB, g, e, hp, stream);
-        return dispatch_igemm<3>(block_n, L->bk, tmA, tmB, g, e, stream);
+        if (dump) {
+            if (L->use_zp) QV2X_FX(3, false, true, true) else QV2X_FX(3, false, false, true)
+        }
+        if (L->use_zp) QV2X_FX(3, false, true, false) else QV2X_FX(3, false, false, false)
+#undef QV2X_FX
     }
     // FP32 outputs live in the generic epilogue only; a shortcut has a saturating fast variant for one input group
     const bool sat8 = (d.out_bits == 8 && d.out_zero_point == 0.f && d.relu) && !f32_out;
@@ -493,19 +532,18 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
     {                                                                            \
         RequantEpilogue<GG, DG, F8> e{};                                         \
         fill(e);                                                                 \
-        if (halo) return dispatch_igemm_halo<GG>(L->bk, tmA, tmB, g, e, hp, stream); \
-        return dispatch_igemm<GG>(block_n, L->bk, tmA, tmB, g, e, stream);       \
+        return run_layer(ctx, e);                                                \
     }
     if (L->groups == 1) {
         if (sat8 && has_res) {
             RequantEpilogue<1, false, true, true> e{};
             fill(e);
-            if (halo) return dispatch_igemm_halo<1>(L->bk, tmA, tmB, g, e, hp, stream);
-            return dispatch_igemm<1>(block_n, L->bk, tmA, tmB, g, e, stream);
+            return run_layer(ctx, e);
         }
         QV2X_RUN(1, false, false)
     }
     if (digits) QV2X_RUN(3, true, false)
+    if (sat8 && !has_res) QV2X_RUN(3, false, true)
     QV2X_RUN(3, false, false)
 #undef QV2X_RUN
 }

@@ -47,12 +47,17 @@ __global__ void __launch_bounds__(384, 1) ld_kernel(int iters, int mma_on, int n
         if (mma_on && elect_one()) {
             const uint64_t ad = umma_smem_desc(smem_u32(smem), 128);
             const uint64_t bd = umma_smem_desc(smem_u32(smem) + 32 * 1024, 128);
+            const unsigned long long m0 = clock64();
+            unsigned long long n_mma = 0;
             while (*stop < n_readers) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) umma_i8(tmem_base + 256, ad + 2 * (k & 3), bd + 2 * (k & 3), idesc, 1);
+                n_mma += 16;
             }
             umma_commit(smem_u32(&bars[0]));
             mbar_wait(smem_u32(&bars[0]), 0);
+            stats[148 * 8 + blockIdx.x * 2] = clock64() - m0;
+            stats[148 * 8 + blockIdx.x * 2 + 1] = n_mma;
         }
     } else if (warp >= 4 && warp < 4 + n_readers) {
         const int quad = warp & 3;
@@ -61,7 +66,14 @@ __global__ void __launch_bounds__(384, 1) ld_kernel(int iters, int mma_on, int n
         __syncwarp();
         const unsigned long long c0 = clock64();
         for (int it = 0; it < iters; ++it) {
-            if constexpr (MODE <= 2) {
+            if constexpr (MODE == 5) {
+                // shared-memory pressure instead of TMEM loads: 64 x LDS.128 (different rows per lane: 512 B per instruction)
+#pragma unroll 8
+                for (int c = 0; c < 64; ++c) {
+                    const int4 v = lds_i4(smem_u32(smem) + 64 * 1024 + ((c * 512 + lane * 16) & 16383));
+                    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+                }
+            } else if constexpr (MODE <= 2) {
                 constexpr int FL = MODE == 0 ? 1 : (MODE == 1 ? 2 : 4);
                 uint32_t r[FL][16];
 #pragma unroll
@@ -113,34 +125,34 @@ static void run(const char* name, int mma_n, int n_readers) {
     cudaFuncSetAttribute(ld_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     unsigned long long* d_stats;
     uint32_t* d_sink;
-    cudaMalloc(&d_stats, 148 * 8 * 8);
+    cudaMalloc(&d_stats, 148 * 10 * 8);
+    cudaMemset(d_stats, 0, 148 * 10 * 8);
     cudaMalloc(&d_sink, 148 * 384 * 4);
     for (int rep = 0; rep < 2; ++rep) {
         ld_kernel<MODE><<<148, 384, smem_bytes>>>(iters, mma_n != 0, n_readers, idesc, d_stats, d_sink);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CUDA error: %s\n", cudaGetErrorString(e)); exit(1); }
     }
-    std::vector<unsigned long long> st(148 * 8);
+    std::vector<unsigned long long> st(148 * 10);
     cudaMemcpy(st.data(), d_stats, st.size() * 8, cudaMemcpyDeviceToHost);
     double cyc = 0;
     for (int b = 0; b < 148; ++b)
         for (int w = 0; w < n_readers; ++w) cyc += st[b * 8 + w];
     cyc /= 148.0 * n_readers;
     const double bytes_sm = static_cast<double>(iters) * 128 * 32 * 4 * n_readers;     // per SM
-    printf("%-28s mma N=%3d readers=%d: %7.1f cyc per 128-col sweep per warp, %6.1f B/clk/SM\n", name, mma_n, n_readers,
-           cyc / iters, bytes_sm / cyc);
+    double mc = 0, mn = 0;
+    for (int b = 0; b < 148; ++b) mc += st[148 * 8 + 2 * b], mn += st[148 * 8 + 2 * b + 1];
+    printf("%-28s mma N=%3d readers=%d: %7.1f cyc per 128-col sweep per warp, %6.1f B/clk/SM   MMA: %6.1f cyc each\n", name,
+           mma_n, n_readers, cyc / iters, bytes_sm / cyc, mn > 0 ? mc / mn : 0.0);
     cudaFree(d_stats);
     cudaFree(d_sink);
 }
 
 int main() {
-    for (int mma_n : {0, 128, 256})
-        for (int nr : {4, 8}) {
+    for (int mma_n : {64, 128, 256})
+        for (int nr : {1, 8}) {
             run<0>("x16, 1 in flight", mma_n, nr);
-            run<1>("x16, 2 in flight", mma_n, nr);
-            run<2>("x16, 4 in flight", mma_n, nr);
-            run<3>("x32, 1 in flight", mma_n, nr);
-            run<4>("x32, 2 in flight", mma_n, nr);
+            run<5>("LDS.128 x64 per sweep", mma_n, nr);
         }
     return 0;
 }
