@@ -59,6 +59,8 @@ void qv2x_debug_trace(long long* d_buf);
 typedef struct qv2x_layer qv2x_layer;
 
 typedef struct {
+    uint32_t struct_size;/* = sizeof(qv2x_layer_desc): a caller built against another revision of this header is
+                            rejected instead of being read as garbage (same first field in every descriptor) */
     int kind;            /* 0: nn.Conv2d, 1: nn.ConvTranspose2d with kernel_size == stride, padding 0 */
     int cin, cout;
     int ksize;           /* conv: 1 or 3; transposed conv: == stride */
@@ -106,6 +108,7 @@ int qv2x_layer_forward(const qv2x_layer* layer, int n_img, int hi, int wi, const
  *     written as FP32 NHWC with row pitch out_f32_cstride; d_y may be NULL and d_rowsum_out must be.
  * extra == NULL is qv2x_layer_forward. */
 typedef struct {
+    uint32_t struct_size;          /* = sizeof(qv2x_layer_extra) */
     const uint8_t* d_res_u8;
     const float* d_res_f32;
     float res_delta;
@@ -132,6 +135,7 @@ int qv2x_rowsum_u8(const uint8_t* d_x, long long n_pixels, int cstride, int cbas
 typedef struct qv2x_codebook qv2x_codebook;
 
 typedef struct {
+    uint32_t struct_size;/* = sizeof(qv2x_codebook_desc) */
     int channel;         /* C: feature channels (256 on the V2X-Real path) */
     int m;               /* seg_num: codebooks per level, each over C/m channels */
     int levels;          /* len(dict_size) residual levels (3 in the reference models) */
@@ -221,6 +225,7 @@ int qv2x_heads_forward_tile(const qv2x_heads* heads, long long pixels, const flo
  * ---------------------------------------------------------------------------------------------- */
 typedef struct qv2x_pillar qv2x_pillar;
 typedef struct {
+    uint32_t struct_size;  /* = sizeof(qv2x_pillar_desc) */
     int n_feat;            /* decorated point features: 10 (use_absolute_xyz, no distance) */
     int cout;              /* PFN output channels: 64 */
     int max_points;        /* points per pillar: 32 */
@@ -253,6 +258,7 @@ int qv2x_pillar_forward(const qv2x_pillar* p, int n_pillars, const float* d_poin
  * ---------------------------------------------------------------------------------------------- */
 typedef struct qv2x_postprocess qv2x_postprocess;
 typedef struct {
+    uint32_t struct_size;           /* = sizeof(qv2x_postprocess_desc) */
     int H, W;                       /* head-map size */
     int n_classes, n_rotations;     /* anchors per cell = n_classes * n_rotations */
     double anchor_x0[4], anchor_y0[4], anchor_dx[4], anchor_dy[4], anchor_z[4];

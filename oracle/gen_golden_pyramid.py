@@ -230,6 +230,11 @@ def gen_backbone():
         assert float((codes * d - feat_rec[li]).abs().max()) < 1e-4 * d
         out[f"l{li}.codes"] = codes.numpy().astype(np.uint8)
         out[f"l{li}.occ"] = occ_list[li].numpy().astype(np.float32)
+        # single_head_i is wrapped WITH an active output quantizer (quant_block.py:474-478): its logits are on a grid
+        hq = getattr(q, f"single_head_{li}").act_quantizer
+        out[f"head{li}.act_delta"] = np.float32(float(hq.delta))
+        out[f"head{li}.act_zp"] = np.float32(float(hq.zero_point))
+        out[f"head{li}.act_bits"] = np.int32(int(hq.n_bits))
         out[f"l{li}.fused"] = fused_rec[li][0].numpy().astype(np.float32)
         # the deblock of this level: its 128 channels of the final [1, 384, H, W] feature, on its own grid
         aq = q.deblocks[li][0].act_quantizer

@@ -68,6 +68,9 @@ def backbone_collab(x, P, aff, layer_nums, q1_override=None):
         h = P[f"head{li}"]
         _, occ = int_oracle.conv_oracle(cur, h["w_int"], h["w_delta"], h["w_zp"], h["bias"], cur_delta, None,
                                         stride=1, pad=0, relu=False)
+        if "act_delta" in h:     # the head's own output quantizer (active in the reference, quant_block.py:474-478)
+            d, zp, qmax = f32(h["act_delta"]), f32(h["act_zp"]), f32(2 ** int(h["act_bits"]) - 1)
+            occ = ((np.clip(np.rint(occ / d) + zp, f32(0), qmax) - zp) * d).astype(f32)
         fused = fusion_oracle.weighted_fusion(cur.astype(f32) * cur_delta, occ[..., 0], aff)
         levels.append(dict(codes=cur, delta=cur_delta, occ=occ[..., 0], fused=fused))
     return levels, q1_first

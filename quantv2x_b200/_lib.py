@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # QV2X_LIB selects another build of the same library (the bring-up build with role traces, `make debug`)
@@ -19,10 +19,19 @@ class Qv2xError(RuntimeError):
     pass
 
 
-class LayerDesc(ctypes.Structure):
+class _SizedStructure(ctypes.Structure):
+    """Descriptors start with `struct_size` = sizeof(struct): the library rejects a mirror whose layout differs."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        self.struct_size = ctypes.sizeof(type(self))
+
+
+class LayerDesc(_SizedStructure):
     """Mirror of qv2x_layer_desc (include/qv2x.h)."""
 
     _fields_ = [
+        ("struct_size", c_uint32),
         ("kind", c_int),
         ("cin", c_int),
         ("cout", c_int),
@@ -40,10 +49,11 @@ class LayerDesc(ctypes.Structure):
     ]
 
 
-class LayerExtra(ctypes.Structure):
+class LayerExtra(_SizedStructure):
     """Mirror of qv2x_layer_extra (include/qv2x.h): shortcut input and FP32 output of residual-block convs."""
 
     _fields_ = [
+        ("struct_size", c_uint32),
         ("d_res_u8", c_void_p),
         ("d_res_f32", c_void_p),
         ("res_delta", c_float),
@@ -102,10 +112,10 @@ def exported_symbols():
     return sorted(set(re.findall(r"\b(qv2x_[a-z0-9_]+)\s*\(", text)))
 
 
-class PillarDesc(ctypes.Structure):
+class PillarDesc(_SizedStructure):
     """Mirror of qv2x_pillar_desc (include/qv2x.h)."""
 
-    _fields_ = [("n_feat", c_int), ("cout", c_int), ("max_points", c_int), ("nx", c_int), ("ny", c_int),
+    _fields_ = [("struct_size", c_uint32), ("n_feat", c_int), ("cout", c_int), ("max_points", c_int), ("nx", c_int), ("ny", c_int),
                 ("voxel_size", c_float * 3), ("offset", c_float * 3), ("has_pre_quant", c_int),
                 ("pre_delta", c_float), ("pre_zero_point", c_float), ("pre_bits", c_int),
                 ("out_delta", c_float), ("out_zero_point", c_float), ("out_bits", c_int)]
@@ -118,10 +128,10 @@ def _declare_pillar(lib):
     lib.qv2x_pillar_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
 
 
-class PostprocessDesc(ctypes.Structure):
+class PostprocessDesc(_SizedStructure):
     """Mirror of qv2x_postprocess_desc (include/qv2x.h)."""
 
-    _fields_ = [("H", c_int), ("W", c_int), ("n_classes", c_int), ("n_rotations", c_int),
+    _fields_ = [("struct_size", c_uint32), ("H", c_int), ("W", c_int), ("n_classes", c_int), ("n_rotations", c_int),
                 ("anchor_x0", ctypes.c_double * 4), ("anchor_y0", ctypes.c_double * 4),
                 ("anchor_dx", ctypes.c_double * 4), ("anchor_dy", ctypes.c_double * 4),
                 ("anchor_z", ctypes.c_double * 4), ("anchor_hwl", (ctypes.c_double * 3) * 4),
@@ -137,10 +147,10 @@ def _declare_postprocess(lib):
     lib.qv2x_postprocess_forward.argtypes = [c_void_p] + [c_void_p] * 8
 
 
-class CodebookDesc(ctypes.Structure):
+class CodebookDesc(_SizedStructure):
     """Mirror of qv2x_codebook_desc (include/qv2x.h)."""
 
-    _fields_ = [("channel", c_int), ("m", c_int), ("levels", c_int), ("k", c_int * 4)]
+    _fields_ = [("struct_size", c_uint32), ("channel", c_int), ("m", c_int), ("levels", c_int), ("k", c_int * 4)]
 
 
 def _declare_codebook(lib):

@@ -92,6 +92,7 @@ class UMGMQuantizer(nn.Module):
         self._encoders = nn.ModuleList(encoders)
         self._decoders = nn.ModuleList(decoders)
         self._engine = None
+        self._input_scale = None      # scale of the uint8 grid the input features lie on (set_input_scale)
 
     @property
     def Codebooks(self):
@@ -124,13 +125,50 @@ class UMGMQuantizer(nn.Module):
         """Call after changing parameters (e.g. load_state_dict)."""
         self._engine = None
 
+    def set_input_scale(self, delta: float | None):
+        """Scale of the uint8 grid the encoder's input lies on (the shrinker's act_quantizer.delta).  Set by
+        attach_engines, so that the reference's one-argument call ``codebook.encode(flattened)`` works unchanged."""
+        self._input_scale = None if delta is None else float(delta)
+
+    @staticmethod
+    def _recover_grid_scale(x: torch.Tensor) -> float:
+        """delta such that x = delta * q with q integer in [0, 255], recovered from on-grid float features: the
+        smallest positive value is q_min * delta for some q_min in 1..255; the largest candidate that puts every
+        element on an integer wins."""
+        xf = x.detach().float()
+        pos = xf[xf > 0]
+        if pos.numel() == 0:
+            return 1.0
+        if bool((xf < 0).any()):
+            raise ValueError("features are negative: not a post-ReLU uint8 grid; pass `delta` explicitly")
+        v_min, v_max = float(pos.min()), float(pos.max())
+        sample = xf.flatten()[:: max(1, xf.numel() // 65536)]
+        for k in range(1, 256):
+            d = v_min / k
+            if v_max / d > 255.5:
+                continue
+            q = sample / d
+            if float((q - torch.round(q)).abs().max()) <= 2e-3:
+                q_all = xf / d
+                if float((q_all - torch.round(q_all)).abs().max()) <= 2e-3:
+                    return d
+        raise ValueError("features do not lie on a uint8 grid: quantize them first or pass `delta`")
+
     # ------------------------------------------------------------------ reference interface
     def encode(self, x: torch.Tensor, delta: float | None = None) -> List[torch.Tensor]:
-        """x: [n, C].  Either uint8 activation codes with their scale `delta` (the quantized path: the
-        shrinker's output never leaves the integer domain), or float32 values lying on a uint8 grid
-        together with `delta`.  Returns the reference's structure: a list (levels) of LongTensor [n, m]."""
+        """x: [n, C] -> list (levels) of LongTensor [n, m], the reference's signature and structure
+        (opencood/models/sub_modules/codebook.py:330-337).
+
+        The GPU encoder consumes uint8 activation codes and their scale.  ``x`` may be those codes (then ``delta``,
+        or the scale registered with ``set_input_scale``, is required), or float32 features lying on a uint8 grid --
+        what the quantized shrinker emits -- in which case the scale is taken from ``delta``, else from
+        ``set_input_scale`` (attach_engines registers it), else recovered exactly from the values."""
         if delta is None:
-            raise ValueError("encode() needs the activation scale `delta` of the (uint8-grid) features")
+            delta = self._input_scale
+        if delta is None:
+            if x.dtype == torch.uint8:
+                raise ValueError("encode() of uint8 codes needs their scale: pass `delta` or call set_input_scale()")
+            delta = self._recover_grid_scale(x)
         if x.dtype != torch.uint8:
             q = torch.round(x / delta)
             if not torch.equal(q * delta, x.to(q.dtype)) and (q * delta - x).abs().max() > 1e-4 * delta:

@@ -578,6 +578,7 @@ void qv2x_codebook_destroy(qv2x_codebook* cb) {
 int qv2x_codebook_create(const qv2x_codebook_desc* desc, const float* const* codebooks, const float* const* weights,
                          const float* const* biases, qv2x_codebook** out) {
     QV2X_REQUIRE(desc && codebooks && weights && biases && out, "qv2x_codebook_create: null argument");
+    QV2X_CHECK_SIZE(desc, qv2x_codebook_desc);
     const int C = desc->channel, m = desc->m, L = desc->levels;
     QV2X_REQUIRE(L >= 1 && L <= kMaxLevels, "levels must be 1..%d", kMaxLevels);
     QV2X_REQUIRE(m >= 1 && m <= kMaxSeg && C % m == 0, "m must be 1..%d and divide channel", kMaxSeg);

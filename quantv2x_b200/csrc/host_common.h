@@ -29,6 +29,12 @@ int num_sms();
                                      __FILE__, __LINE__);                                             \
     } while (0)
 
+// Descriptors carry their own size as first field (include/qv2x.h): reject callers built against another layout.
+#define QV2X_CHECK_SIZE(ptr, type)                                                                              \
+    QV2X_REQUIRE((ptr)->struct_size == sizeof(type), #type ".struct_size is %u, this library expects %zu "     \
+                 "(set it to sizeof(" #type "); the caller was built against another revision of qv2x.h)",       \
+                 (ptr)->struct_size, sizeof(type))
+
 #define QV2X_REQUIRE(cond, ...)                                                  \
     do {                                                                         \
         if (!(cond)) return ::qv2x::set_error(QV2X_ERR_INVALID, __VA_ARGS__);    \

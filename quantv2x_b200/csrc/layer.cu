@@ -75,6 +75,7 @@ extern "C" {
 int qv2x_layer_create(const qv2x_layer_desc* desc, const uint8_t* w_int, const float* w_delta,
                       const float* w_zero_point, const float* bias, qv2x_layer** out) {
     QV2X_REQUIRE(desc && w_int && w_delta && w_zero_point && out, "qv2x_layer_create: null argument");
+    QV2X_CHECK_SIZE(desc, qv2x_layer_desc);
     const qv2x_layer_desc& d = *desc;
     QV2X_REQUIRE(d.kind == 0 || d.kind == 1, "kind must be 0 (conv) or 1 (transposed conv)");
     QV2X_REQUIRE(d.w_bits >= 2 && d.w_bits <= 8 && d.out_bits >= 2 && d.out_bits <= 8, "bit widths must be 2..8");
@@ -273,6 +274,7 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
     const bool has_res = ex && (ex->d_res_u8 || ex->d_res_f32);
     QV2X_REQUIRE(d_y || f32_out, "qv2x_layer_forward: null output");
     if (ex) {
+        QV2X_CHECK_SIZE(ex, qv2x_layer_extra);
         QV2X_REQUIRE(!(ex->d_res_u8 && ex->d_res_f32), "one shortcut at most");
         QV2X_REQUIRE(!ex->d_res_u8 || (ex->res_cstride % 4 == 0 && ex->res_cbase % 4 == 0 && ex->res_delta > 0.f &&
                                        (reinterpret_cast<uintptr_t>(ex->d_res_u8) & 3) == 0),

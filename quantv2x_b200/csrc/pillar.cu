@@ -128,6 +128,7 @@ extern "C" {
 
 int qv2x_pillar_create(const qv2x_pillar_desc* desc, const float* w_hat, const float* bias, qv2x_pillar** out) {
     QV2X_REQUIRE(desc && w_hat && out, "qv2x_pillar_create: null argument");
+    QV2X_CHECK_SIZE(desc, qv2x_pillar_desc);
     QV2X_REQUIRE(desc->n_feat == kPillarFeat && desc->cout == kPillarOut && desc->max_points == kPillarPoints,
                  "the pillar kernel is built for 10 decorated features -> 64 channels over 32 points (got %d -> %d, %d)",
                  desc->n_feat, desc->cout, desc->max_points);

@@ -223,6 +223,7 @@ extern "C" {
 
 int qv2x_postprocess_create(const qv2x_postprocess_desc* d, qv2x_postprocess** out) {
     QV2X_REQUIRE(d && out, "qv2x_postprocess_create: null argument");
+    QV2X_CHECK_SIZE(d, qv2x_postprocess_desc);
     QV2X_REQUIRE(d->n_classes >= 1 && d->n_classes <= kPPMaxClasses && d->n_rotations >= 1 &&
                      d->n_rotations <= kPPMaxRot, "1..%d classes, 1..%d rotations", kPPMaxClasses, kPPMaxRot);
     QV2X_REQUIRE(d->H > 0 && d->W > 0 && d->max_candidates >= 1 && d->top >= 1 && d->top <= kPPTop,

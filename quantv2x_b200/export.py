@@ -32,7 +32,11 @@ def qlayer_from_module(qm: QuantModule, in_delta, extra_pad: int = 0) -> E.QLaye
         raise ValueError("quantizers are not calibrated")
     if qm.disable_act_quant:
         raise ValueError("layer has no output quantizer; it does not belong to the integer path")
-    relu = isinstance(qm.activation_function, (nn.ReLU,))
+    act = qm.activation_function
+    relu = isinstance(act, nn.ReLU)
+    if not relu and not isinstance(act, (StraightThrough, nn.Identity)):
+        # QuantModel also fuses nn.ReLU6 (quant_model.py:50); the integer epilogue implements ReLU or nothing
+        raise NotImplementedError(f"activation {type(act).__name__} has no integer epilogue (ReLU or identity only)")
     out_zp = _scalar(qm.act_quantizer.zero_point)
     if out_zp != 0.0:
         raise ValueError(f"activation zero-point {out_zp} != 0: the integer path needs post-ReLU activations")
@@ -216,6 +220,16 @@ def attach_engines(qmodel, bev_delta: float | None = None, device=None):
 
     model = qmodel.model
     device = device or torch.device("cuda", torch.cuda.current_device())
+    if getattr(model, "shrink_flag", False):
+        # reference heter_baseline_collab_codebook_mc.py:156-157 applies shrink_conv between fusion and the heads;
+        # the ego stage here goes fuse -> heads, so such a config would silently give other predictions
+        raise NotImplementedError("a top-level `shrink_header` (post-fusion shrink_conv) is not on the B200 path; "
+                                  "the shipped V2X-Real configs do not use it")
+    if model.fusion_method == "att":
+        fd = model.args["att"]["feat_dim"]
+        if int(fd) != int(model.channel):
+            raise NotImplementedError(f"AttFusion feat_dim {fd} != feature channels {model.channel}: the fused kernel "
+                                      "scales scores by sqrt(C) (reference fusion_in_one.py:14-45 uses sqrt(feat_dim))")
     for name in model.modality_name_list:
         enc = getattr(model, f"encoder_{name}")
         bb, sh = getattr(model, f"backbone_{name}"), getattr(model, f"shrinker_{name}")
@@ -234,6 +248,7 @@ def attach_engines(qmodel, bev_delta: float | None = None, device=None):
                               heads_from_quant_modules(model.cls_head, model.reg_head, model.dir_head),
                               model.fusion_method, (H, W), device)
         pipe.bev_delta = d_in
+        model.codebook.set_input_scale(engines["out_delta"])   # reference call shape: codebook.encode(flattened)
         # pillar-level input: the PFN + scatter kernel, when the encoder is quantized, calibrated, and its output
         # grid is the one the backbone engine was built for
         if isinstance(enc, QuantPointPillar):

@@ -184,7 +184,17 @@ def heads_from_quant_modules(cls_head, reg_head, dir_head) -> E.HeadsEngine:
     """Concatenate the three 1x1 head QuantModules (act-quant disabled) into one FP32 GEMM with the
     de-quantized fake-quant weights the reference would use (quant_layer.py:392-398)."""
     ws, bs = [], []
-    for qm in (cls_head, reg_head, dir_head):
+    for nm, qm in (("cls_head", cls_head), ("reg_head", reg_head), ("dir_head", dir_head)):
+        if not hasattr(qm, "weight_quantizer"):
+            raise NotImplementedError(f"{nm} is not a QuantModule (listed in skip_quant_module_names?): the heads "
+                                      "engine takes the fake-quant weights of wrapped heads")
+        if not qm.disable_act_quant and qm.use_act_quant:
+            raise NotImplementedError(f"{nm} keeps an output quantizer (disable_output_head_quantization: false); "
+                                      "call QuantModel.disable_network_output_quantization() -- the heads kernel "
+                                      "writes FP32 predictions (reference quant_model.py:129-136)")
+        if not isinstance(qm.activation_function, (torch.nn.Identity, type(None))) and \
+                type(qm.activation_function).__name__ not in ("StraightThrough", "Identity"):
+            raise NotImplementedError(f"{nm} has a fused activation {type(qm.activation_function).__name__}")
         with torch.no_grad():
             w = qm.weight_quantizer(qm.weight) if qm.use_weight_quant else qm.org_weight
             b = qm.bias if qm.use_weight_quant else qm.org_bias

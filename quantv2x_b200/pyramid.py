@@ -7,7 +7,8 @@
   quantizer) and is that shortcut.  Activations stay uint8 NHWC; per-pixel code sums travel with them so no layer
   re-reads its input to correct for the weight zero-points.
 * ``BasicBlockEngine`` -- ``QuantBasicBlock`` (two 3x3 convs; the agent-side ResNetBEVBackbone of the pyramid models).
-* ``OccupancyHead`` -- ``single_head_i`` (1x1 conv to one channel, no quantizer; quant_block.py:474-478).
+* ``OccupancyHead`` -- ``single_head_i`` (1x1 conv to one channel; its output quantizer, active in the reference
+  (quant_block.py:474-478), is applied to the FP32 logits).
 * ``weighted_fuse_level`` -- score-weighted fusion of one level from codes + occupancy logits.
 
 * ``FirstBottleneckEngine`` -- the block that reads the FP32 (off-grid) decoded features: its first 1x1 conv is an
@@ -175,7 +176,9 @@ class OccupancyHead:
     (quant_block.py:474-478, 516-520).  The one real output channel is padded to the 64-column tile of the GEMM
     (columns 1..63 carry the weight zero-point, i.e. zero weights)."""
 
-    def __init__(self, w_int, w_delta, w_zp, bias, in_delta, w_bits=8):
+    def __init__(self, w_int, w_delta, w_zp, bias, in_delta, w_bits=8, act=None):
+        # act = (delta, zero_point, n_bits) of the head's own output quantizer, or None when it is disabled
+        self.act = None if act is None else (float(act[0]), float(act[1]), int(act[2]))
         w_int = np.asarray(w_int, np.uint8)
         c = w_int.shape[1]
         wp = np.full((64, c, 1, 1), int(np.asarray(w_zp).reshape(-1)[0]), np.uint8)
@@ -193,7 +196,13 @@ class OccupancyHead:
         n, h, w, _ = x.shape
         buf = torch.empty((n, h, w, 64), dtype=torch.float32, device=x.device)
         self.layer.forward(x, rowsum_in=None if rowsum is None else [rowsum], out_f32=buf)
-        return buf[..., 0].contiguous()
+        occ = buf[..., 0].contiguous()
+        if self.act is not None:
+            # UniformAffineQuantizer.forward (quant_layer.py:132-148) on the one-channel logit map: true division,
+            # round half to even, clamp, de-quantize
+            d, zp, bits = self.act
+            occ = (torch.clamp(torch.round(occ / d) + zp, 0, float(2 ** bits - 1)) - zp) * d
+        return occ
 
 
 def weighted_fuse_level(codes: torch.Tensor, delta: float, occ: torch.Tensor, affine) -> torch.Tensor:
@@ -255,7 +264,8 @@ class PyramidBackboneEngine:
             self.stages.append(blocks)
             self.deltas.append(delta)
             h = params[f"head{li}"]
-            self.heads.append(OccupancyHead(h["w_int"], h["w_delta"], h["w_zp"], h.get("bias"), delta))
+            act = (h["act_delta"], h["act_zp"], h["act_bits"]) if "act_delta" in h else None
+            self.heads.append(OccupancyHead(h["w_int"], h["w_delta"], h["w_zp"], h.get("bias"), delta, act=act))
         self.deblocks = [DeblockF32(params[f"up{li}"]) for li in range(len(layer_nums)) if f"up{li}" in params]
         self.up_deltas = [d.delta for d in self.deblocks]
 

@@ -48,14 +48,36 @@ class BaseQuantBlock(nn.Module):
         return all(m.weight_quantizer.inited and m.act_quantizer.inited and m.use_weight_quant and m.use_act_quant
                    for m in self.quant_modules())
 
+    def _fingerprint(self):
+        """Identity + in-place version of every tensor an exported engine was built from (weights, biases, quantizer
+        scales / zero-points, bit widths): re-calibration, bitwidth_refactor, load_state_dict or an optimizer step
+        change it.  No device synchronisation."""
+        fp = []
+        for m in self.quant_modules():
+            for t in (m.weight, m.bias, m.weight_quantizer.delta, m.weight_quantizer.zero_point,
+                      m.act_quantizer.delta, m.act_quantizer.zero_point):
+                fp.append((id(t), t._version) if isinstance(t, torch.Tensor) else repr(t))
+            fp.append((m.weight_quantizer.n_bits, m.act_quantizer.n_bits, type(m.weight_quantizer).__name__))
+        return tuple(fp)
+
     def attach_engine(self, engine):
         self._engine = engine
+        self._engine_fp = None if engine is None else self._fingerprint()
 
-    def _run_engine(self, x):
+    def _check_engine(self):
         if self._engine is None:
             raise RuntimeError(
                 f"{type(self).__name__}: quantized inference requested but no libqv2x engine is attached; call "
                 "quantv2x_b200.export.attach_engines(model) after calibration (there is no CPU fallback)")
+        if getattr(self, "_engine_fp", None) is not None and self._engine_fp != self._fingerprint():
+            self._engine = None
+            raise RuntimeError(
+                f"{type(self).__name__}: parameters or quantizer state changed after the libqv2x engine was built "
+                "(re-calibration / bitwidth_refactor / load_state_dict); the stale engine was dropped -- call "
+                "attach_engines(model) again")
+
+    def _run_engine(self, x):
+        self._check_engine()
         return self._engine.forward_nchw(x)
 
 
@@ -318,7 +340,13 @@ class QuantPyramidFusion(BaseQuantBlock):
         for li in range(self.num_levels):
             for bi, blk in enumerate(getattr(self.resnet, f"layer{li}")):
                 P[f"l{li}.b{bi}"] = blk.export_params()
-            P[f"head{li}"] = _conv_params(getattr(self, f"single_head_{li}"))
+            head = getattr(self, f"single_head_{li}")
+            P[f"head{li}"] = _conv_params(head)
+            if not head.disable_act_quant:
+                # the reference wraps single_head_i with an ACTIVE output quantizer (quant_block.py:474-478 builds
+                # QuantModule(single_head_i, wq, aq)): the logits reach sigmoid / weighted_fuse fake-quantized
+                aq = head.act_quantizer
+                P[f"head{li}"].update(act_delta=float(aq.delta), act_zp=float(aq.zero_point), act_bits=int(aq.n_bits))
             if len(self.deblocks) > 0:
                 qm = self.deblocks[li][0]
                 up = _conv_params(qm)

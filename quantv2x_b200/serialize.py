@@ -68,9 +68,14 @@ def pipeline_state(pipe) -> tuple[dict, dict]:
     return arrays, meta
 
 
+def _npz_path(path: str) -> str:
+    """np.savez appends '.npz' to other names: save and load agree on the same normalised path."""
+    return path if str(path).endswith(".npz") else str(path) + ".npz"
+
+
 def save_pipeline(pipe, path: str) -> None:
     arrays, meta = pipeline_state(pipe)
-    np.savez(path, __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
+    np.savez(_npz_path(path), __meta__=np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8), **arrays)
 
 
 def load_pipeline(path: str, device):
@@ -79,7 +84,7 @@ def load_pipeline(path: str, device):
     from .export import BlockEngine
     from .pipeline import CollabPipeline
 
-    z = np.load(path)
+    z = np.load(_npz_path(path))
     meta = json.loads(bytes(z["__meta__"]).decode())
     if meta.get("format") != FORMAT_VERSION:
         raise ValueError(f"unsupported engine file format {meta.get('format')}")
@@ -125,6 +130,8 @@ def pack_codes(codes: np.ndarray, k: int) -> bytes:
     header (24 bytes, little endian): magic 'QV2X', version u16, bits u16, levels u16, m u16, k u32, rows u64."""
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
     levels, m, rows = codes.shape
+    if not 2 <= k <= 256:
+        raise ValueError(f"dictionary size {k} outside 2..256 (codes travel as bytes)")
     if codes.size and int(codes.max()) >= k:
         raise ValueError("code out of range")
     b = _bits(k)
@@ -142,15 +149,26 @@ def unpack_codes(msg: bytes) -> tuple[np.ndarray, int]:
     ver, b, levels, m, k, rows = struct.unpack("<HHHHIQ", msg[4:24])
     if ver != FORMAT_VERSION:
         raise ValueError(f"unsupported wire format {ver}")
+    # the message comes from another agent: never trust its header
+    if not 2 <= k <= 256 or not 1 <= b <= 8 or b != _bits(k):
+        raise ValueError(f"inconsistent header: k={k}, {b} bits per code")
+    if levels < 1 or m < 1:
+        raise ValueError("inconsistent header: no planes")
     n = levels * m * rows
     body = np.frombuffer(msg, dtype=np.uint8, offset=24)
     if b == 8:
         if body.size != n:
             raise ValueError("truncated message")
-        return body.reshape(levels, m, rows).copy(), k
+        out = body.reshape(levels, m, rows).copy()
+        if out.size and int(out.max()) >= k:
+            raise ValueError("code out of range in message")
+        return out, k
     if body.size != (n * b + 7) // 8:
         raise ValueError("truncated message")
     bits = np.unpackbits(body)[:n * b].reshape(n, b)
     full = np.zeros((n, 8), np.uint8)
     full[:, 8 - b:] = bits
-    return np.packbits(full, axis=1).reshape(levels, m, rows), k
+    out = np.packbits(full, axis=1).reshape(levels, m, rows)
+    if out.size and int(out.max()) >= k:
+        raise ValueError("code out of range in message")
+    return out, k

@@ -165,7 +165,10 @@ def test_quant_pyramid_fusion_module_on_engine(cuda_device):
         dd = np.abs(a - b)
         assert dd.max() <= 3 and (dd > 0).mean() < 5e-2 and (dd > 1).mean() < 2e-3, (li, dd.max(), (dd > 0).mean())
         assert tuple(occ_g[li].shape) == tuple(occ[li].shape)
-        np.testing.assert_allclose(occ_g[li].cpu().numpy(), occ[li].numpy(), atol=2e-2 * float(occ[li].abs().max()))
+        # the head's own quantizer is active (as in the reference): both maps lie on its grid, whole steps apart at most
+        hd = float(getattr(q, f"single_head_{li}").act_quantizer.delta)
+        steps = np.abs(occ_g[li].cpu().numpy() - occ[li].numpy()) / hd
+        assert steps.max() <= 2.001 and (steps > 0.5).mean() < 0.12, (li, steps.max(), (steps > 0.5).mean())
 
 
 @pytest.mark.parametrize("idx", [0, 1], ids=["basic_identity", "basic_down_s2"])
