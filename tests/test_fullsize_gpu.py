@@ -31,7 +31,7 @@ def test_one_agent_at_200x704_against_the_integer_oracle(cuda_device):
     feat = pipe.encode_buffers(1)["feat"].cpu().numpy()
     assert feat.shape == (1, 100, 352, 256)
 
-    spec = export_spec(q.cpu(), bev_delta)
+    spec = export_spec(q, bev_delta)
     bev_np = bev.cpu().numpy()
     assert 0.03 < (bev_np.max(-1) > 0).mean() < 0.06, "BEV occupancy is not the 6000-pillar frame"
     _, feat_ref = int_oracle.backbone_chain(spec, bev_np)
