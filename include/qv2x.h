@@ -323,6 +323,13 @@ int qv2x_plan_forward(const qv2x_plan* plan, int n_img, int H, int W, const uint
 /* Copy of the descriptor a layer was created with. */
 int qv2x_layer_desc_get(const qv2x_layer* layer, qv2x_layer_desc* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Measurement aid: the raw tcgen05.mma kind::i8 rate of the device (dense int8 TOP/s, operands resident in shared
+ * memory, one CTA per SM) and the SM clock seen while it ran.  The denominator of the conv kernels' roofline.
+ * Synchronises `stream`.
+ * ---------------------------------------------------------------------------------------------- */
+int qv2x_int8_mma_peak(double* tops, double* sm_mhz, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -148,6 +148,40 @@ def ego_forward(spec, codes, n, h, w, aff):
 
 
 @torch.no_grad()
+def pillar_forward(ps, voxel_features, voxel_coords, voxel_num_points, batch):
+    """The quantized PointPillars front end as the reference runs it, in torch FP32 (QuantPillarVFE.forward
+    quant_block.py:666-716, QuantPFNLayer.forward :611-630, PointPillarScatter.forward point_pillar_scatter.py:19-75):
+    decoration, Linear with fake-quant weights, its own activation quantizer, ReLU, the block quantizer, max over the
+    points, scatter into a dense map.  ps = quantv2x_b200.export.pillar_spec(...).  Returns uint8 codes [batch, ny, nx, 64]."""
+    vf = torch.from_numpy(np.asarray(voxel_features, np.float32))
+    vc = torch.from_numpy(np.asarray(voxel_coords).astype(np.int64))
+    n = torch.from_numpy(np.asarray(voxel_num_points).astype(np.int64))
+    mean = vf[:, :, :3].sum(1, keepdim=True) / n.view(-1, 1, 1).float()
+    vs, off = ps["voxel_size"], ps["offset"]
+    centre = torch.stack([vc[:, 3].float() * vs[0] + off[0], vc[:, 2].float() * vs[1] + off[1],
+                          vc[:, 1].float() * vs[2] + off[2]], 1).unsqueeze(1)
+    f = torch.cat([vf, vf[:, :, :3] - mean, vf[:, :, :3] - centre], -1)
+    f = f * (torch.arange(vf.shape[1]).view(1, -1) < n.view(-1, 1)).unsqueeze(-1).float()
+    y = F.linear(f, torch.from_numpy(ps["w_hat"]), None if ps["bias"] is None else torch.from_numpy(ps["bias"]))
+    if ps["pre_quant"] is not None:
+        y = _fq(y, *ps["pre_quant"])
+    y = torch.relu(y)
+    y = _fq(y, *ps["out_quant"])
+    y = y.max(1).values                                                # [M, 64]
+    d, z, _ = ps["out_quant"]
+    bev = torch.zeros((batch, ps["ny"], ps["nx"], y.shape[1]), dtype=torch.float32)
+    bev[vc[:, 0], vc[:, 2], vc[:, 3]] = y
+    return torch.round(bev / d + z).clamp(0, 255).to(torch.uint8).numpy()
+
+
+@torch.no_grad()
+def frame_from_pillars(spec, ps, voxel_features, voxel_coords, voxel_num_points, n, aff):
+    """One cooperative frame of n agents from pillars to head maps: the work bench.py's GPU arm does per step."""
+    bev = pillar_forward(ps, voxel_features, voxel_coords, voxel_num_points, n)
+    return frame_forward(spec, bev, aff)
+
+
+@torch.no_grad()
 def frame_forward(spec, bev_u8, aff):
     feat, codes = agent_forward(spec, bev_u8)
     n, _, h, w = feat.shape

@@ -191,6 +191,13 @@ class PlanStep(ctypes.Structure):
     _fields_ = [("layer", c_void_p), ("in_buf", c_int), ("in_cbase", c_int), ("out_buf", c_int), ("out_cbase", c_int)]
 
 
+def _declare_peak(lib):
+    lib.qv2x_int8_mma_peak.argtypes = [POINTER(ctypes.c_double), POINTER(ctypes.c_double), c_void_p]
+
+
+_DECLARERS.append(_declare_peak)
+
+
 def _declare_plan(lib):
     lib.qv2x_plan_create.argtypes = [POINTER(PlanStep), c_int, POINTER(c_int), c_int, POINTER(c_void_p)]
     lib.qv2x_plan_destroy.argtypes = [c_void_p]

@@ -415,6 +415,27 @@ class PostProcessEngine:
                 pass
             self._h = None
 
+    def alloc_outputs(self, device):
+        """Static output buffers for forward_into: (corners [top, 4, 2] f64, scores [top] f64, labels [top] i32,
+        boxes [top, 7] f64, counts [2] i32 = boxes kept / candidates above the threshold)."""
+        return (torch.empty((self.top, 4, 2), dtype=torch.float64, device=device),
+                torch.empty((self.top,), dtype=torch.float64, device=device),
+                torch.empty((self.top,), dtype=torch.int32, device=device),
+                torch.empty((self.top, 7), dtype=torch.float64, device=device),
+                torch.zeros((2,), dtype=torch.int32, device=device))
+
+    def forward_into(self, preds: torch.Tensor, outs) -> None:
+        """Asynchronous form (no host synchronisation, capturable in a CUDA graph): results go to `outs` from
+        alloc_outputs(); outs[4][0] holds the number of boxes."""
+        assert preds.is_cuda and preds.dtype == torch.float32 and preds.is_contiguous()
+        p = preds if preds.dim() == 2 else preds.reshape(-1, self.hw)
+        assert p.shape[1] == self.hw and p.shape[0] >= self.channels
+        corners, scores, labels, boxes, n = outs
+        check(_lib.lib().qv2x_postprocess_forward(self._h, c_void_p(p.data_ptr()), c_void_p(corners.data_ptr()),
+                                                  c_void_p(scores.data_ptr()), c_void_p(labels.data_ptr()),
+                                                  c_void_p(boxes.data_ptr()), c_void_p(n.data_ptr()),
+                                                  c_void_p(n.data_ptr() + 4), _stream_ptr()))
+
     def forward(self, preds: torch.Tensor):
         """preds float32 [>= cls + reg channels, H*W] (channel-major head maps, cls first then reg) ->
         (corners [K, 4, 2], scores [K], labels [K], boxes [K, 7]) float64 / int32 CUDA tensors in NMS pick order."""
