@@ -250,6 +250,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Programmatic dependent launch: the next layer's CTAs may move onto SMs as this grid frees them and run their
+    // own set-up (and weight loads) there; every role of THIS kernel waits for the previous layer to complete before
+    // it touches activations, row sums or output buffers (the producer first requests its resident weights).
+    grid_dep_launch_dependents();
+    if (!(HALO && BRES && warp == 0)) grid_dep_wait();
 
     const int total_tiles = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
     const int kblocks_per_group = (g.taps / TPS) * g.cblocks;   // pipeline stages per accumulator group
@@ -285,6 +290,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                     g.b_k_base[grp] + tap * g.b_k_tap_stride + cb * BK, g.b_row_base[grp] + ncol0);
                     }
         }
+        if constexpr (BRES) grid_dep_wait();       // the weights are on their way; activations need the previous layer
         // window stream cursor
         int a_t = blockIdx.x, a_gc = 0, a_x0 = 0, a_y0 = 0, a_img = 0;
         uint32_t sa = 0, aph = 0;

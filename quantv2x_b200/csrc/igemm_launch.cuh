@@ -2,6 +2,7 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "host_common.h"
 #include "igemm.cuh"
@@ -45,6 +46,23 @@ inline void choose_tile_box(int ho, int wo, int* tw, int* th) {
     }
 }
 
+// Launch with programmatic stream serialization (see grid_dep_* in ptx.cuh); QV2X_PDL=0 restores plain launches.
+template <class Kern, class... Args>
+inline cudaError_t launch_pdl(Kern kern, int grid, int threads, int smem_bytes, cudaStream_t stream, Args... args) {
+    static const int pdl = getenv("QV2X_PDL") ? atoi(getenv("QV2X_PDL")) : 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(grid));
+    cfg.blockDim = dim3(static_cast<unsigned>(threads));
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmGeom& g, const Epi& epi,
                         cudaStream_t stream) {
@@ -67,9 +85,8 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
     gg.tw_shift = 0;
     while ((1 << gg.tw_shift) < g.tw) ++gg.tw_shift;
     if ((1 << gg.tw_shift) != g.tw) return set_error(QV2X_ERR_INVALID, "tile width %d is not a power of two", g.tw);
-    kern<<<grid, igemm_threads<Epi, BLOCK_N>(), Cfg::kSmemBytes, stream>>>(tmA, tmB, gg, epi);
+    QV2X_CUDA_OK(launch_pdl(kern, grid, igemm_threads<Epi, BLOCK_N>(), Cfg::kSmemBytes, stream, tmA, tmB, gg, epi));
     g_launch_count.fetch_add(1);
-    QV2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -155,9 +172,8 @@ static int launch_igemm_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     const int total = g.n_img * g.tiles_y * g.tiles_x * g.n_tiles;
     int grid = std::min(total, num_sms());
     if (hp.resident) grid = grid / g.n_tiles * g.n_tiles;
-    kern<<<grid, igemm_threads<Epi, BLOCK_N>(), smem_bytes, stream>>>(tmA, tmB, gg, epi);
+    QV2X_CUDA_OK(launch_pdl(kern, grid, igemm_threads<Epi, BLOCK_N>(), smem_bytes, stream, tmA, tmB, gg, epi));
     g_launch_count.fetch_add(1);
-    QV2X_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -61,6 +61,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// launch_dependents: the next kernel of the stream (launched with programmatic stream serialization) may start placing
+// its CTAs on SMs this grid no longer occupies; grid_dep_wait: block until the preceding grid has completed and its
+// memory is visible.  Everything a kernel does before grid_dep_wait (barrier init, TMEM allocation, tensor-map
+// prefetch, loads of its own WEIGHTS) overlaps the predecessor's tail.
+__device__ __forceinline__ void grid_dep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- proxy fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
