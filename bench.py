@@ -306,8 +306,7 @@ def main():
     g_enc, codes_local = [None] * R, [None] * INFLIGHT
     for r in range(R):
         g_enc[r], codes_local[r % INFLIGHT] = pipe._capture(
-            lambda r=r: pipe.encode_agents(pillar.forward(*pil_pool[r], per, out=bev_slot[r % INFLIGHT]),
-                                           slot=r % INFLIGHT))
+            lambda r=r: pipe.encode_pillars(*pil_pool[r], per, slot=r % INFLIGHT, bev_out=bev_slot[r % INFLIGHT]))
     lc1 = _lib.lib().qv2x_launch_count()
     g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
     recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT

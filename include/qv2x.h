@@ -246,6 +246,10 @@ void qv2x_pillar_destroy(qv2x_pillar* p);
  * d_num_points int32 [n_pillars]; d_bev uint8 [batch][ny][nx][cout] is cleared and filled (empty cells = code 0). */
 int qv2x_pillar_forward(const qv2x_pillar* p, int n_pillars, const float* d_points, const int* d_coords,
                         const int* d_num_points, int batch, uint8_t* d_bev, void* stream);
+/* The same, also writing d_rowsum int32 [batch][ny][nx] = per-cell sum of the 64 codes (cleared, then filled): the
+ * input row sums qv2x_plan_forward_rs takes, so that the plan need not scan the (mostly empty) map again. */
+int qv2x_pillar_forward_rs(const qv2x_pillar* p, int n_pillars, const float* d_points, const int* d_coords,
+                           const int* d_num_points, int batch, uint8_t* d_bev, int32_t* d_rowsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Detection post-processing on the GPU: sigmoid / max over classes / score threshold, box decode
@@ -320,6 +324,11 @@ int qv2x_plan_workspace_bytes(const qv2x_plan* plan, int n_img, int H, int W, si
  * dump_step / d_acc_dump: optional accumulator dump of one step (see qv2x_layer_forward), -1 / NULL to disable. */
 int qv2x_plan_forward(const qv2x_plan* plan, int n_img, int H, int W, const uint8_t* d_in, uint8_t* d_out,
                       void* d_workspace, size_t workspace_bytes, int dump_step, int32_t* d_acc_dump, void* stream);
+/* The same with the per-pixel channel sums of the input supplied by its producer (d_in_rowsum int32 [n_img][H][W] over
+ * ALL buf_channels[0] channels, e.g. from qv2x_pillar_forward_rs); NULL = compute them here (qv2x_plan_forward). */
+int qv2x_plan_forward_rs(const qv2x_plan* plan, int n_img, int H, int W, const uint8_t* d_in, const int32_t* d_in_rowsum,
+                         uint8_t* d_out, void* d_workspace, size_t workspace_bytes, int dump_step, int32_t* d_acc_dump,
+                         void* stream);
 /* Copy of the descriptor a layer was created with. */
 int qv2x_layer_desc_get(const qv2x_layer* layer, qv2x_layer_desc* out);
 

@@ -126,6 +126,8 @@ def _declare_pillar(lib):
     lib.qv2x_pillar_destroy.argtypes = [c_void_p]
     lib.qv2x_pillar_destroy.restype = None
     lib.qv2x_pillar_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
+    lib.qv2x_pillar_forward_rs.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                           c_void_p]
 
 
 class PostprocessDesc(_SizedStructure):
@@ -207,6 +209,8 @@ def _declare_plan(lib):
     lib.qv2x_plan_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, ctypes.c_size_t,
                                       c_int, c_void_p, c_void_p]
     lib.qv2x_layer_desc_get.argtypes = [c_void_p, POINTER(LayerDesc)]
+    lib.qv2x_plan_forward_rs.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         ctypes.c_size_t, c_int, c_void_p, c_void_p]
 
 
 _DECLARERS.append(_declare_plan)

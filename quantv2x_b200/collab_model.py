@@ -122,9 +122,16 @@ class HeterBaselineCollabCodebookMC(nn.Module):
         affine_matrix = normalize_pairwise_tfm(data_dict["pairwise_t_matrix"], self.H, self.W, self.fake_voxel_size)
         record_len = data_dict["record_len"]
         pipe = self._pipeline("m1")
-        bev_u8 = pipe.bev_from_inputs(data_dict)                       # uint8 [N, H, W, 64]
-        codes = pipe.encode_agents(bev_u8)                             # uint8 [levels, m, N*hw]
-        n = bev_u8.shape[0]
+        inp = data_dict["inputs_m1"]
+        if "bev_u8" in inp:                                            # BEV-level callers: uint8 [N, H, W, 64]
+            bev_u8 = pipe.bev_from_inputs(data_dict)
+            n = bev_u8.shape[0]
+            codes = pipe.encode_agents(bev_u8)                         # uint8 [levels, m, N*hw]
+        else:                                                          # the reference's pillar-level dict
+            n = len(agent_modality_list)
+            dev = pipe.device
+            codes = pipe.encode_pillars(inp["voxel_features"].to(dev), inp["voxel_coords"].to(dev),
+                                        inp["voxel_num_points"].to(dev), n)
         other_info = {"affine_matrix": affine_matrix, "record_len": record_len,
                       "agent_modality_list": agent_modality_list,
                       "feature_shape": (n, pipe.c_feat, pipe.ho, pipe.wo)}

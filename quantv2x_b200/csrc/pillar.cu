@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) pillar_bev_kernel(const float4* __restric
                                                          const int* __restrict__ num, int n_pillars, int batch,
                                                          const float* __restrict__ w /*[64][12]*/,
                                                          const float* __restrict__ bias, uint8_t* __restrict__ bev,
-                                                         const PillarParams p) {
+                                                         const PillarParams p, int32_t* __restrict__ rowsum) {
     __shared__ __align__(16) float s_f[8][kPillarPoints][kPillarFeatPad];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // this lane's two output channels: weights and bias stay in registers for the whole kernel
@@ -110,6 +110,14 @@ __global__ void __launch_bounds__(256) pillar_bev_kernel(const float4* __restric
             uint8_t* cell = bev + ((static_cast<long long>(cd.x) * p.ny + cd.z) * p.nx + cd.w) * kPillarOut;
             cell[lane] = q0;
             cell[lane + 32] = q1;
+            if (rowsum != nullptr) {
+                // the cell's channel sum (the uint8 x uint8 zero-point term of the first conv needs it): saves the
+                // separate pass over the 95 % empty map
+                int sum = static_cast<int>(q0) + static_cast<int>(q1);
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+                if (lane == 0) rowsum[(static_cast<long long>(cd.x) * p.ny + cd.z) * p.nx + cd.w] = sum;
+            }
         }
     }
 }
@@ -163,11 +171,17 @@ void qv2x_pillar_destroy(qv2x_pillar* h) {
 
 int qv2x_pillar_forward(const qv2x_pillar* h, int n_pillars, const float* d_points, const int* d_coords,
                         const int* d_num_points, int batch, uint8_t* d_bev, void* stream_) {
+    return qv2x_pillar_forward_rs(h, n_pillars, d_points, d_coords, d_num_points, batch, d_bev, nullptr, stream_);
+}
+
+int qv2x_pillar_forward_rs(const qv2x_pillar* h, int n_pillars, const float* d_points, const int* d_coords,
+                           const int* d_num_points, int batch, uint8_t* d_bev, int32_t* d_rowsum, void* stream_) {
     QV2X_REQUIRE(h && d_bev, "qv2x_pillar_forward: null argument");
     QV2X_REQUIRE(batch >= 1 && n_pillars >= 0, "bad batch / pillar count");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     const size_t bytes = static_cast<size_t>(batch) * h->d.ny * h->d.nx * kPillarOut;
     QV2X_CUDA_OK(cudaMemsetAsync(d_bev, 0, bytes, stream));       // empty cells are code 0 (zero-point 0)
+    if (d_rowsum) QV2X_CUDA_OK(cudaMemsetAsync(d_rowsum, 0, bytes / kPillarOut * sizeof(int32_t), stream));
     if (n_pillars == 0) return 0;
     QV2X_REQUIRE(d_points && d_coords && d_num_points, "qv2x_pillar_forward: null argument");
     PillarParams p{};
@@ -181,7 +195,7 @@ int qv2x_pillar_forward(const qv2x_pillar* h, int n_pillars, const float* d_poin
     const int grid = std::min((n_pillars * 32 + threads - 1) / threads, num_sms() * 8);
     pillar_bev_kernel<<<grid, threads, 0, stream>>>(reinterpret_cast<const float4*>(d_points),
                                                     reinterpret_cast<const int4*>(d_coords), d_num_points, n_pillars,
-                                                    batch, h->d_w, h->d_b, d_bev, p);
+                                                    batch, h->d_w, h->d_b, d_bev, p, d_rowsum);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

@@ -147,6 +147,13 @@ int qv2x_plan_workspace_bytes(const qv2x_plan* P, int n_img, int H, int W, size_
 
 int qv2x_plan_forward(const qv2x_plan* P, int n_img, int H, int W, const uint8_t* d_in, uint8_t* d_out,
                       void* d_workspace, size_t workspace_bytes, int dump_step, int32_t* d_acc_dump, void* stream_) {
+    return qv2x_plan_forward_rs(P, n_img, H, W, d_in, nullptr, d_out, d_workspace, workspace_bytes, dump_step,
+                                d_acc_dump, stream_);
+}
+
+int qv2x_plan_forward_rs(const qv2x_plan* P, int n_img, int H, int W, const uint8_t* d_in, const int32_t* d_in_rowsum,
+                         uint8_t* d_out, void* d_workspace, size_t workspace_bytes, int dump_step, int32_t* d_acc_dump,
+                         void* stream_) {
     QV2X_REQUIRE(P && d_in && d_out && d_workspace, "qv2x_plan_forward: null argument");
     size_t need = 0;
     int rc = qv2x_plan_workspace_bytes(P, n_img, H, W, &need);
@@ -175,6 +182,10 @@ int qv2x_plan_forward(const qv2x_plan* P, int n_img, int H, int W, const uint8_t
     if (ws > rs_begin) QV2X_CUDA_OK(cudaMemsetAsync(rs_begin, 0, static_cast<size_t>(ws - rs_begin), stream));
     for (size_t k = 0; k < P->slots.size(); ++k) {
         if (P->slots[k].producer >= 0) continue;
+        if (d_in_rowsum != nullptr && P->slots[k].cbase == 0 && P->slots[k].width == P->buf_channels[0]) {
+            slot[k] = const_cast<int32_t*>(d_in_rowsum);      // supplied by the producer of the input
+            continue;
+        }
         rc = qv2x_rowsum_u8(d_in, static_cast<long long>(n_img) * H * W, P->buf_channels[0], P->slots[k].cbase,
                             P->slots[k].width, slot[k], stream);
         if (rc) return rc;

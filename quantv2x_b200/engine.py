@@ -345,9 +345,10 @@ class PillarEngine:
             self._h = None
 
     def forward(self, voxel_features: torch.Tensor, voxel_coords: torch.Tensor, voxel_num_points: torch.Tensor,
-                batch: int, out: torch.Tensor | None = None) -> torch.Tensor:
+                batch: int, out: torch.Tensor | None = None, rowsum_out: torch.Tensor | None = None) -> torch.Tensor:
         """voxel_features float32 [M, 32, 4], voxel_coords int [M, 4] (batch, z, y, x), voxel_num_points int [M]
-        (CUDA tensors) -> uint8 BEV codes [batch, ny, nx, 64]."""
+        (CUDA tensors) -> uint8 BEV codes [batch, ny, nx, 64].  rowsum_out int32 [batch, ny, nx]: also receives the
+        per-cell sum of the 64 codes (what the backbone plan's first conv needs, Plan.forward(..., rowsum_in=))."""
         assert voxel_features.is_cuda and voxel_features.dim() == 3 and voxel_features.shape[1:] == (32, 4)
         f = voxel_features.to(torch.float32).contiguous()
         c = voxel_coords.to(torch.int32).contiguous()
@@ -356,9 +357,14 @@ class PillarEngine:
             out = torch.empty((batch, self.ny, self.nx, self.cout), dtype=torch.uint8, device=f.device)
         assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous()
         assert tuple(out.shape) == (batch, self.ny, self.nx, self.cout)
-        check(_lib.lib().qv2x_pillar_forward(self._h, int(f.shape[0]), c_void_p(f.data_ptr()), c_void_p(c.data_ptr()),
-                                             c_void_p(n.data_ptr()), int(batch), c_void_p(out.data_ptr()),
-                                             _stream_ptr()))
+        if rowsum_out is not None:
+            assert rowsum_out.is_cuda and rowsum_out.dtype == torch.int32 and rowsum_out.is_contiguous()
+            assert tuple(rowsum_out.shape) == (batch, self.ny, self.nx)
+        check(_lib.lib().qv2x_pillar_forward_rs(self._h, int(f.shape[0]), c_void_p(f.data_ptr()),
+                                                c_void_p(c.data_ptr()), c_void_p(n.data_ptr()), int(batch),
+                                                c_void_p(out.data_ptr()),
+                                                None if rowsum_out is None else c_void_p(rowsum_out.data_ptr()),
+                                                _stream_ptr()))
         return out
 
 
@@ -566,8 +572,10 @@ class Plan:
             self._ws[key] = torch.empty(nbytes.value, dtype=torch.uint8, device=device)
         return self._ws[key]
 
-    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, dump_step: int = -1, acc_dump=None, slot=0):
-        """x uint8 NHWC [n, H, W, C0] -> uint8 NHWC [n, ho, wo, C_last]."""
+    def forward(self, x: torch.Tensor, out: torch.Tensor | None = None, dump_step: int = -1, acc_dump=None, slot=0,
+                rowsum_in: torch.Tensor | None = None):
+        """x uint8 NHWC [n, H, W, C0] -> uint8 NHWC [n, ho, wo, C_last].  rowsum_in: int32 [n, H, W] per-pixel channel
+        sums of x when its producer already has them (PillarEngine.forward(..., rowsum_out=))."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.dim() == 4
         n, h, w, c = x.shape
         assert c == self.buf_channels[0], f"input has {c} channels, plan expects {self.buf_channels[0]}"
@@ -575,8 +583,12 @@ class Plan:
         if out is None:
             out = torch.empty((n, ho, wo, co), dtype=torch.uint8, device=x.device)
         ws = self.workspace(n, h, w, x.device, slot)
-        check(_lib.lib().qv2x_plan_forward(self._h, n, h, w, c_void_p(x.data_ptr()), c_void_p(out.data_ptr()),
-                                           c_void_p(ws.data_ptr()), ws.numel(), dump_step,
-                                           None if acc_dump is None else c_void_p(acc_dump.data_ptr()),
-                                           _stream_ptr()))
+        if rowsum_in is not None:
+            assert rowsum_in.is_cuda and rowsum_in.dtype == torch.int32 and rowsum_in.is_contiguous()
+            assert tuple(rowsum_in.shape) == (n, h, w)
+        check(_lib.lib().qv2x_plan_forward_rs(self._h, n, h, w, c_void_p(x.data_ptr()),
+                                              None if rowsum_in is None else c_void_p(rowsum_in.data_ptr()),
+                                              c_void_p(out.data_ptr()), c_void_p(ws.data_ptr()), ws.numel(), dump_step,
+                                              None if acc_dump is None else c_void_p(acc_dump.data_ptr()),
+                                              _stream_ptr()))
         return out

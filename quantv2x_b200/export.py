@@ -67,8 +67,8 @@ class BlockEngine:
         self.in_deltas, self.in_group_channels = list(in_deltas), list(in_group_channels)
         self.out_deltas, self.out_group_channels = list(out_deltas), list(out_group_channels)
 
-    def forward_u8(self, x_u8, out=None, slot=0):
-        return self.plan.forward(x_u8, out=out, slot=slot)
+    def forward_u8(self, x_u8, out=None, slot=0, rowsum_in=None):
+        return self.plan.forward(x_u8, out=out, slot=slot, rowsum_in=rowsum_in)
 
     def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
         """FP32 NCHW (values on the producers' grids) -> FP32 NCHW de-quantized output of the block."""

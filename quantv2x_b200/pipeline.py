@@ -59,13 +59,31 @@ class CollabPipeline:
                 codes=torch.empty((self.codebook.levels, self.codebook.m, n * self.hw), dtype=torch.uint8, device=d))
         return self._enc_buf[(n, slot)]
 
-    def encode_agents(self, bev_u8: torch.Tensor, slot=0) -> torch.Tensor:
-        """bev_u8 uint8 [n, H, W, C_bev] -> codes uint8 [levels, m, n*hw] (agent-major rows)."""
+    def encode_agents(self, bev_u8: torch.Tensor, slot=0, rowsum: torch.Tensor | None = None) -> torch.Tensor:
+        """bev_u8 uint8 [n, H, W, C_bev] -> codes uint8 [levels, m, n*hw] (agent-major rows).  rowsum: the map's
+        per-cell channel sums when its producer emitted them (encode_pillars)."""
         n = bev_u8.shape[0]
         b = self.encode_buffers(n, slot)
-        self.fused.forward_u8(bev_u8, out=b["feat"], slot=slot)
+        self.fused.forward_u8(bev_u8, out=b["feat"], slot=slot, rowsum_in=rowsum)
         self.codebook.encode(b["feat"], self.feat_delta, out=b["codes"])
         return b["codes"]
+
+    def encode_pillars(self, voxel_features, voxel_coords, voxel_num_points, n: int, slot=0,
+                       bev_out: torch.Tensor | None = None) -> torch.Tensor:
+        """The agent stage from the model's own input: pillars -> PointPillars front end (BEV codes + their per-cell
+        sums in one kernel) -> backbone + shrinker plan -> codebook encode.  Returns codes uint8 [levels, m, n*hw]."""
+        if getattr(self, "pillar_engine", None) is None:
+            raise RuntimeError("no pillar engine attached (the PointPillar encoder is not quantized / calibrated)")
+        pe = self.pillar_engine
+        key = ("pillar", n, slot)
+        if key not in self._enc_buf:
+            self._enc_buf[key] = dict(
+                bev=torch.empty((n, pe.ny, pe.nx, pe.cout), dtype=torch.uint8, device=self.device),
+                rowsum=torch.empty((n, pe.ny, pe.nx), dtype=torch.int32, device=self.device))
+        pb = self._enc_buf[key]
+        bev = pb["bev"] if bev_out is None else bev_out
+        pe.forward(voxel_features, voxel_coords, voxel_num_points, n, out=bev, rowsum_out=pb["rowsum"])
+        return self.encode_agents(bev, slot, rowsum=pb["rowsum"])
 
     # ------------------------------------------------------------------ ego side
     def ego_buffers(self, n, slot=0):

@@ -140,3 +140,26 @@ def test_saved_engine_reproduces_the_pipeline(cuda_device, tmp_path):
     back, k2 = unpack_codes(msg)
     assert k2 == k and np.array_equal(back, outs[0][2].cpu().numpy())
     assert len(msg) < outs[0][2].numel()            # fewer bytes than one byte per code
+
+
+@pytest.mark.gpu
+def test_front_end_emits_the_row_sums_the_plan_needs(cuda_device):
+    """qv2x_pillar_forward_rs: the per-cell code sums written next to the BEV map equal a scan of the map, and the plan
+    fed with them (qv2x_plan_forward_rs) gives the same features as the plan that scans the map itself."""
+    import bench
+    from quantv2x_b200.export import attach_engines
+    from quantv2x_b200.synthetic import synthetic_pillars
+
+    q, bev_delta = bench.build_calibrated_model(cuda_device, "max", 8)
+    attach_engines(q, bev_delta=bev_delta, device=cuda_device)
+    pipe = q.model._pipelines["m1"]
+    enc = q.hypes["model"]["args"]["m1"]["encoder_args"]
+    pil = [torch.from_numpy(t).to(cuda_device) for t in synthetic_pillars(3, 2, enc["lidar_range"], enc["voxel_size"], 3000)]
+    pe = pipe.pillar_engine
+    rs = torch.full((2, pe.ny, pe.nx), -7, dtype=torch.int32, device=cuda_device)
+    bev = pe.forward(*pil, 2, rowsum_out=rs)
+    assert torch.equal(rs, bev.to(torch.int32).sum(-1).to(torch.int32))
+    a = pipe.encode_agents(bev, slot=0).clone()
+    f_a = pipe.encode_buffers(2, 0)["feat"].clone()
+    b = pipe.encode_pillars(*pil, 2, slot=1)
+    assert torch.equal(pipe.encode_buffers(2, 1)["feat"], f_a) and torch.equal(a, b)

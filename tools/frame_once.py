@@ -19,7 +19,7 @@ attach_engines(q, bev_delta=bev_delta, device=dev)
 pipe = q.model._pipelines["m1"]
 enc_args = q.hypes["model"]["args"]["m1"]["encoder_args"]
 pil = [torch.from_numpy(t).to(dev) for t in synthetic_pillars(0, n, enc_args["lidar_range"], enc_args["voxel_size"], 6000)]
-frame = lambda: pipe.forward(pipe.pillar_engine.forward(*pil, n), aff)
+frame = lambda: pipe.decode_fuse_heads(pipe.encode_pillars(*pil, n), aff)
 aff = normalize_pairwise_tfm(torch.from_numpy(synthetic_poses(n)).float(), 80.0, 281.6, 1)[0, 0, :n].contiguous().to(dev)
 for _ in range(2):
     frame()
