@@ -120,18 +120,16 @@ struct EncodeEpilogue {
                     const int j = 4 * q + e;
                     const float hi = __int2float_rn(acc[0][j]);
                     // |256 * mid + lo| < 2^31 when the reduction has at most 256 terms (pack16)
-                    float lo, lo_mag;
+                    float lo;
                     if (pack16) {
                         lo = __int2float_rn(acc[1][j] * 256 + acc[2][j]);
-                        lo_mag = fabsf(lo);
                     } else {
                         const float md = __int2float_rn(acc[1][j]), l2 = __int2float_rn(acc[2][j]);
                         lo = fmaf(md, 256.f, l2);
-                        lo_mag = fmaf(fabsf(md), 256.f, fabsf(l2));
                     }
                     const float vf = fmaf(hi, 65536.f, lo);
-                    // the error bound needs the magnitude of the PARTS (the high and low digits may cancel in vf)
-                    vm = fmaxf(vm, fmaf(fabsf(hi), 65536.f, lo_mag));
+                    // the error bound takes max |vf| plus a constant for the conversion error of the parts (step_end)
+                    vm = fmaxf(vm, fabsf(vf));
                     sc16[j] = fmaf(vf, dd[e], gg[e]);
                 }
             }
@@ -268,13 +266,14 @@ struct EncodeEpilogue {
         bool exact_merge = true;
         if constexpr (FAST) {
             // ---- merge the fp32 candidates of the two column halves and test the gap.
-            // Error bound of one fp32 score against the float64 evaluation.  With P = 65536 |hi| + |256 mid + lo| (the
-            // magnitude of the digit parts, >= |V| even when they cancel): the conversion of the low part and the
-            // fma that forms V cost <= 2^-23 P; the rounded d32, the score fma, the rounded g32 and each rounded
-            // cross term with its addition cost <= 2^-24 of a partial sum each.  Every partial sum is <= T =
-            // max P * max|d| + max|g0| + sum max|B|, so the total is below (6 + 2 l) 2^-24 T <= 10 * 2^-24 T for the
-            // l <= 2 earlier levels; kEpsRel = 16 * 2^-24 leaves margin.  best + eps < second - eps  =>  same argmin
-            // in float64.  (vmax holds max P over the row's columns.)
+            // Error bound of one fp32 score against the float64 evaluation.  V = 65536 hi + (256 mid + lo) exactly; the
+            // computed vf differs from it by the conversion of the low part (an integer below 2^32: <= 2^8, whatever
+            // the digits cancel to) plus one fma rounding (<= 2^-24 |vf|).  With Vb = max |vf| + 2^30 over the row's
+            // columns -- the constant covers the conversion term 2^10-fold at the 2^-20 scale used below -- the
+            // rounded d32, the score fma, the rounded g32 and each rounded cross term with its addition cost
+            // <= 2^-24 of a partial sum each, and every partial sum is <= T = Vb * max|d| + max|g0| + sum max|B|:
+            // the total is below (6 + 2 l) 2^-24 T <= 10 * 2^-24 T for the l <= 2 earlier levels; kEpsRel = 16 * 2^-24
+            // leaves margin.  best + eps < second - eps  =>  same argmin in float64.  (vmax holds max |vf|.)
             struct FCand {
                 float best, second;
                 int idx;
@@ -298,7 +297,7 @@ struct EncodeEpilogue {
                         const float best = fminf(b0, o.best);
                         const float second = fminf(fminf(ts.fsecond[s], o.second), fmaxf(b0, o.best));
                         const int idx = (o.best < b0) ? o.idx : ts.bidx[s];
-                        const float eps = kEpsRel * fmaf(fmaxf(ts.vmax, o.vmax), dmax[l], cabs[l]);
+                        const float eps = kEpsRel * fmaf(fmaxf(ts.vmax, o.vmax) + 1073741824.f, dmax[l], cabs[l]);
                         unsafe |= !(second - best > 2.f * eps);      // also true for NaN
                         ts.bidx[s] = idx;
                         fc[s].idx = idx;
