@@ -54,7 +54,7 @@ def parse():
 
 # ----------------------------------------------------------------------------------------------- model
 # dram__bytes_read.sum + dram__bytes_write.sum of the shrinker's first conv per agent (profiles/r2_ncu_shrink0.txt)
-NCU_SHRINK0_DRAM_BYTES_PER_AGENT = 15.48e6
+NCU_SHRINK0_DRAM_BYTES_PER_AGENT = 19.08e6
 
 
 def build_calibrated_model(device, fusion, w_bits, seed=1234, dict_size=0):
