@@ -154,6 +154,38 @@ class UMGMQuantizer(nn.Module):
                     return d
         raise ValueError("features do not lie on a uint8 grid: quantize them first or pass `delta`")
 
+    # ------------------------------------------------------------------ float path (offline calibration only)
+    @torch.no_grad()
+    def encode_float(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """The reference's encode in PyTorch FP32 (codebook.py:106-131, 231-239, 330-337): for OFFLINE calibration
+        forwards of models whose quantizers sit behind the codebook (the pyramid model).  Inference uses encode()."""
+        codes = []
+        for enc in self._encoders:
+            z = enc._latentStageEncoder(x)
+            h = enc._quantizationHead(z)
+            cb = enc.Codebook                                           # [m, k, d]
+            n = h.shape[0]
+            hs = h.reshape(n, self._m, -1)
+            d = (hs ** 2).sum(2, keepdim=True) + (cb ** 2).sum(-1)[None] - 2 * torch.einsum("nmd,mkd->nmk", hs, cb)
+            code = d.argmin(-1)                                         # [n, m]
+            codes.append(code)
+            if enc._latentHead is not None:
+                q = cb[torch.arange(self._m)[None], code].reshape(n, -1)
+                x = enc._latentHead(z) - q
+        return codes
+
+    @torch.no_grad()
+    def decode_float(self, codes) -> torch.Tensor:
+        """The reference's decode in PyTorch FP32 (codebook.py:192-201, 263-269, 339-343); calibration only."""
+        former = None
+        for dec, code in zip(reversed(list(self._decoders)), reversed(list(codes))):
+            cb = dec._dequantizer._codebook
+            n = code.shape[0]
+            q = dec._dequantizationHead(cb[torch.arange(self._m)[None], code.long()].reshape(n, -1))
+            xhat = q if former is None else q + dec._sideHead(former)
+            former = dec._restoreHead(xhat)
+        return former
+
     # ------------------------------------------------------------------ reference interface
     def encode(self, x: torch.Tensor, delta: float | None = None) -> List[torch.Tensor]:
         """x: [n, C] -> list (levels) of LongTensor [n, m], the reference's signature and structure

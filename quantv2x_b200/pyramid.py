@@ -20,8 +20,10 @@
   (quant_block.py:441-458): transposed convs (kernel = stride) on the FP32 fused maps as FP32 GEMMs, quantized and
   concatenated into the uint8 [H, W, 384] input of the shrink conv (three scales, as the att/max path's concat).
 
-What is not here yet: the model driver of the pyramid model (shrink header + heads are the kernels of the att/max
-path); see DESIGN.md section 3.8.
+* ``ResNetBackboneEngine`` -- the agent-side ``QuantResNetBEVBackbone`` (a chain of BasicBlockEngine).
+
+The model driver that strings these together (pillars -> agent backbone -> codebook | decode -> pyramid -> shrink
+conv -> heads) is quantv2x_b200.pyramid_model; see DESIGN.md section 3.8.
 """
 from __future__ import annotations
 
@@ -125,6 +127,39 @@ class BasicBlockEngine:
         if taps is not None:
             taps.update(q1=q1, res=res)
         return (out, rs_out) if want_rowsum else out
+
+
+class ResNetBackboneEngine:
+    """The agent-side ``QuantResNetBEVBackbone`` (single stage of BasicBlocks) on libqv2x: uint8 BEV codes in (scale
+    ``in_delta`` = the PointPillar block quantizer), uint8 feature codes out (scale ``out_delta`` = the last block's
+    quantizer) -- the codebook encoder's input.  params: ``QuantResNetBEVBackbone.export_params()``."""
+
+    def __init__(self, block_params: list, in_delta: float):
+        self.blocks, d = [], float(in_delta)
+        for p in block_params:
+            self.blocks.append(BasicBlockEngine(p, d))
+            d = float(p["out_delta"])
+        self.in_delta, self.out_delta = float(in_delta), d
+        self.cin, self.cout = self.blocks[0].cin, self.blocks[-1].cout
+
+    def forward_u8(self, x: torch.Tensor, rowsum: torch.Tensor | None = None) -> torch.Tensor:
+        rs = rowsum
+        for i, b in enumerate(self.blocks):
+            last = i == len(self.blocks) - 1
+            if last:
+                x = b.forward(x, rowsum=rs)
+            else:
+                x, rs = b.forward(x, rowsum=rs, want_rowsum=True)
+        return x
+
+    def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
+        """Module-boundary drop-in: FP32 NCHW on the input grid -> FP32 NCHW de-quantized output."""
+        if not x.is_cuda:
+            raise RuntimeError("quantized inference runs on the GPU library only (no CPU fallback)")
+        n, c, h, w = x.shape
+        xq = E.quantize_nchw_to_nhwc_u8(x.contiguous().float(), self.in_delta)
+        y = self.forward_u8(xq)
+        return E.dequantize_u8(y, self.out_delta).permute(0, 3, 1, 2).contiguous()
 
 
 class FirstBottleneckEngine:

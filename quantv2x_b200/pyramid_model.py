@@ -1,0 +1,241 @@
+"""``HeterPyramidCollabCodebookMC`` (+ ``...EncDec``) -- mirror of the reference's pyramid-fusion model with the
+explicit encode / decode split (opencood/models/heter_pyramid_collab_mc.py:28-121 constructor,
+heter_pyramid_collab_codebook_mc.py:25-58 codebook, heter_pyramid_collab_codebook_mc_encdec.py:33-208 the
+``encode_features / decode_features / forward_with_encdec`` interface) for LiDAR PointPillar agents.
+
+    agent : pillars -> PFN + scatter -> ResNetBEVBackbone (3 BasicBlocks, stride 2) -> AlignNet(identity)
+            -> codebook.encode                                       [C = 64, levels x m byte planes per agent]
+    ego   : codebook.decode -> PyramidFusion.forward_collab (ResNeXt stages over every agent, occupancy heads,
+            score-weighted fusion per level, deblocks + concat) -> shrink_conv (384 -> 256) -> cls / reg / dir heads
+
+Same constructor argument (the yaml ``model.args`` dict), attribute names (state_dict compatible) and input / output
+dicts as the reference.  The torch body is the OFFLINE calibration path (``calibration_forward``: the reference's
+deterministic forward_with_encdec in FP32 / fake-quant); once the model is wrapped in ``QuantModel``, calibrated and
+``attach_pyramid_engines`` has run, ``encode_features`` / ``decode_features`` execute on libqv2x only.
+"""
+from __future__ import annotations
+
+from collections import Counter
+
+import torch
+import torch.nn as nn
+
+from . import engine as E
+from .bev_modules import DownsampleConv
+from .codebook import UMGMQuantizer
+from .collab_model import normalize_pairwise_tfm
+from .pillar_modules import PointPillar
+from .pyramid_modules import AlignNet, PyramidFusion, ResNetBEVBackbone
+
+
+class HeterPyramidCollabCodebookMC(nn.Module):
+    def __init__(self, args):
+        super().__init__()
+        self.args = args
+        self.modality_name_list = [k for k in args.keys() if k.startswith("m") and k[1:].isdigit()]
+        self.num_class = args["num_class"]
+        self.cav_range = args["lidar_range"]
+        self.sensor_type_dict, self.cam_crop_info = {}, {}
+        for name in self.modality_name_list:
+            setting = args[name]
+            self.sensor_type_dict[name] = setting["sensor_type"]
+            if setting["core_method"].replace("_", "").lower() != "pointpillar" or setting["sensor_type"] != "lidar":
+                raise NotImplementedError("only the point_pillar LiDAR encoder is on the B200 path")
+            setattr(self, f"encoder_{name}", PointPillar(setting["encoder_args"]))
+            setattr(self, f"backbone_{name}", ResNetBEVBackbone(setting["backbone_args"]))
+            setattr(self, f"aligner_{name}", AlignNet(setting["aligner_args"]))
+        self.H = self.cav_range[4] - self.cav_range[1]
+        self.W = self.cav_range[3] - self.cav_range[0]
+        self.fake_voxel_size = 1
+        if "compressor" in args:
+            raise NotImplementedError("NaiveCompressor is not on this path: the codebook is the compressor "
+                                      "(reference heter_pyramid_collab_codebook_mc.py:131-133)")
+        self.compress = False
+        fusion_args = args["fusion_backbone"]
+        if fusion_args.get("proj_first", False):
+            raise NotImplementedError("proj_first (pyramid_fuse_onnx) is not built; the shipped yaml uses pyramid_fuse")
+        self.pyramid_backbone = PyramidFusion(fusion_args)
+        self.shrink_flag = "shrink_header" in args
+        if self.shrink_flag:
+            self.shrink_conv = DownsampleConv(args["shrink_header"])
+        nc, na = args["num_class"], args["anchor_number"]
+        self.cls_head = nn.Conv2d(args["in_head"], na * nc * nc, kernel_size=1)
+        self.reg_head = nn.Conv2d(args["in_head"], 7 * na * nc, kernel_size=1)
+        self.dir_head = nn.Conv2d(args["in_head"], args["dir_args"]["num_bins"] * na * nc, kernel_size=1)
+        self.channel = 64
+        if "codebook" in args:
+            self.seg_num = args["codebook"]["seg_num"]
+            self.dict_size = [args["codebook"]["dict_size"]] * 3
+        else:
+            self.seg_num, self.dict_size = 2, [256] * 3
+        self.p_rate = 0.0
+        lin = lambda: nn.Linear(self.channel, self.channel)  # noqa: E731
+        self.codebook = UMGMQuantizer(self.channel, self.seg_num, self.dict_size, self.p_rate,
+                                      {k: lin for k in ("latentStageEncoder", "quantizationHead", "latentHead",
+                                                        "restoreHead", "dequantizationHead", "sideHead")})
+        self._engines = None          # set by attach_pyramid_engines
+
+    # ------------------------------------------------------------------ torch body (offline calibration)
+    def _agent_features(self, data_dict):
+        agent_modality_list = data_dict["agent_modality_list"]
+        count = Counter(agent_modality_list)
+        feats = {}
+        for name in self.modality_name_list:
+            if name not in count:
+                continue
+            f = getattr(self, f"encoder_{name}")(data_dict, name)
+            bb = getattr(self, f"backbone_{name}")
+            f = bb.forward_float(f) if hasattr(bb, "forward_float") else bb(f)
+            feats[name] = getattr(self, f"aligner_{name}")(f)
+        idx = {n: 0 for n in self.modality_name_list}
+        out = []
+        for name in agent_modality_list:
+            out.append(feats[name][idx[name]])
+            idx[name] += 1
+        return torch.stack(out)
+
+    def calibration_forward(self, data_dict):
+        """The reference's deterministic forward_with_encdec in torch (fake-quant once wrapped): every activation
+        quantizer of the model -- agent backbone, pyramid stages, occupancy heads, deblocks, shrink conv -- sees
+        its input, with the codebook's argmin encode / decode in FP32 between the two halves."""
+        affine = normalize_pairwise_tfm(data_dict["pairwise_t_matrix"], self.H, self.W, self.fake_voxel_size)
+        feat = self._agent_features(data_dict)
+        n, c, h, w = feat.shape
+        flat = feat.permute(0, 2, 3, 1).contiguous().view(-1, c)
+        codes = self.codebook.encode_float(flat)
+        q = self.codebook.decode_float(codes).view(n, h, w, c).permute(0, 3, 1, 2).contiguous()
+        pb = self.pyramid_backbone
+        body = pb.forward_collab_float if hasattr(pb, "forward_collab_float") else pb.forward_collab
+        fused, occ = body(q, data_dict["record_len"], affine)
+        if self.shrink_flag:
+            sc = self.shrink_conv
+            fused = sc.forward_float(fused) if hasattr(sc, "forward_float") else sc(fused)
+        cls, reg, dr = self.cls_head(fused), self.reg_head(fused), self.dir_head(fused)
+        return {"pyramid": "collab", "cls_preds": cls, "reg_preds": reg, "dir_preds": dr, "occ_single_list": occ,
+                "preds_tensor": torch.cat([cls, reg, dr], dim=1), "codes": codes, "agent_feature": feat}
+
+    # ------------------------------------------------------------------ inference (libqv2x)
+    def _eng(self):
+        if self._engines is None:
+            raise RuntimeError("no libqv2x engines attached: wrap the model in QuantModel, calibrate (through "
+                               "calibration_forward), then call quantv2x_b200.pyramid_model.attach_pyramid_engines"
+                               "(qmodel) (there is no CPU fallback)")
+        return self._engines
+
+    def encode_features(self, data_dict):
+        agent_modality_list = data_dict["agent_modality_list"]
+        if set(agent_modality_list) != {"m1"}:
+            raise NotImplementedError("single-modality (m1) frames only")
+        eng = self._eng()
+        affine_matrix = normalize_pairwise_tfm(data_dict["pairwise_t_matrix"], self.H, self.W, self.fake_voxel_size)
+        inp = data_dict["inputs_m1"]
+        n = len(agent_modality_list)
+        dev = eng["device"]
+        pe, bb = eng["pillar"], eng["backbone"]
+        if "bev_u8" in inp:
+            bev, rowsum = inp["bev_u8"].to(dev), None
+        else:
+            bev = torch.empty((n, pe.ny, pe.nx, pe.cout), dtype=torch.uint8, device=dev)
+            rowsum = torch.empty((n, pe.ny, pe.nx), dtype=torch.int32, device=dev)
+            pe.forward(inp["voxel_features"].to(dev), inp["voxel_coords"].to(dev), inp["voxel_num_points"].to(dev), n,
+                       out=bev, rowsum_out=rowsum)
+        feat = bb.forward_u8(bev, rowsum)                                   # uint8 [n, h, w, 64]
+        _, h, w, c = feat.shape
+        codes = eng["codebook"].encode(feat.view(n * h * w, c), bb.out_delta)   # uint8 [levels, m, n*h*w]
+        other_info = {"affine_matrix": affine_matrix, "record_len": data_dict["record_len"],
+                      "agent_modality_list": agent_modality_list, "feature_shape": (n, c, h, w)}
+        return [codes[l].t().long() for l in range(codes.shape[0])], agent_modality_list, other_info
+
+    def decode_features(self, codes, other_info, taps: dict | None = None):
+        eng = self._eng()
+        if isinstance(codes, (list, tuple)):
+            codes = torch.stack([c.t() for c in codes]).to(torch.uint8).contiguous()
+        record_len = other_info["record_len"]
+        if int(record_len.numel()) != 1:
+            raise NotImplementedError("batch size 1 at inference (as in the reference's test loader)")
+        n, c, h, w = other_info["feature_shape"]
+        dev = codes.device
+        aff = other_info["affine_matrix"][0][0, :n].to(device=dev, dtype=torch.float32).contiguous()
+        x = eng["codebook"].decode(codes).view(n, h, w, c)                   # float32 NHWC
+        pyr = eng["pyramid"]
+        ptaps = {} if taps is None else taps
+        fused = pyr.forward_collab(x, aff, taps=ptaps)
+        cat = pyr.decode_multiscale_feature(fused)                           # uint8 [1, H, W, 384], 3 scales
+        if self.shrink_flag:
+            y = eng["shrink"].forward_u8(cat)                                # uint8 [1, H, W, 256]
+            y_delta = eng["shrink"].out_deltas[0]
+            feat = E.dequantize_u8(y, y_delta)
+        else:
+            parts, base = [], 0
+            for d in pyr.deblocks:
+                parts.append(E.dequantize_u8(cat[..., base:base + d.cout].contiguous(), d.delta))
+                base += d.cout
+            y, feat = cat, torch.cat(parts, dim=-1)
+        hh, ww = feat.shape[1], feat.shape[2]
+        heads = eng["heads"]
+        preds = torch.empty((heads.cout, hh * ww), dtype=torch.float32, device=dev)
+        heads.forward(feat.view(hh * ww, -1), out=preds)
+        if taps is not None:
+            taps.update(decoded=x, cat=cat, shrink=y)
+        nc, na = self.args["num_class"], self.args["anchor_number"]
+        n_cls, n_reg = na * nc * nc, 7 * na * nc
+        p = preds.view(1, -1, hh, ww)
+        occ = [ptaps[f"l{i}.occ"].unsqueeze(1) for i in range(len(pyr.stages))]
+        return {"pyramid": "collab", "cls_preds": p[:, :n_cls], "reg_preds": p[:, n_cls:n_cls + n_reg],
+                "dir_preds": p[:, n_cls + n_reg:], "occ_single_list": occ, "preds_tensor": p}
+
+    def forward_with_encdec(self, data_dict):
+        codes, _, other_info = self.encode_features(data_dict)
+        return self.decode_features(codes, other_info)
+
+    def forward(self, data_dict):
+        """Deterministic inference forward (encode -> decode); with no engines attached (offline calibration) the
+        torch body.  The reference's forward() samples codes with Gumbel noise even in eval mode;
+        parity is defined on the encode/decode path."""
+        if self._engines is None:
+            return self.calibration_forward(data_dict)
+        return self.forward_with_encdec(data_dict)
+
+
+HeterPyramidCollabCodebookMCEncDec = HeterPyramidCollabCodebookMC
+
+
+def attach_pyramid_engines(qmodel, device=None):
+    """Build the libqv2x engines of a calibrated ``QuantModel(HeterPyramidCollabCodebookMC)``: the PointPillars front
+    end, the agent backbone (chain of BasicBlockEngine), the codebook, the pyramid backbone, the shrink conv plan and
+    the heads GEMM; block-level engines are also attached to their wrappers (module-boundary drop-in)."""
+    from .export import BlockEngine, _make_plan, _shrinker_steps, build_pillar_engine
+    from .pipeline import heads_from_quant_modules
+    from .pyramid import PyramidBackboneEngine, ResNetBackboneEngine
+    from .quant.quant_block import (QuantDownsampleConv, QuantPointPillar, QuantPyramidFusion,
+                                    QuantResNetBEVBackbone)
+
+    model = qmodel.model
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    if model.modality_name_list != ["m1"]:
+        raise NotImplementedError("single-modality (m1) pyramid models only")
+    enc, bb, pf = model.encoder_m1, model.backbone_m1, model.pyramid_backbone
+    if not isinstance(enc, QuantPointPillar) or not isinstance(bb, QuantResNetBEVBackbone) or \
+            not isinstance(pf, QuantPyramidFusion):
+        raise ValueError("the model is not quantized: wrap it in QuantModel and calibrate first")
+    bev_delta = enc.bev_delta()
+    engines = {"device": device, "pillar": build_pillar_engine(enc)}
+    engines["backbone"] = ResNetBackboneEngine(bb.export_params(), bev_delta)
+    bb.attach_engine(engines["backbone"])
+    engines["codebook"] = model.codebook.engine()
+    model.codebook.set_input_scale(engines["backbone"].out_delta)
+    engines["pyramid"] = PyramidBackboneEngine(pf.export_params(), pf.layer_nums())
+    pf.attach_engine(engines["pyramid"])
+    if model.shrink_flag:
+        sc = model.shrink_conv
+        if not isinstance(sc, QuantDownsampleConv):
+            raise ValueError("shrink_conv is not quantized")
+        pyr = engines["pyramid"]
+        widths = [d.cout for d in pyr.deblocks]
+        steps, chans, out_buf, out_delta, _ = _shrinker_steps(sc, pyr.up_deltas, 0, 1)
+        engines["shrink"] = BlockEngine(_make_plan(steps, chans, sum(widths), out_buf), pyr.up_deltas, widths,
+                                        [out_delta], [chans[out_buf]])
+        sc.attach_engine(engines["shrink"])
+    engines["heads"] = heads_from_quant_modules(model.cls_head, model.reg_head, model.dir_head)
+    model._engines = engines
+    return model

@@ -95,6 +95,72 @@ class ResNeXtStages(nn.Module):
         return feats
 
 
+class BasicBlockStages(nn.Module):
+    """``layer{i}`` = Sequential of ``layer_nums[i]`` BasicBlocks (reference resblock.ResNetModified with BasicBlock,
+    resblock.py:125-227: the first block of a stage carries the stride and, when the shape changes, a 1x1 conv + BN
+    shortcut).  forward returns the output of every stage."""
+
+    def __init__(self, layer_nums, layer_strides, num_filters, inplanes=64):
+        super().__init__()
+        self.layernum = len(num_filters)
+        for i, (n, stride, planes) in enumerate(zip(layer_nums, layer_strides, num_filters)):
+            blocks = []
+            for b in range(n):
+                s = stride if b == 0 else 1
+                down = None
+                if b == 0 and (s != 1 or inplanes != planes * BasicBlock.expansion):
+                    down = nn.Sequential(nn.Conv2d(inplanes, planes * BasicBlock.expansion, 1, stride=s, bias=False),
+                                         nn.BatchNorm2d(planes * BasicBlock.expansion))
+                blocks.append(BasicBlock(inplanes, planes, s, down))
+                inplanes = planes * BasicBlock.expansion
+            setattr(self, f"layer{i}", nn.Sequential(*blocks))
+
+    def forward(self, x):
+        feats = []
+        for i in range(self.layernum):
+            x = getattr(self, f"layer{i}")(x)
+            feats.append(x)
+        return feats
+
+
+class ResNetBEVBackbone(nn.Module):
+    """The agent-side backbone of the pyramid models (reference base_bev_backbone_resnet.py:12-118): BasicBlock stages;
+    the shipped configs (``layer_nums: [3]``, no ``upsample_strides``) have no deblocks, so the output is the last
+    stage's feature.  Same attribute names (``resnet.layer{i}.{j}.conv1`` ...) as the reference."""
+
+    def __init__(self, model_cfg, input_channels=64):
+        super().__init__()
+        self.model_cfg = model_cfg
+        if model_cfg.get("upsample_strides"):
+            raise NotImplementedError("agent-side deblocks (upsample_strides) are not built: the pyramid configs of the "
+                                      "hot path have none")
+        nums, strides, filters = (list(model_cfg[k]) for k in ("layer_nums", "layer_strides", "num_filters"))
+        self.num_levels = len(nums)
+        self.resnet = BasicBlockStages(nums, strides, filters, inplanes=model_cfg.get("inplanes", input_channels))
+        self.deblocks = nn.ModuleList()
+        self.num_bev_features = filters[-1]
+
+    def get_multiscale_feature(self, spatial_features):
+        return self.resnet(spatial_features)
+
+    def forward(self, spatial_features):
+        x = self.resnet(spatial_features)
+        return torch.cat(x, dim=1) if len(x) > 1 else x[0]
+
+
+class AlignNet(nn.Module):
+    """reference feature_alignnet.py:12-43; only ``core_method: identity`` (the LiDAR configs) is on this path."""
+
+    def __init__(self, args):
+        super().__init__()
+        if args.get("core_method", "identity") != "identity":
+            raise NotImplementedError(f"aligner {args.get('core_method')!r} is not on the B200 path (identity only)")
+        self.channel_align = nn.Identity()
+
+    def forward(self, x):
+        return self.channel_align(x)
+
+
 def warp_affine_simple(src, m, dsize):
     """F.affine_grid + F.grid_sample (bilinear, zeros, align_corners=False): torch_transformation_utils.py:323-332."""
     grid = F.affine_grid(m, [src.shape[0], src.shape[1], dsize[0], dsize[1]], align_corners=False).to(src)

@@ -142,12 +142,15 @@ class QuantDownsampleConv(BaseQuantBlock):
         self.layers = nn.ModuleList(QuantDoubleConv(layer, weight_quant_params, act_quant_params)
                                     for layer in downsample_conv.layers)
 
-    def forward(self, x):
-        if self.engine_ready():
-            return self._run_engine(x)
+    def forward_float(self, x):
         for layer in self.layers:
             x = layer(x)
         return x
+
+    def forward(self, x):
+        if self.engine_ready():
+            return self._run_engine(x)
+        return self.forward_float(x)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -156,7 +159,8 @@ class QuantDownsampleConv(BaseQuantBlock):
 # calibration ``export_params`` hands the integer parameters to quantv2x_b200.pyramid.PyramidBackboneEngine and
 # ``attach_engine`` makes ``forward_collab`` run there.
 # --------------------------------------------------------------------------------------------------
-from ..pyramid_modules import BasicBlock, Bottleneck, PyramidFusion, ResNeXtStages, weighted_fuse_torch  # noqa: E402
+from ..pyramid_modules import (BasicBlock, BasicBlockStages, Bottleneck, PyramidFusion, ResNetBEVBackbone,  # noqa: E402
+                               ResNeXtStages, weighted_fuse_torch)
 
 
 def _conv_params(qm: QuantModule):
@@ -267,6 +271,65 @@ class QuantResNeXtStages(BaseQuantBlock):
             x = getattr(self, f"layer{i}")(x)
             feats.append(x)
         return feats
+
+
+class QuantResNetBEVBackbone(BaseQuantBlock):
+    """Mirror of the reference QuantResNetBEVBackbone (quant_block.py:398-460) for the agent-side backbone of the pyramid
+    models: BasicBlock stages wrapped as QuantBasicBlocks.  Calibrate with the torch body; ``export_params()`` ->
+    quantv2x_b200.pyramid.ResNetBackboneEngine; with an engine attached, quantized forwards run on libqv2x."""
+
+    def __init__(self, backbone: ResNetBEVBackbone, weight_quant_params={}, act_quant_params={}):
+        super().__init__()
+        self.model_cfg = backbone.model_cfg
+        self.num_levels = backbone.num_levels
+        self.num_bev_features = backbone.num_bev_features
+        self.resnet = nn.Module()
+        self.resnet.layernum = backbone.resnet.layernum
+        for i in range(backbone.resnet.layernum):
+            setattr(self.resnet, f"layer{i}", nn.Sequential(*[QuantBasicBlock(b, weight_quant_params, act_quant_params)
+                                                               for b in getattr(backbone.resnet, f"layer{i}")]))
+        self.deblocks = nn.ModuleList()
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        super().set_quant_state(weight_quant, act_quant)
+        for m in self.modules():
+            if isinstance(m, BaseQuantBlock) and m is not self:
+                m.use_weight_quant, m.use_act_quant = weight_quant, act_quant
+
+    def blocks(self):
+        return [b for i in range(self.resnet.layernum) for b in getattr(self.resnet, f"layer{i}")]
+
+    def get_multiscale_feature(self, spatial_features):
+        feats, x = [], spatial_features
+        for i in range(self.resnet.layernum):
+            x = getattr(self.resnet, f"layer{i}")(x)
+            feats.append(x)
+        return feats
+
+    def forward_float(self, spatial_features):
+        x = self.get_multiscale_feature(spatial_features)
+        return torch.cat(x, dim=1) if len(x) > 1 else x[0]
+
+    def engine_ready(self) -> bool:
+        if not (self.use_weight_quant and self.use_act_quant):
+            return False
+        return all(m.weight_quantizer.inited and (m.disable_act_quant or m.act_quantizer.inited)
+                   for m in self.quant_modules()) and all(b.act_quantizer.inited for b in self.blocks())
+
+    def forward(self, spatial_features):
+        if self.engine_ready() and spatial_features.is_cuda:
+            return self._run_engine(spatial_features)
+        return self.forward_float(spatial_features)
+
+    def export_params(self) -> list:
+        """One dict per block, in execution order (see quantv2x_b200.pyramid.BasicBlockEngine)."""
+        if self.resnet.layernum != 1:
+            raise NotImplementedError("multi-stage agent backbones concatenate several scales; the engine covers the "
+                                      "single-stage configuration of the pyramid yamls")
+        return [b.export_params() for b in self.blocks()]
+
+    def out_delta(self) -> float:
+        return _act_delta(self.blocks()[-1].act_quantizer)
 
 
 class QuantPyramidFusion(BaseQuantBlock):
@@ -383,6 +446,7 @@ opencood_specials = {
     BaseBEVBackbone: QuantBaseBEVBackbone,
     DownsampleConv: QuantDownsampleConv,
     PyramidFusion: QuantPyramidFusion,
+    ResNetBEVBackbone: QuantResNetBEVBackbone,
 }
 
 # modules the reference keeps in FP32 by attribute name (quant_block.py:1599-1615)

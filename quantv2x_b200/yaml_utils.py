@@ -60,11 +60,13 @@ def create_model(hypes):
     """Instantiate hypes['model']['core_method'] (snake_case file name -> CamelCase class) with its args."""
     name = hypes["model"]["core_method"]
     target = name.replace("_", "").lower()
-    lib = importlib.import_module("quantv2x_b200.collab_model")
-    for attr, cls in lib.__dict__.items():
-        if attr.lower() == target:
-            return cls(hypes["model"]["args"])
-    raise NotImplementedError(f"model {name!r} is not on the B200 path (available: heter_baseline_collab_codebook_mc)")
+    for mod in ("quantv2x_b200.collab_model", "quantv2x_b200.pyramid_model"):
+        lib = importlib.import_module(mod)
+        for attr, cls in lib.__dict__.items():
+            if attr.lower() == target and isinstance(cls, type):
+                return cls(hypes["model"]["args"])
+    raise NotImplementedError(f"model {name!r} is not on the B200 path (available: heter_baseline_collab_codebook_mc"
+                              "[_encdec], heter_pyramid_collab_codebook_mc[_encdec])")
 
 
 def load_saved_model(saved_path, model):
