@@ -29,7 +29,12 @@ __device__ __forceinline__ double i2d_exact(int x) {
 // (0 = run-time m).  Both are template parameters so that the hot loop carries no code of the other variants.
 template <bool FAST, int MSEG>
 struct EncodeEpilogue {
-    static constexpr int col_split(int) { return 2; }   // two epilogue warps per row quadrant, merged per level
+    // Epilogue warps per row quadrant (their candidates are merged per level).  The chunk loop is latency-bound
+    // (TMEM read, parameter loads, table gathers, dependent min/max chains): the hot configuration (fp32 filter, one
+    // segment) runs four warps per quadrant -- 16 epilogue warps, 32 columns of a 128-column level each.
+    static constexpr int kSplit = (FAST && MSEG == 1) ? 4 : 2;
+    static constexpr int kSegSlots = MSEG > 0 ? MSEG : kMaxSeg;      // candidate slots per row in the merge scratch
+    static constexpr int col_split(int) { return kSplit; }
     static constexpr int kMaxStages = 4;   // K is only C bytes: a short ring leaves L1 room for the table gathers
     static constexpr bool kSideWarp = false;
     static constexpr bool kSeqDrain = false;
@@ -95,12 +100,13 @@ struct EncodeEpilogue {
     __device__ __forceinline__ void chunk(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int step, int c0,
                                           const int32_t (*acc)[W]) const {
         static_assert(W == 16, "the encode epilogue works on 16-column chunks");
-        if constexpr (FAST) chunk_fast(ts, step, c0, acc);
+        if constexpr (FAST) chunk_fast(ts, step, c0, acc, dbg_flags(g));
         else chunk_exact<16>(ts, g, tc, step, c0, acc);
     }
 
     // fp32 scores of 16 columns + running (best, runner-up, index) and max |V| of the row
-    __device__ __forceinline__ void chunk_fast(Tile& ts, int step, int c0, const int32_t (*acc)[16]) const {
+    __device__ __forceinline__ void chunk_fast(Tile& ts, int step, int c0, const int32_t (*acc)[16],
+                                               const int dbg = 0) const {
         const int l = step_level[step];
         const int n0 = step_col0[step] + c0;
         const int nl = n_level[l];
@@ -137,7 +143,7 @@ struct EncodeEpilogue {
         }
 #pragma unroll
         for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
-            if (jl < l) {
+            if (jl < l && !(dbg & 512)) {
 #pragma unroll
                 for (int s2 = 0; s2 < kMaxSeg; ++s2) {
                     if (s2 < nseg()) {
@@ -162,8 +168,10 @@ struct EncodeEpilogue {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const float v = sc16[j];
-            second = fminf(second, fmaxf(best, v));
-            if (v < best) bidx = kk0 + j;      // the exact index only matters when the gap test passes
+            if (!(dbg & 128)) {
+                second = fminf(second, fmaxf(best, v));
+                if (v < best) bidx = kk0 + j;      // the exact index only matters when the gap test passes
+            }
             best = fminf(best, v);
         }
 #pragma unroll
@@ -279,44 +287,54 @@ struct EncodeEpilogue {
                 int idx;
                 float vmax;
             };
-            FCand* fc = reinterpret_cast<FCand*>(scratch) + (quad * 32 + lane) * kMaxSeg;
+            // slot p - 1 of a row holds the candidates of part p; part 0 publishes the merged index in slot 0
+            static_assert((kSplit - 1) * 128 * kSegSlots * 16 <= 8192, "merge scratch");
+            FCand* fc = reinterpret_cast<FCand*>(scratch) + (quad * 32 + lane) * kSegSlots;
+            constexpr int kPartStride = 128 * kSegSlots;
             int* qflag = reinterpret_cast<int*>(scratch + 8192);
-            if (part == 1) {
+            if (part != 0) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < nseg()) fc[s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
+                    if (s < nseg())
+                        fc[(part - 1) * kPartStride + s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
             if (part == 0) {
                 bool unsafe = false;
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
                     if (s < nseg()) {
-                        const FCand o = fc[s];
-                        const float b0 = ts.fbest[s];
-                        const float best = fminf(b0, o.best);
-                        const float second = fminf(fminf(ts.fsecond[s], o.second), fmaxf(b0, o.best));
-                        const int idx = (o.best < b0) ? o.idx : ts.bidx[s];
-                        const float eps = kEpsRel * fmaf(fmaxf(ts.vmax, o.vmax) + 1073741824.f, dmax[l], cabs[l]);
+                        float best = ts.fbest[s], second = ts.fsecond[s], vmax = ts.vmax;
+                        int idx = ts.bidx[s];
+#pragma unroll
+                        for (int p = 1; p < kSplit; ++p) {       // ascending parts = ascending columns
+                            const FCand o = fc[(p - 1) * kPartStride + s];
+                            second = fminf(fminf(second, o.second), fmaxf(best, o.best));
+                            idx = (o.best < best) ? o.idx : idx;
+                            best = fminf(best, o.best);
+                            vmax = fmaxf(vmax, o.vmax);
+                        }
+                        const float eps = kEpsRel * fmaf(vmax + 1073741824.f, dmax[l], cabs[l]);
                         unsafe |= !(second - best > 2.f * eps);      // also true for NaN
                         ts.bidx[s] = idx;
                         fc[s].idx = idx;
                     }
+                if (dbg_flags(g) & 256) unsafe = false;
                 const int any = __any_sync(0xffffffffu, unsafe) ? 1 : 0;
                 if (lane == 0) qflag[quad] = any;
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
             exact_merge = (qflag[quad] != 0);
             if (exact_merge) {
                 // rare: some row of this quadrant sits in a near-tie -- evaluate the level exactly for all 32 rows
                 // (the accumulators are still in TMEM because the slots are released only after step_end)
                 redo_level_exact(ts, g, tc, step, tv);
-                // part 0 may still be reading fc[] above when part 1 starts overwriting the slots below
-                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                // part 0 may still be reading fc[] above when the other parts start overwriting the slots below
+                asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
             } else {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < nseg() && part == 1) ts.bidx[s] = fc[s].idx;
+                    if (s < nseg() && part != 0) ts.bidx[s] = fc[s].idx;
             }
         }
         struct Cand {
@@ -324,28 +342,36 @@ struct EncodeEpilogue {
             int idx;
             int pad;
         };
-        Cand* cand = reinterpret_cast<Cand*>(scratch) + (quad * 32 + lane) * kMaxSeg;
+        static_assert(sizeof(Cand) == 16, "Cand shares the FCand slots");
+        Cand* cand = reinterpret_cast<Cand*>(scratch) + (quad * 32 + lane) * kSegSlots;
+        constexpr int kCandStride = 128 * kSegSlots;
         if (exact_merge) {
-            // merge the two column halves of this row quadrant: part 1 publishes its running minima, part 0 keeps
-            // its own on ties (it owns the lower column indices) and publishes the final codes back.
-            if (part == 1) {
+            // merge the column parts of this row quadrant: parts 1.. publish their running minima, part 0 keeps
+            // the lowest index on ties and publishes the final codes back (slot 0).
+            if (part != 0) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
-                    if (s < nseg()) cand[s].best = ts.best[s], cand[s].idx = ts.bidx[s];
+                    if (s < nseg())
+                        cand[(part - 1) * kCandStride + s].best = ts.best[s],
+                        cand[(part - 1) * kCandStride + s].idx = ts.bidx[s];
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
             if (part == 0) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
                     if (s < nseg()) {
-                        const double ob = cand[s].best;
-                        const int oi = cand[s].idx;
-                        if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s])) ts.bidx[s] = oi;   // ties -> lowest
+#pragma unroll
+                        for (int p = 1; p < kSplit; ++p) {
+                            const double ob = cand[(p - 1) * kCandStride + s].best;
+                            const int oi = cand[(p - 1) * kCandStride + s].idx;
+                            if (ob < ts.best[s] || (ob == ts.best[s] && oi < ts.bidx[s]))      // ties -> lowest
+                                ts.best[s] = ob, ts.bidx[s] = oi;
+                        }
                         cand[s].idx = ts.bidx[s];
                     }
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
-            if (part == 1) {
+            asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
+            if (part != 0) {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
                     if (s < nseg()) ts.bidx[s] = cand[s].idx;
@@ -367,8 +393,28 @@ struct EncodeEpilogue {
             }
         }
         ts.vmax = 0.f;
-        // part 1 must have read the final codes before part 0 can overwrite the slots at the next level end
-        asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+        if constexpr (FAST) {
+            // The next level gathers one row of every cross-term table per earlier level, chosen by the codes that
+            // are final as of now: pull this thread's slice of those rows into L1 while the tensor core is busy with
+            // the next level's GEMM, so that the chunk loop does not expose the L2 latency of the gathers.
+            if (l + 1 < levels && !(dbg_flags(g) & 1024)) {
+                const int nl = n_level[l + 1];
+#pragma unroll
+                for (int jl = 0; jl < kMaxLevels - 1; ++jl)
+                    if (jl <= l) {
+#pragma unroll
+                        for (int s2 = 0; s2 < kMaxSeg; ++s2)
+                            if (s2 < nseg()) {
+                                const float* bp = btab32 + boff[l + 1][jl] +
+                                                  (static_cast<long long>(s2) * k[jl] + ts.code[jl][s2]) * nl;
+                                for (int c = tv.c_begin; c < tv.c_end && c < nl; c += 32)
+                                    asm volatile("prefetch.global.L1 [%0];" ::"l"(bp + c));
+                            }
+                    }
+            }
+        }
+        // the other parts must have read the final codes before anyone overwrites the slots at the next level end
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
     }
 
     __device__ __forceinline__ void end(Tile&, const IgemmGeom&, const TileCoord&) const {}

@@ -597,7 +597,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const bool tracer = (lane == 0 && quad == 0);
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
             const TileCoord tc = decode_tile(g, t);
-            if (tracer) trace_stamp(g, tl, part == 0 ? 6 : 11);
+            if (tracer && !(part == 1 && (dbg_flags(g) & 32))) trace_stamp(g, tl, part == 0 ? 6 : 11);
             typename Epi::Tile ts;
             const uint8_t* slot = epi_scratch + (Epi::kSideWarp ? tile_par * (kEpiSmemBytes / 2) : 0);
             if constexpr (Epi::kSideWarp) mbar_wait(smem_u32(&side_full[tile_par]), sph);
@@ -653,7 +653,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     mbar_wait(smem_u32(&tfull_bar[a % kSlots]), (a / kSlots) & 1);
                 }
                 tcgen05_fence_after();
-                if (tracer && step == 0) trace_stamp(g, tl, part == 0 ? 8 : 12);
+                if (tracer && step == 0 && !(part == 1 && (dbg_flags(g) & 32))) trace_stamp(g, tl, part == 0 ? 8 : 12);
+                if (tracer && part == 0 && step == 1 && (dbg_flags(g) & 32)) trace_stamp(g, tl, 12);
                 if constexpr (EpiStaticCols<Epi>::value) {
                     // Per-column parameters are kernel-parameter constants: make the warp's column base a compile-time
                     // value (one code copy per (column tile, part); a CTA only ever runs its own two), so that after
@@ -725,6 +726,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                 }
                 if (tracer && part == 0 && step == 0) trace_stamp(g, tl, 9);
+                if (tracer && part == 0 && step == 1 && (dbg_flags(g) & 32)) trace_stamp(g, tl, 13);
                 TmemView tv{};
 #pragma unroll
                 for (int grp = 0; grp < G; ++grp)
@@ -732,6 +734,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tv.c_begin = c_begin;
                 tv.c_end = c_end;
                 if constexpr (Epi::kHoldSlots) epi.step_end(ts, g, tc, step, part, quad, lane, epi_scratch, tv);
+                if (tracer && part == 0 && step == 0 && (dbg_flags(g) & 32)) trace_stamp(g, tl, 11);
                 tcgen05_fence_before();
                 __syncwarp();
                 if (lane == 0) {
@@ -746,7 +749,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (lane == 0) mbar_arrive(smem_u32(&side_empty[tile_par]));
             }
             if ((tile_par ^= 1) == 0) sph ^= 1;
-            if (tracer) trace_stamp(g, tl, part == 0 ? 10 : 13);
+            if (tracer && !(part == 1 && (dbg_flags(g) & 32))) trace_stamp(g, tl, part == 0 ? 10 : 13);
         }
     }
 

@@ -45,3 +45,24 @@ torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / iters * 1e3
 gmac = rows * 3 * k * 256 * 3 / 1e9
 print(f"encode k={k} agents={n} debug={dbg}: {us:.1f} us/launch  ({2 * gmac / us / 1e3:.1f} TOP/s of int8 digit MMA)", flush=True)
+
+if "--trace" in sys.argv:
+    from ctypes import c_void_p
+
+    cta = 40
+    buf = torch.zeros((148, 32, 16), dtype=torch.int64, device=dev)
+    _lib.lib().qv2x_debug_trace(c_void_p(buf.data_ptr()))
+    _lib.lib().qv2x_set_debug_flags((dbg[0] if dbg else 0) | 32)
+    eng.encode(q, 0.173, out=out)
+    torch.cuda.synchronize()
+    _lib.lib().qv2x_debug_trace(c_void_p(0))
+    tr = buf.cpu().numpy()[cta]
+    t0 = tr[0][:14][tr[0][:14] > 0].min()
+    names = ["P:start", "P:issued", "M:start", "M:slot", "M:full0", "M:issued", "E0:start", "E0:begun", "E0:tfull",
+             "E0:chunk0", "E0:end", "E0:lvl0end", "E0:tfull1", "E0:chunk1"]
+    print("tile " + " ".join(f"{nm:>9s}" for nm in names))
+    for i in range(20):
+        if tr[i, 6] == 0:
+            break
+        print(f"{i:4d} " + " ".join(f"{(tr[i, k] - t0) if tr[i, k] else -1:9d}" for k in range(len(names))) +
+              f"   Pwait {tr[i, 14]:6d} Mwait {tr[i, 15]:6d}")
