@@ -1,10 +1,14 @@
 #!/usr/bin/env python
 """bench.py -- W8A8 fused BEV frames/s of the quantized cooperative-perception forward on B200.
 
-A "step" = one cooperative frame: N_AGENTS (ego + 7) agents each run the W8A8 BEV backbone + shrinker +
-codebook encode; the code planes are gathered on the ego rank, which decodes, warps, fuses (attention) and
-runs the detection heads.  Agents are sharded over the GPUs (8/N per GPU, strong scaling); the only exchange is
-the gather of uint8 code planes to rank 0.
+A cooperative frame: N_AGENTS (ego + 7) agents each run the PointPillars front end, the W8A8 BEV backbone +
+shrinker and the codebook encoder; the code planes travel to the ego, which decodes, warps, fuses (attention) and runs
+the detection heads.  On 1 GPU a "step" is one frame.  On G GPUs the agents are sharded over the ranks (8/G per GPU)
+and a step is a batch of G consecutive frames: rank r runs the agent stage of ITS agents for the G frames in one launch
+sequence (so every launch has the 1-GPU shape, 8 agent maps), the uint8 code planes travel all-to-all (frame f's
+planes to rank f, peer-memory stores by qv2x_scatter_planes), and rank f runs the ego stage of frame f.  Per-GPU work
+per step does not depend on G (weak scaling); `value` = frames of all ranks / time.  QV2X_MGPU=tiles selects the
+latency-oriented round-1 layout instead (one frame per step, ego output tiled over the ranks, strong scaling).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
@@ -236,6 +240,21 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     assert N_AGENTS % world == 0, "agent count must divide over the GPUs"
     per = N_AGENTS // world
+    # Multi-GPU modes (both shard the AGENTS over the ranks, 8/G per rank, and exchange integer code planes):
+    #   frames (default): a step is a batch of G consecutive frames.  Rank r runs the agent stage of ITS agents for all
+    #       G frames in one launch sequence (8 agent maps per launch, the 1-GPU kernel shapes), the code planes travel
+    #       all-to-all (frame f's planes go to rank f) and rank f runs the whole ego stage of frame f: the ego role
+    #       rotates over the ranks.  Per-GPU work per step is constant in G (weak scaling).
+    #   tiles: one frame per step; every rank receives all code planes and computes one TILE of the ego output
+    #       (lowest latency, but 8/G-agent launches leave the SMs under-filled; round-1 design).
+    MGPU = os.environ.get("QV2X_MGPU", "frames") if world > 1 else "single"
+    assert MGPU in ("frames", "tiles", "single")
+    F = world if MGPU == "frames" else 1          # frames per step
+    n_img = per * F                               # agent maps per launch on this rank
+    config["frames_per_step"] = F
+    if world > 1:
+        config["parallelism"] = (f"agents/{world}gpu, {F} frames per step, ego role rotates over the ranks"
+                                 if MGPU == "frames" else f"agents/{world}gpu, ego output tiled over the ranks")
 
     q, bev_delta = build_calibrated_model(device, args.fusion, args.w_bits, dict_size=args.dict_size)
     attach_engines(q, bev_delta=bev_delta, device=device)
@@ -258,7 +277,7 @@ def main():
         return (torch.from_numpy(np.ascontiguousarray(vf[sel])), torch.from_numpy(vc),
                 torch.from_numpy(np.ascontiguousarray(vn[sel])))
 
-    pil_host = tuple(t.pin_memory() for t in pillar_set(0))
+    pil_frame0 = pillar_set(0)
     poses = torch.from_numpy(synthetic_poses(N_AGENTS)).float()
     aff = normalize_pairwise_tfm(poses, 80.0, 281.6, 1)[0, 0, :N_AGENTS].contiguous().to(device)
     aff_host = aff.cpu().numpy()
@@ -274,14 +293,18 @@ def main():
     # path.  The input of step i is buffer i % R of a pool of R distinct frames whose total size exceeds the 126 MB
     # L2, so no step finds its input in L2 (this replaces the flush buffer, which would serialise the pipeline).
     INFLIGHT = int(os.environ.get("QV2X_INFLIGHT", "2" if world == 1 else "4"))     # short per-rank stages: deeper pipeline
-    in_bytes = sum(int(t.numel()) * t.element_size() for t in pil_host)
+    in_bytes = F * sum(int(t.numel()) * t.element_size() for t in pil_frame0)      # one step's input on this rank
     R = max(INFLIGHT, -(-(140 * 1024 * 1024) // in_bytes))
     R += R % INFLIGHT
-    pil_pool = [tuple(t.to(device) for t in pil_host)]
-    for r in range(1, R):
-        # distinct frames of the same statistics: the point clouds of frame 0, every pillar moved to another cell
-        f0, c0, n0 = pil_pool[0]
-        shift_y, shift_x = 3 * r, 5 * r
+    base = tuple(t.to(device) for t in pil_frame0)
+
+    def frame_variant(v):
+        """Frame v of this rank's agents: distinct frames of the same statistics -- the point clouds of frame 0 with
+        every pillar moved to another cell (v = 0: frame 0 itself)."""
+        f0, c0, n0 = base
+        if v == 0:
+            return f0, c0, n0
+        shift_y, shift_x = 3 * v, 5 * v
         c = c0.clone()
         dy = (c[:, 2] + shift_y) % BEV_H - c[:, 2]
         dx = (c[:, 3] + shift_x) % BEV_W - c[:, 3]
@@ -291,10 +314,23 @@ def main():
         live = (torch.arange(32, device=device)[None, :] < n0[:, None]).to(f.dtype)
         f[:, :, 0] += dx[:, None].to(f.dtype) * enc_args["voxel_size"][0] * live
         f[:, :, 1] += dy[:, None].to(f.dtype) * enc_args["voxel_size"][1] * live
-        pil_pool.append((f, c, n0.clone()))
-    bev_slot = [torch.empty((per, BEV_H, BEV_W, BEV_C), dtype=torch.uint8, device=device) for _ in range(INFLIGHT)]
+        return f, c, n0
+
+    pil_pool = []
+    for r in range(R):
+        # the input of step r: frames r*F .. r*F+F-1, frame-major agent maps (map index = frame * per + local agent)
+        fs, cs, ns = [], [], []
+        for fi in range(F):
+            f_, c_, n_ = frame_variant(r * F + fi)
+            c_ = c_.clone()
+            c_[:, 0] += fi * per
+            fs.append(f_), cs.append(c_), ns.append(n_)
+        pil_pool.append((torch.cat(fs).contiguous(), torch.cat(cs).contiguous(), torch.cat(ns).contiguous()))
+    pil_host = tuple(t.cpu().pin_memory() for t in pil_pool[0])
+    bev_slot = [torch.empty((n_img, BEV_H, BEV_W, BEV_C), dtype=torch.uint8, device=device) for _ in range(INFLIGHT)]
     config["inflight"] = INFLIGHT
-    config["input"] = f"pillars [{per}x{PILLARS}, 32, 4] f32 + coords + point counts per rank ({in_bytes / 2**20:.1f} MB per step)"
+    config["input"] = (f"pillars [{n_img}x{PILLARS}, 32, 4] f32 + coords + point counts per rank and step "
+                       f"({in_bytes / 2**20:.1f} MB)")
     config["l2"] = (f"the input of step i is pillar set i % {R} of {R} distinct frames ({R * in_bytes / 2**20:.0f} MB per "
                     "rank, more than the 126 MB L2); no flush between steps because frames are pipelined")
 
@@ -306,11 +342,11 @@ def main():
     g_enc, codes_local = [None] * R, [None] * INFLIGHT
     for r in range(R):
         g_enc[r], codes_local[r % INFLIGHT] = pipe._capture(
-            lambda r=r: pipe.encode_pillars(*pil_pool[r], per, slot=r % INFLIGHT, bev_out=bev_slot[r % INFLIGHT]))
+            lambda r=r: pipe.encode_pillars(*pil_pool[r], n_img, slot=r % INFLIGHT, bev_out=bev_slot[r % INFLIGHT]))
     lc1 = _lib.lib().qv2x_launch_count()
     g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
     recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT
-    tile = rank_tile(rank, world, pipe.ho, pipe.wo) if world > 1 else None
+    tile = rank_tile(rank, world, pipe.ho, pipe.wo) if MGPU == "tiles" else None
     # Multi-GPU exchange: peer-memory stores from our own kernels + two device barriers (PeerExchange); NCCL
     # all-gather / gather only if the symmetric-memory mapping cannot be set up on this box.
     px = None
@@ -326,10 +362,22 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             px = None
-    config["exchange"] = "none (1 GPU)" if world == 1 else ("peer-memory stores + device barriers" if px else "NCCL all_gather + gather")
+    if world == 1:
+        config["exchange"] = "none (1 GPU)"
+    elif MGPU == "frames":
+        config["exchange"] = ("all-to-all of code planes by peer-memory stores (qv2x_scatter_planes) + device barriers"
+                              if px else "NCCL all_to_all of code planes")
+    else:
+        config["exchange"] = "peer-memory stores + device barriers" if px else "NCCL all_gather + gather"
     for sl in range(INFLIGHT):
         if world == 1:
             g_ego[sl], preds_dev[sl] = pipe.capture_ego(codes_local[sl], aff, slot=sl)
+        elif MGPU == "frames":
+            codes_full[sl] = (px.codes_full(sl) if px is not None else
+                              torch.zeros((levels, m, N_AGENTS * hw), dtype=torch.uint8, device=device))
+            if px is None:
+                recv_codes[sl] = torch.empty((world, levels, m, per * hw), dtype=torch.uint8, device=device)
+            g_ego[sl], preds_dev[sl] = pipe.capture_ego(codes_full[sl], aff, slot=sl)
         elif px is not None:
             codes_full[sl] = px.codes_full(sl)
             g_ego[sl], _ = pipe._capture(
@@ -348,8 +396,12 @@ def main():
     launches_per_step = (lc1 - lc0) // (3 * R) + (lc2 - lc1) // (3 * INFLIGHT)
     streams = [torch.cuda.Stream() for _ in range(INFLIGHT)]
 
+    from quantv2x_b200.distributed import all_to_all_code_planes
+    from quantv2x_b200.engine import scatter_planes
+
     def step(i):
-        """Step i on the CURRENT stream: input buffer i % R, buffer set i % INFLIGHT.  Returns preds on rank 0."""
+        """Step i on the CURRENT stream: input buffer i % R, buffer set i % INFLIGHT.  Returns the head maps of the
+        frame this rank fused (frames mode: frame `rank` of the step; tiles mode: the frame, on rank 0 only)."""
         r, sl = i % R, i % INFLIGHT
         g_enc[r].replay()
         if world == 1:
@@ -360,6 +412,13 @@ def main():
         return collect_preds(sl)
 
     def exchange_codes(sl):
+        if MGPU == "frames":
+            if px is not None:
+                scatter_planes(codes_local[sl], N_AGENTS * hw, rank * per * hw, px.code_ptrs(sl))
+                px.barrier(sl)          # every rank's planes of MY frame have landed in my buffer
+            else:
+                codes_full[sl].copy_(all_to_all_code_planes(codes_local[sl], recv=recv_codes[sl]))
+            return
         if px is not None:
             push_planes(codes_local[sl], N_AGENTS * hw, rank * per * hw, px.code_ptrs(sl))
             px.barrier(sl)              # every rank's planes have landed in this rank's buffer
@@ -367,6 +426,10 @@ def main():
             codes_full[sl].copy_(all_gather_code_planes(codes_local[sl], hw, recv=recv_codes[sl]))
 
     def collect_preds(sl):
+        if MGPU == "frames":
+            if px is not None:
+                px.barrier(sl)          # every rank has consumed its code buffer: the slot may be refilled
+            return preds_dev[sl]
         if px is not None:
             px.barrier(sl)              # every rank's head tile has landed in the ego rank's buffer
             return preds_dev[sl] if rank == 0 else None
@@ -374,7 +437,8 @@ def main():
 
     def phase_times(k=10):
         """Device time of the step's phases on this rank (CUDA events between them, one frame at a time)."""
-        names = ["encode_graph", "exchange_codes", "ego_graph", "gather_preds"] if world > 1 else ["encode_graph", "ego_graph"]
+        names = (["encode_graph", "exchange_codes", "ego_graph", "gather_preds" if MGPU == "tiles" else "slot_barrier"]
+                 if world > 1 else ["encode_graph", "ego_graph"])
         acc = [0.0] * len(names)
         for i in range(k):
             r, sl = i % R, i % INFLIGHT
@@ -452,7 +516,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, serial_ms = float(t[0].item()), float(t[1].item())
     ms_per_step = total_ms / args.steps
-    fps = 1e3 / ms_per_step
+    fps = 1e3 * F / ms_per_step
 
     # ---- e2e: host buffers in, host result out, through the same public calls.  Every step copies ITS inputs from
     # pinned host memory into its input buffer and reads ITS result back; the copies run on their own streams so
@@ -464,8 +528,9 @@ def main():
     # detection post-processing on the GPU (qv2x_postprocess_*: score threshold, box decode, rotated NMS) -- inside the
     # reference's timed region too (inference_mc_quant.py:581-606, on the CPU there); one handle per frame in flight
     from quantv2x_b200.postprocess import PostProcessor
+    owns_result = rank == 0 or MGPU == "frames"      # frames mode: every rank fuses (and post-processes) one frame
     ppe, pp_out, pp_host = [], [], []
-    if rank == 0:
+    if owns_result:
         grid_wh = (BEV_W, BEV_H)
         for _ in range(INFLIGHT):
             e = PostProcessor(q.hypes, grid_wh).engine
@@ -473,7 +538,7 @@ def main():
             outs = e.alloc_outputs(device)
             pp_out.append(outs)
             pp_host.append(tuple(torch.empty_like(o, device="cpu").pin_memory() for o in outs))
-    box_bytes = sum(int(o.numel()) * o.element_size() for o in pp_out[0]) if rank == 0 else 0
+    box_bytes = sum(int(o.numel()) * o.element_size() for o in pp_out[0]) if owns_result else 0
 
     def e2e_run(k, boxes):
         """boxes=True: the step's result is the detection list (post-processing on the GPU, D2H = boxes);
@@ -510,7 +575,7 @@ def main():
                 p = step(i)
                 enc_done[r] = ev()
                 enc_done[r].record(st)
-                if rank == 0:
+                if owns_result:
                     if d2h_done[sl] is not None:
                         st.wait_event(d2h_done[sl])
                     if boxes:
@@ -519,7 +584,7 @@ def main():
                         preds_stage[sl].copy_(p, non_blocking=True)
                 ego_done[sl] = ev()
                 ego_done[sl].record(st)
-            if rank == 0:
+            if owns_result:
                 with torch.cuda.stream(s_d2h):
                     s_d2h.wait_event(ego_done[sl])
                     if boxes:
@@ -545,7 +610,7 @@ def main():
         t = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_fps[boxes] = 1e3 / (float(t.item()) / args.steps)
+        e2e_fps[boxes] = 1e3 * F / (float(t.item()) / args.steps)
     n_boxes = int(pp_host[0][4][0].item()) if rank == 0 else 0
 
     # the frame's result as a checksum: integers travel between the GPUs and every output pixel is computed by the
@@ -565,10 +630,10 @@ def main():
         reps = max(args.steps, 10)
 
         def time_layer(layer, cin, groups):
-            xin = torch.randint(0, 256, (per, pipe.ho, pipe.wo, cin), dtype=torch.uint8, device=device)
+            xin = torch.randint(0, 256, (n_img, pipe.ho, pipe.wo, cin), dtype=torch.uint8, device=device)
             cg = cin // groups
             rs = [rowsum_u8(xin, i * cg, cg) for i in range(groups)]
-            yout = torch.empty((per, pipe.ho, pipe.wo, 256), dtype=torch.uint8, device=device)
+            yout = torch.empty((n_img, pipe.ho, pipe.wo, 256), dtype=torch.uint8, device=device)
             for _ in range(3):
                 layer.forward(xin, rowsum_in=rs, out=yout)
             torch.cuda.synchronize()
@@ -576,8 +641,8 @@ def main():
 
         k0_ms = time_layer(pipe.fused.plan.layers[-2], 384, 3)
         k1_ms = time_layer(pipe.fused.plan.layers[-1], 256, 1)
-        ach0 = 2.0 * SHRINK0_GMAC_PER_AGENT * 1e9 * per / (k0_ms * 1e-3) / 1e12
-        ach1 = 2.0 * SHRINK1_GMAC_PER_AGENT * 1e9 * per / (k1_ms * 1e-3) / 1e12
+        ach0 = 2.0 * SHRINK0_GMAC_PER_AGENT * 1e9 * n_img / (k0_ms * 1e-3) / 1e12
+        ach1 = 2.0 * SHRINK1_GMAC_PER_AGENT * 1e9 * n_img / (k1_ms * 1e-3) / 1e12
         # int8 tensor-pipe peak, measured live two ways (MEASURED_PEAKS.json has bf16 only):
         #  (a) the raw tcgen05.mma kind::i8 rate by the library's own issue loop (qv2x_int8_mma_peak): the pipe's ceiling;
         #  (b) a library int8 GEMM (cuBLASLt through torch._int_mm, 8192^3, best of 10): what a tuned GEMM kernel reaches.
@@ -611,13 +676,13 @@ def main():
                 # dram__bytes_read + dram__bytes_write of this kernel from one `ncu --set full` capture
                 # (profiles/r2_ncu_shrink0.txt: 4 agents), per agent, scaled to this rank's agent count; algorithmic:
                 # 13.5 MB in + 9 MB out + 0.9 MB weights per agent (the output mostly stays in L2 for the next layer)
-                "traffic": NCU_SHRINK0_DRAM_BYTES_PER_AGENT * per, "traffic_unit": "bytes per launch (ncu, per agent x agents)",
+                "traffic": NCU_SHRINK0_DRAM_BYTES_PER_AGENT * n_img, "traffic_unit": "bytes per launch (ncu, per agent x agents)",
                 "us_per_launch": k0_ms * 1e3,
                 "other_kernels": [{"kernel": "igemm_kernel<256,128,1,FixedEpilogueC<1>,HALO> (shrinker conv3x3 256->256)",
                                    "achieved": ach1, "frac": ach1 / peak, "frac_vs_cublaslt": ach1 / peak_lib,
                                    "us_per_launch": k1_ms * 1e3}],
-                "step_tensor_frac": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * per / (ms_per_step * 1e-3) / 1e12 / peak,
-                "step_tensor_frac_vs_cublaslt": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * per / (ms_per_step * 1e-3) / 1e12 / peak_lib}
+                "step_tensor_frac": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * n_img / (ms_per_step * 1e-3) / 1e12 / peak,
+                "step_tensor_frac_vs_cublaslt": 2.0 * GMAC_INT8_PER_AGENT * 1e9 * n_img / (ms_per_step * 1e-3) / 1e12 / peak_lib}
         peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         if os.path.exists(peaks_file):
@@ -707,19 +772,20 @@ def main():
 
     if rank == 0:
         h2d = in_bytes * world
+        n_results = F                               # results read back per step over all ranks
         line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "u8 (int8 tensor cores, int32 accumulate)",
+                "scaling": "strong" if MGPU == "tiles" else "weak", "vs_baseline": None, "dtype": "u8 (int8 tensor cores, int32 accumulate)",
                 "data": "synthetic", "preds_sha1": preds_sha1, "parity": parity, "config": config,
                 "e2e": {"value": e2e_fps[True], "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": int(box_bytes),
+                        "d2h_bytes_per_step": int(box_bytes) * n_results,
                         "result": f"detections after GPU post-processing (score threshold, box decode, rotated NMS): "
                                   f"{n_boxes} boxes in the last frame; buffers of top-1000 boxes are read back"},
                 "e2e_head_maps": {"value": e2e_fps[False], "unit": "frames/s", "h2d_bytes_per_step": h2d,
-                                  "d2h_bytes_per_step": int(preds_host.numel() * 4)},
+                                  "d2h_bytes_per_step": int(preds_host.numel() * 4) * n_results},
                 "gpu_launches": int(launches), "clocks": summarize_clocks(samples),
                 "phases_ms_rank0": phases,
-                "latency_ms_one_frame_at_a_time": serial_ms / args.steps, "roofline": roof,
+                "latency_ms_one_step_at_a_time": serial_ms / args.steps, "roofline": roof,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -291,6 +291,13 @@ int qv2x_postprocess_forward(const qv2x_postprocess* p, const float* d_preds, do
 int qv2x_push_planes(const uint8_t* d_local, int planes, long long rows_local, long long dst_plane_stride,
                      long long dst_row0, void* const* peer_bases, int n_peers, void* stream);
 
+/* The all-to-all form, for frame-batched serving (rank r holds the codes of ITS agents for n_peers consecutive frames,
+ * frame f is fused on rank f): d_local is [planes][n_peers * rows_per_peer] bytes with frame-major rows; peer p
+ * receives rows [p * rows_per_peer, (p + 1) * rows_per_peer) of plane i at
+ * peer_bases[p] + i * dst_plane_stride + dst_row0. */
+int qv2x_scatter_planes(const uint8_t* d_local, int planes, long long rows_per_peer, long long dst_plane_stride,
+                        long long dst_row0, void* const* peer_bases, int n_peers, void* stream);
+
 /* Layout / quantization converters for the module boundaries of the drop-in wrappers (the reference
  * passes float32 NCHW between modules; the kernels work on uint8 / float32 pixel-major tensors).
  * quantize: q = clamp(rint(x / delta) + zp, 0, 2^bits-1) (reference quant_layer.py:132-133). */

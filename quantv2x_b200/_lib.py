@@ -224,6 +224,7 @@ def _declare_tiles(lib):
     lib.qv2x_heads_forward_tile.argtypes = [c_void_p, c_longlong, c_void_p, c_void_p, c_int, c_longlong, c_longlong,
                                             c_void_p]
     lib.qv2x_push_planes.argtypes = [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_void_p, c_int, c_void_p]
+    lib.qv2x_scatter_planes.argtypes = [c_void_p, c_int, c_longlong, c_longlong, c_longlong, c_void_p, c_int, c_void_p]
     lib.qv2x_layer_forward_ex.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, POINTER(c_void_p),
                                           c_void_p, c_int, c_int, c_void_p, c_void_p, POINTER(LayerExtra), c_void_p]
     lib.qv2x_dequant_u8.argtypes = [c_void_p, c_longlong, c_float, c_void_p, c_void_p]

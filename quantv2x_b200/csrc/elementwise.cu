@@ -38,16 +38,22 @@ struct PushPeers {
     uint8_t* base[8];
     int n;
 };
-__global__ void push_planes_kernel(const uint8_t* __restrict__ local, int planes, long long rows_local,
-                                   long long dst_plane_stride, long long dst_row0, const PushPeers peers) {
-    const long long vec_per_plane = rows_local / 16;
+// SCATTER = false: every peer receives all `rows` of each plane (all-gather);
+// SCATTER = true : peer p receives rows [p * rows, (p + 1) * rows) of each plane (all-to-all; src_plane_stride =
+//                  n_peers * rows).
+template <bool SCATTER>
+__global__ void push_planes_kernel(const uint8_t* __restrict__ local, int planes, long long rows,
+                                   long long src_plane_stride, long long dst_plane_stride, long long dst_row0,
+                                   const PushPeers peers) {
+    const long long vec_per_plane = rows / 16;
     const long long total = static_cast<long long>(peers.n) * planes * vec_per_plane;
     for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long v = i % vec_per_plane;
         const long long pp = i / vec_per_plane;
         const int plane = static_cast<int>(pp % planes), peer = static_cast<int>(pp / planes);
-        const uint4 val = __ldg(reinterpret_cast<const uint4*>(local + plane * rows_local) + v);
+        const uint8_t* src = local + plane * src_plane_stride + (SCATTER ? peer * rows : 0);
+        const uint4 val = __ldg(reinterpret_cast<const uint4*>(src) + v);
         *reinterpret_cast<uint4*>(peers.base[peer] + plane * dst_plane_stride + dst_row0 + 16 * v) = val;
     }
 }
@@ -102,8 +108,32 @@ extern "C" int qv2x_push_planes(const uint8_t* d_local, int planes, long long ro
     const long long total = static_cast<long long>(n_peers) * planes * (rows_local / 16);
     const int threads = 256;
     const int grid = static_cast<int>(std::min<long long>((total + threads - 1) / threads, num_sms() * 4LL));
-    push_planes_kernel<<<grid, threads, 0, static_cast<cudaStream_t>(stream_)>>>(d_local, planes, rows_local,
-                                                                                dst_plane_stride, dst_row0, pp);
+    push_planes_kernel<false><<<grid, threads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        d_local, planes, rows_local, rows_local, dst_plane_stride, dst_row0, pp);
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int qv2x_scatter_planes(const uint8_t* d_local, int planes, long long rows_per_peer,
+                                   long long dst_plane_stride, long long dst_row0, void* const* peer_bases, int n_peers,
+                                   void* stream_) {
+    QV2X_REQUIRE(d_local && peer_bases, "qv2x_scatter_planes: null argument");
+    QV2X_REQUIRE(n_peers >= 1 && n_peers <= 8, "1..8 peers");
+    QV2X_REQUIRE(rows_per_peer % 16 == 0 && dst_plane_stride % 16 == 0 && dst_row0 % 16 == 0,
+                 "plane sizes and offsets must be multiples of 16 bytes");
+    if (planes <= 0 || rows_per_peer <= 0) return 0;
+    PushPeers pp{};
+    pp.n = n_peers;
+    for (int i = 0; i < n_peers; ++i) {
+        QV2X_REQUIRE(peer_bases[i] != nullptr, "null peer buffer %d", i);
+        pp.base[i] = static_cast<uint8_t*>(peer_bases[i]);
+    }
+    const long long total = static_cast<long long>(n_peers) * planes * (rows_per_peer / 16);
+    const int threads = 256;
+    const int grid = static_cast<int>(std::min<long long>((total + threads - 1) / threads, num_sms() * 4LL));
+    push_planes_kernel<true><<<grid, threads, 0, static_cast<cudaStream_t>(stream_)>>>(
+        d_local, planes, rows_per_peer, rows_per_peer * n_peers, dst_plane_stride, dst_row0, pp);
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;

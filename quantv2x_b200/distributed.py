@@ -60,6 +60,24 @@ def all_gather_code_planes(codes: torch.Tensor, hw: int, recv: torch.Tensor | No
     return recv.permute(1, 2, 0, 3).reshape(levels, m, world * rows).contiguous()
 
 
+def all_to_all_code_planes(codes: torch.Tensor, recv: torch.Tensor | None = None) -> torch.Tensor:
+    """Frame-batched serving: this rank holds the codes of ITS agents for `world` consecutive frames, uint8
+    [levels, m, world * rows] with frame-major rows; frame f is fused on rank f.  Returns the codes of ALL agents for
+    this rank's frame, uint8 [levels, m, world * rows] with rank-major (= global agent order) rows.  The collective
+    form of qv2x_scatter_planes (used when peer-mapped memory is unavailable, and on CPU in the tests)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return codes
+    world = dist.get_world_size()
+    levels, m, rows_all = codes.shape
+    assert rows_all % world == 0
+    rows = rows_all // world
+    send = codes.view(levels, m, world, rows).permute(2, 0, 1, 3).contiguous()            # [frame, levels, m, rows]
+    if recv is None:
+        recv = torch.empty_like(send)
+    dist.all_to_all_single(recv.view(-1), send.view(-1))
+    return recv.permute(1, 2, 0, 3).reshape(levels, m, world * rows).contiguous()        # [levels, m, rank-major rows]
+
+
 def gather_pred_tiles(preds_tile: torch.Tensor, h: int, w: int, dst: int = 0, recv: torch.Tensor | None = None):
     """preds_tile: [Cout, tile_pixels] of this rank's tile.  Returns [Cout, h*w] on `dst`, None elsewhere."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

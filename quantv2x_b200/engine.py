@@ -481,6 +481,17 @@ def push_planes(codes: torch.Tensor, dst_plane_stride: int, dst_row0: int, peer_
                                       len(peer_ptrs), _stream_ptr()))
 
 
+def scatter_planes(codes: torch.Tensor, dst_plane_stride: int, dst_row0: int, peer_ptrs):
+    """All-to-all of code planes: codes uint8 [levels, m, n_peers * rows] (frame-major rows); peer p receives the rows
+    of frame p (see qv2x_scatter_planes)."""
+    assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+    planes, rows_all = codes.shape[0] * codes.shape[1], codes.shape[2]
+    assert rows_all % len(peer_ptrs) == 0
+    arr = (c_void_p * len(peer_ptrs))(*[c_void_p(int(p)) for p in peer_ptrs])
+    check(_lib.lib().qv2x_scatter_planes(c_void_p(codes.data_ptr()), planes, rows_all // len(peer_ptrs),
+                                         dst_plane_stride, dst_row0, arr, len(peer_ptrs), _stream_ptr()))
+
+
 def quantize_nchw_to_nhwc_u8(x: torch.Tensor, delta: float, zero_point: float = 0.0, bits: int = 8,
                              out: torch.Tensor | None = None, out_cbase: int = 0) -> torch.Tensor:
     """float32 NCHW -> uint8 NHWC activation codes (module-boundary converter)."""

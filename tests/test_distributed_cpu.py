@@ -82,3 +82,28 @@ def test_two_rank_tiles_and_allgather():
         ret = mgr.dict()
         mp.spawn(_worker_tiles, args=(2, port, ret), nprocs=2, join=True)
         assert ret[0] and ret[1]
+
+
+def _worker_a2a(rank, world, port, n_agents, hw, ret):
+    """Frame-batched serving: rank r encodes ITS agents for `world` frames; frame f is fused on rank f."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from quantv2x_b200.distributed import all_to_all_code_planes, shard_agents
+
+    levels, m = 3, 2
+    rng = np.random.default_rng(1)
+    frames = rng.integers(0, 256, size=(world, levels, m, n_agents * hw), dtype=np.uint8)   # frame f: all agents' codes
+    mine = shard_agents(n_agents, world, rank)
+    local = np.concatenate([frames[f][:, :, mine.start * hw:mine.stop * hw] for f in range(world)], axis=2)
+    out = all_to_all_code_planes(torch.from_numpy(np.ascontiguousarray(local)))
+    ret[f"ok{rank}"] = bool(np.array_equal(out.numpy(), frames[rank]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_all_to_all_gives_each_rank_its_frame():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker_a2a, args=(2, port, 8, 48, ret), nprocs=2, join=True)
+        assert ret["ok0"] and ret["ok1"]

@@ -169,6 +169,18 @@ def test_push_planes_and_heads_tile_addressing(cuda_device):
         assert np.array_equal(got[:, rank * rows_local:(rank + 1) * rows_local], codes.cpu().numpy().reshape(planes, -1))
         assert got[:, :rank * rows_local].max() == 0 and got[:, (rank + 1) * rows_local:].max() == 0
 
+    # all-to-all form: destination p receives the rows of frame p at this rank's agent offset
+    per_rows, nfr = 704, 4
+    batch = torch.from_numpy(rng.integers(0, 256, size=(3, 2, nfr * per_rows), dtype=np.uint8)).to(cuda_device)
+    dsts = [torch.zeros((planes, nfr * per_rows), dtype=torch.uint8, device=cuda_device) for _ in range(nfr)]
+    E.scatter_planes(batch, nfr * per_rows, rank * per_rows, [d.data_ptr() for d in dsts])
+    torch.cuda.synchronize()
+    b = batch.cpu().numpy().reshape(planes, nfr, per_rows)
+    for f, d in enumerate(dsts):
+        got = d.cpu().numpy()
+        assert np.array_equal(got[:, rank * per_rows:(rank + 1) * per_rows], b[:, f])
+        assert got[:, :rank * per_rows].max() == 0 and got[:, (rank + 1) * per_rows:].max() == 0
+
     ho, wo, C = 20, 48, 256
     hd = E.HeadsEngine(rng.normal(size=(72, C)).astype(np.float32) / 16, rng.normal(size=72).astype(np.float32))
     y0, y1, x0, x1 = 10, 20, 12, 24

@@ -211,6 +211,7 @@ def test_c_abi_error_convention_without_gpu():
     # null arguments
     assert L.qv2x_fuse(1, 2, 4, 4, 256, None, None, None, None) == -1
     assert L.qv2x_push_planes(None, 3, 16, 16, 0, None, 1, None) == -1
+    assert L.qv2x_scatter_planes(None, 3, 16, 16, 0, None, 1, None) == -1
     assert L.qv2x_fuse_weighted(2, 4, 4, 64, None, None, 1, None, None, None) == -1
     assert b"score" in L.qv2x_last_error()
     assert L.qv2x_dequant_u8(None, 16, 0.1, None, None) == -1
