@@ -267,6 +267,9 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
         for (int i = 0; i < 2; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = pack2(0.f, 0.f);
+        // unrolled so that the shared-memory loads of the next k groups are in flight under the FMAs of the current one
+        // (nine warps per SM cannot hide the LDS latency by themselves)
+#pragma unroll 4
         for (int k = 0; k < C; k += 4) {
             float4 xv[2];
 #pragma unroll
@@ -308,6 +311,115 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
                         float lo, hi;
                         unpack2(acc[i][j], lo, hi);
                         if (off[i] >= 0) out[static_cast<long long>(o) * out_npix + off[i]] = (h == 0 ? lo : hi) + b;
+                    }
+                }
+            }
+        }
+        __syncthreads();          // everyone is done with this buffer before the next iteration refills it
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+// The same GEMM with a 4 pixel x 8 output register tile (C a multiple of 128): half the weight loads per FMA of the
+// 2 x 8 kernel above.  Pixel tiles of 128 are staged in K halves of 128 channels (two 66 KB buffers next to the 72 KB
+// weight matrix), the accumulators live across the K chunks of a tile.  Per output the fma order is k ascending as
+// above, so both kernels give identical bits.
+constexpr int kHeadsPix4 = 128, kHeadsKC = 128;
+
+__global__ void __launch_bounds__(kHeadsThreads) heads_kernel_p4(const float* __restrict__ x,
+                                                                 const float* __restrict__ wt,
+                                                                 const float* __restrict__ bias,
+                                                                 float* __restrict__ out, long long npix, int C,
+                                                                 int cout, int tile_w, long long out_w,
+                                                                 long long out_npix) {
+    extern __shared__ float4 hsm4[];
+    float* hsm = reinterpret_cast<float*>(hsm4);
+    constexpr int pitch = kHeadsKC + kHeadsPitchPad;
+    float* ws = hsm;                                   // [C][72]
+    float* xs0 = hsm + C * kHeadsOut;                  // 2 x [128][pitch]
+    const int tid = threadIdx.x;
+    const int nkc = C / kHeadsKC;
+    const long long ntiles = (npix + kHeadsPix4 - 1) / kHeadsPix4;
+    const long long n_my = (static_cast<long long>(blockIdx.x) < ntiles)
+                               ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const long long n_chunks = n_my * nkc;
+
+    auto load_chunk = [&](long long c, int buf) {
+        const long long t = blockIdx.x + (c / nkc) * gridDim.x;
+        const int kc = static_cast<int>(c % nkc);
+        const long long p0 = t * kHeadsPix4;
+        const uint32_t dst = smem_u32(xs0 + buf * kHeadsPix4 * pitch);
+        for (int idx = tid; idx < kHeadsPix4 * (kHeadsKC / 4); idx += kHeadsThreads) {
+            const int pp = idx / (kHeadsKC / 4), v = idx % (kHeadsKC / 4);
+            const bool ok = (p0 + pp < npix);
+            cp_async_16(dst + (pp * pitch + 4 * v) * 4, ok ? x + (p0 + pp) * C + kc * kHeadsKC + 4 * v : x, ok);
+        }
+    };
+    for (int idx = tid; idx < C * kHeadsOut / 4; idx += kHeadsThreads)
+        cp_async_16(smem_u32(ws) + idx * 16, wt + idx * 4, true);
+    if (n_chunks > 0) load_chunk(0, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+
+    const int pg = tid & 31, og = tid >> 5;    // pixels pg + 32 i; outputs og*8 + 2*j, og*8 + 2*j + 1
+    f32x2 acc[4][4];
+    int buf = 0;
+    for (long long c = 0; c < n_chunks; ++c, buf ^= 1) {
+        const int kc = static_cast<int>(c % nkc);
+        if (c + 1 < n_chunks) load_chunk(c + 1, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const float* xs = xs0 + buf * kHeadsPix4 * pitch;
+        const float* wk = ws + kc * kHeadsKC * kHeadsOut + og * 8;
+        if (kc == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = pack2(0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int k = 0; k < kHeadsKC; k += 4) {
+            float4 xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + (pg + 32 * i) * pitch + k);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const float4 w01 = *reinterpret_cast<const float4*>(wk + (k + kk) * kHeadsOut);
+                const float4 w23 = *reinterpret_cast<const float4*>(wk + (k + kk) * kHeadsOut + 4);
+                const f32x2 wp[4] = {pack2(w01.x, w01.y), pack2(w01.z, w01.w), pack2(w23.x, w23.y),
+                                     pack2(w23.z, w23.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float xk = (kk == 0) ? xv[i].x : (kk == 1) ? xv[i].y : (kk == 2) ? xv[i].z : xv[i].w;
+                    const f32x2 xx = pack2(xk, xk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma2(xx, wp[j], acc[i][j]);
+                }
+            }
+        }
+        if (kc == nkc - 1) {
+            const long long p0 = (blockIdx.x + (c / nkc) * gridDim.x) * kHeadsPix4;
+            long long off[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long pp = p0 + pg + 32 * i;
+                const int ty = static_cast<int>(pp / tile_w);
+                off[i] = (pp < npix) ? ty * out_w + (pp - static_cast<long long>(ty) * tile_w) : -1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int o = og * 8 + 2 * j + h;
+                    if (o < cout) {
+                        const float b = bias ? __ldg(bias + o) : 0.f;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            float lo, hi;
+                            unpack2(acc[i][j], lo, hi);
+                            if (off[i] >= 0)
+                                out[static_cast<long long>(o) * out_npix + off[i]] = (h == 0 ? lo : hi) + b;
+                        }
                     }
                 }
             }
@@ -489,16 +601,31 @@ int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* 
     QV2X_REQUIRE(tile_w >= 1 && out_w >= tile_w && out_pixels >= 1, "bad output tile geometry");
     if (pixels <= 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) * static_cast<int>(sizeof(float));
     static bool attr = false;
     if (!attr) {
         QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel_p4, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
-    const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
-    const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
-    heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout, tile_w,
-                                                        out_w, out_pixels);
+    static const bool p4_enabled = [] {
+        const char* e = getenv("QV2X_HEADS_P4");
+        return !(e && e[0] == '0');
+    }();
+    if (p4_enabled && h->cin % kHeadsKC == 0 && pixels >= 4LL * kHeadsPix4 * num_sms() / 8) {
+        const int smem = (2 * kHeadsPix4 * (kHeadsKC + kHeadsPitchPad) + h->cin * kHeadsOut) *
+                         static_cast<int>(sizeof(float));
+        const long long ntiles = (pixels + kHeadsPix4 - 1) / kHeadsPix4;
+        const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
+        heads_kernel_p4<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
+                                                               tile_w, out_w, out_pixels);
+    } else {
+        const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) *
+                         static_cast<int>(sizeof(float));
+        const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
+        const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
+        heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
+                                                            tile_w, out_w, out_pixels);
+    }
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
