@@ -475,7 +475,16 @@ class QuantPFNLayer(BaseQuantBlock):
         self.act_quantizer = UniformAffineQuantizer(**act_quant_params)
 
     def forward(self, inputs):
-        x = F.relu(self.linear(inputs))
+        # Above `part` pillars the reference feeds the Linear in slices of `part` rows (quant_block.py:611-618).  It
+        # matters for calibration: an un-initialised output quantizer of the Linear updates its scale on every call
+        # (running min / max), so the calibrated delta depends on the slicing; the mirror slices the same way.
+        m = inputs.shape[0]
+        if m > self.part:
+            pieces = [self.linear(inputs[lo:lo + self.part]) for lo in range(0, (m // self.part + 1) * self.part,
+                                                                            self.part)]
+            x = F.relu(torch.cat(pieces, dim=0))
+        else:
+            x = F.relu(self.linear(inputs))
         if self.use_act_quant:
             x = self.act_quantizer(x)
         x_max = torch.max(x, dim=1, keepdim=True)[0]

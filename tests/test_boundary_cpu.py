@@ -149,3 +149,42 @@ def test_wire_header_is_validated():
     m100[24] = 0xfe
     with pytest.raises(ValueError, match="out of range"):
         unpack_codes(bytes(m100))
+
+
+def test_quant_pfn_layer_slices_like_the_reference():
+    """Above `part` rows the Linear runs slice by slice (reference quant_block.py:611-618): an un-initialised output
+    quantizer updates its scale on every call (running min / max), so the calibrated scale depends on the slicing."""
+    import torch
+    from quantv2x_b200.pillar_modules import PFNLayer
+    from quantv2x_b200.quant.quant_block import QuantPFNLayer
+
+    torch.manual_seed(0)
+    pfn = PFNLayer(10, 64, use_norm=False, last_layer=True)
+    pfn.part = 8
+    wq = dict(n_bits=8, channel_wise=True, scale_method="minmax")
+    aq = dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)
+    q = QuantPFNLayer(pfn, wq, aq)
+    x = torch.randn(20, 32, 10)
+    x[:16] *= 50.0                                  # the last slice (rows 16..19) has a much smaller range
+    q.set_quant_state(True, True)
+    q.linear.weight_quantizer.set_inited(False)
+    q.linear.act_quantizer.set_inited(False)
+    q.act_quantizer.set_inited(False)
+    out = q(x)
+    assert out.shape == (20, 1, 64)
+    d_last = float(q.linear.act_quantizer.delta)
+    q2 = QuantPFNLayer(pfn, wq, aq)
+    q2.set_quant_state(True, True)
+    for z in (q2.linear.weight_quantizer, q2.linear.act_quantizer, q2.act_quantizer):
+        z.set_inited(False)
+    for lo in (0, 8, 16):
+        q2.linear(x[lo:lo + 8])
+    assert abs(float(q2.linear.act_quantizer.delta) - d_last) <= 1e-7 * d_last
+    q3 = QuantPFNLayer(pfn, wq, aq)
+    q3.part = 10 ** 6
+    q3.set_quant_state(True, True)
+    for z in (q3.linear.weight_quantizer, q3.linear.act_quantizer, q3.act_quantizer):
+        z.set_inited(False)
+    q3(x)
+    d_whole = float(q3.linear.act_quantizer.delta)                      # one call over the whole input
+    assert abs(d_whole - d_last) > 1e-3 * d_whole
