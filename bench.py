@@ -621,6 +621,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_fps[boxes] = 1e3 * F / (float(t.item()) / args.steps)
     n_boxes = int(pp_host[0][4][0].item()) if rank == 0 else 0
+    n_cand = int(pp_host[0][4][1].item()) if rank == 0 else 0
 
     # the frame's result as a checksum: integers travel between the GPUs and every output pixel is computed by the
     # same arithmetic whatever the tiling, so this must be identical for every --gpus N
@@ -789,7 +790,9 @@ def main():
                 "e2e": {"value": e2e_fps[True], "unit": "frames/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": int(box_bytes) * n_results,
                         "result": f"detections after GPU post-processing (score threshold, box decode, rotated NMS): "
-                                  f"{n_boxes} boxes in the last frame; buffers of top-1000 boxes are read back; "
+                                  f"{n_cand} candidates above the threshold ranked and run through the rotated-IoU "
+                                  f"matrix, {n_boxes} boxes kept in the last frame (random-init regression maps put "
+                                  "most boxes outside the range mask); buffers of top-1000 boxes are read back; "
                                   f"score threshold {pp_threshold:.4f} = the 300th highest score of frame 0 "
                                   "(random-init heads never reach the yaml's 0.2)"},
                 "e2e_head_maps": {"value": e2e_fps[False], "unit": "frames/s", "h2d_bytes_per_step": h2d,
