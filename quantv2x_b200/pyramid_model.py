@@ -184,6 +184,26 @@ class HeterPyramidCollabCodebookMC(nn.Module):
         return {"pyramid": "collab", "cls_preds": p[:, :n_cls], "reg_preds": p[:, n_cls:n_cls + n_reg],
                 "dir_preds": p[:, n_cls + n_reg:], "occ_single_list": occ, "preds_tensor": p}
 
+    def capture_decode(self, codes: torch.Tensor, other_info):
+        """CUDA graph of decode_features over STATIC code planes (uint8 [levels, m, rows], refilled in place between
+        replays) and poses: one replay instead of ~115 launches from Python.  Returns (graph, output dict whose
+        tensors the replay overwrites)."""
+        assert codes.is_cuda and codes.dtype == torch.uint8 and codes.dim() == 3
+        dev = codes.device
+        info = dict(other_info)
+        info["affine_matrix"] = other_info["affine_matrix"].to(dev)
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.decode_features(codes, info)      # warm-up: one-time attribute / workspace setup is not captured
+        torch.cuda.current_stream(dev).wait_stream(s)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.decode_features(codes, info)
+        return g, out
+
     def forward_with_encdec(self, data_dict):
         codes, _, other_info = self.encode_features(data_dict)
         return self.decode_features(codes, other_info)

@@ -71,11 +71,17 @@ def timed(fn, iters=5):
 
 enc_ms, enc_l, (codes, _, info) = timed(lambda: mdl.encode_features(data))
 dec_ms, dec_l, out = timed(lambda: mdl.decode_features(codes, info))
-res = {"agents": n, "bev": [200, 704], "encode_features_ms": enc_ms, "encode_launches": int(enc_l),
+codes_u8 = torch.stack([c.t() for c in codes]).to(torch.uint8).contiguous()
+graph, gout = mdl.capture_decode(codes_u8, info)
+graph_ms, _, _ = timed(lambda: graph.replay())
+same = bool(torch.equal(gout["preds_tensor"], out["preds_tensor"]))
+res = {"agents": n, "decode_features_graph_ms": graph_ms, "graph_equals_eager": same,
+       "frame_ms_with_graph": enc_ms + graph_ms, "frames_per_s_with_graph": 1e3 / (enc_ms + graph_ms), "bev": [200, 704], "encode_features_ms": enc_ms, "encode_launches": int(enc_l),
        "decode_features_ms": dec_ms, "decode_launches": int(dec_l), "frame_ms": enc_ms + dec_ms,
        "frames_per_s": 1e3 / (enc_ms + dec_ms), "preds_shape": list(out["preds_tensor"].shape),
        "preds_finite": bool(torch.isfinite(out["preds_tensor"]).all()),
-       "note": "eager launches from Python with torch allocations in the loop (no qv2x_plan / CUDA graph for this model)"}
+       "note": "decode_features_ms: eager launches from Python with torch allocations in the loop; "
+               "decode_features_graph_ms: the same stage replayed from a CUDA graph (capture_decode)"}
 print(json.dumps(res))
 if out_path:
     with open(out_path, "w") as f:
