@@ -541,6 +541,12 @@ def main():
         torch.cuda.synchronize()
         sc = torch.sigmoid(p0[:n_cls].float().flatten())
         pp_threshold = float(torch.topk(sc, 300).values[-1].item())
+        if os.environ.get("QV2X_BENCH_DEBUG"):
+            e_dbg = PostProcessor(q.hypes, grid_wh, score_threshold=pp_threshold).engine
+            r_dbg = e_dbg.forward(p0.contiguous())
+            print(f"[bench debug] threshold {pp_threshold}, elements above {(sc > pp_threshold).sum().item()}, "
+                  f"candidates {e_dbg.last_candidates}, boxes {r_dbg[0].shape[0]}, cls logits min/max "
+                  f"{p0[:n_cls].min().item():.3f}/{p0[:n_cls].max().item():.3f}", file=sys.stderr)
         for _ in range(INFLIGHT):
             e = PostProcessor(q.hypes, grid_wh, score_threshold=pp_threshold).engine
             ppe.append(e)
@@ -791,8 +797,8 @@ def main():
                         "d2h_bytes_per_step": int(box_bytes) * n_results,
                         "result": f"detections after GPU post-processing (score threshold, box decode, rotated NMS): "
                                   f"{n_cand} candidates above the threshold ranked and run through the rotated-IoU "
-                                  f"matrix, {n_boxes} boxes kept in the last frame (random-init regression maps put "
-                                  "most boxes outside the range mask); buffers of top-1000 boxes are read back; "
+                                  f"matrix, {n_boxes} boxes kept in the last frame; buffers of top-1000 boxes are read "
+                                  "back; "
                                   f"score threshold {pp_threshold:.4f} = the 300th highest score of frame 0 "
                                   "(random-init heads never reach the yaml's 0.2)"},
                 "e2e_head_maps": {"value": e2e_fps[False], "unit": "frames/s", "h2d_bytes_per_step": h2d,

@@ -188,3 +188,24 @@ def test_quant_pfn_layer_slices_like_the_reference():
     q3(x)
     d_whole = float(q3.linear.act_quantizer.delta)                      # one call over the whole input
     assert abs(d_whole - d_last) > 1e-3 * d_whole
+
+
+def test_yaml_anchor_config_matches_the_heads():
+    """The post-processor reads postprocess.anchor_args.anchor_generator_config (reference
+    voxel_postprocessor_3heads.py:28-40): one entry per class, consistent with the model's head widths."""
+    import glob
+    import os
+
+    from quantv2x_b200 import yaml_utils
+    from quantv2x_b200.postprocess import anchor_config_from_hypes
+
+    here = os.path.dirname(os.path.abspath(yaml_utils.__file__))
+    files = sorted(glob.glob(os.path.join(here, "hypes_yaml/v2x_real/Codebook/*/*.yaml")))
+    assert len(files) == 3
+    for fn in files:
+        hy = yaml_utils.load_yaml(fn)
+        cfg = anchor_config_from_hypes(hy["postprocess"])
+        args = hy["model"]["args"]
+        assert len(cfg) == args["num_class"] == 3, fn
+        assert all(len(c["anchor_rotations"]) == args["anchor_number"] for c in cfg), fn
+        assert {c["feature_map_stride"] for c in cfg} == {2}
