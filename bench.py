@@ -327,7 +327,6 @@ def main():
             fs.append(f_), cs.append(c_), ns.append(n_)
         pil_pool.append((torch.cat(fs).contiguous(), torch.cat(cs).contiguous(), torch.cat(ns).contiguous()))
     pil_host = tuple(t.cpu().pin_memory() for t in pil_pool[0])
-    bev_slot = [torch.empty((n_img, BEV_H, BEV_W, BEV_C), dtype=torch.uint8, device=device) for _ in range(INFLIGHT)]
     config["inflight"] = INFLIGHT
     config["input"] = (f"pillars [{n_img}x{PILLARS}, 32, 4] f32 + coords + point counts per rank and step "
                        f"({in_bytes / 2**20:.1f} MB)")
@@ -342,7 +341,7 @@ def main():
     g_enc, codes_local = [None] * R, [None] * INFLIGHT
     for r in range(R):
         g_enc[r], codes_local[r % INFLIGHT] = pipe._capture(
-            lambda r=r: pipe.encode_pillars(*pil_pool[r], n_img, slot=r % INFLIGHT, bev_out=bev_slot[r % INFLIGHT]))
+            lambda r=r: pipe.encode_pillars(*pil_pool[r], n_img, slot=r % INFLIGHT))
     lc1 = _lib.lib().qv2x_launch_count()
     g_ego, preds_dev = [None] * INFLIGHT, [None] * INFLIGHT
     recv_codes, codes_full, recv_preds = [None] * INFLIGHT, [None] * INFLIGHT, [None] * INFLIGHT

@@ -128,6 +128,8 @@ def _declare_pillar(lib):
     lib.qv2x_pillar_forward.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]
     lib.qv2x_pillar_forward_rs.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                                            c_void_p]
+    lib.qv2x_pillar_scatter.argtypes = lib.qv2x_pillar_forward_rs.argtypes
+    lib.qv2x_pillar_clear.argtypes = [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]
 
 
 class PostprocessDesc(_SizedStructure):

@@ -345,10 +345,12 @@ class PillarEngine:
             self._h = None
 
     def forward(self, voxel_features: torch.Tensor, voxel_coords: torch.Tensor, voxel_num_points: torch.Tensor,
-                batch: int, out: torch.Tensor | None = None, rowsum_out: torch.Tensor | None = None) -> torch.Tensor:
+                batch: int, out: torch.Tensor | None = None, rowsum_out: torch.Tensor | None = None,
+                assume_zero: bool = False) -> torch.Tensor:
         """voxel_features float32 [M, 32, 4], voxel_coords int [M, 4] (batch, z, y, x), voxel_num_points int [M]
         (CUDA tensors) -> uint8 BEV codes [batch, ny, nx, 64].  rowsum_out int32 [batch, ny, nx]: also receives the
-        per-cell sum of the 64 codes (what the backbone plan's first conv needs, Plan.forward(..., rowsum_in=))."""
+        per-cell sum of the 64 codes (what the backbone plan's first conv needs, Plan.forward(..., rowsum_in=)).
+        assume_zero: `out` (and `rowsum_out`) are all-zero already -- skip the clear (see clear())."""
         assert voxel_features.is_cuda and voxel_features.dim() == 3 and voxel_features.shape[1:] == (32, 4)
         f = voxel_features.to(torch.float32).contiguous()
         c = voxel_coords.to(torch.int32).contiguous()
@@ -360,12 +362,21 @@ class PillarEngine:
         if rowsum_out is not None:
             assert rowsum_out.is_cuda and rowsum_out.dtype == torch.int32 and rowsum_out.is_contiguous()
             assert tuple(rowsum_out.shape) == (batch, self.ny, self.nx)
-        check(_lib.lib().qv2x_pillar_forward_rs(self._h, int(f.shape[0]), c_void_p(f.data_ptr()),
-                                                c_void_p(c.data_ptr()), c_void_p(n.data_ptr()), int(batch),
-                                                c_void_p(out.data_ptr()),
-                                                None if rowsum_out is None else c_void_p(rowsum_out.data_ptr()),
-                                                _stream_ptr()))
+        fn = _lib.lib().qv2x_pillar_scatter if assume_zero else _lib.lib().qv2x_pillar_forward_rs
+        check(fn(self._h, int(f.shape[0]), c_void_p(f.data_ptr()), c_void_p(c.data_ptr()), c_void_p(n.data_ptr()),
+                 int(batch), c_void_p(out.data_ptr()),
+                 None if rowsum_out is None else c_void_p(rowsum_out.data_ptr()), _stream_ptr()))
         return out
+
+    def clear(self, voxel_coords: torch.Tensor, batch: int, bev: torch.Tensor,
+              rowsum: torch.Tensor | None = None) -> None:
+        """Zero the cells (and row sums) of these pillars in a map forward() filled: after its consumer has run, the
+        map is all-zero again and the next forward(..., assume_zero=True) needs no 9 MB-per-agent clear."""
+        assert voxel_coords.is_cuda and voxel_coords.dtype == torch.int32 and voxel_coords.is_contiguous()
+        assert bev.is_cuda and bev.dtype == torch.uint8 and tuple(bev.shape) == (batch, self.ny, self.nx, self.cout)
+        check(_lib.lib().qv2x_pillar_clear(self._h, int(voxel_coords.shape[0]), c_void_p(voxel_coords.data_ptr()),
+                                           int(batch), c_void_p(bev.data_ptr()),
+                                           None if rowsum is None else c_void_p(rowsum.data_ptr()), _stream_ptr()))
 
 
 class PostProcessEngine:

@@ -71,19 +71,31 @@ class CollabPipeline:
     def encode_pillars(self, voxel_features, voxel_coords, voxel_num_points, n: int, slot=0,
                        bev_out: torch.Tensor | None = None) -> torch.Tensor:
         """The agent stage from the model's own input: pillars -> PointPillars front end (BEV codes + their per-cell
-        sums in one kernel) -> backbone + shrinker plan -> codebook encode.  Returns codes uint8 [levels, m, n*hw]."""
+        sums in one kernel) -> backbone + shrinker plan -> codebook encode.  Returns codes uint8 [levels, m, n*hw].
+
+        The stage's own BEV map and row sums are kept ALL-ZERO between calls: the front end only scatters, and once
+        the plan has consumed the map the cells of this frame's pillars are zeroed again (3 MB instead of a 76 MB
+        clear per 8-agent frame).  A caller-provided `bev_out` keeps its contents (full clear, as before)."""
         if getattr(self, "pillar_engine", None) is None:
             raise RuntimeError("no pillar engine attached (the PointPillar encoder is not quantized / calibrated)")
         pe = self.pillar_engine
         key = ("pillar", n, slot)
         if key not in self._enc_buf:
             self._enc_buf[key] = dict(
-                bev=torch.empty((n, pe.ny, pe.nx, pe.cout), dtype=torch.uint8, device=self.device),
-                rowsum=torch.empty((n, pe.ny, pe.nx), dtype=torch.int32, device=self.device))
+                bev=torch.zeros((n, pe.ny, pe.nx, pe.cout), dtype=torch.uint8, device=self.device),
+                rowsum=torch.zeros((n, pe.ny, pe.nx), dtype=torch.int32, device=self.device))
         pb = self._enc_buf[key]
-        bev = pb["bev"] if bev_out is None else bev_out
-        pe.forward(voxel_features, voxel_coords, voxel_num_points, n, out=bev, rowsum_out=pb["rowsum"])
-        return self.encode_agents(bev, slot, rowsum=pb["rowsum"])
+        if bev_out is not None:
+            if "rowsum_ext" not in pb:
+                pb["rowsum_ext"] = torch.empty((n, pe.ny, pe.nx), dtype=torch.int32, device=self.device)
+            pe.forward(voxel_features, voxel_coords, voxel_num_points, n, out=bev_out, rowsum_out=pb["rowsum_ext"])
+            return self.encode_agents(bev_out, slot, rowsum=pb["rowsum_ext"])
+        coords = voxel_coords.to(torch.int32).contiguous()
+        pe.forward(voxel_features, coords, voxel_num_points, n, out=pb["bev"], rowsum_out=pb["rowsum"],
+                   assume_zero=True)
+        codes = self.encode_agents(pb["bev"], slot, rowsum=pb["rowsum"])
+        pe.clear(coords, n, pb["bev"], pb["rowsum"])
+        return codes
 
     # ------------------------------------------------------------------ ego side
     def ego_buffers(self, n, slot=0):

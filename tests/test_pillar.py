@@ -163,3 +163,30 @@ def test_front_end_emits_the_row_sums_the_plan_needs(cuda_device):
     f_a = pipe.encode_buffers(2, 0)["feat"].clone()
     b = pipe.encode_pillars(*pil, 2, slot=1)
     assert torch.equal(pipe.encode_buffers(2, 1)["feat"], f_a) and torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_keep_zero_protocol_of_the_agent_stage(cuda_device):
+    """encode_pillars scatters into an all-zero map and zeroes this frame's cells again after the plan has consumed it
+    (qv2x_pillar_scatter / qv2x_pillar_clear): successive DIFFERENT frames through the same slot give the same codes as
+    the clearing path, and the stage's buffers are all-zero between frames."""
+    import bench
+    from quantv2x_b200.export import attach_engines
+    from quantv2x_b200.synthetic import synthetic_pillars
+
+    q, bev_delta = bench.build_calibrated_model(cuda_device, "max", 8)
+    attach_engines(q, bev_delta=bev_delta, device=cuda_device)
+    pipe = q.model._pipelines["m1"]
+    enc = q.hypes["model"]["args"]["m1"]["encoder_args"]
+    pe = pipe.pillar_engine
+    frames = [[torch.from_numpy(t).to(cuda_device) for t in
+               synthetic_pillars(seed, 2, enc["lidar_range"], enc["voxel_size"], 2500)] for seed in (11, 12, 13)]
+    # out-of-grid rows are dropped by the scatter and must be ignored by the clear as well
+    frames[1][1][0, 2] = 10 ** 6
+    ext = torch.empty((2, pe.ny, pe.nx, pe.cout), dtype=torch.uint8, device=cuda_device)
+    for pil in frames:
+        ref = pipe.encode_pillars(*pil, 2, slot=3, bev_out=ext).clone()          # full clear, caller's buffer
+        got = pipe.encode_pillars(*pil, 2, slot=3)
+        assert torch.equal(ref, got)
+        buf = pipe._enc_buf[("pillar", 2, 3)]
+        assert int(buf["bev"].max()) == 0 and int(buf["rowsum"].abs().max()) == 0
