@@ -16,8 +16,9 @@ from quantv2x_b200.pyramid_model import attach_pyramid_engines  # noqa: E402
 from quantv2x_b200.quant import QuantModel, set_weight_quantize_params  # noqa: E402
 from quantv2x_b200.synthetic import seeded_init, seeded_init_codebook, synthetic_pillars, synthetic_poses  # noqa: E402
 
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
-out_path = sys.argv[2] if len(sys.argv) > 2 else None
+pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(pos[0]) if pos else 8
+out_path = pos[1] if len(pos) > 1 else None
 dev = torch.device("cuda:0")
 here = os.path.dirname(os.path.abspath(yaml_utils.__file__))
 hy = yaml_utils.load_yaml(os.path.join(here, "hypes_yaml/v2x_real/Codebook/Pyramid/lidar_pyramid_stage3.yaml"))
@@ -69,6 +70,17 @@ def timed(fn, iters=5):
     return e0.elapsed_time(e1) / iters, (_lib.lib().qv2x_launch_count() - l0) // iters, r
 
 
+if "--once" in sys.argv:          # one frame inside an NVTX range, for `ncu --nvtx --nvtx-include "timed/"`
+    for _ in range(2):
+        codes, _, info = mdl.encode_features(data)
+        mdl.decode_features(codes, info)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_push("timed")
+    codes, _, info = mdl.encode_features(data)
+    mdl.decode_features(codes, info)
+    torch.cuda.synchronize()
+    torch.cuda.nvtx.range_pop()
+    sys.exit(0)
 enc_ms, enc_l, (codes, _, info) = timed(lambda: mdl.encode_features(data))
 dec_ms, dec_l, out = timed(lambda: mdl.decode_features(codes, info))
 codes_u8 = torch.stack([c.t() for c in codes]).to(torch.uint8).contiguous()
