@@ -205,7 +205,8 @@ int qv2x_fuse_weighted(int n_agents, int H, int W, int C, const float* d_feat, c
  * heter_model_baseline_mc.py:137-142) concatenated along the output channel; weights are the de-quantized
  * fake-quant weights (W-quant only, FP32 activations: quant_model.py:129-136).
  * w: HOST [cout][cin], bias HOST [cout] or NULL.  d_x [pixels][cin] pixel-major -> d_out [cout][pixels]
- * (= preds_tensor in NCHW for one frame). */
+ * (= preds_tensor in NCHW for one frame).  cin <= 256, a multiple of 4; cout is arbitrary (72-column output chunks of
+ * one launch: the FP32 1x1 / transposed convs of the pyramid path use the same GEMM). */
 typedef struct qv2x_heads qv2x_heads;
 int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out);
 void qv2x_heads_destroy(qv2x_heads* heads);

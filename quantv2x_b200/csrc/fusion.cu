@@ -233,6 +233,12 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
                                                               long long out_w, long long out_npix) {
     extern __shared__ float4 hsm4[];
     float* hsm = reinterpret_cast<float*>(hsm4);
+    // blockIdx.y = chunk of 72 outputs (wider GEMMs: the FP32 deblocks of the pyramid path): own weight slab, bias
+    // slice and output rows
+    wt += static_cast<long long>(blockIdx.y) * C * kHeadsOut;
+    if (bias) bias += blockIdx.y * kHeadsOut;
+    out += static_cast<long long>(blockIdx.y) * kHeadsOut * out_npix;
+    cout = min(cout - static_cast<int>(blockIdx.y) * kHeadsOut, kHeadsOut);
     const int pitch = C + kHeadsPitchPad;
     float* ws = hsm;                                   // [C][72]   k-major, outputs contiguous (pairs for FFMA2)
     float* xs0 = hsm + C * kHeadsOut;                  // 2 x [64][pitch] pixel-major
@@ -334,6 +340,10 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel_p4(const float* __
                                                                  long long out_npix) {
     extern __shared__ float4 hsm4[];
     float* hsm = reinterpret_cast<float*>(hsm4);
+    wt += static_cast<long long>(blockIdx.y) * C * kHeadsOut;           // chunk of 72 outputs, as in heads_kernel
+    if (bias) bias += blockIdx.y * kHeadsOut;
+    out += static_cast<long long>(blockIdx.y) * kHeadsOut * out_npix;
+    cout = min(cout - static_cast<int>(blockIdx.y) * kHeadsOut, kHeadsOut);
     constexpr int pitch = kHeadsKC + kHeadsPitchPad;
     float* ws = hsm;                                   // [C][72]
     float* xs0 = hsm + C * kHeadsOut;                  // 2 x [128][pitch]
@@ -564,16 +574,21 @@ extern "C" {
 int qv2x_heads_create(int cin, int cout, const float* w, const float* bias, qv2x_heads** out) {
     QV2X_REQUIRE(w && out, "qv2x_heads_create: null argument");
     QV2X_REQUIRE(cin % 4 == 0 && cin <= 256, "cin must be a multiple of 4 and <= 256");
-    QV2X_REQUIRE(cout >= 1 && cout <= kHeadsOut, "cout must be 1..%d", kHeadsOut);
+    QV2X_REQUIRE(cout >= 1 && cout <= 65535 * kHeadsOut, "cout must be 1..%d", 65535 * kHeadsOut);
     auto h = new qv2x_heads();
     h->cin = cin;
     h->cout = cout;
-    // k-major, padded to 72 outputs: wt[k][o] = w[o][k] (what the kernel stages in shared memory)
-    std::vector<float> wt(static_cast<size_t>(cin) * kHeadsOut, 0.f);
-    for (int o = 0; o < cout; ++o)
-        for (int k = 0; k < cin; ++k) wt[static_cast<size_t>(k) * kHeadsOut + o] = w[static_cast<size_t>(o) * cin + k];
+    // chunks of 72 outputs, each k-major and zero-padded: wt[chunk][k][o] = w[chunk * 72 + o][k] (what a CTA stages in
+    // shared memory); the bias is padded the same way
+    const int chunks = (cout + kHeadsOut - 1) / kHeadsOut;
+    std::vector<float> wt(static_cast<size_t>(chunks) * cin * kHeadsOut, 0.f), bp(static_cast<size_t>(chunks) * kHeadsOut, 0.f);
+    for (int o = 0; o < cout; ++o) {
+        const size_t base = static_cast<size_t>(o / kHeadsOut) * cin * kHeadsOut + (o % kHeadsOut);
+        for (int k = 0; k < cin; ++k) wt[base + static_cast<size_t>(k) * kHeadsOut] = w[static_cast<size_t>(o) * cin + k];
+        if (bias) bp[o] = bias[o];          // chunk stride == chunk width: only the tail is padding
+    }
     int rc = upload(&h->d_w, wt.data(), wt.size());
-    if (!rc && bias) rc = upload(&h->d_b, bias, static_cast<size_t>(cout));
+    if (!rc && bias) rc = upload(&h->d_b, bp.data(), bp.size());
     if (rc) {
         cudaFree(h->d_w);
         delete h;
@@ -611,18 +626,22 @@ int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* 
         const char* e = getenv("QV2X_HEADS_P4");
         return !(e && e[0] == '0');
     }();
-    if (p4_enabled && h->cin % kHeadsKC == 0 && pixels >= 4LL * kHeadsPix4 * num_sms() / 8) {
+    // one CTA per SM overall: the output chunks of 72 columns are blockIdx.y, the pixel tiles of a chunk are shared
+    // by ceil(#SMs / chunks) persistent CTAs
+    const int chunks = (h->cout + kHeadsOut - 1) / kHeadsOut;
+    const int per_chunk = std::max(1, (num_sms() + chunks - 1) / chunks);
+    if (p4_enabled && h->cin % kHeadsKC == 0 && pixels * chunks >= 4LL * kHeadsPix4 * num_sms() / 8) {
         const int smem = (2 * kHeadsPix4 * (kHeadsKC + kHeadsPitchPad) + h->cin * kHeadsOut) *
                          static_cast<int>(sizeof(float));
         const long long ntiles = (pixels + kHeadsPix4 - 1) / kHeadsPix4;
-        const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
+        const dim3 grid(static_cast<unsigned>(std::min<long long>(ntiles, per_chunk)), chunks);
         heads_kernel_p4<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
                                                                tile_w, out_w, out_pixels);
     } else {
         const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) *
                          static_cast<int>(sizeof(float));
         const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
-        const int grid = static_cast<int>(std::min<long long>(ntiles, num_sms()));
+        const dim3 grid(static_cast<unsigned>(std::min<long long>(ntiles, per_chunk)), chunks);
         heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
                                                             tile_w, out_w, out_pixels);
     }

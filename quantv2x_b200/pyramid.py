@@ -178,7 +178,7 @@ class FirstBottleneckEngine:
         bias = np.zeros(w_hat.shape[0], np.float32) if c1.get("bias") is None else np.asarray(c1["bias"], np.float32)
         self.width, self.cin = w_hat.shape
         assert self.width % 64 == 0
-        self.conv1 = [E.HeadsEngine(w_hat[o:o + 64], bias[o:o + 64]) for o in range(0, self.width, 64)]
+        self.conv1 = E.HeadsEngine(w_hat, bias)            # one launch: 72-column output chunks are grid.y
         self.conv2 = _layer(p["conv2"], ksize=3, stride=1, pad=1, relu=True, in_delta=self.d1, out_delta=d2,
                             groups=int(p["groups"]))
         self.conv3 = _layer(p["conv3"], ksize=1, stride=1, pad=0, relu=True, in_delta=d2, out_delta=self.out_delta)
@@ -191,8 +191,7 @@ class FirstBottleneckEngine:
         n, h, w, _ = x.shape
         dev = x.device
         planar = torch.empty((self.width, n * h * w), dtype=torch.float32, device=dev)
-        for i, eng in enumerate(self.conv1):
-            eng.forward(x, out=planar[64 * i:64 * (i + 1)])
+        self.conv1.forward(x, out=planar)
         q1 = E.quantize_nchw_to_nhwc_u8(planar.view(1, self.width, n * h, w), self.d1).view(n, h, w, self.width)
         if taps is not None:
             taps["q1_first"] = q1
@@ -251,8 +250,8 @@ def weighted_fuse_level(codes: torch.Tensor, delta: float, occ: torch.Tensor, af
 class DeblockF32:
     """QuantModule(ConvTranspose2d(cin, cout, s, stride=s)) + ReLU + act quantizer on an FP32 input (the fused map of
     a level is off every quantization grid).  Output pixel (y*s + dy, x*s + dx) is a 1x1 conv of input pixel (y, x)
-    with the weight slice [:, :, dy, dx]: one FP32 GEMM with s*s*cout columns (64-column chunks of the heads kernel),
-    then the quantizing converter and a pixel shuffle."""
+    with the weight slice [:, :, dy, dx]: one FP32 GEMM with s*s*cout columns (the heads kernel, 72-column output
+    chunks as grid.y), then the quantizing converter and a pixel shuffle."""
 
     def __init__(self, up: dict):
         self.s = int(up["stride"])
@@ -263,8 +262,7 @@ class DeblockF32:
         rows = np.ascontiguousarray(w_hat.transpose(2, 3, 1, 0).reshape(self.s * self.s * self.cout, self.cin))
         b = np.zeros(self.cout, np.float32) if up.get("bias") is None else np.asarray(up["bias"], np.float32)
         bias = np.tile(b, self.s * self.s)
-        assert rows.shape[0] % 64 == 0
-        self.gemm = [E.HeadsEngine(rows[o:o + 64], bias[o:o + 64]) for o in range(0, rows.shape[0], 64)]
+        self.gemm = E.HeadsEngine(rows, bias)              # one launch for all s*s sub-positions
 
     def forward(self, fused: torch.Tensor, out: torch.Tensor, out_cbase: int = 0) -> torch.Tensor:
         """fused float32 [h, w, cin] -> codes written to out[:, :, out_cbase : out_cbase + cout] (uint8 [h*s, w*s, C])."""
@@ -272,8 +270,7 @@ class DeblockF32:
         h, w, _ = fused.shape
         s, n_col = self.s, self.s * self.s * self.cout
         planar = torch.empty((n_col, h * w), dtype=torch.float32, device=fused.device)
-        for i, eng in enumerate(self.gemm):
-            eng.forward(fused, out=planar[64 * i:64 * (i + 1)])
+        self.gemm.forward(fused, out=planar)
         q = E.quantize_nchw_to_nhwc_u8(planar.view(1, n_col, h, w), self.delta)        # [1, h, w, s*s*cout]
         q = q.view(h, w, s, s, self.cout).permute(0, 2, 1, 3, 4).reshape(h * s, w * s, self.cout)
         out[:, :, out_cbase:out_cbase + self.cout].copy_(q)

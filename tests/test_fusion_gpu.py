@@ -86,7 +86,9 @@ def test_heads(cuda_device):
     from quantv2x_b200.engine import HeadsEngine
 
     rng = np.random.default_rng(3)
-    for pixels, cin, cout in [(1000, 256, 72), (35200, 256, 72), (77, 64, 20)]:
+    # cout > 72: wider FP32 GEMMs (the deblocks of the pyramid path) run as 72-column output chunks of one launch
+    for pixels, cin, cout in [(1000, 256, 72), (35200, 256, 72), (77, 64, 20), (2200, 256, 2048), (8800, 128, 512),
+                              (35200, 64, 128), (300, 64, 100)]:
         x = rng.normal(size=(pixels, cin)).astype(np.float32)
         w = rng.normal(size=(cout, cin)).astype(np.float32) / 16
         b = rng.normal(size=cout).astype(np.float32)
