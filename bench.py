@@ -53,6 +53,9 @@ def parse():
     # parity / sweep configurations of BASELINE.json (the default is the metric's configuration)
     ap.add_argument("--agents", type=int, default=8, help="agents in the frame (ego included): 2, 4 or 8")
     ap.add_argument("--dict-size", type=int, default=0, help="codebook size k (0 = the yaml's 128)")
+    ap.add_argument("--model", default="att", choices=["att", "pyramid"],
+                    help="att (default): the metric's model; pyramid: an auxiliary line for the pyramid-fusion model "
+                         "(SURVEY 8(f)-2: HeterPyramidCollabCodebookMC, codebook C=64 m=1 k=128), 1 GPU")
     return ap.parse_args()
 
 
@@ -183,9 +186,126 @@ def cpu_reference_frames_per_s(spec, pspec, enc_args, n_agents, steps, warmup, b
 
 
 # ----------------------------------------------------------------------------------------------- main
+def pyramid_main(args):
+    """Auxiliary bench line of the pyramid-fusion model driver (1 GPU): one frame = pillars of N agents -> front end ->
+    agent ResNet backbone -> codebook encode | decode -> ResNeXt pyramid over all agents -> deblocks -> shrink conv ->
+    heads.  The agent stage is launched from Python, the ego stage replays a CUDA graph (capture_decode)."""
+    import torch
+
+    from quantv2x_b200 import _lib, yaml_utils
+    from quantv2x_b200.pyramid_model import attach_pyramid_engines
+    from quantv2x_b200.quant import QuantModel, set_weight_quantize_params
+    from quantv2x_b200.synthetic import seeded_init, seeded_init_codebook, synthetic_pillars, synthetic_poses
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    n = args.agents
+    here = os.path.dirname(os.path.abspath(yaml_utils.__file__))
+    hy = yaml_utils.load_yaml(os.path.join(here, "hypes_yaml/v2x_real/Codebook/Pyramid/lidar_pyramid_stage3.yaml"))
+    model = yaml_utils.create_model(hy).eval()
+    seeded_init(model, 1234)
+    seeded_init_codebook(model.codebook, 4321)
+    q = QuantModel(model, dict(n_bits=8, channel_wise=True, scale_method="minmax"),
+                   dict(n_bits=8, channel_wise=False, scale_method="minmax", leaf_param=True, prob=1.0)).eval()
+    q.disable_network_output_quantization()
+    q.to(dev)
+    set_weight_quantize_params(q)
+    enc = hy["model"]["args"]["m1"]["encoder_args"]
+
+    def frame(seed, agents, device):
+        vf, vc, vn = synthetic_pillars(seed, agents, enc["lidar_range"], enc["voxel_size"], PILLARS)
+        return {"inputs_m1": {"voxel_features": torch.from_numpy(vf).to(device),
+                              "voxel_coords": torch.from_numpy(vc).to(device),
+                              "voxel_num_points": torch.from_numpy(vn).to(device)},
+                "agent_modality_list": ["m1"] * agents,
+                "pairwise_t_matrix": torch.from_numpy(synthetic_poses(agents)).float(),
+                "record_len": torch.tensor([agents])}
+
+    mods = [m for m in q.modules() if hasattr(m, "act_quantizer")]
+    q.set_quant_state(True, True)
+    for m in mods:
+        m.act_quantizer.set_inited(False)
+    with torch.no_grad():
+        q.model.calibration_forward(frame(99, 2, dev))          # offline calibration (torch body)
+    for m in mods:
+        m.act_quantizer.set_inited(True)
+    attach_pyramid_engines(q, device=dev)
+    mdl = q.model
+    host = frame(0, n, "cpu")
+    host_in = {k: v.pin_memory() for k, v in host["inputs_m1"].items()}
+    data = dict(host, inputs_m1={k: v.to(dev) for k, v in host_in.items()})
+    codes, _, info = mdl.encode_features(data)
+    codes_u8 = torch.stack([c.t() for c in codes]).to(torch.uint8).contiguous()
+    graph, gout = mdl.capture_decode(codes_u8, info)
+    eng = mdl._engines
+    l0 = _lib.lib().qv2x_launch_count()
+    mdl.decode_features(codes_u8, info)
+    ego_launches = _lib.lib().qv2x_launch_count() - l0
+
+    def step(upload):
+        if upload:
+            for k, v in host_in.items():
+                data["inputs_m1"][k].copy_(v, non_blocking=True)
+        c, _, _ = mdl.encode_features(data)
+        for l in range(len(c)):                    # the wire payload: byte planes into the graph's static buffer
+            codes_u8[l].copy_(c[l].t())
+        graph.replay()
+        return gout["preds_tensor"]
+
+    preds_host = torch.empty(tuple(gout["preds_tensor"].shape), dtype=torch.float32).pin_memory()
+
+    def timed(k, upload):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            p = step(upload)
+            if upload:
+                preds_host.copy_(p, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    timed(max(args.warmup, 3), False)
+    stop, samples = threading.Event(), []
+    th = threading.Thread(target=clock_sampler, args=(stop, samples, 0), daemon=True)
+    th.start()
+    l0 = _lib.lib().qv2x_launch_count()
+    ms = timed(args.steps, False)
+    enc_launches = (_lib.lib().qv2x_launch_count() - l0) // args.steps
+    timed(2, True)
+    e2e_ms = timed(args.steps, True)
+    stop.set()
+    th.join(timeout=2)
+    import hashlib
+    in_bytes = sum(int(v.numel()) * v.element_size() for v in host_in.values())
+    line = {"metric": f"W8A8 pyramid-fusion frames/s (ego + {n - 1} agents, PointPillars V2X-Real 704x200, ResNet agent "
+                      "backbone, codebook C=64 m=1 k=128, ResNeXt pyramid [3,5,8], shrink conv, heads)",
+            "value": 1e3 * args.steps / ms, "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 (int8 tensor cores, int32 accumulate)", "data": "synthetic",
+            "preds_sha1": hashlib.sha1(gout["preds_tensor"].cpu().numpy().tobytes()).hexdigest(),
+            "config": {"workload": f"pyramid model, ego+{n - 1} agents, {PILLARS} pillars per agent; SURVEY 8(f)-2 "
+                                   "(auxiliary line: BASELINE.json's metric is the att-fusion model)",
+                       "agents": n, "l2": "activations of the 16 ResNeXt blocks over all agents (> 126 MB per frame) "
+                                          "are rewritten every step; the input pillars are the same frame"},
+            "e2e": {"value": 1e3 * args.steps / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": in_bytes,
+                    "d2h_bytes_per_step": int(preds_host.numel() * 4)},
+            "gpu_launches": int((enc_launches + ego_launches) * args.steps), "clocks": summarize_clocks(samples),
+            "roofline": None, "cpu_baseline": None,
+            "note": "agent stage launched from Python, ego stage replayed from a CUDA graph; see "
+                    "profiles/r2_launches_pyramid_model.txt for the per-kernel split"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     global N_AGENTS, METRIC
     args = parse()
+    if args.model == "pyramid":
+        if int(os.environ.get("RANK", "0")) == 0:
+            pyramid_main(args)
+        return
     if args.agents != 8 or args.dict_size or args.w_bits != 8 or args.fusion != "att":
         N_AGENTS = args.agents
         METRIC = (f"W{args.w_bits}A8 fused BEV frames/s (ego + {N_AGENTS - 1} agents, PointPillars V2X-Real 704x200, "
