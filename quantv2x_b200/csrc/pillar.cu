@@ -79,9 +79,14 @@ __global__ void __launch_bounds__(256) pillar_bev_kernel(const float4* __restric
         dst[1] = make_float4(f[4], f[5], f[6], f[7]);
         dst[2] = make_float4(f[8], f[9], 0.f, 0.f);
         __syncwarp();
+        // Padded rows have all-zero features, so their linear output is the bias exactly (fma(0, w, u) = u) and they
+        // are all alike: the maximum over the 32 rows = max(bias if any row is padded, rows of the nv valid points).
+        // The loop runs over the valid points only (half the work at a uniform 1..32 points per pillar).
+        const int nv = min(max(n, 0), kPillarPoints);
         float y0 = -INFINITY, y1 = -INFINITY;
+        if (nv < kPillarPoints) unpack2(bp, y0, y1);
 #pragma unroll 4
-        for (int q = 0; q < kPillarPoints; ++q) {
+        for (int q = 0; q < nv; ++q) {
             const float4* src = reinterpret_cast<const float4*>(&s_f[wib][q][0]);     // broadcast reads
             const float4 a = src[0], b = src[1], c = src[2];
             const float g[kPillarFeat] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y};
