@@ -269,6 +269,9 @@ struct FixedEpilogueC : FixedEpilogue<G, false, ZP, false> {
     using Tile = typename Base::Tile;
     using Side = typename Base::Side;
     static constexpr bool kStaticCols = true;      // igemm.cuh: the column base of every chunk is a compile-time value
+    // 128-column tiles of short-K layers (stage 1, K = 1152) are epilogue-bound: four warps per lane quadrant halve
+    // the chunk loop of a tile (role traces: 1.9 k of a 2.9 k-cycle tile period)
+    static constexpr int col_split(int block_n) { return block_n == 128 ? 4 : 2; }
     FixedTable<G> tab;
 
     __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
