@@ -102,6 +102,34 @@ struct FixedEpilogue {
         cp_async_wait_all();
     }
 
+    // Two-phase form (igemm.cuh uses it when present): the receptive-field sums of the tile are computed into
+    // registers BEFORE the slot is free -- they only need the warp's private halo buffer -- and stored afterwards.
+    struct SidePre {
+        int32_t sums[G][4];
+    };
+    __device__ __forceinline__ void side_prefetch(const IgemmGeom& g, const TileCoord& tc, int lane, int32_t* halo,
+                                                  const Side& sd, SidePre& pre) const {
+        sd.template compute<G>(g, tc, lane, halo, rowsum_in, pre.sums);
+    }
+    __device__ __forceinline__ void side_store(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
+                                               int& staged_nt, const Side& sd, const SidePre& pre) const {
+        if (staged_nt != tc.nt) {
+            const uint32_t sp = smem_u32(slot);
+            const int n_base = tc.nt * g.block_n;
+            for (int i = lane; i < g.block_n; i += 32) {
+#pragma unroll
+                for (int q = 0; q < (DIGITS ? 1 : G); ++q) cp_async_4(sp + 4 * (q * kPar + i), mul[q] + n_base + i, true);
+                cp_async_4(sp + kOffC + 8 * i, &cadd[n_base + i].x, true);
+                cp_async_4(sp + kOffC + 8 * i + 4, &cadd[n_base + i].y, true);
+                cp_async_4(sp + kOffSh + 4 * i, shr + n_base + i, true);
+                if constexpr (ZP) cp_async_4(sp + kOffZ + 4 * i, zpw + n_base + i, true);
+            }
+            staged_nt = tc.nt;
+        }
+        sd.template store<G>(lane, reinterpret_cast<int32_t*>(slot + kSlotS), pre.sums);
+        cp_async_wait_all();
+    }
+
     __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
                                           const uint8_t* slot) const {
         ts.sm_par = smem_u32(slot);
@@ -271,13 +299,22 @@ struct FixedEpilogueC : FixedEpilogue<G, false, ZP, false> {
     static constexpr bool kStaticCols = true;      // igemm.cuh: the column base of every chunk is a compile-time value
     // 128-column tiles of short-K layers (stage 1, K = 1152) are epilogue-bound: four warps per lane quadrant halve
     // the chunk loop of a tile (role traces: 1.9 k of a 2.9 k-cycle tile period)
-    static constexpr int col_split(int block_n) { return block_n == 128 ? 4 : 2; }
+    static constexpr int col_split(int) { return 2; }
+    // short-K layers (stages 0 and 1) are bound by the per-tile fixed costs of the epilogue warps: two groups of
+    // eight warps alternate over the tiles (igemm.cuh, EpiTileSplit)
+    static constexpr int tile_split(int block_n) { return block_n <= 128 ? 2 : 1; }
     FixedTable<G> tab;
 
     __device__ __forceinline__ void side_load(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
                                               int32_t* halo, int& staged_nt, const Side& sd) const {
         (void)staged_nt;
         sd.template stage<G>(g, tc, lane, reinterpret_cast<int32_t*>(slot + Base::kSlotS), halo, this->rowsum_in);
+    }
+    __device__ __forceinline__ void side_store(const IgemmGeom&, const TileCoord&, int lane, uint8_t* slot,
+                                               int& staged_nt, const Side& sd,
+                                               const typename Base::SidePre& pre) const {
+        (void)staged_nt;
+        sd.template store<G>(lane, reinterpret_cast<int32_t*>(slot + Base::kSlotS), pre.sums);
     }
 
     template <int W>

@@ -56,6 +56,25 @@ struct SideHalo {
     template <int G>
     __device__ __forceinline__ void stage(const IgemmGeom& g, const TileCoord& tc, int lane, int32_t* s_S,
                                           int32_t* halo, const int32_t* const (&rowsum_in)[kMaxGroups]) const {
+        int32_t sums[G][4];
+        compute<G>(g, tc, lane, halo, rowsum_in, sums);
+        store<G>(lane, s_S, sums);
+    }
+
+    template <int G>
+    __device__ __forceinline__ void store(int lane, int32_t* s_S, const int32_t (&sums)[G][4]) const {
+#pragma unroll
+        for (int grp = 0; grp < G; ++grp)
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = sums[grp][rr];
+    }
+
+    // The sums of this lane's four tile rows, in registers: touches only the warp's private halo buffer, so the side
+    // warp can run it for the NEXT tile of its slot while the epilogue still reads the slot (igemm.cuh).
+    template <int G>
+    __device__ __forceinline__ void compute(const IgemmGeom& g, const TileCoord& tc, int lane, int32_t* halo,
+                                            const int32_t* const (&rowsum_in)[kMaxGroups],
+                                            int32_t (&sums)[G][4]) const {
         const int ix0 = tc.tx * g.tw * g.stride - g.pad, iy0 = tc.ty * g.th * g.stride - g.pad;
         const uint32_t halo_s = smem_u32(halo);
 #pragma unroll
@@ -63,7 +82,7 @@ struct SideHalo {
             const int32_t* rs = rowsum_in[grp];
             if (rs == nullptr) {
 #pragma unroll
-                for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = 0;
+                for (int rr = 0; rr < 4; ++rr) sums[grp][rr] = 0;
                 continue;
             }
             rs += static_cast<long long>(tc.img) * g.Hi * g.Wi;
@@ -105,7 +124,7 @@ struct SideHalo {
                         for (int kx = 0; kx < 3; ++kx)
                             if (ky < g.taps_h && kx < g.taps_w) sum += h0[ky * hw + kx];
                 }
-                s_S[grp * kTileM + lane + 32 * rr] = sum;     // rows outside the image are never stored
+                sums[grp][rr] = sum;                          // rows outside the image are never stored
             }
         }
     }

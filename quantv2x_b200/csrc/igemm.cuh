@@ -183,8 +183,34 @@ struct EpiStaticCols : std::false_type {};
 template <class Epi>
 struct EpiStaticCols<Epi, std::enable_if_t<Epi::kStaticCols>> : std::true_type {};
 
+// Optional epilogue trait `static constexpr int tile_split(int block_n)` (1 or 2): with 2, TWO groups of
+// 4 * col_split epilogue warps alternate over the CTA's tiles (group j takes the tiles k = j mod 2 of the CTA's
+// sequence, i.e. the side-input slot j), so the per-tile fixed costs of an epilogue warp (side-input barrier, row-sum
+// loads, accumulator barrier + fence, slot release, tile decode: ~1.2 k cycles) overlap with the other group's chunk
+// loop.  Short-K layers are bound by exactly these costs (profiles/r2_trace_short_layers.log).
+template <class Epi, class = void>
+struct EpiTileSplit {
+    static constexpr int get(int) { return 1; }
+};
+template <class Epi>
+struct EpiTileSplit<Epi, decltype(void(Epi::tile_split(0)))> {
+    static constexpr int get(int block_n) { return Epi::tile_split(block_n); }
+};
+
+// Optional two-phase side staging (epilogue members SidePre / side_prefetch / side_store).
+template <class Epi, class = void>
+struct EpiHasSidePre {
+    static constexpr bool value = false;
+};
+template <class Epi>
+struct EpiHasSidePre<Epi, decltype(void(sizeof(typename Epi::SidePre)))> {
+    static constexpr bool value = true;
+};
+
 template <class Epi, int BLOCK_N>
-constexpr int igemm_threads() { return (4 + 4 * Epi::col_split(BLOCK_N)) * 32; }
+constexpr int igemm_threads() {
+    return (4 + 4 * Epi::col_split(BLOCK_N) * EpiTileSplit<Epi>::get(BLOCK_N)) * 32;
+}
 
 template <int BLOCK_N, int BK, int G, class Epi, int TPS = 1, bool HALO = false, bool BRES = false, bool SRING = false>
 __global__ void __launch_bounds__(igemm_threads<Epi, BLOCK_N>(), 1)
@@ -198,7 +224,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     static_assert(!HALO || TPS == 1, "the HALO mainloop has one tap per B stage");
     static_assert(!(BRES && SRING), "a static ring is a streamed-weights mode");
     constexpr int kColSplit = Epi::col_split(BLOCK_N);
-    constexpr int kNumEpiWarps = 4 * kColSplit;
+    constexpr int kTileSplit = EpiTileSplit<Epi>::get(BLOCK_N);
+    static_assert(kTileSplit == 1 || (kTileSplit == 2 && Epi::kSideWarp), "tile groups map onto the two side slots");
+    constexpr int kNumEpiWarps = 4 * kColSplit;      // warps that work on ONE tile (barrier arrival counts)
     static_assert(BLOCK_N % (16 * kColSplit) == 0, "BLOCK_N must split into 16-column-aligned parts");
 
     extern __shared__ uint8_t smem_raw[];
@@ -577,8 +605,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             epi.side_init(sd, g, lane);
             for (int t = blockIdx.x + par * gridDim.x; t < total_tiles; t += 2 * gridDim.x, sph ^= 1) {
                 const TileCoord tc = decode_tile(g, t);
-                mbar_wait(smem_u32(&side_empty[par]), sph ^ 1);
-                epi.side_load(g, tc, lane, slot, halo, staged_nt, sd);
+                if constexpr (EpiHasSidePre<Epi>::value) {
+                    // the tile's sums are formed (global fetch of the halo + shared-memory taps) while the epilogue
+                    // may still be reading the slot; only the final stores wait for it
+                    typename Epi::SidePre pre;
+                    epi.side_prefetch(g, tc, lane, halo, sd, pre);
+                    mbar_wait(smem_u32(&side_empty[par]), sph ^ 1);
+                    epi.side_store(g, tc, lane, slot, staged_nt, sd, pre);
+                } else {
+                    mbar_wait(smem_u32(&side_empty[par]), sph ^ 1);
+                    epi.side_load(g, tc, lane, slot, halo, staged_nt, sd);
+                }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&side_full[par]));     // release: the slot's writes are visible
             }
@@ -586,16 +623,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp >= 4) {
         // ------------------------------------------------------------ epilogue
         const int quad = warp & 3;            // TMEM lane quadrant this warp may access
-        const int part = (warp - 4) >> 2;     // which part of the step's columns (kColSplit parts)
+        const int part = ((warp - 4) >> 2) % kColSplit;     // which part of the step's columns (kColSplit parts)
+        const int tgroup = ((warp - 4) >> 2) / kColSplit;   // which tiles of the CTA's sequence (kTileSplit groups)
         const int row = quad * 32 + lane;     // tile row == TMEM lane
         constexpr int kColsPerWarp = BLOCK_N / kColSplit;
-        uint32_t ac = 0;
-        uint32_t tile_par = 0;
+        uint32_t ac = static_cast<uint32_t>(tgroup) * g.n_steps * G;     // accumulator index of this group's first tile
+        uint32_t tile_par = tgroup;           // kTileSplit == 2: the group's side slot, fixed
         const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
         uint32_t sph = 0;
-        int tl = 0;
+        int tl = tgroup;
         const bool tracer = (lane == 0 && quad == 0);
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        for (int t = blockIdx.x + tgroup * gridDim.x; t < total_tiles; t += kTileSplit * gridDim.x, tl += kTileSplit) {
             const TileCoord tc = decode_tile(g, t);
             if (tracer && !(part == 1 && (dbg_flags(g) & 32))) trace_stamp(g, tl, part == 0 ? 6 : 11);
             typename Epi::Tile ts;
@@ -748,7 +786,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&side_empty[tile_par]));
             }
-            if ((tile_par ^= 1) == 0) sph ^= 1;
+            if constexpr (kTileSplit == 1) {
+                if ((tile_par ^= 1) == 0) sph ^= 1;
+            } else {
+                sph ^= 1;                                      // the group's own side slot, one phase per own tile
+                ac += (kTileSplit - 1) * g.n_steps * G;        // skip the other group's tiles
+            }
             if (tracer && !(part == 1 && (dbg_flags(g) & 32))) trace_stamp(g, tl, part == 0 ? 10 : 13);
         }
     }
