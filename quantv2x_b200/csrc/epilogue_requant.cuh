@@ -33,11 +33,17 @@ struct SideHalo {
     int hw, hh, n;
     int hoff[4];
     int hy[kFlat], hx[kFlat];
+    // 3x3 stride-1 convs on 8 x 16 pixel tiles (every HALO layer): separable box sum -- lane (lx, q) owns the four
+    // vertically adjacent rows 4q..4q+3 of column lx, reads six halo values of its column (plus six of the tile's
+    // outer column on the edge lanes), forms the vertical 3-sums and gets its neighbours' by shuffle: 12 shared-memory
+    // loads per lane instead of 36 (they are starved while the tensor core streams operands).
+    bool box;
 
     __device__ __forceinline__ void init(const IgemmGeom& g, int lane) {
         hw = (g.tw - 1) * g.stride + g.taps_w;
         hh = (g.th - 1) * g.stride + g.taps_h;
         n = hw * hh;
+        box = (g.stride == 1 && g.taps_h == 3 && g.taps_w == 3 && g.tw == 8 && g.th == 16);
 #pragma unroll
         for (int j = 0; j < kFlat; ++j) {
             const int e = lane + 32 * j;
@@ -63,10 +69,13 @@ struct SideHalo {
 
     template <int G>
     __device__ __forceinline__ void store(int lane, int32_t* s_S, const int32_t (&sums)[G][4]) const {
+        // tile row of sums[.][rr]: lane + 32 rr, or (box) row 4q + rr of column lx = 32 q + 8 rr + lx
+        const int r0 = box ? 32 * (lane >> 3) + (lane & 7) : lane;
+        const int rstep = box ? 8 : 32;
 #pragma unroll
         for (int grp = 0; grp < G; ++grp)
 #pragma unroll
-            for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + lane + 32 * rr] = sums[grp][rr];
+            for (int rr = 0; rr < 4; ++rr) s_S[grp * kTileM + r0 + rstep * rr] = sums[grp][rr];
     }
 
     // The sums of this lane's four tile rows, in registers: touches only the warp's private halo buffer, so the side
@@ -110,6 +119,23 @@ struct SideHalo {
             }
             cp_async_wait_all();
             __syncwarp();
+            if (box) {
+                const int lx = lane & 7, q = lane >> 3;
+                const int32_t* col = halo + (4 * q) * 10 + lx + 1;                     // own column, halo rows 4q..4q+5
+                const int32_t* edge = halo + (4 * q) * 10 + (lx == 7 ? 9 : (lx == 0 ? 0 : lx + 1));
+                int32_t a[6], e[6];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) a[r] = col[10 * r], e[r] = edge[10 * r];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int32_t own = (a[j] + a[j + 1]) + a[j + 2];
+                    const int32_t out = (e[j] + e[j + 1]) + e[j + 2];                  // only used on the edge lanes
+                    const int32_t up = __shfl_up_sync(0xffffffffu, own, 1, 8);         // column lx - 1
+                    const int32_t dn = __shfl_down_sync(0xffffffffu, own, 1, 8);       // column lx + 1
+                    sums[grp][j] = (lx == 0 ? out : up) + own + (lx == 7 ? out : dn);
+                }
+                continue;
+            }
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr) {
                 const int32_t* h0 = halo + hoff[rr];
