@@ -230,6 +230,33 @@ struct RequantEpilogue {
         cp_async_wait_all();                       // the parameter copies, when no group waited for them
     }
 
+    // Two-phase form (igemm.cuh): the tile's receptive-field sums are formed in registers before the slot is free.
+    struct SidePre {
+        int32_t sums[G][4];
+    };
+    __device__ __forceinline__ void side_prefetch(const IgemmGeom& g, const TileCoord& tc, int lane, int32_t* halo,
+                                                  const Side& sd, SidePre& pre) const {
+        sd.template compute<G>(g, tc, lane, halo, rowsum_in, pre.sums);
+    }
+    __device__ __forceinline__ void side_store(const IgemmGeom& g, const TileCoord& tc, int lane, uint8_t* slot,
+                                               int& staged_nt, const Side& sd, const SidePre& pre) const {
+        if (staged_nt != tc.nt) {
+            float* s_cs = reinterpret_cast<float*>(slot);
+            float* s_b = s_cs + 256;
+            int32_t* s_z = reinterpret_cast<int32_t*>(s_b + 256);
+            const int n_base = tc.nt * g.block_n;
+            const bool has_zp = (zpw[0] != nullptr);
+            for (int i = lane; i < g.block_n; i += 32) {
+                cp_async_4(smem_u32(s_cs + i), cscale + n_base + i, true);
+                cp_async_4(smem_u32(s_b + i), bias + n_base + i, true);
+                cp_async_4(smem_u32(s_z + i), has_zp ? static_cast<const void*>(zpw[0] + n_base + i) : cscale, has_zp);
+            }
+            staged_nt = tc.nt;
+        }
+        sd.template store<G>(lane, reinterpret_cast<int32_t*>(slot + kSlotS), pre.sums);
+        cp_async_wait_all();
+    }
+
     __device__ __forceinline__ void begin(Tile& ts, const IgemmGeom& g, const TileCoord& tc, int row,
                                           const uint8_t* slot) const {
         ts.sm_par = smem_u32(slot);
