@@ -370,8 +370,10 @@ int qv2x_layer_forward_ex(const qv2x_layer* L, int n_img, int hi, int wi, const 
         const int sub_cols = (d.kind == 0) ? L->n_total : d.cout;   // a tile must not straddle sub-positions
         const long long k_steps = static_cast<long long>(L->groups) * g.taps * g.cblocks * (L->bk / 32);
         long long best = -1;
+        static const int env_bn = getenv("QV2X_BN") ? atoi(getenv("QV2X_BN")) : 0;      // experiments
         for (int bn = L->block_n; bn >= 64; bn >>= 1) {
             if (sub_cols % bn != 0) continue;
+            if (env_bn && bn != env_bn && sub_cols % env_bn == 0 && env_bn <= L->block_n) continue;
             const long long tiles = m_tiles * (L->n_total / bn);
             const long long waves = (tiles + num_sms() - 1) / num_sms();
             const long long cost = waves * (4500 + k_steps * (bn / 2));
