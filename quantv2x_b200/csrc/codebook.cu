@@ -71,7 +71,7 @@ struct EncodeEpilogue {
         double best[kMaxSeg];
         int bidx[kMaxSeg];
         int code[kMaxLevels][kMaxSeg];
-        float fbest[kMaxSeg], fsecond[kMaxSeg], vmax;
+        float fbest[kMaxSeg], fsecond[kMaxSeg];
     };
 
     struct Side {};
@@ -89,7 +89,6 @@ struct EncodeEpilogue {
             ts.fbest[s] = INFINITY;
             ts.fsecond[s] = INFINITY;
         }
-        ts.vmax = 0.f;
 #pragma unroll
         for (int l = 0; l < kMaxLevels; ++l)
 #pragma unroll
@@ -116,7 +115,6 @@ struct EncodeEpilogue {
         {
             const float4* dp = reinterpret_cast<const float4*>(d32 + colbase[l] + n0);
             const float4* gp = reinterpret_cast<const float4*>(g32 + colbase[l] + n0);
-            float vm = ts.vmax;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 dv = __ldg(dp + q), gv = __ldg(gp + q);
@@ -134,12 +132,9 @@ struct EncodeEpilogue {
                         lo = fmaf(md, 256.f, l2);
                     }
                     const float vf = fmaf(hi, 65536.f, lo);
-                    // the error bound takes max |vf| plus a constant for the conversion error of the parts (step_end)
-                    vm = fmaxf(vm, fabsf(vf));
                     sc16[j] = fmaf(vf, dd[e], gg[e]);
                 }
             }
-            ts.vmax = vm;
         }
 #pragma unroll
         for (int jl = 0; jl < kMaxLevels - 1; ++jl) {
@@ -274,18 +269,20 @@ struct EncodeEpilogue {
         bool exact_merge = true;
         if constexpr (FAST) {
             // ---- merge the fp32 candidates of the two column halves and test the gap.
-            // Error bound of one fp32 score against the float64 evaluation.  V = 65536 hi + (256 mid + lo) exactly; the
-            // computed vf differs from it by the conversion of the low part (an integer below 2^32: <= 2^8, whatever
-            // the digits cancel to) plus one fma rounding (<= 2^-24 |vf|).  With Vb = max |vf| + 2^30 over the row's
-            // columns -- the constant covers the conversion term 2^10-fold at the 2^-20 scale used below -- the
-            // rounded d32, the score fma, the rounded g32 and each rounded cross term with its addition cost
-            // <= 2^-24 of a partial sum each, and every partial sum is <= T = Vb * max|d| + max|g0| + sum max|B|:
-            // the total is below (6 + 2 l) 2^-24 T <= 10 * 2^-24 T for the l <= 2 earlier levels; kEpsRel = 16 * 2^-24
-            // leaves margin.  best + eps < second - eps  =>  same argmin in float64.  (vmax holds max |vf|.)
+            // Error bound of one fp32 score s against its float64 evaluation.  V = 65536 hi + (256 mid + lo) exactly;
+            // the computed vf differs from it by the conversion of the low part (an integer below 2^32: <= 2^8 units,
+            // whatever the digits cancel to) plus one fma rounding.  The rounded d32, the score fma, the rounded g32
+            // and each rounded cross term with its addition cost <= 2^-24 of a partial sum each, and every partial
+            // sum is bounded by |vf d| + |g0| + sum |B| <= |s| + 2 C with C = max|g0| + sum max|B| (cabs): in total
+            //     |s - s64| <= (6 + 2 l) 2^-24 (|s| + 2 C) + 2^8 max|d|  <=  eps(s) = 2^-20 (|s| + 2 C + 2^30 max|d|)
+            // for the l <= 2 earlier levels (16 * 2^-24 against 10 * 2^-24, and 2^10 max|d| for the conversion term).
+            // s - eps(s) is increasing in s, so the runner-up bounds every other column from below:
+            //     second - eps(second) > best + eps(best)  =>  the fp32 argmin is the float64 argmin.
+            // (Round 1 tracked max |vf| of the row for a uniform eps: one more ALU-pipe instruction per score.)
             struct FCand {
                 float best, second;
                 int idx;
-                float vmax;
+                int pad;
             };
             // slot p - 1 of a row holds the candidates of part p; part 0 publishes the merged index in slot 0
             static_assert((kSplit - 1) * 128 * kSegSlots * 16 <= 8192, "merge scratch");
@@ -296,7 +293,7 @@ struct EncodeEpilogue {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
                     if (s < nseg())
-                        fc[(part - 1) * kPartStride + s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], ts.vmax};
+                        fc[(part - 1) * kPartStride + s] = FCand{ts.fbest[s], ts.fsecond[s], ts.bidx[s], 0};
             }
             asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(32 * kSplit) : "memory");
             if (part == 0) {
@@ -304,7 +301,7 @@ struct EncodeEpilogue {
 #pragma unroll
                 for (int s = 0; s < kMaxSeg; ++s)
                     if (s < nseg()) {
-                        float best = ts.fbest[s], second = ts.fsecond[s], vmax = ts.vmax;
+                        float best = ts.fbest[s], second = ts.fsecond[s];
                         int idx = ts.bidx[s];
 #pragma unroll
                         for (int p = 1; p < kSplit; ++p) {       // ascending parts = ascending columns
@@ -312,10 +309,10 @@ struct EncodeEpilogue {
                             second = fminf(fminf(second, o.second), fmaxf(best, o.best));
                             idx = (o.best < best) ? o.idx : idx;
                             best = fminf(best, o.best);
-                            vmax = fmaxf(vmax, o.vmax);
                         }
-                        const float eps = kEpsRel * fmaf(vmax + 1073741824.f, dmax[l], cabs[l]);
-                        unsafe |= !(second - best > 2.f * eps);      // also true for NaN
+                        const float k2 = 2.f * fmaf(1073741824.f, dmax[l], 2.f * cabs[l]);
+                        const float eps2 = kEpsRel * (fabsf(second) + fabsf(best) + k2);     // eps(second) + eps(best)
+                        unsafe |= !(second - best > eps2);           // also true for NaN / a single column
                         ts.bidx[s] = idx;
                         fc[s].idx = idx;
                     }
@@ -392,7 +389,6 @@ struct EncodeEpilogue {
                 ts.fsecond[s] = INFINITY;
             }
         }
-        ts.vmax = 0.f;
         if constexpr (FAST) {
             // The next level gathers one row of every cross-term table per earlier level, chosen by the codes that
             // are final as of now: pull this thread's slice of those rows into L1 while the tensor core is busy with
