@@ -169,6 +169,9 @@ int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride
                                  const long long* base_row, const int* rect, const uint8_t* d_codes, float* d_out,
                                  void* stream);
 
+/* The descriptor the handle was created from (desc->struct_size must be set by the caller). */
+int qv2x_codebook_desc_get(const qv2x_codebook* cb, qv2x_codebook_desc* desc);
+
 /* Test hook: the folded tables the kernels use.  which = 0 digits (int8 [sum_l 3*m*k_l][C], level-major then
  * digit-major), 1 per-column scale (double), 2 per-column constant (double), 3 codeword cross terms (double),
  * 4 decode constant (float [C]), 5 decode tables (float, level-major then segment-major [k_l][C]). */
@@ -216,6 +219,29 @@ int qv2x_heads_forward(const qv2x_heads* heads, long long pixels, const float* d
  * buffer (multi-GPU: every rank writes its tile of the head maps straight into the ego rank's result). */
 int qv2x_heads_forward_tile(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, int tile_w,
                             long long out_w, long long out_pixels, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ego stage of an attention-fusion frame in one kernel: code planes in, head maps out.  Replaces the chain
+ * UMGMQuantizer.decode (opencood/models/sub_modules/codebook.py:192-201, 263-269) -> warp_affine_simple
+ * (opencood/models/sub_modules/torch_transformation_utils.py:323-332) -> AttFusion.forward
+ * (opencood/models/fuse_modules/fusion_in_one.py:126-151) -> cls/reg/dir heads
+ * (opencood/models/heter_model_baseline_mc.py:137-142), i.e. qv2x_codebook_decode + qv2x_fuse(mode 1) +
+ * qv2x_heads_forward, without materialising any feature map: decode, warp and the heads are linear in the codeword
+ * tables, so the attention scores come from the Gram matrix of the decode tables and the head maps from the tables
+ * pushed through the head weights (both folded at create time in float64).  Floating-point tier: agrees with the
+ * three-kernel chain to fp32 rounding (different summation order).
+ * w: HOST [cout][C] head weights (as qv2x_heads_create), bias HOST [cout] or NULL.
+ * Supported when levels*m is 1, 2, 3, 4 or 6, cout <= 72 and the [sum_l m*k_l][72] head table fits in shared memory
+ * (qv2x_ego_att_supported returns 1); other configurations and max fusion use the three-kernel chain.
+ * forward: d_codes [levels*m][plane_stride] uint8, agent a's rows at a*H*W (agent 0 = ego); d_affine DEVICE
+ * [n_agents][2][3] as qv2x_fuse; d_out [cout][H*W] float32.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_ego_att qv2x_ego_att;
+int qv2x_ego_att_supported(const qv2x_codebook* cb, int cout);
+int qv2x_ego_att_create(const qv2x_codebook* cb, int cout, const float* w, const float* bias, qv2x_ego_att** out);
+void qv2x_ego_att_destroy(qv2x_ego_att* h);
+int qv2x_ego_att_forward(const qv2x_ego_att* h, int n_agents, int H, int W, const uint8_t* d_codes,
+                         long long plane_stride, const float* d_affine, float* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * PointPillars front end: pillars -> decorated points -> quantized Linear(10 -> 64) ->

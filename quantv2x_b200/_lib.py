@@ -189,6 +189,19 @@ def _declare_fusion(lib):
 _DECLARERS.append(_declare_fusion)
 
 
+def _declare_ego_att(lib):
+    lib.qv2x_codebook_desc_get.argtypes = [c_void_p, POINTER(CodebookDesc)]
+    lib.qv2x_ego_att_supported.argtypes = [c_void_p, c_int]
+    lib.qv2x_ego_att_create.argtypes = [c_void_p, c_int, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.qv2x_ego_att_destroy.argtypes = [c_void_p]
+    lib.qv2x_ego_att_destroy.restype = None
+    lib.qv2x_ego_att_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_longlong, c_void_p, c_void_p,
+                                         c_void_p]
+
+
+_DECLARERS.append(_declare_ego_att)
+
+
 class PlanStep(ctypes.Structure):
     """Mirror of qv2x_plan_step (include/qv2x.h)."""
 

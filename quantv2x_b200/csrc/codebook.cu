@@ -1020,6 +1020,13 @@ int qv2x_codebook_decode_regions(const qv2x_codebook* cb, long long plane_stride
     return launch_decode(cb, plane_stride, rg, d_codes, d_out, static_cast<cudaStream_t>(stream_));
 }
 
+int qv2x_codebook_desc_get(const qv2x_codebook* cb, qv2x_codebook_desc* desc) {
+    QV2X_REQUIRE(cb && desc, "qv2x_codebook_desc_get: null argument");
+    QV2X_CHECK_SIZE(desc, qv2x_codebook_desc);
+    *desc = cb->d;
+    return 0;
+}
+
 long long qv2x_codebook_folded_size(const qv2x_codebook* cb, int which) {
     if (!cb) return -1;
     switch (which) {

@@ -1,0 +1,426 @@
+// qv2x_ego_att: the ego stage of an attention-fusion frame as ONE kernel, from the received code planes to the head
+// maps, without ever forming a 256-channel feature map (HBM traffic: the code planes in, the head maps out).
+//
+// Every operator between the wire and the head maps is linear in the codeword tables except the softmax over agents:
+//   decode   (reference UMGMQuantizer.decode, opencood/models/sub_modules/codebook.py:192-201, 263-269)
+//            f_a(q) = const + sum_i T_i[code_i(a, q)]          -- T'_i := T_i (+ const on table 0): f = sum_i T'_i[.]
+//   warp     (warp_affine_simple, opencood/models/sub_modules/torch_transformation_utils.py:323-332)
+//            x_a(p) = sum_t w_t(a, p) f_a(q_t(a, p))            -- 4 bilinear taps, zeros outside the map
+//   AttFusion.forward (opencood/models/fuse_modules/fusion_in_one.py:126-151), ego query row only
+//            s_a(p) = <x_0(p), x_a(p)> / sqrt(C),  alpha = softmax_a(s),  fused(p) = sum_a alpha_a x_a(p)
+//   heads    (cls/reg/dir 1x1 convs, opencood/models/heter_model_baseline_mc.py:137-142)
+//            y(p) = bias + Wh fused(p)
+// so with the Gram matrix  Gm[r][r'] = <T'[r], T'[r']> / sqrt(C)  and the head table  HT[r] = Wh T'[r]  over the
+// R = sum_i k_i codeword rows (both formed once at create time in float64, stored as fp32):
+//   s_a(p) = sum_t w_t sum_{t'} w0_t' sum_{i,j} Gm[row_i(0, q_t')][row_j(a, q_t)]
+//   y(p)   = bias + sum_a alpha_a sum_t w_t sum_j HT[row_j(a, q_t)]
+// One warp per output pixel, lane = (agent, tap).  The warp first forms P = sum_{t',i} w0_t' Gm[row_i(0, q_t')][:]
+// (R floats, coalesced row reads from L2) in shared memory, each lane then looks up its own NT entries; the softmax
+// runs on shuffles; the 72-wide head rows come from the shared-memory copy of HT (110 KB at R = 384).
+// The ego's own matrix is the identity in every frame the reference builds (pairwise_t_matrix[0, 0]): that case is
+// sampled exactly (one tap of weight 1 instead of the fp32 coordinate round trip, which lands within 2e-5 of the
+// pixel centre); any other matrix takes the general four-tap query.
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "host_common.h"
+#include "ptx.cuh"
+
+namespace qv2x {
+
+constexpr int kEgoOut = 72;            // head-table row pitch (floats) = the widest head block
+constexpr int kEgoMain = 64;           // channels 2*lane, 2*lane+1; the other 8 go four rows at a time
+constexpr int kEgoMaxAgents = 8;
+constexpr int kEgoMaxTables = 7;
+constexpr int kEgoStash = 36;         // stash entries per warp: 32 (agent, tap) pairs + 4 zero entries of padding
+constexpr int kEgoGroups = 4;          // independent warp groups per CTA (own barrier, own staging tile)
+
+struct EgoAttParams {
+    int n, H, W, nt, R, cout;
+    int rowbase[kEgoMaxTables + 1];
+    int kk[kEgoMaxTables + 1];
+    long long plane_stride;
+    const uint8_t* codes;       // [nt][plane_stride], agent-major rows (agent a: rows a*H*W ..)
+    const float* aff;           // DEVICE [n][6]
+    const float* gram;          // [R][R]
+    const float* ht;            // [R][72]
+    const float* bias;          // [72] (zero padded)
+    float* out;                 // [cout][H*W]
+    int warps_per_group;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(1024, 1) ego_att_kernel(const EgoAttParams p) {
+    constexpr int SW = NT <= 3 ? 4 : 8;                   // words per stash entry: coefficient + NT row offsets
+    extern __shared__ float4 esm4[];
+    float* sm = reinterpret_cast<float*>(esm4);
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int GP = p.warps_per_group;                     // warps (= pixels per batch) of a group
+    const int grp = wib / GP, wg = wib - grp * GP;
+    const int nwarps = blockDim.x >> 5;
+    const int R = p.R;
+    // shared memory: HT [R][72] | per warp: P [R], stash [36][SW] | per group: 2 staging tiles [72][GP + 1]
+    float* s_ht = sm;
+    float* s_p = s_ht + R * kEgoOut + wib * R;
+    int* s_stash = reinterpret_cast<int*>(s_ht + R * kEgoOut + nwarps * R) + wib * kEgoStash * SW;
+    float* s_stage = s_ht + R * kEgoOut + nwarps * R + nwarps * kEgoStash * SW + grp * 2 * kEgoOut * (GP + 1);
+    __shared__ float am[kEgoMaxAgents][6];
+    __shared__ int s_ident;
+    for (int idx = tid; idx < R * kEgoOut / 4; idx += blockDim.x)
+        reinterpret_cast<float4*>(s_ht)[idx] = __ldg(reinterpret_cast<const float4*>(p.ht) + idx);
+    if (tid < p.n * 6) am[tid / 6][tid % 6] = __ldg(p.aff + tid);
+    if (tid == 0) {
+        const float* a0 = p.aff;
+        s_ident = (__ldg(a0) == 1.f && __ldg(a0 + 1) == 0.f && __ldg(a0 + 2) == 0.f && __ldg(a0 + 3) == 0.f &&
+                   __ldg(a0 + 4) == 1.f && __ldg(a0 + 5) == 0.f);
+    }
+    __syncthreads();
+    const bool ident = s_ident != 0;
+    const int hw = p.H * p.W;
+    const int a = lane >> 2, t = lane & 3;
+    const int lg = lane >> 3, lc = lane & 7;
+    const int r4 = R >> 2;
+    const int n_batches = (hw + GP - 1) / GP;
+    const int units = gridDim.x * kEgoGroups;
+    const int gthreads = GP * 32, gtid = wg * 32 + lane;
+    // Geometry and code bytes of lane (agent a, tap t) for pixel `pix`: weight and source pixel (clamped, weight 0
+    // outside the map), then the NT code bytes of that source pixel.  Issued one batch ahead, so that the loads are
+    // in flight under the previous pixel's arithmetic; the codes are only touched at the top of their own batch.
+    auto fetch = [&](int pix, float& w, int (&code)[NT]) {
+        w = 0.f;
+        int q = 0;
+        if (pix < hw && a < p.n) {
+            if (a == 0 && ident) {
+                w = (t == 0) ? 1.f : 0.f;
+                q = pix;
+            } else {
+                const int i = pix / p.W, j = pix - i * p.W;
+                const float xn = (2.f * j + 1.f) / p.W - 1.f;
+                const float yn = (2.f * i + 1.f) / p.H - 1.f;
+                const float xs = am[a][0] * xn + am[a][1] * yn + am[a][2];
+                const float ys = am[a][3] * xn + am[a][4] * yn + am[a][5];
+                const float ix = ((xs + 1.f) * p.W - 1.f) * 0.5f;
+                const float iy = ((ys + 1.f) * p.H - 1.f) * 0.5f;
+                const float fx = fminf(fmaxf(floorf(ix), -2.f), static_cast<float>(p.W) + 1.f);
+                const float fy = fminf(fmaxf(floorf(iy), -2.f), static_cast<float>(p.H) + 1.f);
+                const float tx = ix - fx, ty = iy - fy;
+                const int xx = static_cast<int>(fx) + (t & 1), yy = static_cast<int>(fy) + (t >> 1);
+                const bool inb = (xx >= 0 && xx < p.W && yy >= 0 && yy < p.H);
+                const float wt = ((t & 1) ? tx : 1.f - tx) * ((t >> 1) ? ty : 1.f - ty);
+                w = inb ? wt : 0.f;
+                q = min(max(yy, 0), p.H - 1) * p.W + min(max(xx, 0), p.W - 1);
+            }
+        }
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt) {
+            code[jt] = 0;
+            if (w != 0.f) code[jt] = __ldg(p.codes + jt * p.plane_stride + static_cast<long long>(a) * hw + q);
+        }
+    };
+    int buf = 0;
+    float w_next;
+    int code_next[NT];
+    {
+        const int b0 = blockIdx.x * kEgoGroups + grp;
+        fetch(b0 < n_batches ? b0 * GP + wg : hw, w_next, code_next);
+    }
+    for (int b = blockIdx.x * kEgoGroups + grp; b < n_batches; b += units, buf ^= 1) {
+        const int pix = b * GP + wg;
+        float* stage = s_stage + buf * kEgoOut * (GP + 1);
+        const float w = w_next;
+        int rows[NT];
+#pragma unroll
+        for (int jt = 0; jt < NT; ++jt)
+            rows[jt] = p.rowbase[jt] + min(code_next[jt], p.kk[jt] - 1);      // a corrupt code must not leave its table
+        fetch((b + units < n_batches) ? (b + units) * GP + wg : hw, w_next, code_next);
+        if (pix < hw) {
+            // ---- P = sum over the ego's taps t' and tables i of w0_t' * Gm[row_i(0, q_t')][:]
+            float4 acc4[3];
+#pragma unroll
+            for (int u = 0; u < 3; ++u) acc4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int v0 = 0; v0 < r4; v0 += 96) {          // 96 float4 per pass of the warp (R <= 384: one pass)
+#pragma unroll
+                for (int tq = 0; tq < 4; ++tq) {
+                    const float wq = __shfl_sync(0xffffffffu, w, tq);
+                    int er[NT];
+#pragma unroll
+                    for (int it = 0; it < NT; ++it) er[it] = __shfl_sync(0xffffffffu, rows[it], tq);
+                    if (wq == 0.f) continue;
+#pragma unroll
+                    for (int it = 0; it < NT; ++it) {
+                        const float4* gr = reinterpret_cast<const float4*>(p.gram + static_cast<long long>(er[it]) * R);
+#pragma unroll
+                        for (int u = 0; u < 3; ++u) {
+                            const int v = v0 + lane + 32 * u;
+                            if (v < r4) {
+                                const float4 g = __ldg(gr + v);
+                                acc4[u].x = fmaf(wq, g.x, acc4[u].x);
+                                acc4[u].y = fmaf(wq, g.y, acc4[u].y);
+                                acc4[u].z = fmaf(wq, g.z, acc4[u].z);
+                                acc4[u].w = fmaf(wq, g.w, acc4[u].w);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 3; ++u) {
+                    const int v = v0 + lane + 32 * u;
+                    if (v < r4) reinterpret_cast<float4*>(s_p)[v] = acc4[u];
+                    acc4[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            __syncwarp();
+            // ---- score of agent a: sum over its taps of w_t * sum_j P[row_j]; softmax over the agents
+            float d = 0.f;
+#pragma unroll
+            for (int jt = 0; jt < NT; ++jt) d += s_p[rows[jt]];
+            d *= w;
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            const float s = (a < p.n) ? d : -INFINITY;
+            float mx = s;
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+            const float e = (a < p.n) ? expf(s - mx) : 0.f;
+            float den = e;
+            den += __shfl_xor_sync(0xffffffffu, den, 4);
+            den += __shfl_xor_sync(0xffffffffu, den, 8);
+            den += __shfl_xor_sync(0xffffffffu, den, 16);
+            const float coef = (e / den) * w;
+            // ---- the (agent, tap) pairs that contribute are compacted into the stash (lane order = agent order, so
+            // the summation order of a pixel is fixed); four all-zero entries pad the list to the unrolled loop
+            const unsigned live = __ballot_sync(0xffffffffu, coef != 0.f);
+            const int nlive = __popc(live);
+            if (coef != 0.f) {
+                int* st = s_stash + __popc(live & ((1u << lane) - 1u)) * SW;
+                st[0] = __float_as_int(coef);
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) st[1 + jt] = rows[jt] * kEgoOut;
+            }
+            if (lane < 4) {
+                int* st = s_stash + (nlive + lane) * SW;
+#pragma unroll
+                for (int x = 0; x < SW; ++x) st[x] = 0;
+            }
+            __syncwarp();
+            // ---- y = sum over the list of coef * sum_j HT[row_j]: channels 2*lane, 2*lane+1 from every entry;
+            // channel 64 + lc from entry i0 + lg of each group of four (reduced over lg at the end)
+            float ya[4], yb[4], yl = 0.f;
+#pragma unroll
+            for (int ss = 0; ss < 4; ++ss) ya[ss] = yb[ss] = 0.f;
+            for (int i0 = 0; i0 < nlive; i0 += 4) {
+                int e4[4][SW], el[SW];
+#pragma unroll
+                for (int ss = 0; ss < 4; ++ss) {
+                    const int* st = s_stash + (i0 + ss) * SW;
+                    *reinterpret_cast<int4*>(e4[ss]) = *reinterpret_cast<const int4*>(st);
+                    if (SW == 8) *reinterpret_cast<int4*>(e4[ss] + 4) = *reinterpret_cast<const int4*>(st + 4);
+                }
+                {
+                    const int* st = s_stash + (i0 + lg) * SW;
+                    *reinterpret_cast<int4*>(el) = *reinterpret_cast<const int4*>(st);
+                    if (SW == 8) *reinterpret_cast<int4*>(el + 4) = *reinterpret_cast<const int4*>(st + 4);
+                }
+#pragma unroll
+                for (int ss = 0; ss < 4; ++ss) {
+                    const float c = __int_as_float(e4[ss][0]);
+#pragma unroll
+                    for (int jt = 0; jt < NT; ++jt) {
+                        const float2 h = *reinterpret_cast<const float2*>(s_ht + e4[ss][1 + jt] + 2 * lane);
+                        ya[ss] = fmaf(c, h.x, ya[ss]);
+                        yb[ss] = fmaf(c, h.y, yb[ss]);
+                    }
+                }
+                const float cl = __int_as_float(el[0]);
+#pragma unroll
+                for (int jt = 0; jt < NT; ++jt) yl = fmaf(cl, s_ht[el[1 + jt] + kEgoMain + lc], yl);
+            }
+            const float y0 = (ya[0] + ya[1]) + (ya[2] + ya[3]), y1 = (yb[0] + yb[1]) + (yb[2] + yb[3]);
+            yl += __shfl_xor_sync(0xffffffffu, yl, 8);
+            yl += __shfl_xor_sync(0xffffffffu, yl, 16);
+            stage[(2 * lane) * (GP + 1) + wg] = y0;
+            stage[(2 * lane + 1) * (GP + 1) + wg] = y1;
+            if (lane < 8) stage[(kEgoMain + lane) * (GP + 1) + wg] = yl;
+        }
+        // ---- the group's GP pixels are consecutive: transposed, coalesced store of the [cout][GP] tile
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
+        const int pix0 = b * GP;
+        for (int idx = gtid; idx < p.cout * GP; idx += gthreads) {
+            const int c = idx / GP, pp = idx - c * GP;
+            if (pix0 + pp < hw) p.out[static_cast<long long>(c) * hw + pix0 + pp] = stage[c * (GP + 1) + pp] + __ldg(p.bias + c);
+        }
+        // no second barrier: the next batch writes the other staging tile, and the batch after that passes the
+        // next barrier only when every warp of the group has finished these reads
+    }
+}
+
+}  // namespace qv2x
+
+using namespace qv2x;
+
+struct qv2x_ego_att {
+    int C, nt, R, cout;
+    int rowbase[kEgoMaxTables + 1], kk[kEgoMaxTables + 1];
+    float *d_gram = nullptr, *d_ht = nullptr, *d_bias = nullptr;
+    int warps_per_group, smem;
+};
+
+// Shared-memory plan: as many warps as fit beside the head table (multiples of kEgoGroups, at most 32).
+static bool ego_att_plan(int R, int nt, int* warps_per_group, int* smem) {
+    const int sw = nt <= 3 ? 4 : 8;
+    const long long budget = 220 * 1024;
+    for (int wpg = 32 / kEgoGroups; wpg >= 2; --wpg) {
+        const int nw = wpg * kEgoGroups;
+        const long long need = 4ll * (static_cast<long long>(R) * kEgoOut + static_cast<long long>(nw) * R +
+                                      static_cast<long long>(nw) * kEgoStash * sw +
+                                      static_cast<long long>(kEgoGroups) * 2 * kEgoOut * (wpg + 1));
+        if (need <= budget) {
+            *warps_per_group = wpg;
+            *smem = static_cast<int>(need);
+            return true;
+        }
+    }
+    return false;
+}
+
+extern "C" {
+
+int qv2x_ego_att_supported(const qv2x_codebook* cb, int cout) {
+    qv2x_codebook_desc d{};
+    d.struct_size = sizeof(d);
+    if (!cb || qv2x_codebook_desc_get(cb, &d) != 0) return 0;
+    const int nt = d.levels * d.m;
+    int R = 0;
+    for (int l = 0; l < d.levels; ++l) R += d.m * d.k[l];
+    int wpg, smem;
+    const bool nt_ok = (nt == 1 || nt == 2 || nt == 3 || nt == 4 || nt == 6);
+    return (nt_ok && cout >= 1 && cout <= kEgoOut && R % 4 == 0 && ego_att_plan(R, nt, &wpg, &smem)) ? 1 : 0;
+}
+
+int qv2x_ego_att_create(const qv2x_codebook* cb, int cout, const float* w, const float* bias, qv2x_ego_att** out) {
+    QV2X_REQUIRE(cb && w && out, "qv2x_ego_att_create: null argument");
+    QV2X_REQUIRE(qv2x_ego_att_supported(cb, cout),
+                 "qv2x_ego_att: unsupported configuration (needs levels*m in {1,2,3,4,6}, cout <= %d and a head "
+                 "table of sum(k)*m rows that fits in shared memory); use decode + fuse + heads", kEgoOut);
+    qv2x_codebook_desc d{};
+    d.struct_size = sizeof(d);
+    int rc = qv2x_codebook_desc_get(cb, &d);
+    if (rc) return rc;
+    const int C = d.channel, nt = d.levels * d.m;
+    auto h = new qv2x_ego_att();
+    h->C = C;
+    h->nt = nt;
+    h->cout = cout;
+    int R = 0;
+    for (int l = 0; l < d.levels; ++l)
+        for (int s = 0; s < d.m; ++s) {
+            h->rowbase[l * d.m + s] = R;
+            h->kk[l * d.m + s] = d.k[l];
+            R += d.k[l];
+        }
+    h->R = R;
+    ego_att_plan(R, nt, &h->warps_per_group, &h->smem);
+    // T' = the decode tables as the decode kernel holds them (fp32), the constant added to table 0
+    std::vector<float> tab(static_cast<size_t>(qv2x_codebook_folded_size(cb, 5))), cst(static_cast<size_t>(C));
+    if (static_cast<long long>(tab.size()) != static_cast<long long>(R) * C ||
+        qv2x_codebook_folded_size(cb, 4) != C) {
+        delete h;
+        return set_error(QV2X_ERR_INVALID, "qv2x_ego_att_create: unexpected decode table size");
+    }
+    qv2x_codebook_folded_copy(cb, 5, tab.data());
+    qv2x_codebook_folded_copy(cb, 4, cst.data());
+    std::vector<double> T(static_cast<size_t>(R) * C);
+    for (int r = 0; r < R; ++r)
+        for (int c = 0; c < C; ++c)
+            T[static_cast<size_t>(r) * C + c] = static_cast<double>(tab[static_cast<size_t>(r) * C + c]) +
+                                                (r < h->kk[0] ? static_cast<double>(cst[c]) : 0.0);
+    const double inv = static_cast<double>(1.0f / sqrtf(static_cast<float>(C)));     // the fuse kernel's scale
+    std::vector<float> gram(static_cast<size_t>(R) * R), ht(static_cast<size_t>(R) * kEgoOut, 0.f), bp(kEgoOut, 0.f);
+    for (int r = 0; r < R; ++r)
+        for (int r2 = r; r2 < R; ++r2) {
+            double s = 0.0;
+            const double *x = &T[static_cast<size_t>(r) * C], *y = &T[static_cast<size_t>(r2) * C];
+            for (int c = 0; c < C; ++c) s += x[c] * y[c];
+            gram[static_cast<size_t>(r) * R + r2] = gram[static_cast<size_t>(r2) * R + r] = static_cast<float>(s * inv);
+        }
+    for (int r = 0; r < R; ++r)
+        for (int o = 0; o < cout; ++o) {
+            double s = 0.0;
+            for (int c = 0; c < C; ++c) s += static_cast<double>(w[static_cast<size_t>(o) * C + c]) * T[static_cast<size_t>(r) * C + c];
+            ht[static_cast<size_t>(r) * kEgoOut + o] = static_cast<float>(s);
+        }
+    if (bias)
+        for (int o = 0; o < cout; ++o) bp[o] = bias[o];
+    rc = upload(&h->d_gram, gram.data(), gram.size());
+    if (!rc) rc = upload(&h->d_ht, ht.data(), ht.size());
+    if (!rc) rc = upload(&h->d_bias, bp.data(), bp.size());
+    if (rc) {
+        qv2x_ego_att_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return 0;
+}
+
+void qv2x_ego_att_destroy(qv2x_ego_att* h) {
+    if (!h) return;
+    cudaFree(h->d_gram);
+    cudaFree(h->d_ht);
+    cudaFree(h->d_bias);
+    delete h;
+}
+
+int qv2x_ego_att_forward(const qv2x_ego_att* h, int n_agents, int H, int W, const uint8_t* d_codes,
+                         long long plane_stride, const float* d_affine, float* d_out, void* stream_) {
+    QV2X_REQUIRE(h && d_codes && d_affine && d_out, "qv2x_ego_att_forward: null argument");
+    QV2X_REQUIRE(n_agents >= 1 && n_agents <= kEgoMaxAgents, "n_agents must be 1..%d", kEgoMaxAgents);
+    QV2X_REQUIRE(H > 0 && W > 0 && static_cast<long long>(H) * W * n_agents <= plane_stride,
+                 "code planes are shorter than n_agents * H * W rows");
+    QV2X_REQUIRE(static_cast<long long>(H) * W < (1ll << 30), "map too large");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    EgoAttParams p{};
+    p.n = n_agents;
+    p.H = H;
+    p.W = W;
+    p.nt = h->nt;
+    p.R = h->R;
+    p.cout = h->cout;
+    for (int i = 0; i < h->nt; ++i) {
+        p.rowbase[i] = h->rowbase[i];
+        p.kk[i] = h->kk[i];
+    }
+    p.plane_stride = plane_stride;
+    p.codes = d_codes;
+    p.aff = d_affine;
+    p.gram = h->d_gram;
+    p.ht = h->d_ht;
+    p.bias = h->d_bias;
+    p.out = d_out;
+    p.warps_per_group = h->warps_per_group;
+    const int threads = h->warps_per_group * kEgoGroups * 32;
+    const long long batches = (static_cast<long long>(H) * W + h->warps_per_group - 1) / h->warps_per_group;
+    const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(num_sms(), (batches + kEgoGroups - 1) / kEgoGroups)));
+#define QV2X_EGO_CASE(N)                                                                                           \
+    case N: {                                                                                                      \
+        static bool attr = false;                                                                                  \
+        if (!attr) {                                                                                               \
+            QV2X_CUDA_OK(cudaFuncSetAttribute(ego_att_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                              224 * 1024));                                                        \
+            attr = true;                                                                                           \
+        }                                                                                                          \
+        ego_att_kernel<N><<<grid, threads, h->smem, stream>>>(p);                                                  \
+        break;                                                                                                     \
+    }
+    switch (h->nt) {
+        QV2X_EGO_CASE(1) QV2X_EGO_CASE(2) QV2X_EGO_CASE(3) QV2X_EGO_CASE(4) QV2X_EGO_CASE(6)
+        default: return set_error(QV2X_ERR_INVALID, "qv2x_ego_att_forward: unsupported table count %d", h->nt);
+    }
+#undef QV2X_EGO_CASE
+    g_launch_count.fetch_add(1);
+    QV2X_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -304,6 +304,46 @@ class HeadsEngine:
         return out
 
 
+class EgoAttEngine:
+    """The ego stage of an attention-fusion frame as one kernel (qv2x_ego_att): code planes -> head maps, i.e.
+    UMGMQuantizer.decode (codebook.py:192-201) + warp_affine_simple + AttFusion.forward (fusion_in_one.py:126-151) +
+    the cls/reg/dir heads, folded over the codeword tables (no feature map is formed)."""
+
+    @staticmethod
+    def supported(codebook: "CodebookEngine", heads: "HeadsEngine") -> bool:
+        return bool(_lib.lib().qv2x_ego_att_supported(codebook._h, heads.cout)) and heads.cin == codebook.channel
+
+    def __init__(self, codebook: "CodebookEngine", heads: "HeadsEngine"):
+        self.cout = heads.cout
+        self.nt = codebook.levels * codebook.m
+        self._h = c_void_p()
+        w, b = heads.spec["w"], heads.spec["bias"]
+        check(_lib.lib().qv2x_ego_att_create(codebook._h, heads.cout, _np_ptr(w), None if b is None else _np_ptr(b),
+                                              byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_ego_att_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward(self, codes: torch.Tensor, affine: torch.Tensor, n: int, h: int, w: int,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+        """codes uint8 [levels, m, rows >= n*h*w] (agent-major rows, agent 0 = ego); affine CUDA float32 [n, 2, 3]
+        -> float32 [Cout, h*w]."""
+        assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+        assert codes.numel() // codes.shape[-1] == self.nt
+        assert affine.is_cuda and affine.dtype == torch.float32 and affine.is_contiguous() and affine.numel() >= 6 * n
+        if out is None:
+            out = torch.empty((self.cout, h * w), dtype=torch.float32, device=codes.device)
+        check(_lib.lib().qv2x_ego_att_forward(self._h, n, h, w, c_void_p(codes.data_ptr()), codes.shape[-1],
+                                              c_void_p(affine.data_ptr()), c_void_p(out.data_ptr()), _stream_ptr()))
+        return out
+
+
 class PillarEngine:
     """libqv2x handle of the quantized PointPillars front end (qv2x_pillar_*): pillars -> uint8 NHWC BEV map."""
 

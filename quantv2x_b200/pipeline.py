@@ -11,6 +11,8 @@ whole frame can be captured in a CUDA graph.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -31,6 +33,13 @@ class CollabPipeline:
         self.hw = self.ho * self.wo
         self._enc_buf = {}
         self._ego_buf = {}
+        # attention fusion: decode, warp, fuse and heads fold into one kernel over the codeword tables (no feature
+        # map in HBM); max fusion (not linear) and codebooks whose head table exceeds shared memory keep the
+        # three-kernel chain.  QV2X_EGO_CHAIN=1 forces the chain (comparison runs).
+        self.ego_att = None
+        if (fusion_mode == "att" and os.environ.get("QV2X_EGO_CHAIN", "0") != "1"
+                and E.EgoAttEngine.supported(codebook, heads)):
+            self.ego_att = E.EgoAttEngine(codebook, heads)
 
     # ------------------------------------------------------------------ agent side
     def bev_from_inputs(self, data_dict, modality: str = "m1") -> torch.Tensor:
@@ -109,6 +118,18 @@ class CollabPipeline:
 
     def decode_fuse_heads(self, codes: torch.Tensor, affine: torch.Tensor, slot=0) -> torch.Tensor:
         """codes uint8 [levels, m, n*hw]; affine CUDA float32 [n, 2, 3] -> preds float32 [Cout, hw]."""
+        n = codes.shape[-1] // self.hw
+        if self.ego_att is not None:
+            key = ("att", n, slot)
+            if key not in self._ego_buf:
+                self._ego_buf[key] = torch.empty((self.heads.cout, self.hw), dtype=torch.float32, device=self.device)
+            aff = affine if (affine.dtype == torch.float32 and affine.is_contiguous()) else \
+                affine.to(torch.float32).contiguous()
+            return self.ego_att.forward(codes, aff, n, self.ho, self.wo, out=self._ego_buf[key])
+        return self.decode_fuse_heads_chain(codes, affine, slot)
+
+    def decode_fuse_heads_chain(self, codes: torch.Tensor, affine: torch.Tensor, slot=0) -> torch.Tensor:
+        """The same stage as three kernels through decoded FP32 feature maps (decode -> warp + fuse -> heads)."""
         n = codes.shape[-1] // self.hw
         b = self.ego_buffers(n, slot)
         self.codebook.decode(codes, out=b["feat"].view(n * self.hw, self.c_feat))

@@ -142,7 +142,13 @@ def test_tiled_ego_stage_equals_whole(cuda_device):
     codes = torch.from_numpy(rng.integers(0, 128, size=(3, 1, n * ho * wo), dtype=np.uint8)).to(cuda_device)
     for mode in ("att", "max"):
         pipe = CollabPipeline(_Fused(), 0.1, cb, hd, mode, (2 * ho, 2 * wo), cuda_device)
-        whole = pipe.decode_fuse_heads(codes, aff_d).clone()
+        whole = pipe.decode_fuse_heads_chain(codes, aff_d).clone()
+        if mode == "att":
+            # the one-kernel ego stage (qv2x_ego_att) is the same function up to fp32 summation order
+            assert pipe.ego_att is not None
+            folded = pipe.decode_fuse_heads(codes, aff_d)
+            tol = 1e-4 * float(whole.abs().max())
+            assert float((folded - whole).abs().max()) <= tol
         for world in (2, 4, 8):
             gy, gx = tile_grid(world)
             th, tw = ho // gy, wo // gx
@@ -151,6 +157,91 @@ def test_tiled_ego_stage_equals_whole(cuda_device):
                 out[r] = pipe.decode_fuse_heads_tile(codes, aff_d, aff, rank_tile(r, world, ho, wo))
             full = out.view(gy, gx, 72, th, tw).permute(2, 0, 3, 1, 4).reshape(72, ho * wo)
             assert torch.equal(full, whole), f"{mode}, {world} tiles: tiled ego stage differs from the whole frame"
+
+
+EGO_ATT_CASES = [
+    # n, ho, wo, C, m, ks, cout, ego matrix perturbed
+    (5, 20, 48, 256, 1, [128] * 3, 72, False),
+    (8, 25, 44, 256, 1, [64] * 3, 72, False),
+    (1, 12, 20, 64, 1, [64, 64], 20, False),
+    (2, 9, 7, 128, 2, [64] * 3, 72, False),        # six code planes
+    (3, 17, 33, 256, 1, [128] * 3, 72, True),      # general (non-identity) ego matrix: four-tap query
+    (4, 100, 352, 256, 1, [128] * 3, 72, False),   # the benchmark's map
+]
+
+
+@pytest.mark.parametrize("case", EGO_ATT_CASES, ids=lambda c: f"n{c[0]}_{c[1]}x{c[2]}_c{c[3]}_m{c[4]}_k{c[5][0]}x{len(c[5])}"
+                                                               f"_o{c[6]}{'_egowarp' if c[7] else ''}")
+def test_ego_att_one_kernel(cuda_device, case):
+    """qv2x_ego_att (codes -> head maps in one kernel over the folded tables) against the float64 restatement of
+    decode -> warp -> attention fusion -> heads on the library's own fp32 decode tables, and against the three-kernel
+    chain; tolerance tier, atol = 1e-4 * max|y|."""
+    from quantv2x_b200 import engine as E
+    from tests.codebook_cases import make_codebook_params
+
+    n, ho, wo, C, m, ks, cout, egowarp = case
+    rng = np.random.default_rng(n * 131 + ho)
+    cbs, hds = make_codebook_params(7, C, m, ks)
+    cb = E.CodebookEngine(cbs, hds)
+    w = rng.normal(size=(cout, C)).astype(np.float32) / 16
+    b = rng.normal(size=cout).astype(np.float32)
+    hd = E.HeadsEngine(w, b)
+    assert E.EgoAttEngine.supported(cb, hd)
+    eng = E.EgoAttEngine(cb, hd)
+    aff = make_affines(n, rng).astype(np.float32)
+    if n > 2:
+        aff[n - 1, 0, 2] += 0.4                       # one agent partly out of view
+    if egowarp:
+        th = np.deg2rad(2.0)
+        aff[0] = np.array([[np.cos(th), -np.sin(th) * ho / wo, 0.01], [np.sin(th) * wo / ho, np.cos(th), -0.02]])
+    hw = ho * wo
+    nt = len(ks) * m
+    kk = [k for k in ks for _ in range(m)]
+    codes = np.stack([rng.integers(0, kk[i], size=n * hw, dtype=np.uint8) for i in range(nt)]).reshape(len(ks), m, -1)
+    codes_d = torch.from_numpy(codes).to(cuda_device)
+    aff_d = torch.from_numpy(aff).to(cuda_device)
+    out = eng.forward(codes_d, aff_d, n, ho, wo).cpu().numpy()
+
+    tab = cb.folded(5).astype(np.float64).reshape(-1, C)
+    cst = cb.folded(4).astype(np.float64)
+    feat = np.tile(cst, (n * hw, 1))
+    base = 0
+    for i in range(nt):
+        feat += tab[base + codes.reshape(nt, -1)[i].astype(np.int64)]
+        base += kk[i]
+    feat = feat.reshape(n, ho, wo, C)
+    ref = fo.heads(fo.att_fusion(feat, aff), w, b).reshape(cout, hw)
+    np.testing.assert_allclose(out, ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+    chain = hd.forward(E.fuse(cb.decode(codes_d).view(n, ho, wo, C), aff_d, "att")).cpu().numpy()
+    np.testing.assert_allclose(out, chain, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+
+def test_ego_att_unsupported_configurations(cuda_device):
+    """A head table that does not fit in shared memory (k = 256 x 3 levels) is reported as unsupported and the
+    pipeline keeps the three-kernel chain; so does max fusion."""
+    from quantv2x_b200 import engine as E
+    from quantv2x_b200.pipeline import CollabPipeline
+    from tests.codebook_cases import make_codebook_params
+
+    rng = np.random.default_rng(1)
+    hd = E.HeadsEngine(rng.normal(size=(72, 256)).astype(np.float32) / 16, None)
+    big = E.CodebookEngine(*make_codebook_params(3, 256, 1, [256] * 3))
+    assert not E.EgoAttEngine.supported(big, hd)
+    with pytest.raises(Exception, match="unsupported configuration"):
+        E.EgoAttEngine(big, hd)
+    small = E.CodebookEngine(*make_codebook_params(3, 256, 1, [128] * 3))
+
+    class _Plan:
+        def out_shape(self, h, w):
+            return 10, 16, 256
+
+    class _Fused:
+        plan = _Plan()
+
+    assert CollabPipeline(_Fused(), 0.1, big, hd, "att", (20, 32), cuda_device).ego_att is None
+    assert CollabPipeline(_Fused(), 0.1, small, hd, "max", (20, 32), cuda_device).ego_att is None
+    assert CollabPipeline(_Fused(), 0.1, small, hd, "att", (20, 32), cuda_device).ego_att is not None
 
 
 def test_push_planes_and_heads_tile_addressing(cuda_device):
