@@ -28,6 +28,8 @@ struct PPParams {
     double size[kPPMaxClasses][3];      // h, w, l
     double rot[kPPMaxRot];
     double score_thr;
+    float logit_cut;                    // use_cut: logits <= logit_cut are below the score threshold for certain
+    int use_cut;
     float nms_thr;
     double lo[2], hi[2];                // range mask on the BEV corners
     int cap, top;
@@ -48,6 +50,15 @@ __global__ void pp_select_kernel(const float* __restrict__ preds, long long hw, 
          a += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long pix = a / A;
         const int k = static_cast<int>(a - pix * A);
+        if (p.use_cut) {
+            // sigmoid is monotonic: logits at least 1e-6 below logit(threshold) cannot pass the float64 test below
+            // (margin p (1 - p) 1e-6 >= 1e-10 against an evaluation error of ~1e-16), so the float64 exponentials
+            // are only spent on the few anchors near or above the threshold
+            bool any = false;
+            for (int j = 0; j < p.n_cls; ++j)
+                any = any || __ldg(preds + static_cast<long long>(k * p.n_cls + j) * hw + pix) > p.logit_cut;
+            if (!any) continue;
+        }
         double best = -1.0;
         int arg = 0;
         for (int j = 0; j < p.n_cls; ++j) {
@@ -88,19 +99,24 @@ __global__ void pp_select_kernel(const float* __restrict__ preds, long long hw, 
     }
 }
 
-// order[rank] = candidate index, for rank < top (score descending; ties: larger anchor index first)
+// order[rank] = candidate index, for rank < top (score descending; ties: larger anchor index first).
+// One warp per candidate: the lanes share the count over the other candidates.
 __global__ void pp_rank_kernel(const PPCand* __restrict__ cand, const int* __restrict__ count, int cap, int top,
                                int* __restrict__ order, int* __restrict__ n_top) {
     const int K = min(*count, cap);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < K; i += nwarps) {
         const double s = cand[i].score;
         const int a = cand[i].anchor;
         int rank = 0;
-        for (int j = 0; j < K; ++j) {
+        for (int j = lane; j < K; j += 32) {
             const double sj = cand[j].score;
             rank += (sj > s) || (sj == s && cand[j].anchor > a);
         }
-        if (rank < top) order[rank] = i;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, off);
+        if (lane == 0 && rank < top) order[rank] = i;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_top = min(K, top);
 }
@@ -164,46 +180,112 @@ __global__ void pp_iou_kernel(const PPCand* __restrict__ cand, const int* __rest
     const int i = blockIdx.x;
     if (i >= K) return;
     const PPCand& ci = cand[order[i]];
-    for (int w = threadIdx.x >> 5; w < kPPWords; w += blockDim.x >> 5) {
+    const double ix0 = fmin(fmin(ci.cx[0], ci.cx[1]), fmin(ci.cx[2], ci.cx[3]));
+    const double ix1 = fmax(fmax(ci.cx[0], ci.cx[1]), fmax(ci.cx[2], ci.cx[3]));
+    const double iy0 = fmin(fmin(ci.cy[0], ci.cy[1]), fmin(ci.cy[2], ci.cy[3]));
+    const double iy1 = fmax(fmax(ci.cy[0], ci.cy[1]), fmax(ci.cy[2], ci.cy[3]));
+    // words beyond the last candidate are never read by the greedy pass
+    for (int w = threadIdx.x >> 5; w < (K + 31) / 32; w += blockDim.x >> 5) {
         const int j = 32 * w + (threadIdx.x & 31);
         bool bit = false;
         if (j > i && j < K) {
             const PPCand& cj = cand[order[j]];
-            bit = static_cast<float>(quad_iou(ci.cx, ci.cy, cj.cx, cj.cy)) > nms_thr;
+            // quadrilaterals whose bounding boxes are disjoint have an empty clip (IoU 0, never above a positive
+            // threshold): only overlapping pairs pay for the float64 clipping
+            bool apart = false;
+            if (nms_thr > 1e-6f) {
+                const double jx0 = fmin(fmin(cj.cx[0], cj.cx[1]), fmin(cj.cx[2], cj.cx[3]));
+                const double jx1 = fmax(fmax(cj.cx[0], cj.cx[1]), fmax(cj.cx[2], cj.cx[3]));
+                const double jy0 = fmin(fmin(cj.cy[0], cj.cy[1]), fmin(cj.cy[2], cj.cy[3]));
+                const double jy1 = fmax(fmax(cj.cy[0], cj.cy[1]), fmax(cj.cy[2], cj.cy[3]));
+                apart = jx0 > ix1 || jx1 < ix0 || jy0 > iy1 || jy1 < iy0;
+            }
+            if (!apart) bit = static_cast<float>(quad_iou(ci.cx, ci.cy, cj.cx, cj.cy)) > nms_thr;
         }
         const unsigned word = __ballot_sync(0xffffffffu, bit);
         if ((threadIdx.x & 31) == 0) sup[i * kPPWords + w] = word;
     }
 }
 
-// One warp: greedy pick in order, then the range mask; outputs compacted in pick order.
+// One warp, no shared memory (it runs beside the persistent conv kernels of the next frame).  Phase 1 walks the
+// candidates in order and ORs the suppression rows of the kept ones into the removed mask (lane w owns word w); the
+// rows of the next 16 candidates are requested together, so the walk pays one memory latency per 16 candidates
+// instead of one (plus two dependent ones) per candidate.  Phase 2 applies the range mask to 32 kept candidates at
+// a time, one per lane, and compacts them in pick order.
 __global__ void pp_greedy_kernel(const PPCand* __restrict__ cand, const int* __restrict__ order,
                                  const int* __restrict__ n_top, const unsigned* __restrict__ sup, PPParams p,
                                  double* __restrict__ out_corners, double* __restrict__ out_scores,
                                  int* __restrict__ out_labels, double* __restrict__ out_boxes, int* __restrict__ out_n) {
     const int lane = threadIdx.x;
     const int K = *n_top;
-    unsigned removed = 0;                 // lane w owns word w of the removed mask
+    const int nwords = (K + 31) / 32;
+    unsigned removed = 0, kept = 0;       // lane w owns word w of both masks
+    // this lane's candidates of phase 2 (rank 32 w + lane): their indices are requested before the walk starts
+    int ord[kPPWords];
+#pragma unroll
+    for (int w = 0; w < kPPWords; ++w) ord[w] = (32 * w + lane < K) ? __ldg(order + 32 * w + lane) : 0;
+    constexpr int kAhead = 16;
+    auto load_rows = [&](int i0, unsigned (&row)[kAhead]) {
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u)
+            row[u] = (i0 + u < K && lane < nwords) ? __ldg(sup + (i0 + u) * kPPWords + lane) : 0u;
+    };
+    unsigned row[kAhead], nxt[kAhead];
+    load_rows(0, row);
+    for (int i0 = 0; i0 < K; i0 += kAhead) {
+        load_rows(i0 + kAhead, nxt);       // in flight while this batch is walked
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) {
+            const int i = i0 + u;
+            const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
+            const bool take = i < K && !((word >> (i & 31)) & 1u);
+            if (take) {
+                removed |= row[u];
+                if (lane == (i >> 5)) kept |= 1u << (i & 31);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) row[u] = nxt[u];
+    }
     int n_out = 0;
-    for (int i = 0; i < K; ++i) {
-        const unsigned word = __shfl_sync(0xffffffffu, removed, i >> 5);
-        if ((word >> (i & 31)) & 1u) continue;
-        removed |= sup[i * kPPWords + lane];
-        const PPCand& c = cand[order[i]];
-        bool inside = true;
-        for (int q = 0; q < 4; ++q)
-            inside = inside && c.cx[q] >= p.lo[0] && c.cx[q] <= p.hi[0] && c.cy[q] >= p.lo[1] && c.cy[q] <= p.hi[1];
-        if (!inside) continue;
-        if (lane < 4) {
-            out_corners[(n_out * 4 + lane) * 2 + 0] = c.cx[lane];
-            out_corners[(n_out * 4 + lane) * 2 + 1] = c.cy[lane];
+#pragma unroll
+    for (int w = 0; w < kPPWords; ++w) {
+        if (w >= nwords) break;
+        const unsigned kw = __shfl_sync(0xffffffffu, kept, w);
+        if (kw == 0u) continue;
+        const bool mine = (kw >> lane) & 1u;
+        const PPCand* c = cand + ord[w];
+        // every value of the candidate is requested before the first one is looked at (one memory latency per word)
+        double cx[4], cy[4], box[7], score = 0.0;
+        int label = 0;
+        if (mine) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) cx[q] = c->cx[q], cy[q] = c->cy[q];
+#pragma unroll
+            for (int t = 0; t < 7; ++t) box[t] = c->box[t];
+            score = c->score;
+            label = c->label;
         }
-        if (lane < 7) out_boxes[n_out * 7 + lane] = c.box[lane];
-        if (lane == 0) {
-            out_scores[n_out] = c.score;
-            out_labels[n_out] = c.label;
+        bool inside = mine;
+        if (mine) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                inside = inside & (cx[q] >= p.lo[0]) & (cx[q] <= p.hi[0]) & (cy[q] >= p.lo[1]) & (cy[q] <= p.hi[1]);
         }
-        ++n_out;
+        const unsigned ok = __ballot_sync(0xffffffffu, inside);
+        if (inside) {
+            const int slot = n_out + __popc(ok & ((1u << lane) - 1u));
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                out_corners[(slot * 4 + q) * 2 + 0] = cx[q];
+                out_corners[(slot * 4 + q) * 2 + 1] = cy[q];
+            }
+#pragma unroll
+            for (int t = 0; t < 7; ++t) out_boxes[slot * 7 + t] = box[t];
+            out_scores[slot] = score;
+            out_labels[slot] = label;
+        }
+        n_out += __popc(ok);
     }
     if (lane == 0) *out_n = n_out;
 }
@@ -238,6 +320,14 @@ int qv2x_postprocess_create(const qv2x_postprocess_desc* d, qv2x_postprocess** o
     }
     for (int r = 0; r < d->n_rotations; ++r) p.rot[r] = d->anchor_rot[r];
     p.score_thr = d->score_threshold;
+    p.use_cut = (d->score_threshold > 1e-4 && d->score_threshold < 1.0 - 1e-4) ? 1 : 0;
+    if (p.use_cut) {
+        // the largest float that is still >= 1e-6 below logit(threshold)
+        const double lc = std::log(d->score_threshold / (1.0 - d->score_threshold)) - 1e-6;
+        float f = static_cast<float>(lc);
+        if (static_cast<double>(f) > lc) f = std::nextafter(f, -INFINITY);
+        p.logit_cut = f;
+    }
     p.nms_thr = d->nms_threshold;
     p.lo[0] = d->range_lo[0], p.lo[1] = d->range_lo[1], p.hi[0] = d->range_hi[0], p.hi[1] = d->range_hi[1];
     p.cap = d->max_candidates, p.top = d->top;
@@ -275,7 +365,7 @@ int qv2x_postprocess_forward(const qv2x_postprocess* h, const float* d_preds, do
     const long long n = hw * p.n_cls * p.n_rot;
     pp_select_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, num_sms() * 8LL)), 256, 0, stream>>>(
         d_preds, hw, p, h->d_cand, h->d_count);
-    pp_rank_kernel<<<std::max(1, std::min((p.cap + 255) / 256, num_sms())), 256, 0, stream>>>(
+    pp_rank_kernel<<<std::max(1, std::min((p.cap + 7) / 8, 2 * num_sms())), 256, 0, stream>>>(
         h->d_cand, h->d_count, p.cap, p.top, h->d_order, h->d_ntop);
     pp_iou_kernel<<<p.top, 256, 0, stream>>>(h->d_cand, h->d_order, h->d_ntop, p.nms_thr, h->d_sup);
     pp_greedy_kernel<<<1, 32, 0, stream>>>(h->d_cand, h->d_order, h->d_ntop, h->d_sup, p, d_corners, d_scores,
