@@ -252,3 +252,40 @@ def test_wire_format_roundtrip():
         unpack_codes(b"XXXX" + bytes(40))
     with pytest.raises(ValueError):
         unpack_codes(pack_codes(np.zeros((3, 1, 100), np.uint8), 128)[:-3])
+
+
+def test_ego_fold_equals_chain():
+    """The folded form of the attention-fusion ego stage (oracle/ego_fold_oracle.py = what qv2x_ego_att evaluates:
+    Gram matrix of the decode tables for the scores, head table for the outputs) equals the operator-by-operator
+    restatement decode -> warp -> attention fusion -> heads, including an agent partly out of view, a rotated ego
+    matrix and two segments per level."""
+    from oracle import codebook_oracle as co
+    from oracle import ego_fold_oracle as ef
+    from oracle import fusion_oracle as fo
+    from tests.codebook_cases import make_codebook_params, oracle_params
+
+    for n, H, W, C, m, ks, cout, egowarp in [(3, 9, 14, 64, 1, [32, 32, 32], 20, False),
+                                             (4, 8, 11, 64, 2, [16, 16], 12, True)]:
+        rng = np.random.default_rng(n * 7 + H)
+        fd = co.fold_decode(oracle_params(*make_codebook_params(3, C, m, ks)))
+        tables = [fd["tables"][l][s] for l in range(len(ks)) for s in range(m)]
+        kk = [k for k in ks for _ in range(m)]
+        hw = H * W
+        codes = np.stack([rng.integers(0, kk[i], size=n * hw) for i in range(len(kk))])
+        t = np.tile(np.eye(4), (1, n, n, 1, 1))
+        for j in range(1, n):
+            th = np.deg2rad(7.0 * j)
+            t[0, 0, j, :2, :2] = [[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]
+            t[0, 0, j, 0, 3], t[0, 0, j, 1, 3] = 2.0 * j, -1.0 * j
+        aff = fo.normalize_pairwise_tfm(t, 8.0, 12.0, 1.0)[0, 0, :n]
+        aff[n - 1, 0, 2] += 0.5
+        if egowarp:
+            aff[0] = np.array([[0.99, -0.05, 0.02], [0.06, 0.98, -0.03]])
+        w = rng.normal(size=(cout, C)) / 8
+        b = rng.normal(size=cout)
+        feat = np.tile(fd["const"], (n * hw, 1))
+        for i in range(len(kk)):
+            feat += tables[i][codes[i]]
+        ref = fo.heads(fo.att_fusion(feat.reshape(n, H, W, C), aff), w, b).reshape(cout, hw)
+        got = ef.ego_att_folded(codes, tables, fd["const"], aff, w, b, H, W)
+        np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
