@@ -244,6 +244,25 @@ int qv2x_ego_att_forward(const qv2x_ego_att* h, int n_agents, int H, int W, cons
                          long long plane_stride, const float* d_affine, float* d_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Decode + first 1x1 conv + activation quantizer of the pyramid model's ego stage, folded over the codeword tables
+ * (SURVEY 8(f)-2).  Replaces UMGMQuantizer.decode (opencood/models/sub_modules/codebook.py:192-201, 263-269)
+ * followed by conv1 (+ folded BN, ReLU, act quantizer) of the first ResNeXt bottleneck of PyramidFusion
+ * (opencood/models/sub_modules/resblock.py:67-122 under QuantBottleneck, opencood/quant/quant_block.py:100-134):
+ *   out[row][c] = clamp(rint((bias[c] + sum_k w[c][k] * decode(codes)[row][k]) / out_delta), 0, 255)
+ * w: HOST [cout][C] de-quantized fake-quant weights, bias HOST [cout] or NULL; cout a multiple of 4.
+ * forward: d_codes [levels*m][plane_stride] uint8 -> d_out [rows][cout] uint8 (pixel-major, zero-point 0) and, when
+ * d_rowsum != NULL, the per-row sums of the output codes (the next layer's zero-point term).
+ * Supported when levels*m <= 4 and the [sum_l m*k_l][cout] folded table fits in shared memory.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct qv2x_decode_linear qv2x_decode_linear;
+int qv2x_decode_linear_supported(const qv2x_codebook* cb, int cout);
+int qv2x_decode_linear_create(const qv2x_codebook* cb, int cout, const float* w, const float* bias, float out_delta,
+                              qv2x_decode_linear** out);
+void qv2x_decode_linear_destroy(qv2x_decode_linear* h);
+int qv2x_decode_linear_forward(const qv2x_decode_linear* h, long long rows, const uint8_t* d_codes,
+                               long long plane_stride, uint8_t* d_out, int32_t* d_rowsum, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * PointPillars front end: pillars -> decorated points -> quantized Linear(10 -> 64) ->
  * pre-ReLU activation quantizer -> ReLU -> block activation quantizer -> max over the pillar's points -> scatter
  * into the uint8 NHWC BEV map, in one kernel.  Replaces QuantPointPillar.forward

@@ -202,6 +202,17 @@ def _declare_ego_att(lib):
 _DECLARERS.append(_declare_ego_att)
 
 
+def _declare_decode_linear(lib):
+    lib.qv2x_decode_linear_supported.argtypes = [c_void_p, c_int]
+    lib.qv2x_decode_linear_create.argtypes = [c_void_p, c_int, c_void_p, c_void_p, c_float, POINTER(c_void_p)]
+    lib.qv2x_decode_linear_destroy.argtypes = [c_void_p]
+    lib.qv2x_decode_linear_destroy.restype = None
+    lib.qv2x_decode_linear_forward.argtypes = [c_void_p, c_longlong, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p]
+
+
+_DECLARERS.append(_declare_decode_linear)
+
+
 class PlanStep(ctypes.Structure):
     """Mirror of qv2x_plan_step (include/qv2x.h)."""
 

@@ -344,6 +344,46 @@ class EgoAttEngine:
         return out
 
 
+class DecodeLinearEngine:
+    """Codebook decode + 1x1 conv + activation quantizer folded over the codeword tables (qv2x_decode_linear): code
+    planes -> uint8 NHWC codes of the conv's output and their per-pixel sums.  Entry of the pyramid model's ego stage
+    (UMGMQuantizer.decode -> conv1 of the first QuantBottleneck, quant_block.py:100-134)."""
+
+    @staticmethod
+    def supported(codebook: "CodebookEngine", cout: int) -> bool:
+        return bool(_lib.lib().qv2x_decode_linear_supported(codebook._h, int(cout)))
+
+    def __init__(self, codebook: "CodebookEngine", w_hat: np.ndarray, bias, out_delta: float):
+        w = np.ascontiguousarray(w_hat, dtype=np.float32)
+        assert w.shape[1] == codebook.channel
+        self.cout = int(w.shape[0])
+        self.nt = codebook.levels * codebook.m
+        b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        self._h = c_void_p()
+        check(_lib.lib().qv2x_decode_linear_create(codebook._h, self.cout, _np_ptr(w), None if b is None else _np_ptr(b),
+                                                    float(out_delta), byref(self._h)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                _lib.lib().qv2x_decode_linear_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def forward(self, codes: torch.Tensor, rows: int, want_rowsum: bool = True):
+        """codes uint8 [levels, m, >= rows] -> (uint8 [rows, cout], int32 [rows] or None)."""
+        assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous()
+        assert codes.numel() // codes.shape[-1] == self.nt and codes.shape[-1] >= rows
+        out = torch.empty((rows, self.cout), dtype=torch.uint8, device=codes.device)
+        rs = torch.empty((rows,), dtype=torch.int32, device=codes.device) if want_rowsum else None
+        check(_lib.lib().qv2x_decode_linear_forward(self._h, rows, c_void_p(codes.data_ptr()), codes.shape[-1],
+                                                    c_void_p(out.data_ptr()),
+                                                    None if rs is None else c_void_p(rs.data_ptr()), _stream_ptr()))
+        return out, rs
+
+
 class PillarEngine:
     """libqv2x handle of the quantized PointPillars front end (qv2x_pillar_*): pillars -> uint8 NHWC BEV map."""
 

@@ -179,25 +179,45 @@ class FirstBottleneckEngine:
         self.width, self.cin = w_hat.shape
         assert self.width % 64 == 0
         self.conv1 = E.HeadsEngine(w_hat, bias)            # one launch: 72-column output chunks are grid.y
+        self._w_hat, self._bias = w_hat, bias
+        self.fold = None                                   # attach_decode_fold: decode . conv1 . quantizer from codes
         self.conv2 = _layer(p["conv2"], ksize=3, stride=1, pad=1, relu=True, in_delta=self.d1, out_delta=d2,
                             groups=int(p["groups"]))
         self.conv3 = _layer(p["conv3"], ksize=1, stride=1, pad=0, relu=True, in_delta=d2, out_delta=self.out_delta)
         self.cout = self.conv3.cout
         assert self.cout == self.cin, "identity shortcut"
 
-    def forward(self, x: torch.Tensor, want_rowsum: bool = False, taps: dict | None = None, q1_override=None):
-        """x float32 NHWC [n, H, W, cin] -> uint8 NHWC [n, H, W, cout] (scale out_delta)."""
+    def attach_decode_fold(self, codebook) -> bool:
+        """When x is the decode of code planes of `codebook` (the pyramid model's ego stage), conv1 and its quantizer
+        fold over the codeword tables: q1 comes straight from the codes (qv2x_decode_linear), without the FP32 GEMM
+        on the decoded features and the transposing quantizer pass.  Returns whether the fold is supported."""
+        self.fold = None
+        if codebook.channel == self.cin and E.DecodeLinearEngine.supported(codebook, self.width):
+            self.fold = E.DecodeLinearEngine(codebook, self._w_hat, self._bias, self.d1)
+        return self.fold is not None
+
+    def forward(self, x: torch.Tensor, want_rowsum: bool = False, taps: dict | None = None, q1_override=None,
+                codes: torch.Tensor | None = None):
+        """x float32 NHWC [n, H, W, cin] -> uint8 NHWC [n, H, W, cout] (scale out_delta).  codes: the uint8 code
+        planes [levels, m, n*H*W] x was decoded from (x is then only read as the shortcut of conv3)."""
         assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == self.cin
         n, h, w, _ = x.shape
         dev = x.device
-        planar = torch.empty((self.width, n * h * w), dtype=torch.float32, device=dev)
-        self.conv1.forward(x, out=planar)
-        q1 = E.quantize_nchw_to_nhwc_u8(planar.view(1, self.width, n * h, w), self.d1).view(n, h, w, self.width)
-        if taps is not None:
-            taps["q1_first"] = q1
-        if q1_override is not None:            # test hook: teacher-force the only FP32-accumulated codes
-            q1 = q1_override
-        rs1 = E.rowsum_u8(q1, 0, self.width)
+        if codes is not None and self.fold is not None and q1_override is None:
+            q1, rs1 = self.fold.forward(codes, n * h * w)
+            q1 = q1.view(n, h, w, self.width)
+            rs1 = rs1.view(n, h, w)
+            if taps is not None:
+                taps["q1_first"] = q1
+        else:
+            planar = torch.empty((self.width, n * h * w), dtype=torch.float32, device=dev)
+            self.conv1.forward(x, out=planar)
+            q1 = E.quantize_nchw_to_nhwc_u8(planar.view(1, self.width, n * h, w), self.d1).view(n, h, w, self.width)
+            if taps is not None:
+                taps["q1_first"] = q1
+            if q1_override is not None:            # test hook: teacher-force the only FP32-accumulated codes
+                q1 = q1_override
+            rs1 = E.rowsum_u8(q1, 0, self.width)
         rs2 = torch.zeros((n, h, w), dtype=torch.int32, device=dev)
         q2 = self.conv2.forward(q1, rowsum_in=[rs1], rowsum_out=rs2)
         rs_out = torch.zeros((n, h, w), dtype=torch.int32, device=dev) if want_rowsum else None
@@ -301,7 +321,16 @@ class PyramidBackboneEngine:
         self.deblocks = [DeblockF32(params[f"up{li}"]) for li in range(len(layer_nums)) if f"up{li}" in params]
         self.up_deltas = [d.delta for d in self.deblocks]
 
-    def forward_collab(self, x: torch.Tensor, affine, taps: dict | None = None, q1_override=None):
+    def attach_decode_fold(self, codebook) -> bool:
+        """See FirstBottleneckEngine.attach_decode_fold (the first block of stage 0)."""
+        ok = False
+        for blk in self.stages[0]:
+            if isinstance(blk, FirstBottleneckEngine):
+                ok = blk.attach_decode_fold(codebook)
+        return ok
+
+    def forward_collab(self, x: torch.Tensor, affine, taps: dict | None = None, q1_override=None,
+                       codes: torch.Tensor | None = None):
         """x float32 NHWC [N, H, W, 64] decoded features of the N agents in range (agent 0 = ego); affine [N, 2, 3]
         = normalize_pairwise_tfm(...)[b][0, :N].  Returns the fused float32 [h_i, w_i, C_i] map of every level."""
         if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
@@ -311,7 +340,7 @@ class PyramidBackboneEngine:
         for li, blocks in enumerate(self.stages):
             for blk in blocks:
                 if isinstance(blk, FirstBottleneckEngine):
-                    cur, rs = blk.forward(cur, want_rowsum=True, taps=taps, q1_override=q1_override)
+                    cur, rs = blk.forward(cur, want_rowsum=True, taps=taps, q1_override=q1_override, codes=codes)
                 else:
                     cur, rs = blk.forward(cur, rowsum=rs, want_rowsum=True)
             occ = self.heads[li].forward(cur, rowsum=rs)

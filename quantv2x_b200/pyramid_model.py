@@ -17,6 +17,8 @@ from __future__ import annotations
 
 from collections import Counter
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -159,7 +161,7 @@ class HeterPyramidCollabCodebookMC(nn.Module):
         x = eng["codebook"].decode(codes).view(n, h, w, c)                   # float32 NHWC
         pyr = eng["pyramid"]
         ptaps = {} if taps is None else taps
-        fused = pyr.forward_collab(x, aff, taps=ptaps)
+        fused = pyr.forward_collab(x, aff, taps=ptaps, codes=codes if codes.dtype == torch.uint8 else None)
         cat = pyr.decode_multiscale_feature(fused)                           # uint8 [1, H, W, 384], 3 scales
         if self.shrink_flag:
             y = eng["shrink"].forward_u8(cat)                                # uint8 [1, H, W, 256]
@@ -246,6 +248,8 @@ def attach_pyramid_engines(qmodel, device=None):
     model.codebook.set_input_scale(engines["backbone"].out_delta)
     engines["pyramid"] = PyramidBackboneEngine(pf.export_params(), pf.layer_nums())
     pf.attach_engine(engines["pyramid"])
+    if os.environ.get("QV2X_PYRAMID_FOLD", "1") == "1":
+        engines["pyramid"].attach_decode_fold(engines["codebook"])       # decode . conv1 . quantizer from the codes
     if model.shrink_flag:
         sc = model.shrink_conv
         if not isinstance(sc, QuantDownsampleConv):

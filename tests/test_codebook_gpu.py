@@ -138,3 +138,42 @@ def test_encode_exact_ties_lowest_index(cuda_device):
         assert np.array_equal(codes[l].T, ref_fx[l]), f"level {l}: kernel codes differ from the fixed-point oracle"
     # the folded columns of duplicated codewords are identical bit for bit at level 0 (same digits, scale, g0)
     assert codes[0].max() < 64, "a duplicate (higher) index won an exact tie at level 0"
+
+
+@pytest.mark.parametrize("case", [(64, 1, [128] * 3, 128, 5000), (64, 1, [64, 64], 64, 777), (256, 1, [128] * 3, 72 + 4, 1234)],
+                         ids=lambda c: f"c{c[0]}_m{c[1]}_k{c[2][0]}x{len(c[2])}_o{c[3]}_r{c[4]}")
+def test_decode_linear_fold(cuda_device, case):
+    """qv2x_decode_linear (decode . 1x1 conv . ReLU . activation quantizer folded over the codeword tables, the entry
+    of the pyramid model's ego stage) against the float64 evaluation on the library's fp32 decode tables: codes equal
+    except where the float64 value sits within 1e-3 of a rounding boundary (then within 1 LSB), row sums consistent;
+    and against the unfolded chain decode -> FP32 GEMM -> quantizing converter within 1 LSB on < 1e-3 of the codes."""
+    from quantv2x_b200 import engine as E
+    from tests.codebook_cases import make_codebook_params
+
+    C, m, ks, cout, rows = case
+    rng = np.random.default_rng(rows)
+    cb = E.CodebookEngine(*make_codebook_params(11, C, m, ks))
+    w = (rng.normal(size=(cout, C)) * 0.5).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32) * 0.1
+    nt = len(ks) * m
+    kk = [k for k in ks for _ in range(m)]
+    codes = np.stack([rng.integers(0, kk[i], size=rows + 13, dtype=np.uint8) for i in range(nt)]).reshape(len(ks), m, -1)
+    codes_d = torch.from_numpy(codes).to(cuda_device)
+    feat = cb.decode(codes_d).cpu().numpy().astype(np.float64)[:rows]
+    y = feat @ w.astype(np.float64).T + b
+    delta = float(np.float32(np.abs(y).max() / 200.0))
+    assert E.DecodeLinearEngine.supported(cb, cout)
+    eng = E.DecodeLinearEngine(cb, w, b, delta)
+    q, rs = eng.forward(codes_d, rows)
+    q, rs = q.cpu().numpy().astype(np.int64), rs.cpu().numpy()
+    t = y / delta
+    ref = np.clip(np.rint(t), 0, 255).astype(np.int64)
+    near = np.abs(np.abs(t - np.floor(t)) - 0.5) < 1e-3
+    assert np.array_equal(q[~near], ref[~near])
+    assert np.abs(q - ref).max() <= 1
+    assert np.array_equal(rs, q.sum(axis=1))
+    # the unfolded chain of this library
+    planar = E.HeadsEngine(w, b).forward(cb.decode(codes_d)[:rows].contiguous())
+    q2 = E.quantize_nchw_to_nhwc_u8(planar.view(1, cout, 1, rows), delta).view(rows, cout).cpu().numpy().astype(np.int64)
+    d = np.abs(q - q2)
+    assert d.max() <= 1 and (d > 0).mean() < 1e-3
