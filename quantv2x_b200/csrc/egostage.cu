@@ -47,7 +47,9 @@ struct EgoAttParams {
     const float* ht;            // [R][72]
     const float* bias;          // [72] (zero padded)
     float* out;                 // [cout][H*W]
-    int warps_per_group;
+    int warps_per_group;        // a power of two
+    int gp_shift;               // log2(warps_per_group)
+    uint32_t w_magic;           // ceil(2^32 / W): pix / W == umulhi(pix, w_magic) for pix * W < 2^32 (checked on the host)
 };
 
 template <int NT>
@@ -95,7 +97,8 @@ __global__ void __launch_bounds__(1024, 1) ego_att_kernel(const EgoAttParams p) 
                 w = (t == 0) ? 1.f : 0.f;
                 q = pix;
             } else {
-                const int i = pix / p.W, j = pix - i * p.W;
+                const int i = (p.W == 1) ? pix : static_cast<int>(__umulhi(static_cast<uint32_t>(pix), p.w_magic));
+                const int j = pix - i * p.W;
                 const float xn = (2.f * j + 1.f) / p.W - 1.f;
                 const float yn = (2.f * i + 1.f) / p.H - 1.f;
                 const float xs = am[a][0] * xn + am[a][1] * yn + am[a][2];
@@ -143,10 +146,10 @@ __global__ void __launch_bounds__(1024, 1) ego_att_kernel(const EgoAttParams p) 
 #pragma unroll
                 for (int tq = 0; tq < 4; ++tq) {
                     const float wq = __shfl_sync(0xffffffffu, w, tq);
+                    if (wq == 0.f) continue;               // warp-uniform (identity ego matrix: only tap 0 is left)
                     int er[NT];
 #pragma unroll
                     for (int it = 0; it < NT; ++it) er[it] = __shfl_sync(0xffffffffu, rows[it], tq);
-                    if (wq == 0.f) continue;
 #pragma unroll
                     for (int it = 0; it < NT; ++it) {
                         const float4* gr = reinterpret_cast<const float4*>(p.gram + static_cast<long long>(er[it]) * R);
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(1024, 1) ego_att_kernel(const EgoAttParams p) 
         asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "r"(gthreads) : "memory");
         const int pix0 = b * GP;
         for (int idx = gtid; idx < p.cout * GP; idx += gthreads) {
-            const int c = idx / GP, pp = idx - c * GP;
+            const int c = idx >> p.gp_shift, pp = idx & (GP - 1);
             if (pix0 + pp < hw) p.out[static_cast<long long>(c) * hw + pix0 + pp] = stage[c * (GP + 1) + pp] + __ldg(p.bias + c);
         }
         // no second barrier: the next batch writes the other staging tile, and the batch after that passes the
@@ -271,7 +274,7 @@ struct qv2x_ego_att {
 static bool ego_att_plan(int R, int nt, int* warps_per_group, int* smem) {
     const int sw = nt <= 3 ? 4 : 8;
     const long long budget = 220 * 1024;
-    for (int wpg = 32 / kEgoGroups; wpg >= 2; --wpg) {
+    for (int wpg = 32 / kEgoGroups; wpg >= 2; wpg >>= 1) {      // a power of two (the store loop shifts by it)
         const int nw = wpg * kEgoGroups;
         const long long need = 4ll * (static_cast<long long>(R) * kEgoOut + static_cast<long long>(nw) * R +
                                       static_cast<long long>(nw) * kEgoStash * sw +
@@ -378,7 +381,8 @@ int qv2x_ego_att_forward(const qv2x_ego_att* h, int n_agents, int H, int W, cons
     QV2X_REQUIRE(n_agents >= 1 && n_agents <= kEgoMaxAgents, "n_agents must be 1..%d", kEgoMaxAgents);
     QV2X_REQUIRE(H > 0 && W > 0 && static_cast<long long>(H) * W * n_agents <= plane_stride,
                  "code planes are shorter than n_agents * H * W rows");
-    QV2X_REQUIRE(static_cast<long long>(H) * W < (1ll << 30), "map too large");
+    QV2X_REQUIRE(static_cast<long long>(H) * W < (1ll << 30) && static_cast<long long>(H) * W * W < (1ll << 32),
+                 "map too large");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     EgoAttParams p{};
     p.n = n_agents;
@@ -399,6 +403,9 @@ int qv2x_ego_att_forward(const qv2x_ego_att* h, int n_agents, int H, int W, cons
     p.bias = h->d_bias;
     p.out = d_out;
     p.warps_per_group = h->warps_per_group;
+    p.gp_shift = 0;
+    while ((1 << p.gp_shift) < h->warps_per_group) ++p.gp_shift;
+    p.w_magic = W > 1 ? static_cast<uint32_t>((0x100000000ull + W - 1) / W) : 0u;
     const int threads = h->warps_per_group * kEgoGroups * 32;
     const long long batches = (static_cast<long long>(H) * W + h->warps_per_group - 1) / h->warps_per_group;
     const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(num_sms(), (batches + kEgoGroups - 1) / kEgoGroups)));
