@@ -33,6 +33,41 @@ import torch
 from . import engine as E
 
 
+class _ZeroPool:
+    """Per-pixel code sums are accumulated with atomic adds by the producing conv, so every such buffer starts from
+    zero.  One memset kernel per buffer was 52 launches (0.12 ms) of a pyramid frame: inside begin() / end() the
+    buffers are slices of ONE zeroed allocation whose size was learned on the first pass over the same shapes."""
+
+    def __init__(self):
+        self.sizes, self.key, self.buf, self.off, self.used = {}, None, None, 0, 0
+
+    def begin(self, key, device):
+        if self.key is not None:             # nested use (block engines driven inside a model pass): keep the outer
+            return False
+        self.key, self.off, self.used = key, 0, 0
+        need = self.sizes.get(key, 0)
+        self.buf = torch.zeros((need,), dtype=torch.int32, device=device) if need else None
+        return True
+
+    def take(self, shape, device):
+        numel = int(np.prod(shape))
+        pad = (numel + 63) // 64 * 64        # 256-byte aligned slices
+        if self.key is not None:
+            self.used += pad
+            if self.buf is not None and self.off + pad <= self.buf.numel() and self.buf.device == device:
+                t = self.buf[self.off:self.off + numel].view(shape)
+                self.off += pad
+                return t
+        return torch.zeros(shape, dtype=torch.int32, device=device)
+
+    def end(self):
+        self.sizes[self.key] = max(self.sizes.get(self.key, 0), self.used)
+        self.key, self.buf = None, None
+
+
+_zeros = _ZeroPool()
+
+
 def _layer(c, *, ksize, stride, pad, relu, in_delta, out_delta, groups=1):
     return E.QLayer(kind=0, w_int=c["w_int"], w_delta=c["w_delta"], w_zp=c["w_zp"], bias=c.get("bias"), ksize=ksize,
                     stride=stride, pad=pad, w_bits=int(c.get("w_bits", 8)), relu=relu, in_delta=in_delta,
@@ -69,12 +104,12 @@ class BottleneckEngine:
         dev = x.device
         if rowsum is None:
             rowsum = E.rowsum_u8(x, 0, self.cin)
-        rs1 = torch.zeros((n, h, w), dtype=torch.int32, device=dev)
+        rs1 = _zeros.take((n, h, w), dev)
         q1 = self.conv1.forward(x, rowsum_in=[rowsum], rowsum_out=rs1)
         ho, wo = self.conv2.out_shape(h, w)
-        rs2 = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev)
+        rs2 = _zeros.take((n, ho, wo), dev)
         q2 = self.conv2.forward(q1, rowsum_in=[rs1], rowsum_out=rs2)
-        rs_out = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev) if want_rowsum else None
+        rs_out = _zeros.take((n, ho, wo), dev) if want_rowsum else None
         if self.down is not None:
             res = torch.empty((n, ho, wo, self.cout), dtype=torch.float32, device=dev)
             self.down.forward(x, rowsum_in=[rowsum], out_f32=res)
@@ -114,9 +149,9 @@ class BasicBlockEngine:
         if rowsum is None:
             rowsum = E.rowsum_u8(x, 0, self.cin)
         ho, wo = self.conv1.out_shape(h, w)
-        rs1 = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev)
+        rs1 = _zeros.take((n, ho, wo), dev)
         q1 = self.conv1.forward(x, rowsum_in=[rowsum], rowsum_out=rs1)
-        rs_out = torch.zeros((n, ho, wo), dtype=torch.int32, device=dev) if want_rowsum else None
+        rs_out = _zeros.take((n, ho, wo), dev) if want_rowsum else None
         if self.down is not None:
             res = torch.empty((n, ho, wo, self.cout), dtype=torch.float32, device=dev)
             self.down.forward(x, rowsum_in=[rowsum], out_f32=res)
@@ -143,14 +178,19 @@ class ResNetBackboneEngine:
         self.cin, self.cout = self.blocks[0].cin, self.blocks[-1].cout
 
     def forward_u8(self, x: torch.Tensor, rowsum: torch.Tensor | None = None) -> torch.Tensor:
-        rs = rowsum
-        for i, b in enumerate(self.blocks):
-            last = i == len(self.blocks) - 1
-            if last:
-                x = b.forward(x, rowsum=rs)
-            else:
-                x, rs = b.forward(x, rowsum=rs, want_rowsum=True)
-        return x
+        owner = _zeros.begin(("resnet",) + tuple(x.shape), x.device)
+        try:
+            rs = rowsum
+            for i, b in enumerate(self.blocks):
+                last = i == len(self.blocks) - 1
+                if last:
+                    x = b.forward(x, rowsum=rs)
+                else:
+                    x, rs = b.forward(x, rowsum=rs, want_rowsum=True)
+            return x
+        finally:
+            if owner:
+                _zeros.end()
 
     def forward_nchw(self, x: torch.Tensor) -> torch.Tensor:
         """Module-boundary drop-in: FP32 NCHW on the input grid -> FP32 NCHW de-quantized output."""
@@ -218,9 +258,9 @@ class FirstBottleneckEngine:
             if q1_override is not None:            # test hook: teacher-force the only FP32-accumulated codes
                 q1 = q1_override
             rs1 = E.rowsum_u8(q1, 0, self.width)
-        rs2 = torch.zeros((n, h, w), dtype=torch.int32, device=dev)
+        rs2 = _zeros.take((n, h, w), dev)
         q2 = self.conv2.forward(q1, rowsum_in=[rs1], rowsum_out=rs2)
-        rs_out = torch.zeros((n, h, w), dtype=torch.int32, device=dev) if want_rowsum else None
+        rs_out = _zeros.take((n, h, w), dev) if want_rowsum else None
         out = self.conv3.forward(q2, rowsum_in=[rs2], residual=x, rowsum_out=rs_out)
         return (out, rs_out) if want_rowsum else out
 
@@ -335,6 +375,14 @@ class PyramidBackboneEngine:
         = normalize_pairwise_tfm(...)[b][0, :N].  Returns the fused float32 [h_i, w_i, C_i] map of every level."""
         if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
             affine = torch.as_tensor(np.asarray(affine, dtype=np.float32)).to(x.device)
+        owner = _zeros.begin(("collab",) + tuple(x.shape), x.device)
+        try:
+            return self._forward_collab(x, affine, taps, q1_override, codes)
+        finally:
+            if owner:
+                _zeros.end()
+
+    def _forward_collab(self, x, affine, taps, q1_override, codes):
         fused = []
         cur, rs = x, None
         for li, blocks in enumerate(self.stages):
