@@ -203,6 +203,11 @@ int qv2x_dequant_u8(const uint8_t* d_x, long long n, float delta, float* d_out, 
  * out = sum_j softmax_j(score_j) x_j, or 0 where every agent is excluded.  Layouts as qv2x_fuse. */
 int qv2x_fuse_weighted(int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
                        int score_is_logit, const float* d_affine, float* d_out, void* stream);
+/* The same on the level's uint8 codes (scale delta, zero-point 0; C a multiple of 4): equals qv2x_dequant_u8 followed by
+ * qv2x_fuse_weighted bit for bit, without the FP32 copy of every agent's map. */
+int qv2x_fuse_weighted_u8(int n_agents, int H, int W, int C, const uint8_t* d_feat_u8, float delta,
+                          const float* d_score, int score_is_logit, const float* d_affine, float* d_out,
+                          void* stream);
 
 /* Detection heads = the three 1x1 convs cls_head / reg_head / dir_head (reference
  * heter_model_baseline_mc.py:137-142) concatenated along the output channel; weights are the de-quantized

@@ -213,6 +213,14 @@ def _declare_decode_linear(lib):
 _DECLARERS.append(_declare_decode_linear)
 
 
+def _declare_fuse_u8(lib):
+    lib.qv2x_fuse_weighted_u8.argtypes = [c_int, c_int, c_int, c_int, c_void_p, c_float, c_void_p, c_int, c_void_p,
+                                          c_void_p, c_void_p]
+
+
+_DECLARERS.append(_declare_fuse_u8)
+
+
 class PlanStep(ctypes.Structure):
     """Mirror of qv2x_plan_step (include/qv2x.h)."""
 

@@ -29,6 +29,7 @@ struct FuseParams {
     float inv_sqrt_c;
     const float* score;         // MODE 2: DEVICE [n][H][W] occupancy logits (score_is_logit) or ready-made scores
     int score_is_logit;
+    float u8_delta;             // U8 input: features are uint8 codes of scale u8_delta (value = fl(delta * code))
 };
 
 // One warp per output pixel; lane owns float4 chunks v = lane + 32*t of the channel vector.
@@ -36,7 +37,10 @@ struct FuseParams {
 // is independent of every branch: out-of-image taps read a clamped address with weight 0 (adds +-0, exact), and
 // the compiler can keep all of an agent's loads (and the next agent's) in flight together.  The kernel is
 // HBM/L2-latency bound, so memory-level parallelism per warp is what sets its speed.
-template <int MODE, int NA, int VPL /* float4 chunks per lane */>
+// U8: `feat` points at uint8 codes [n][H][W][C] instead of floats; a lane's chunk of four channels is one 32-bit word,
+// de-quantized on load exactly as qv2x_dequant_u8 does (fl(delta * code)), so the result equals dequantize + fuse bit
+// for bit while reading a quarter of the bytes and skipping the FP32 copy of every agent's map.
+template <int MODE, int NA, int VPL /* float4 chunks per lane */, bool U8 = false>
 __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const float* __restrict__ feat, float* __restrict__ out,
                                                    const FuseParams p) {
     const int lane = threadIdx.x & 31;
@@ -88,9 +92,27 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
         float4 xa[NA][VPL];
 #pragma unroll
         for (int a = 0; a < NA; ++a) {
-            const float4* base = reinterpret_cast<const float4*>(feat + static_cast<long long>(a) * npix * p.C);
             float4 s[4][VPL];
             float w[4];
+            if constexpr (U8) {
+                const uint32_t* base = reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(feat) +
+                                                                         static_cast<long long>(a) * npix * p.C);
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    w[tap] = __shfl_sync(0xffffffffu, tw_[tap], a);
+                    const uint32_t* src = base + __shfl_sync(0xffffffffu, to_[tap], a);
+#pragma unroll
+                    for (int t = 0; t < VPL; ++t) {
+                        const int v = lane + 32 * t;
+                        const uint32_t q = (v < vec) ? __ldg(src + v) : 0u;
+                        s[tap][t] = make_float4(__fmul_rn(static_cast<float>(q & 0xffu), p.u8_delta),
+                                                __fmul_rn(static_cast<float>((q >> 8) & 0xffu), p.u8_delta),
+                                                __fmul_rn(static_cast<float>((q >> 16) & 0xffu), p.u8_delta),
+                                                __fmul_rn(static_cast<float>(q >> 24), p.u8_delta));
+                    }
+                }
+            } else {
+            const float4* base = reinterpret_cast<const float4*>(feat + static_cast<long long>(a) * npix * p.C);
 #pragma unroll
             for (int tap = 0; tap < 4; ++tap) {
                 w[tap] = __shfl_sync(0xffffffffu, tw_[tap], a);
@@ -100,6 +122,7 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
                     const int v = lane + 32 * t;
                     s[tap][t] = (v < vec) ? __ldg(src + v) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
+            }
             }
 #pragma unroll
             for (int t = 0; t < VPL; ++t) {
@@ -200,18 +223,18 @@ __global__ void __launch_bounds__(256, (VPL > 2 ? 1 : 2)) fuse_kernel(const floa
     }
 }
 
-template <int MODE, int VPL>
+template <int MODE, int VPL, bool U8 = false>
 static void launch_fuse(int n, int grid, int threads, cudaStream_t stream, const float* feat, float* out,
                         const FuseParams& p) {
     switch (n) {
-        case 1: fuse_kernel<MODE, 1, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 2: fuse_kernel<MODE, 2, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 3: fuse_kernel<MODE, 3, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 4: fuse_kernel<MODE, 4, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 5: fuse_kernel<MODE, 5, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 6: fuse_kernel<MODE, 6, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        case 7: fuse_kernel<MODE, 7, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
-        default: fuse_kernel<MODE, 8, VPL><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 1: fuse_kernel<MODE, 1, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 2: fuse_kernel<MODE, 2, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 3: fuse_kernel<MODE, 3, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 4: fuse_kernel<MODE, 4, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 5: fuse_kernel<MODE, 5, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 6: fuse_kernel<MODE, 6, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        case 7: fuse_kernel<MODE, 7, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
+        default: fuse_kernel<MODE, 8, VPL, U8><<<grid, threads, 0, stream>>>(feat, out, p); break;
     }
 }
 
@@ -501,7 +524,7 @@ struct qv2x_heads {
 
 static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
                      int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
-                     void* stream_);
+                     void* stream_, float u8_delta = 0.f);
 
 extern "C" {
 
@@ -522,11 +545,20 @@ int qv2x_fuse_weighted(int n_agents, int H, int W, int C, const float* d_feat, c
     return fuse_impl(2, n_agents, H, W, C, d_feat, d_score, score_is_logit, d_affine, d_out, 0, H, 0, W, stream_);
 }
 
+int qv2x_fuse_weighted_u8(int n_agents, int H, int W, int C, const uint8_t* d_feat_u8, float delta,
+                          const float* d_score, int score_is_logit, const float* d_affine, float* d_out,
+                          void* stream_) {
+    QV2X_REQUIRE(d_score, "qv2x_fuse_weighted_u8: null score map");
+    QV2X_REQUIRE(delta > 0.f, "qv2x_fuse_weighted_u8: delta must be positive");
+    return fuse_impl(2, n_agents, H, W, C, reinterpret_cast<const float*>(d_feat_u8), d_score, score_is_logit,
+                     d_affine, d_out, 0, H, 0, W, stream_, delta);
+}
+
 }  // extern "C"
 
 static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d_feat, const float* d_score,
                      int score_is_logit, const float* d_affine, float* d_out, int y0, int y1, int x0, int x1,
-                     void* stream_) {
+                     void* stream_, float u8_delta) {
     QV2X_REQUIRE(d_feat && d_affine && d_out, "qv2x_fuse: null argument");
     QV2X_REQUIRE(0 <= y0 && y0 < y1 && y1 <= H && 0 <= x0 && x0 < x1 && x1 <= W, "bad output tile");
     QV2X_REQUIRE(n_agents >= 1 && n_agents <= kMaxAgents, "n_agents must be 1..%d", kMaxAgents);
@@ -546,6 +578,7 @@ static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d
     p.inv_sqrt_c = 1.0f / sqrtf(static_cast<float>(C));
     p.score = d_score;
     p.score_is_logit = score_is_logit;
+    p.u8_delta = u8_delta;
     const long long npix = static_cast<long long>(p.th) * p.tw;
     const int threads = 256;
     const int grid = static_cast<int>(std::min<long long>((npix * 32 + threads - 1) / threads,
@@ -559,6 +592,10 @@ static int fuse_impl(int mode, int n_agents, int H, int W, int C, const float* d
         if (vpl == 1) launch_fuse<1, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else if (vpl == 2) launch_fuse<1, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else launch_fuse<1, 4>(n_agents, grid, threads, stream, d_feat, d_out, p);
+    } else if (u8_delta > 0.f) {
+        if (vpl == 1) launch_fuse<2, 1, true>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else if (vpl == 2) launch_fuse<2, 2, true>(n_agents, grid, threads, stream, d_feat, d_out, p);
+        else launch_fuse<2, 4, true>(n_agents, grid, threads, stream, d_feat, d_out, p);
     } else {
         if (vpl == 1) launch_fuse<2, 1>(n_agents, grid, threads, stream, d_feat, d_out, p);
         else if (vpl == 2) launch_fuse<2, 2>(n_agents, grid, threads, stream, d_feat, d_out, p);

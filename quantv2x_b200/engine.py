@@ -272,6 +272,25 @@ def fuse_weighted(feat: torch.Tensor, score: torch.Tensor, affine, score_is_logi
     return out
 
 
+def fuse_weighted_u8(codes: torch.Tensor, delta: float, score: torch.Tensor, affine, score_is_logit: bool = True,
+                     out: torch.Tensor | None = None) -> torch.Tensor:
+    """fuse_weighted on the level's uint8 codes [N, H, W, C] of scale delta: the same result as
+    fuse_weighted(dequantize_u8(codes, delta), ...) bit for bit, without the FP32 copy (qv2x_fuse_weighted_u8)."""
+    assert codes.is_cuda and codes.dtype == torch.uint8 and codes.is_contiguous() and codes.dim() == 4
+    n, h, w, c = codes.shape
+    assert c % 4 == 0
+    assert score.is_cuda and score.dtype == torch.float32 and score.is_contiguous() and score.numel() == n * h * w
+    if not (isinstance(affine, torch.Tensor) and affine.is_cuda):
+        affine = torch.as_tensor(np.asarray(affine, dtype=np.float32)).to(codes.device)
+    aff = affine.to(torch.float32).reshape(n, 6).contiguous()
+    if out is None:
+        out = torch.empty((h, w, c), dtype=torch.float32, device=codes.device)
+    check(_lib.lib().qv2x_fuse_weighted_u8(n, h, w, c, c_void_p(codes.data_ptr()), float(delta),
+                                           c_void_p(score.data_ptr()), 1 if score_is_logit else 0,
+                                           c_void_p(aff.data_ptr()), c_void_p(out.data_ptr()), _stream_ptr()))
+    return out
+
+
 class HeadsEngine:
     """cls/reg/dir 1x1 heads as one [Cout, Cin] FP32 GEMM (qv2x_heads)."""
 

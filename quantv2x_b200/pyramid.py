@@ -303,6 +303,8 @@ def weighted_fuse_level(codes: torch.Tensor, delta: float, occ: torch.Tensor, af
     """One level of QuantPyramidFusion.forward_collab (quant_block.py:516-539): codes uint8 NHWC [N, H, W, C] of the
     level's features (scale delta, agent 0 = ego), occ float32 [N, H, W] logits of single_head_i, affine [N, 2, 3]
     -> fused float32 [H, W, C]."""
+    if codes.shape[-1] % 4 == 0 and codes.is_contiguous():
+        return E.fuse_weighted_u8(codes, delta, occ, affine, score_is_logit=True)     # de-quantizes on load
     feat = E.dequantize_u8(codes, delta)
     return E.fuse_weighted(feat, occ, affine, score_is_logit=True)
 

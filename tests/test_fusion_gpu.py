@@ -82,6 +82,28 @@ def test_weighted_fuse_vs_oracle(cuda_device, shape):
     assert not z.any()
 
 
+@pytest.mark.parametrize("shape", [(1, 12, 20, 64), (5, 25, 44, 128), (8, 10, 16, 256), (2, 9, 8, 512), (3, 7, 12, 72)])
+def test_weighted_fuse_u8_equals_dequant_then_fuse(cuda_device, shape):
+    """qv2x_fuse_weighted_u8 (the level fusion straight from the uint8 codes) is dequantize_u8 + fuse_weighted bit for
+    bit: the codes are de-quantized on load by the same fl(delta * code)."""
+    from quantv2x_b200.engine import dequantize_u8, fuse_weighted, fuse_weighted_u8
+
+    n, H, W, C = shape
+    rng = np.random.default_rng(n * 31 + C)
+    codes = rng.integers(0, 256, size=(n, H, W, C), dtype=np.uint8)
+    codes[rng.random(codes.shape) > 0.6] = 0
+    occ = (rng.standard_normal((n, H, W)) * 3).astype(np.float32)
+    aff = make_affines(n, rng)
+    delta = 0.0371
+    cd = torch.from_numpy(codes).to(cuda_device)
+    od = torch.from_numpy(occ).to(cuda_device)
+    a = fuse_weighted_u8(cd, delta, od, aff)
+    b = fuse_weighted(dequantize_u8(cd, delta), od, aff)
+    assert torch.equal(a, b)
+    ref = fo.weighted_fusion(codes.astype(np.float64) * np.float64(np.float32(delta)), occ, aff)
+    np.testing.assert_allclose(a.cpu().numpy(), ref, atol=1e-4 * np.abs(ref).max(), rtol=1e-4)
+
+
 def test_heads(cuda_device):
     from quantv2x_b200.engine import HeadsEngine
 
