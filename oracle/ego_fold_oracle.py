@@ -1,6 +1,7 @@
 """ORACLE (test infrastructure): the attention-fusion ego stage in its FOLDED form -- what csrc/egostage.cu
 (qv2x_ego_att) evaluates -- restated in float64 numpy, so that the algebra can be checked on the CPU against the
-operator-by-operator restatement (codebook_oracle.decode_tables -> fusion_oracle.att_fusion -> fusion_oracle.heads).
+operator-by-operator restatement (codebook_oracle.decode_tables -> fusion_oracle.att_fusion -> fusion_oracle.heads); at the end of
+the file the same for the folded entry of the pyramid model (decode -> conv1 -> quantizer, csrc/decode_linear.cu).
 
 Operators folded (reference files):
   * UMGMQuantizer.decode        opencood/models/sub_modules/codebook.py:192-201, 263-269   f = const + sum_i T_i[code_i]
@@ -83,3 +84,17 @@ def ego_att_folded(codes, tables, const, aff, w_heads, bias, H, W):
     p /= p.sum(axis=0, keepdims=True)
     y = (p[..., None] * Y).sum(axis=0) + np.asarray(bias, np.float64)[None, :]
     return y.T
+
+
+def decode_linear_folded(codes, tables, const, w, bias, delta):
+    """The folded entry of the pyramid model's ego stage (csrc/decode_linear.cu, qv2x_decode_linear): decode
+    (codebook.py:192-201) -> conv1 of the first QuantBottleneck (quant_block.py:100-134; 1x1 conv, ReLU, activation
+    quantizer of scale delta, zero-point 0) as a sum of folded table rows.  codes int [NT, rows]; tables list of
+    [k_i, C]; w [Cout, C].  Returns (uint8 codes [rows, Cout], their row sums, the pre-quantizer values)."""
+    w64 = np.asarray(w, np.float64)
+    b = (np.zeros(w64.shape[0]) if bias is None else np.asarray(bias, np.float64)) + w64 @ np.asarray(const, np.float64)
+    y = np.tile(b, (codes.shape[1], 1))
+    for i, t in enumerate(tables):
+        y += (np.asarray(t, np.float64) @ w64.T)[np.asarray(codes[i], np.int64)]
+    q = np.clip(np.rint(y / np.float64(delta)), 0, 255).astype(np.uint8)
+    return q, q.astype(np.int64).sum(axis=1), y

@@ -289,3 +289,28 @@ def test_ego_fold_equals_chain():
         ref = fo.heads(fo.att_fusion(feat.reshape(n, H, W, C), aff), w, b).reshape(cout, hw)
         got = ef.ego_att_folded(codes, tables, fd["const"], aff, w, b, H, W)
         np.testing.assert_allclose(got, ref, rtol=1e-9, atol=1e-9 * np.abs(ref).max())
+
+
+def test_decode_linear_fold_equals_chain():
+    """oracle/ego_fold_oracle.decode_linear_folded (what qv2x_decode_linear evaluates: folded table rows, then the
+    activation quantizer) equals decode -> 1x1 conv -> ReLU -> quantizer evaluated operator by operator."""
+    from oracle import codebook_oracle as co
+    from oracle import ego_fold_oracle as ef
+    from tests.codebook_cases import make_codebook_params, oracle_params
+
+    rng = np.random.default_rng(5)
+    C, m, ks, cout, rows = 64, 1, [32, 32, 32], 24, 500
+    fd = co.fold_decode(oracle_params(*make_codebook_params(9, C, m, ks)))
+    tables = [fd["tables"][l][s] for l in range(len(ks)) for s in range(m)]
+    codes = np.stack([rng.integers(0, k, size=rows) for k in ks])
+    w = rng.normal(size=(cout, C)) * 0.5
+    b = rng.normal(size=cout) * 0.1
+    feat = co.decode_tables(fd, [codes[l][:, None] for l in range(len(ks))])
+    y = feat @ w.T + b
+    delta = np.abs(y).max() / 200.0
+    q_ref = np.clip(np.rint(np.maximum(y, 0.0) / delta), 0, 255)
+    q, rs, yy = ef.decode_linear_folded(codes, tables, fd["const"], w, b, delta)
+    np.testing.assert_allclose(yy, y, rtol=1e-10, atol=1e-10)
+    t = y / delta
+    near = np.abs(np.abs(t - np.floor(t)) - 0.5) < 1e-6
+    assert np.array_equal(q[~near], q_ref[~near].astype(np.uint8)) and np.array_equal(rs, q.astype(np.int64).sum(1))
