@@ -224,6 +224,15 @@ int qv2x_heads_forward(const qv2x_heads* heads, long long pixels, const float* d
  * buffer (multi-GPU: every rank writes its tile of the head maps straight into the ego rank's result). */
 int qv2x_heads_forward_tile(const qv2x_heads* heads, long long pixels, const float* d_x, float* d_out, int tile_w,
                             long long out_w, long long out_pixels, void* stream);
+/* The same GEMM as a transposed conv with kernel = stride on an FP32 map, with the ReLU + activation quantizer and the
+ * pixel shuffle in its epilogue (the deblocks of the pyramid path on the fused FP32 level maps: QuantModule(
+ * ConvTranspose2d(cin, c, s, stride=s)) + ReLU + act quantizer, opencood/quant/quant_block.py:441-458).  `heads` was
+ * created with cout = s*s*c rows ordered (dy, dx, channel); d_x [in_h*in_w][cin] float32; output pixel
+ * (y*s + dy, x*s + dx), channel out_cbase + ch of the uint8 NHWC buffer d_out_u8 [in_h*s][in_w*s][out_cstride] gets
+ * clamp(rint(value / out_delta), 0, 255) -- the codes of qv2x_heads_forward + qv2x_quantize_nchw_to_nhwc_u8, bit for
+ * bit.  c, out_cbase and out_cstride must be multiples of 8. */
+int qv2x_heads_forward_deconv_u8(const qv2x_heads* heads, int in_h, int in_w, const float* d_x, int stride,
+                                 float out_delta, uint8_t* d_out_u8, int out_cstride, int out_cbase, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ego stage of an attention-fusion frame in one kernel: code planes in, head maps out.  Replaces the chain

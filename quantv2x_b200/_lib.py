@@ -218,6 +218,10 @@ def _declare_fuse_u8(lib):
                                           c_void_p, c_void_p]
 
 
+    lib.qv2x_heads_forward_deconv_u8.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_float, c_void_p, c_int,
+                                                 c_int, c_void_p]
+
+
 _DECLARERS.append(_declare_fuse_u8)
 
 

@@ -246,14 +246,47 @@ static void launch_fuse(int n, int grid, int threads, cudaStream_t stream, const
 // runs on packed fp32 pairs (FFMA2: two IEEE fp32 fmas per instruction, the pixel value as the broadcast operand).
 constexpr int kHeadsPix = 64, kHeadsOut = 72, kHeadsPitchPad = 4, kHeadsThreads = 288;
 
+// Quantizing output of the FP32 GEMM (QOUT instantiations): the transposed convs of the pyramid path (kernel = stride
+// = s) on FP32 fused maps.  Column o of the GEMM is (dy, dx, c) = (o / (s * cs), (o / cs) % s, o % cs) with cs the
+// conv's output channels; input pixel (y, x) of a w-wide map lands at output pixel (y s + dy, x s + dx) of the uint8
+// NHWC concat buffer (channel stride cstride, first channel cbase).  A thread owns 8 consecutive columns = 8
+// consecutive channels of one sub-position: one 8-byte store per pixel.  The codes equal the quantizing converter's
+// (IEEE division): the product with fl(1 / delta) is redone exactly within 1e-3 of a rounding boundary.
+struct HeadsQOut {
+    uint8_t* out;
+    float delta, inv_delta;
+    int s, cs, w, cstride, cbase;
+};
+__device__ __forceinline__ unsigned heads_quant_u8(float v, float delta, float inv_delta) {
+    const float t = v * inv_delta;
+    float r = rintf(t);
+    if (fabsf(t - r) > 0.499f) r = rintf(__fdiv_rn(v, delta));
+    return static_cast<unsigned>(fminf(fmaxf(r, 0.f), 255.f));
+}
+// 8 columns starting at global column gcol0 of input pixel pp -> 8 bytes
+__device__ __forceinline__ void heads_store_q8(const HeadsQOut& q, long long pp, int gcol0, const float (&v)[8]) {
+    const int sub = gcol0 / q.cs, c0 = gcol0 - sub * q.cs;
+    const int dy = sub / q.s, dx = sub - dy * q.s;
+    const long long y = pp / q.w, x = pp - y * q.w;
+    const long long opix = (y * q.s + dy) * (static_cast<long long>(q.w) * q.s) + x * q.s + dx;
+    uint2 pk;
+    pk.x = heads_quant_u8(v[0], q.delta, q.inv_delta) | (heads_quant_u8(v[1], q.delta, q.inv_delta) << 8) |
+           (heads_quant_u8(v[2], q.delta, q.inv_delta) << 16) | (heads_quant_u8(v[3], q.delta, q.inv_delta) << 24);
+    pk.y = heads_quant_u8(v[4], q.delta, q.inv_delta) | (heads_quant_u8(v[5], q.delta, q.inv_delta) << 8) |
+           (heads_quant_u8(v[6], q.delta, q.inv_delta) << 16) | (heads_quant_u8(v[7], q.delta, q.inv_delta) << 24);
+    *reinterpret_cast<uint2*>(q.out + opix * q.cstride + q.cbase + c0) = pk;
+}
+
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, bool valid) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
 }
 
+template <bool QOUT>
 __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __restrict__ x, const float* __restrict__ wt,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               long long npix, int C, int cout, int tile_w,
-                                                              long long out_w, long long out_npix) {
+                                                              long long out_w, long long out_npix,
+                                                              const HeadsQOut qo) {
     extern __shared__ float4 hsm4[];
     float* hsm = reinterpret_cast<float*>(hsm4);
     // blockIdx.y = chunk of 72 outputs (wider GEMMs: the FP32 deblocks of the pyramid path): own weight slab, bias
@@ -328,6 +361,26 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
             const int ty = static_cast<int>(pp / tile_w);
             off[i] = (pp < npix) ? ty * out_w + (pp - static_cast<long long>(ty) * tile_w) : -1;
         }
+        if constexpr (QOUT) {
+            if (og * 8 < cout) {
+                float bb[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) bb[k] = bias ? __ldg(bias + og * 8 + k) : 0.f;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const long long pp = p0 + pg + 32 * i;
+                    if (pp >= npix) continue;
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        unpack2(acc[i][j], v[2 * j], v[2 * j + 1]);
+                        v[2 * j] += bb[2 * j];
+                        v[2 * j + 1] += bb[2 * j + 1];
+                    }
+                    heads_store_q8(qo, pp, static_cast<int>(blockIdx.y) * kHeadsOut + og * 8, v);
+                }
+            }
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -344,6 +397,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
                 }
             }
         }
+        }
         __syncthreads();          // everyone is done with this buffer before the next iteration refills it
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -355,12 +409,13 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel(const float* __res
 // above, so both kernels give identical bits.
 constexpr int kHeadsPix4 = 128, kHeadsKC = 128;
 
+template <bool QOUT>
 __global__ void __launch_bounds__(kHeadsThreads) heads_kernel_p4(const float* __restrict__ x,
                                                                  const float* __restrict__ wt,
                                                                  const float* __restrict__ bias,
                                                                  float* __restrict__ out, long long npix, int C,
                                                                  int cout, int tile_w, long long out_w,
-                                                                 long long out_npix) {
+                                                                 long long out_npix, const HeadsQOut qo) {
     extern __shared__ float4 hsm4[];
     float* hsm = reinterpret_cast<float*>(hsm4);
     wt += static_cast<long long>(blockIdx.y) * C * kHeadsOut;           // chunk of 72 outputs, as in heads_kernel
@@ -439,6 +494,26 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel_p4(const float* __
                 const int ty = static_cast<int>(pp / tile_w);
                 off[i] = (pp < npix) ? ty * out_w + (pp - static_cast<long long>(ty) * tile_w) : -1;
             }
+            if constexpr (QOUT) {
+                if (og * 8 < cout) {
+                    float bb[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bb[k] = bias ? __ldg(bias + og * 8 + k) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const long long pp = p0 + pg + 32 * i;
+                        if (pp >= npix) continue;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            unpack2(acc[i][j], v[2 * j], v[2 * j + 1]);
+                            v[2 * j] += bb[2 * j];
+                            v[2 * j + 1] += bb[2 * j + 1];
+                        }
+                        heads_store_q8(qo, pp, static_cast<int>(blockIdx.y) * kHeadsOut + og * 8, v);
+                    }
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
 #pragma unroll
@@ -455,6 +530,7 @@ __global__ void __launch_bounds__(kHeadsThreads) heads_kernel_p4(const float* __
                         }
                     }
                 }
+            }
             }
         }
         __syncthreads();          // everyone is done with this buffer before the next iteration refills it
@@ -647,16 +723,16 @@ int qv2x_heads_forward(const qv2x_heads* h, long long pixels, const float* d_x, 
                                    pixels, pixels, stream_);
 }
 
-int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, int tile_w,
-                            long long out_w, long long out_pixels, void* stream_) {
-    QV2X_REQUIRE(h && d_x && d_out, "qv2x_heads_forward: null argument");
-    QV2X_REQUIRE(tile_w >= 1 && out_w >= tile_w && out_pixels >= 1, "bad output tile geometry");
+static int heads_launch(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, int tile_w,
+                        long long out_w, long long out_pixels, const HeadsQOut* qo, void* stream_) {
     if (pixels <= 0) return 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     static bool attr = false;
     if (!attr) {
-        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel_p4, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel_p4<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        QV2X_CUDA_OK(cudaFuncSetAttribute(heads_kernel_p4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr = true;
     }
     static const bool p4_enabled = [] {
@@ -667,24 +743,61 @@ int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* 
     // by ceil(#SMs / chunks) persistent CTAs
     const int chunks = (h->cout + kHeadsOut - 1) / kHeadsOut;
     const int per_chunk = std::max(1, (num_sms() + chunks - 1) / chunks);
+    const HeadsQOut q0{};
     if (p4_enabled && h->cin % kHeadsKC == 0 && pixels * chunks >= 4LL * kHeadsPix4 * num_sms() / 8) {
         const int smem = (2 * kHeadsPix4 * (kHeadsKC + kHeadsPitchPad) + h->cin * kHeadsOut) *
                          static_cast<int>(sizeof(float));
         const long long ntiles = (pixels + kHeadsPix4 - 1) / kHeadsPix4;
         const dim3 grid(static_cast<unsigned>(std::min<long long>(ntiles, per_chunk)), chunks);
-        heads_kernel_p4<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
-                                                               tile_w, out_w, out_pixels);
+        if (qo)
+            heads_kernel_p4<true><<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin,
+                                                                         h->cout, tile_w, out_w, out_pixels, *qo);
+        else
+            heads_kernel_p4<false><<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin,
+                                                                          h->cout, tile_w, out_w, out_pixels, q0);
     } else {
         const int smem = (2 * kHeadsPix * (h->cin + kHeadsPitchPad) + h->cin * kHeadsOut) *
                          static_cast<int>(sizeof(float));
         const long long ntiles = (pixels + kHeadsPix - 1) / kHeadsPix;
         const dim3 grid(static_cast<unsigned>(std::min<long long>(ntiles, per_chunk)), chunks);
-        heads_kernel<<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin, h->cout,
-                                                            tile_w, out_w, out_pixels);
+        if (qo)
+            heads_kernel<true><<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin,
+                                                                      h->cout, tile_w, out_w, out_pixels, *qo);
+        else
+            heads_kernel<false><<<grid, kHeadsThreads, smem, stream>>>(d_x, h->d_w, h->d_b, d_out, pixels, h->cin,
+                                                                       h->cout, tile_w, out_w, out_pixels, q0);
     }
     g_launch_count.fetch_add(1);
     QV2X_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int qv2x_heads_forward_tile(const qv2x_heads* h, long long pixels, const float* d_x, float* d_out, int tile_w,
+                            long long out_w, long long out_pixels, void* stream_) {
+    QV2X_REQUIRE(h && d_x && d_out, "qv2x_heads_forward: null argument");
+    QV2X_REQUIRE(tile_w >= 1 && out_w >= tile_w && out_pixels >= 1, "bad output tile geometry");
+    return heads_launch(h, pixels, d_x, d_out, tile_w, out_w, out_pixels, nullptr, stream_);
+}
+
+int qv2x_heads_forward_deconv_u8(const qv2x_heads* h, int in_h, int in_w, const float* d_x, int stride, float out_delta,
+                                 uint8_t* d_out_u8, int out_cstride, int out_cbase, void* stream_) {
+    QV2X_REQUIRE(h && d_x && d_out_u8, "qv2x_heads_forward_deconv_u8: null argument");
+    QV2X_REQUIRE(in_h > 0 && in_w > 0 && stride >= 1 && out_delta > 0.f, "bad map size / stride / scale");
+    QV2X_REQUIRE(h->cout % (stride * stride) == 0, "the GEMM has %d columns, not a multiple of stride^2", h->cout);
+    const int cs = h->cout / (stride * stride);
+    QV2X_REQUIRE(cs % 8 == 0 && out_cbase % 8 == 0 && out_cstride % 8 == 0 && out_cbase + cs <= out_cstride,
+                 "output channels, channel base and channel stride must be multiples of 8");
+    HeadsQOut qo{};
+    qo.out = d_out_u8;
+    qo.delta = out_delta;
+    qo.inv_delta = 1.0f / out_delta;
+    qo.s = stride;
+    qo.cs = cs;
+    qo.w = in_w;
+    qo.cstride = out_cstride;
+    qo.cbase = out_cbase;
+    const long long pixels = static_cast<long long>(in_h) * in_w;
+    return heads_launch(h, pixels, d_x, reinterpret_cast<float*>(d_out_u8), in_w, pixels, pixels, &qo, stream_);
 }
 
 int qv2x_quantize_nchw_to_nhwc_u8(const float* d_x, int n, int c, long long pixels, float delta, float zero_point,

@@ -403,6 +403,21 @@ class DecodeLinearEngine:
         return out, rs
 
 
+def heads_forward_deconv_u8(heads: "HeadsEngine", x: torch.Tensor, stride: int, out_delta: float, out: torch.Tensor,
+                            out_cbase: int = 0) -> torch.Tensor:
+    """Transposed conv (kernel = stride) on an FP32 map [h, w, cin] as one GEMM whose epilogue applies ReLU + the
+    activation quantizer and the pixel shuffle: codes go to out[:, :, out_cbase : out_cbase + c] of the uint8 NHWC
+    buffer [h*stride, w*stride, C] (qv2x_heads_forward_deconv_u8)."""
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.dim() == 3 and x.shape[-1] == heads.cin
+    assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.dim() == 3
+    h, w, _ = x.shape
+    assert out.shape[0] == h * stride and out.shape[1] == w * stride
+    check(_lib.lib().qv2x_heads_forward_deconv_u8(heads._h, h, w, c_void_p(x.data_ptr()), int(stride), float(out_delta),
+                                                  c_void_p(out.data_ptr()), out.shape[2], int(out_cbase),
+                                                  _stream_ptr()))
+    return out
+
+
 class PillarEngine:
     """libqv2x handle of the quantized PointPillars front end (qv2x_pillar_*): pillars -> uint8 NHWC BEV map."""
 

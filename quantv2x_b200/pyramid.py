@@ -27,6 +27,8 @@ conv -> heads) is quantv2x_b200.pyramid_model; see DESIGN.md section 3.8.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -331,6 +333,10 @@ class DeblockF32:
         assert fused.is_cuda and fused.dtype == torch.float32 and fused.is_contiguous() and fused.shape[-1] == self.cin
         h, w, _ = fused.shape
         s, n_col = self.s, self.s * self.s * self.cout
+        if (self.cout % 8 == 0 and out_cbase % 8 == 0 and out.shape[-1] % 8 == 0 and out.is_contiguous()
+                and os.environ.get("QV2X_DEBLOCK_CHAIN", "0") != "1"):
+            # quantizer + pixel shuffle in the GEMM's epilogue: the same codes as the three-step path below
+            return E.heads_forward_deconv_u8(self.gemm, fused, s, self.delta, out, out_cbase)
         planar = torch.empty((n_col, h * w), dtype=torch.float32, device=fused.device)
         self.gemm.forward(fused, out=planar)
         q = E.quantize_nchw_to_nhwc_u8(planar.view(1, n_col, h, w), self.delta)        # [1, h, w, s*s*cout]

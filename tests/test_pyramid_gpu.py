@@ -191,3 +191,28 @@ def test_basic_block_bit_exact(cuda_device, idx):
     assert np.array_equal(rs.cpu().numpy(), ref["out"].astype(np.int64).sum(-1))
     d = np.abs(out.cpu().numpy().astype(np.int64) - g[f"{name}.out.codes"].transpose(0, 2, 3, 1).astype(np.int64))
     assert d.max() <= 1 and (d > 0).mean() < 1e-2
+
+
+@pytest.mark.parametrize("case", [(64, 128, 1, 20, 44), (128, 128, 2, 25, 44), (256, 128, 4, 13, 22), (64, 16, 2, 5, 7)],
+                         ids=lambda c: f"cin{c[0]}_c{c[1]}_s{c[2]}_{c[3]}x{c[4]}")
+def test_deblock_f32_quantizing_epilogue(cuda_device, case, monkeypatch):
+    """DeblockF32 with the quantizer + pixel shuffle in the GEMM's epilogue (qv2x_heads_forward_deconv_u8) writes the
+    same codes, bit for bit, as GEMM -> planar FP32 -> quantizing converter -> permuted copy, and leaves the other
+    channels of the concat buffer untouched."""
+    from quantv2x_b200.pyramid import DeblockF32
+
+    cin, cout, s, h, w = case
+    rng = np.random.default_rng(cin + s)
+    up = dict(stride=s, act_delta=0.043, w_int=rng.integers(0, 256, size=(cin, cout, s, s)).astype(np.uint8),
+              w_zp=rng.integers(100, 156, size=cin).astype(np.float32),
+              w_delta=(rng.random(cin) * 0.004 + 0.001).astype(np.float32), bias=rng.normal(size=cout).astype(np.float32))
+    d = DeblockF32(up)
+    x = torch.from_numpy((rng.standard_normal((h, w, cin)) * 1.5).astype(np.float32)).to(cuda_device)
+    ctot, cbase = 2 * cout + 8, 8
+    a = torch.full((h * s, w * s, ctot), 7, dtype=torch.uint8, device=cuda_device)
+    b = a.clone()
+    d.forward(x, a, cbase)
+    monkeypatch.setenv("QV2X_DEBLOCK_CHAIN", "1")
+    d.forward(x, b, cbase)
+    assert torch.equal(a, b)
+    assert int(a[..., cbase:cbase + cout].max()) > 7 and bool((a[..., :cbase] == 7).all())
